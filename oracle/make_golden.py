@@ -1,0 +1,104 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by executing the unmodified reference in this container.
+
+    python oracle/make_golden.py
+
+The reference ships no golden vectors, so these fixtures are outputs of the
+reference itself run here (numpy / scipy versions recorded inside each file); they are what
+pins the oracle and the CUDA path on the GPU box, where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from feprogram_b200 import mesh  # noqa: E402  (host-side generators only; no CUDA involved)
+from oracle import ref_runner  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def case_mesh(kind, n, perturbed, shuffled):
+    if kind == 4:
+        conn, coords, bc = mesh.structured_quad4(n)
+        mx = n
+    else:
+        conn, coords, bc = mesh.structured_quad9(n)
+        mx = 2 * n
+    if perturbed:
+        coords = mesh.perturb_interior(coords, mx, mx, 0.2, seed=0)
+    if shuffled:
+        conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=1)
+    return conn, coords, bc
+
+
+def bc_arrays(bc):
+    return {"bc%d" % i: np.array(sorted(s), dtype=np.int64) for i, s in enumerate(bc)}
+
+
+def full_case(name, kind, n, perturbed, shuffled, nke=6):
+    conn, coords, bc = case_mesh(kind, n, perturbed, shuffled)
+    K0 = ref_runner.assemble_prebc(conn, coords)
+    run = ref_runner.full_run(conn, coords, bc)
+    fem = ref_runner.make_problem(conn, coords)
+    ke = np.array([ref_runner.element_matrix(fem, conn[e] - 1) for e in range(min(nke, len(conn)))])
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        conn=conn, coords=coords, **bc_arrays(bc),
+        k0_indptr=K0.indptr, k0_indices=K0.indices, k0_data=K0.data,
+        k_indptr=run["K"].indptr, k_indices=run["K"].indices, k_data=run["K"].data,
+        brhs=run["brhs"], U=run["U"], dofDir=run["dofDir"], dofNeu=run["dofNeu"], ke=ke,
+        versions=np.array([np.__version__, scipy.__version__]),
+    )
+    print(name, "nnz0", K0.nnz, "nnz", run["K"].nnz, "|U|max", np.abs(run["U"]).max())
+
+
+def scalar_case(kind, n):
+    conn, coords, bc = case_mesh(kind, n, False, False)
+    K0 = ref_runner.assemble_prebc(conn, coords)
+    run = ref_runner.full_run(conn, coords, bc)
+    U = run["U"]
+    return np.array([K0.nnz, np.sqrt((K0.data ** 2).sum()), K0.diagonal().sum(), run["K"].nnz,
+                     len(run["dofDir"]), len(run["dofNeu"]), U.min(), U.max(), np.linalg.norm(U)])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # tables (T1-T4)
+    d4, h4, w4 = ref_runner.tables(4)
+    d9, h9, w9 = ref_runner.tables(9)
+    # single distorted elements (E1-E3)
+    X4 = np.array([[0, 0], [2, 0.1], [2.3, 1.2], [-0.1, 0.9]], dtype=np.float64)
+    fem4 = ref_runner.make_problem(np.array([[1, 2, 3, 4]]), X4)
+    ke4 = ref_runner.element_matrix(fem4, np.arange(4))
+    rng = np.random.default_rng(7)
+    c9, x9, _ = mesh.structured_quad9(1)
+    x9 = 3.0 * x9 + rng.uniform(-0.12, 0.12, size=x9.shape)
+    fem9 = ref_runner.make_problem(c9, x9)
+    ke9 = ref_runner.element_matrix(fem9, c9[0] - 1)
+    np.savez_compressed(os.path.join(OUT, "tables_and_single.npz"), dH4=d4, H4=h4, w4=w4, dH9=d9, H9=h9,
+                        w9=w9, X4=X4, ke4=ke4, conn9=c9, X9=x9, ke9=ke9,
+                        versions=np.array([np.__version__, scipy.__version__]))
+    # full small problems: structure, values, BCs, solution
+    full_case("q4_4x4", 4, 4, False, False)
+    full_case("q4_12x12_pert_shuf", 4, 12, True, True)
+    full_case("q4_16x16_pert", 4, 16, True, False)
+    full_case("q9_4x4", 9, 4, False, False)
+    full_case("q9_6x6_pert_shuf", 9, 6, True, True)
+    # scalar known answers on BASELINE cfg1 and a Quad9 case
+    np.savez_compressed(os.path.join(OUT, "scalars.npz"),
+                        fields=np.array(["nnz0", "normF0", "trace0", "nnz_bc", "nDir", "nNeu", "Umin", "Umax",
+                                         "Unorm"]),
+                        q4_64=scalar_case(4, 64), q9_32=scalar_case(9, 32), q4_4=scalar_case(4, 4),
+                        q9_4=scalar_case(9, 4),
+                        versions=np.array([np.__version__, scipy.__version__]))
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
