@@ -1,0 +1,121 @@
+"""In-tree build of the CUDA library: nvcc -> feprogram_b200/libfeprogram_b200.so (sm_100a only).
+
+    python -m feprogram_b200.build [--force] [--verbose]
+
+Cross-compiles without a GPU.  The built .so is git-ignored but travels to the GPU box with the
+repository snapshot.  Also builds the C oracle (oracle/libfe_oracle.so) with gcc when asked to
+(``build_oracle``) -- building the checker is not using it.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "csrc", "build")
+LIB = os.path.join(PKG, "libfeprogram_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA library cannot be built")
+
+
+def _nccl_paths():
+    """NCCL header + library: prefer the torch-bundled one (it is what torch.distributed uses)."""
+    try:
+        import nvidia.nccl as n  # type: ignore
+        base = os.path.dirname(n.__file__) if getattr(n, "__file__", None) else list(n.__path__)[0]
+        inc, lib = os.path.join(base, "include"), os.path.join(base, "lib")
+        if os.path.exists(os.path.join(inc, "nccl.h")):
+            return inc, lib
+    except Exception:
+        pass
+    if os.path.exists("/usr/include/nccl.h"):
+        return "/usr/include", "/usr/lib/x86_64-linux-gnu"
+    return None, None
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stamp(srcs) -> str:
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "feprogram_b200.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    srcs = _sources()
+    os.makedirs(OBJ, exist_ok=True)
+    stamp_file = os.path.join(OBJ, "stamp")
+    stamp = _stamp(srcs)
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
+    nvcc = _nvcc()
+    inc, nccl_lib = _nccl_paths()
+    extra_inc = ["-I", inc] if inc else []
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, src[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_inc, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(os.path.join(OBJ, src[:-3] + ".ptxas.log"), "w") as f:
+            f.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    if any("dist" in s for s in srcs) and nccl_lib:
+        # resolved at load time against the libnccl torch has already loaded
+        link += ["-Xlinker", "--allow-shlib-undefined"]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return LIB
+
+
+def build_oracle(force: bool = False) -> str | None:
+    """gcc build of the plain-C oracle (test infrastructure); returns the .so path or None if absent."""
+    src = os.path.join(ROOT, "oracle", "fe_oracle.c")
+    if not os.path.exists(src):
+        return None
+    out = os.path.join(ROOT, "oracle", "libfe_oracle.so")
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cmd = ["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", out, src, "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed on the C oracle:\n%s" % r.stderr)
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

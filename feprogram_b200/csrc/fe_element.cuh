@@ -1,0 +1,142 @@
+// Per-element arithmetic of the hot path (device functions), tables in __constant__ memory.
+//
+// Restates Elem.funB + FemProblem.getKe (/root/reference/elements.py:15-23, 153-163):
+//   J = dH_g X, det = |J|, Dh = J^-1 dH_g, Ke += B^T B det with
+//   B rows [Dx on u | Dy on v | Dy on u + Dx on v | 0]  =>  per node pair (a,b)
+//     Ke[2a  ,2b  ] = Ke[2a+1,2b+1] = sum_g (Dx_a Dx_b + Dy_a Dy_b) det     ("L")
+//     Ke[2a  ,2b+1] = sum_g Dy_a Dx_b det                                    ("P")
+//     Ke[2a+1,2b  ] = sum_g Dx_a Dy_b det                                    ("Q")
+// evaluated through the adjugate A = det * J^-1 dH so that each Gauss point needs one division:
+//   (Dx_a Dx_b + ..) det = (Ax_a Ax_b + ..) / det.
+// fp64 throughout, no tensor cores (blocks are 8x8 / 18x18 and the kernel is HBM-bound).
+#pragma once
+
+#include "fe_common.cuh"
+
+namespace fe {
+
+// One private copy per translation unit (no relocatable device code needed).
+static __constant__ TablesQ4 c_q4;
+static __constant__ TablesQ9 c_q9;
+static __constant__ TablesT3 c_t3;
+
+// Uploads this translation unit's tables once per device.
+static int ensure_tables_tu(cudaStream_t stream) {
+    static bool done[64] = {false};
+    int dev = 0;
+    FE_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (done[dev]) return FE_OK;
+    TablesQ4 q4;
+    TablesQ9 q9;
+    TablesT3 t3;
+    fe_tables(FE_QUAD4, &q4.dH[0][0][0], nullptr, q4.w, nullptr, nullptr);
+    fe_tables(FE_QUAD9, &q9.dH[0][0][0], nullptr, q9.w, nullptr, nullptr);
+    fe_tables(FE_TRI3, &t3.dH[0][0][0], nullptr, t3.w, nullptr, nullptr);
+    FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_q4, &q4, sizeof(q4), 0, cudaMemcpyHostToDevice, stream));
+    FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_q9, &q9, sizeof(q9), 0, cudaMemcpyHostToDevice, stream));
+    FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_t3, &t3, sizeof(t3), 0, cudaMemcpyHostToDevice, stream));
+    FE_CUDA_TRY(cudaStreamSynchronize(stream));  // host buffers are on this stack frame
+    done[dev] = true;
+    return FE_OK;
+}
+
+template <int ET> struct Elem;
+template <> struct Elem<FE_QUAD4> {
+    static constexpr int NNPE = 4, NG = 4;
+    __device__ __forceinline__ static double dHr(int g, int a) { return c_q4.dH[g][0][a]; }
+    __device__ __forceinline__ static double dHs(int g, int a) { return c_q4.dH[g][1][a]; }
+    __device__ __forceinline__ static double w(int g) { return c_q4.w[g]; }
+};
+template <> struct Elem<FE_QUAD9> {
+    static constexpr int NNPE = 9, NG = 9;
+    __device__ __forceinline__ static double dHr(int g, int a) { return c_q9.dH[g][0][a]; }
+    __device__ __forceinline__ static double dHs(int g, int a) { return c_q9.dH[g][1][a]; }
+    __device__ __forceinline__ static double w(int g) { return c_q9.w[g]; }
+};
+template <> struct Elem<FE_TRI3> {
+    static constexpr int NNPE = 3, NG = 1;
+    __device__ __forceinline__ static double dHr(int g, int a) { return c_t3.dH[g][0][a]; }
+    __device__ __forceinline__ static double dHs(int g, int a) { return c_t3.dH[g][1][a]; }
+    __device__ __forceinline__ static double w(int g) { return c_t3.w[g]; }
+};
+
+// Gathers the element's node ids and coordinates (Elem.getpos, elements.py:34-38).
+template <int ET>
+__device__ __forceinline__ void load_element(const int32_t* __restrict__ conn, const double2* __restrict__ coords,
+                                             int64_t e, int (&t)[Elem<ET>::NNPE], double (&x)[Elem<ET>::NNPE],
+                                             double (&y)[Elem<ET>::NNPE]) {
+    constexpr int N = Elem<ET>::NNPE;
+    if constexpr (N == 4) {
+        const int4 c = __ldg(reinterpret_cast<const int4*>(conn) + e);
+        t[0] = c.x; t[1] = c.y; t[2] = c.z; t[3] = c.w;
+    } else {
+#pragma unroll
+        for (int a = 0; a < N; ++a) t[a] = __ldg(conn + e * N + a);
+    }
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+        const double2 p = __ldg(coords + t[a]);
+        x[a] = p.x;
+        y[a] = p.y;
+    }
+}
+
+// Adjugate gradients at Gauss point g:  Ax_b = J11 dHr_b - J01 dHs_b, Ay_b = -J10 dHr_b + J00 dHs_b,
+// returns 1/det (times the Gauss weight when weighted).
+template <int ET>
+__device__ __forceinline__ double gauss_point(int g, const double (&x)[Elem<ET>::NNPE],
+                                              const double (&y)[Elem<ET>::NNPE], bool weighted,
+                                              double (&ax)[Elem<ET>::NNPE], double (&ay)[Elem<ET>::NNPE]) {
+    using E = Elem<ET>;
+    double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
+#pragma unroll
+    for (int b = 0; b < E::NNPE; ++b) {
+        j00 = fma(E::dHr(g, b), x[b], j00);
+        j01 = fma(E::dHr(g, b), y[b], j01);
+        j10 = fma(E::dHs(g, b), x[b], j10);
+        j11 = fma(E::dHs(g, b), y[b], j11);
+    }
+    const double det = j00 * j11 - j01 * j10;
+#pragma unroll
+    for (int b = 0; b < E::NNPE; ++b) {
+        ax[b] = j11 * E::dHr(g, b) - j01 * E::dHs(g, b);
+        ay[b] = j00 * E::dHs(g, b) - j10 * E::dHr(g, b);
+    }
+    double s = 1.0 / det;
+    if (weighted) s *= E::w(g);
+    return s;
+}
+
+// Row pair of local node a:  L[b], P[b], Q[b] for all b (see file header).  `a` is a run-time
+// value; the own-node gradients are picked with selects so everything stays in registers.
+template <int ET>
+__device__ __forceinline__ void element_row_pair(const double (&x)[Elem<ET>::NNPE],
+                                                 const double (&y)[Elem<ET>::NNPE], int a, bool weighted,
+                                                 double (&L)[Elem<ET>::NNPE], double (&P)[Elem<ET>::NNPE],
+                                                 double (&Q)[Elem<ET>::NNPE]) {
+    using E = Elem<ET>;
+#pragma unroll
+    for (int b = 0; b < E::NNPE; ++b) L[b] = P[b] = Q[b] = 0.0;
+#pragma unroll
+    for (int g = 0; g < E::NG; ++g) {
+        double ax[E::NNPE], ay[E::NNPE];
+        const double s = gauss_point<ET>(g, x, y, weighted, ax, ay);
+        double axa = 0.0, aya = 0.0;
+#pragma unroll
+        for (int b = 0; b < E::NNPE; ++b) {
+            axa = (b == a) ? ax[b] : axa;
+            aya = (b == a) ? ay[b] : aya;
+        }
+        axa *= s;
+        aya *= s;
+#pragma unroll
+        for (int b = 0; b < E::NNPE; ++b) {
+            L[b] = fma(axa, ax[b], fma(aya, ay[b], L[b]));
+            P[b] = fma(aya, ax[b], P[b]);
+            Q[b] = fma(axa, ay[b], Q[b]);
+        }
+    }
+}
+
+}  // namespace fe

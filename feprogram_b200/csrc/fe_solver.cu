@@ -1,0 +1,429 @@
+// K5 (CSR SpMV) and K6 (fused Jacobi-PCG vector kernels).
+//
+// Replaces spsolve(K, brhs) (/root/reference/elements.py:241-243) by Jacobi-preconditioned CG on the
+// SPD system the reference's row-only Dirichlet treatment is equivalent to:
+// x_D = g_D, K_II x_I = b_I - K_ID g_D.  The matrix is never modified: the search direction is kept
+// zero on Dirichlet dofs and the SpMV zeroes Dirichlet rows, which is the same operator.
+//
+// Per iteration: 3 kernels, 2 deterministic two-stage reductions, all scalars stay on the device.
+//   A: Ap = A p (masked), partial dots p.Ap                       [fe SpMV traffic]
+//   B: alpha = rz/pAp; x += alpha p; r -= alpha Ap; partial r.z, r.r with z = Minv r   [7 vector streams]
+//   C: beta = rz'/rz; p = Minv r + beta p; convergence flag                            [4 vector streams]
+#include <stdlib.h>
+
+#include "fe_common.cuh"
+
+namespace fe {
+
+constexpr int kVecThreads = 256;
+constexpr int kMaxPartials = 4096;  // upper bound on persistent grid sizes
+constexpr int kScalarDoubles = 16;
+
+// scalar block layout (doubles)
+// Flags and scalars are double-buffered between kernels so that no kernel reads a location one of its
+// own blocks writes:  DONE_C / RZ_CUR are written by kernel C and read by A and B;  DONE_B / RZ_PREV
+// are written by kernel B and read by C.
+enum { S_RZ_CUR = 0, S_RZ_PREV = 1, S_RR = 2, S_RR0 = 3, S_TOL2 = 4, S_ITERS = 5, S_DONE_C = 6, S_PAP = 7, S_DONE_B = 8 };
+
+// ---- deterministic block reduction (fixed shuffle tree, then warp 0 over the warp sums) ----------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// Result valid in thread 0.  `sm` needs blockDim/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect sm reuse
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (warp == 0) {
+        t = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;
+}
+
+// Every block sums the same `n` partials in the same order => identical value in all blocks.
+// Result broadcast to all threads.
+__device__ __forceinline__ double sum_partials(const double* __restrict__ part, int n, int stride, double* sm) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[(size_t)i * stride];
+    v = block_sum(v, sm);
+    __shared__ double bc;
+    if (threadIdx.x == 0) bc = v;
+    __syncthreads();
+    return bc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: CSR SpMV, LPR lanes per row, persistent grid-stride over row groups.  Lanes of a row read
+// consecutive (val, col) entries, adjacent rows are adjacent in memory => coalesced streams; x is
+// gathered through L1/L2.  Fixed in-row reduction tree => deterministic.
+// DOT: also accumulates sum_r x[r]*y[r] per block into partials[blockIdx.x] (x is the SpMV input).
+// ------------------------------------------------------------------------------------------------
+template <typename IdxT, int LPR, bool DOT>
+__global__ void __launch_bounds__(kVecThreads) k_spmv(int64_t nrows, const IdxT* __restrict__ row_ptr,
+                                                      const int32_t* __restrict__ col_idx,
+                                                      const double* __restrict__ vals, const double* __restrict__ x,
+                                                      double* __restrict__ y, const uint8_t* __restrict__ rowmask,
+                                                      double* __restrict__ partials,
+                                                      const double* __restrict__ scal) {
+    __shared__ double sm[kVecThreads / 32];
+    if (DOT && scal[S_DONE_C] != 0.0) return;
+    constexpr int RPB = kVecThreads / LPR;
+    const int lane = threadIdx.x % LPR;
+    const int grp = threadIdx.x / LPR;
+    double dot = 0.0;
+    for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < nrows; row0 += (int64_t)gridDim.x * RPB) {
+        const int64_t row = row0 + grp;
+        double sum = 0.0;
+        if (row < nrows) {
+            const int64_t j0 = row_ptr[row], j1 = row_ptr[row + 1];
+            for (int64_t j = j0 + lane; j < j1; j += LPR) sum = fma(__ldg(vals + j), __ldg(x + __ldg(col_idx + j)), sum);
+        }
+#pragma unroll
+        for (int d = LPR / 2; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d, LPR);
+        if (lane == 0 && row < nrows) {
+            if (rowmask && rowmask[row]) sum = 0.0;
+            y[row] = sum;
+            if (DOT) dot = fma(__ldg(x + row), sum, dot);
+        }
+    }
+    if (DOT) {
+        dot = block_sum(dot, sm);
+        if (threadIdx.x == 0) partials[blockIdx.x] = dot;
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256) k_csr_diagonal(int64_t nrows, const IdxT* __restrict__ row_ptr,
+                                                      const int32_t* __restrict__ col_idx,
+                                                      const double* __restrict__ vals, double* __restrict__ diag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    double d = 0.0;
+    for (int64_t j = row_ptr[r]; j < row_ptr[r + 1]; ++j)
+        if (col_idx[j] == r) d = vals[j];
+    diag[r] = d;
+}
+
+// ---- PCG vector kernels ---------------------------------------------------------------------------
+// init 1: x = g on Dirichlet dofs, 0 elsewhere;  minv = 1/diag (0 on Dirichlet dofs and empty rows)
+__global__ void __launch_bounds__(kVecThreads) k_pcg_init1(int64_t n, const double* __restrict__ rhs,
+                                                           const uint8_t* __restrict__ mask, double* __restrict__ x,
+                                                           double* __restrict__ minv) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool d = mask && mask[i];
+        x[i] = d ? rhs[i] : 0.0;
+        const double dg = minv[i];  // holds diag on entry
+        minv[i] = (d || dg == 0.0) ? 0.0 : 1.0 / dg;
+    }
+}
+
+// init 2: r = rhs - A x0 on free dofs (Ap holds A x0 with Dirichlet rows zeroed), p = Minv r
+__global__ void __launch_bounds__(kVecThreads) k_pcg_init2(int64_t n, const double* __restrict__ rhs,
+                                                           const uint8_t* __restrict__ mask,
+                                                           const double* __restrict__ Ax0,
+                                                           const double* __restrict__ minv, double* __restrict__ r,
+                                                           double* __restrict__ p, double* __restrict__ partB) {
+    __shared__ double sm[kVecThreads / 32];
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = (mask && mask[i]) ? 0.0 : rhs[i] - Ax0[i];
+        const double zi = minv[i] * ri;
+        r[i] = ri;
+        p[i] = zi;
+        rz = fma(ri, zi, rz);
+        rr = fma(ri, ri, rr);
+    }
+    rz = block_sum(rz, sm);
+    rr = block_sum(rr, sm);
+    if (threadIdx.x == 0) {
+        partB[2 * blockIdx.x] = rz;
+        partB[2 * blockIdx.x + 1] = rr;
+    }
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_pcg_init3(int nb, const double* __restrict__ partB, double rtol,
+                                                           double atol, double* __restrict__ scal) {
+    __shared__ double sm[kVecThreads / 32];
+    const double rz = sum_partials(partB, nb, 2, sm);
+    const double rr = sum_partials(partB + 1, nb, 2, sm);
+    if (threadIdx.x == 0) {
+        scal[S_RZ_CUR] = rz;
+        scal[S_RZ_PREV] = rz;
+        scal[S_RR] = rr;
+        scal[S_RR0] = rr;
+        const double t = fmax(rtol * rtol * rr, atol * atol);
+        scal[S_TOL2] = t;
+        scal[S_ITERS] = 0.0;
+        scal[S_DONE_C] = (rr <= t) ? 1.0 : 0.0;
+        scal[S_DONE_B] = 0.0;
+        scal[S_PAP] = 0.0;
+    }
+}
+
+// B: x += alpha p; r -= alpha Ap; partial (r.z, r.r)
+__global__ void __launch_bounds__(kVecThreads) k_pcg_update(int64_t n, int nbA, const double* __restrict__ partA,
+                                                            const double* __restrict__ p,
+                                                            const double* __restrict__ Ap,
+                                                            const double* __restrict__ minv, double* __restrict__ x,
+                                                            double* __restrict__ r, double* __restrict__ partB,
+                                                            double* __restrict__ scal) {
+    __shared__ double sm[kVecThreads / 32];
+    const bool done = scal[S_DONE_C] != 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE_B] = done ? 1.0 : 0.0;
+    if (done) return;
+    const double pAp = sum_partials(partA, nbA, 1, sm);
+    const double rz_cur = scal[S_RZ_CUR];
+    const double alpha = rz_cur / pAp;
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, Ap[i], r[i]);
+        r[i] = ri;
+        const double zi = minv[i] * ri;
+        rz = fma(ri, zi, rz);
+        rr = fma(ri, ri, rr);
+    }
+    rz = block_sum(rz, sm);
+    rr = block_sum(rr, sm);
+    if (threadIdx.x == 0) {
+        partB[2 * blockIdx.x] = rz;
+        partB[2 * blockIdx.x + 1] = rr;
+        if (blockIdx.x == 0) {
+            scal[S_RZ_PREV] = rz_cur;  // nobody reads RZ_PREV during this kernel
+            scal[S_PAP] = pAp;
+        }
+    }
+}
+
+// C: beta = rz'/rz; p = Minv r + beta p; block 0 publishes rz', r.r, iteration count, done flag
+__global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int64_t n, int nbB, const double* __restrict__ partB,
+                                                               const double* __restrict__ r,
+                                                               const double* __restrict__ minv,
+                                                               double* __restrict__ p, double* __restrict__ scal) {
+    __shared__ double sm[kVecThreads / 32];
+    if (scal[S_DONE_B] != 0.0) return;
+    const double rz_new = sum_partials(partB, nbB, 2, sm);
+    const double rr = sum_partials(partB + 1, nbB, 2, sm);
+    const double beta = rz_new / scal[S_RZ_PREV];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = fma(beta, p[i], minv[i] * r[i]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[S_RZ_CUR] = rz_new;
+        scal[S_RR] = rr;
+        scal[S_ITERS] += 1.0;
+        if (rr <= scal[S_TOL2] || !(rr == rr)) scal[S_DONE_C] = 1.0;
+    }
+}
+
+static int persistent_grid(const void* func, int threads, int* out) {
+    int dev = 0, sms = 0, occ = 0;
+    FE_CUDA_TRY(cudaGetDevice(&dev));
+    FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, 0));
+    if (occ < 1) occ = 1;
+    int g = sms * occ;
+    if (g > kMaxPartials) g = kMaxPartials;
+    *out = g;
+    return FE_OK;
+}
+
+static int pick_lpr(int64_t nrows, int64_t nnz) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("FE_SPMV_LPR");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+    if (avg <= 3.0) return 2;
+    if (avg <= 6.0) return 4;
+    if (avg <= 24.0) return 8;
+    if (avg <= 48.0) return 16;
+    return 32;
+}
+
+template <typename IdxT, bool DOT>
+static int launch_spmv(int lpr, int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, const double* vals,
+                       const double* x, double* y, const uint8_t* mask, double* partials, const double* scal,
+                       int* grid_out, cudaStream_t st) {
+#define FE_SPMV_CASE(L)                                                                                          \
+    case L: {                                                                                                    \
+        int g = 0;                                                                                               \
+        int rc = persistent_grid((const void*)k_spmv<IdxT, L, DOT>, kVecThreads, &g);                            \
+        if (rc != FE_OK) return rc;                                                                              \
+        const int64_t need = (nrows + (kVecThreads / L) - 1) / (kVecThreads / L);                                \
+        if (!DOT && need < g) g = (int)(need > 0 ? need : 1);                                                    \
+        k_spmv<IdxT, L, DOT><<<g, kVecThreads, 0, st>>>(nrows, row_ptr, col_idx, vals, x, y, mask, partials, scal); \
+        if (grid_out) *grid_out = g;                                                                             \
+        break;                                                                                                   \
+    }
+    switch (lpr) {
+        FE_SPMV_CASE(2)
+        FE_SPMV_CASE(4)
+        FE_SPMV_CASE(8)
+        FE_SPMV_CASE(16)
+        FE_SPMV_CASE(32)
+        default:
+            set_error("spmv: bad lanes-per-row %d", lpr);
+            return FE_ERR_INVALID;
+    }
+#undef FE_SPMV_CASE
+    FE_CHECK_LAUNCH("k_spmv");
+    return FE_OK;
+}
+
+struct PcgWork {
+    double *r, *p, *Ap, *minv, *scal, *partA, *partB;
+};
+
+static PcgWork carve(void* work, int64_t nrows) {
+    PcgWork w;
+    double* d = static_cast<double*>(work);
+    const int64_t n = (nrows + 31) / 32 * 32;
+    w.r = d;
+    w.p = d + n;
+    w.Ap = d + 2 * n;
+    w.minv = d + 3 * n;
+    w.scal = d + 4 * n;
+    w.partA = w.scal + kScalarDoubles;
+    w.partB = w.partA + kMaxPartials;
+    return w;
+}
+
+template <typename IdxT>
+static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, const double* vals, const double* rhs,
+                    const uint8_t* mask, double* x, double rtol, double atol, int64_t maxit, int check_every,
+                    void* work, double* info, cudaStream_t st) {
+    PcgWork w = carve(work, nrows);
+    int64_t nnz_host = 0;
+    {
+        IdxT last;
+        FE_CUDA_TRY(cudaMemcpyAsync(&last, row_ptr + nrows, sizeof(IdxT), cudaMemcpyDeviceToHost, st));
+        FE_CUDA_TRY(cudaStreamSynchronize(st));
+        nnz_host = (int64_t)last;
+    }
+    const int lpr = pick_lpr(nrows, nnz_host);
+    int gv = 0, rc;
+    if ((rc = persistent_grid((const void*)k_pcg_update, kVecThreads, &gv)) != FE_OK) return rc;
+    const int64_t need = (nrows + kVecThreads - 1) / kVecThreads;
+    if (need < gv) gv = (int)(need > 0 ? need : 1);
+
+    // setup: minv <- diag; x0; r0 = b - A x0; p0
+    k_csr_diagonal<IdxT><<<grid_for(nrows, 256), 256, 0, st>>>(nrows, row_ptr, col_idx, vals, w.minv);
+    FE_CHECK_LAUNCH("k_csr_diagonal");
+    k_pcg_init1<<<gv, kVecThreads, 0, st>>>(nrows, rhs, mask, x, w.minv);
+    FE_CHECK_LAUNCH("k_pcg_init1");
+    if ((rc = launch_spmv<IdxT, false>(lpr, nrows, row_ptr, col_idx, vals, x, w.Ap, mask, nullptr, nullptr, nullptr,
+                                       st)) != FE_OK)
+        return rc;
+    k_pcg_init2<<<gv, kVecThreads, 0, st>>>(nrows, rhs, mask, w.Ap, w.minv, w.r, w.p, w.partB);
+    FE_CHECK_LAUNCH("k_pcg_init2");
+    k_pcg_init3<<<1, kVecThreads, 0, st>>>(gv, w.partB, rtol, atol, w.scal);
+    FE_CHECK_LAUNCH("k_pcg_init3");
+
+    double hs[kScalarDoubles];
+    int64_t launched = 0;
+    for (;;) {
+        FE_CUDA_TRY(cudaMemcpyAsync(hs, w.scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        FE_CUDA_TRY(cudaStreamSynchronize(st));
+        if (hs[S_DONE_C] != 0.0 || launched >= maxit) break;
+        int64_t batch = check_every;
+        if (launched + batch > maxit) batch = maxit - launched;
+        for (int64_t k = 0; k < batch; ++k) {
+            int ga = 0;
+            if ((rc = launch_spmv<IdxT, true>(lpr, nrows, row_ptr, col_idx, vals, w.p, w.Ap, mask, w.partA, w.scal, &ga,
+                                              st)) != FE_OK)
+                return rc;
+            k_pcg_update<<<gv, kVecThreads, 0, st>>>(nrows, ga, w.partA, w.p, w.Ap, w.minv, x, w.r, w.partB, w.scal);
+            k_pcg_direction<<<gv, kVecThreads, 0, st>>>(nrows, gv, w.partB, w.r, w.minv, w.p, w.scal);
+        }
+        FE_CHECK_LAUNCH("pcg iteration");
+        launched += batch;
+    }
+    if (info) {
+        info[0] = hs[S_ITERS];
+        info[1] = hs[S_RR0] > 0.0 ? sqrt(hs[S_RR] / hs[S_RR0]) : 0.0;
+        info[2] = sqrt(hs[S_RR0]);
+        info[3] = hs[S_DONE_C];
+    }
+    return FE_OK;
+}
+
+}  // namespace fe
+
+extern "C" {
+
+int fe_spmv(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals, const double* x,
+            double* y, const uint8_t* rowmask, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(nrows >= 0 && row_ptr && col_idx && vals && x && y, "null pointer or negative size");
+    if (nrows == 0) return FE_OK;
+    cudaStream_t st = as_stream(stream);
+    // lanes per row from the average row length; read back nnz once (tiny, stream-ordered)
+    int64_t nnz = 0;
+    if (idx64) {
+        int64_t last;
+        FE_CUDA_TRY(cudaMemcpyAsync(&last, static_cast<const int64_t*>(row_ptr) + nrows, 8, cudaMemcpyDeviceToHost, st));
+        FE_CUDA_TRY(cudaStreamSynchronize(st));
+        nnz = last;
+    } else {
+        int32_t last;
+        FE_CUDA_TRY(cudaMemcpyAsync(&last, static_cast<const int32_t*>(row_ptr) + nrows, 4, cudaMemcpyDeviceToHost, st));
+        FE_CUDA_TRY(cudaStreamSynchronize(st));
+        nnz = last;
+    }
+    const int lpr = pick_lpr(nrows, nnz);
+    if (idx64)
+        return launch_spmv<int64_t, false>(lpr, nrows, static_cast<const int64_t*>(row_ptr), col_idx, vals, x, y,
+                                           rowmask, nullptr, nullptr, nullptr, st);
+    return launch_spmv<int32_t, false>(lpr, nrows, static_cast<const int32_t*>(row_ptr), col_idx, vals, x, y, rowmask,
+                                       nullptr, nullptr, nullptr, st);
+}
+
+int fe_csr_diagonal(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+                    double* diag, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(nrows >= 0 && row_ptr && col_idx && vals && diag, "null pointer or negative size");
+    if (nrows == 0) return FE_OK;
+    cudaStream_t st = as_stream(stream);
+    if (idx64)
+        k_csr_diagonal<int64_t><<<grid_for(nrows, 256), 256, 0, st>>>(nrows, static_cast<const int64_t*>(row_ptr),
+                                                                      col_idx, vals, diag);
+    else
+        k_csr_diagonal<int32_t><<<grid_for(nrows, 256), 256, 0, st>>>(nrows, static_cast<const int32_t*>(row_ptr),
+                                                                      col_idx, vals, diag);
+    FE_CHECK_LAUNCH("k_csr_diagonal");
+    return FE_OK;
+}
+
+size_t fe_pcg_workspace_bytes(int64_t nrows) {
+    const int64_t n = (nrows + 31) / 32 * 32;
+    return (size_t)(4 * n + fe::kScalarDoubles + 3 * fe::kMaxPartials) * sizeof(double);
+}
+
+int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals, const double* rhs,
+           const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit, int32_t check_every, void* work,
+           double* info, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(nrows >= 0 && row_ptr && col_idx && vals && rhs && x && work, "null pointer or negative size");
+    FE_REQUIRE(maxit >= 0 && check_every >= 1, "maxit must be >= 0 and check_every >= 1");
+    if (nrows == 0) {
+        if (info) info[0] = info[1] = info[2] = 0.0, info[3] = 1.0;
+        return FE_OK;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (idx64)
+        return pcg_impl<int64_t>(nrows, static_cast<const int64_t*>(row_ptr), col_idx, vals, rhs, dirmask, x, rtol,
+                                 atol, maxit, check_every, work, info, st);
+    return pcg_impl<int32_t>(nrows, static_cast<const int32_t*>(row_ptr), col_idx, vals, rhs, dirmask, x, rtol, atol,
+                             maxit, check_every, work, info, st);
+}
+
+}  // extern "C"

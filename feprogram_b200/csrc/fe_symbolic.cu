@@ -1,0 +1,239 @@
+// K2: one-time symbolic phase -- node/element incidence, node adjacency (the CSR pattern at node
+// granularity), the element -> CSR-slot map, and the scipy-compatible dof-level CSR pattern.
+//
+// Replaces getRowData (/root/reference/elements.py:143-151) and the structural half of
+// coo_matrix(...).tolil() (elements.py:183).  Instead of one global sort over the
+// nelem*(ndof*nnpe)^2 element->DOF pairs (1.07 G keys for a 4096^2 Quad4 mesh) the pairs are
+// bucketed by node with a counting pass and sorted/uniqued per node -- a segmented sort + unique
+// whose segments are tiny (<= 36 candidates), at node granularity (ndof^2 fewer keys).
+// Integer atomics are used only to bucket; every bucket is sorted afterwards, so all outputs are
+// deterministic.
+#include "fe_common.cuh"
+
+namespace fe {
+
+__global__ void k_zero_i32(int32_t* p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+__global__ void k_count_incidence(int64_t nslots, const int32_t* __restrict__ conn, int32_t* __restrict__ deg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nslots) atomicAdd(deg + conn[i], 1);
+}
+
+__global__ void k_fill_incidence(int64_t nslots, int nnpe, const int32_t* __restrict__ conn,
+                                 const int32_t* __restrict__ eptr, int32_t* __restrict__ cursor,
+                                 int32_t* __restrict__ einc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    const int n = conn[i];
+    const int e = (int)(i / nnpe);
+    const int a = (int)(i - (int64_t)e * nnpe);
+    const int slot = atomicAdd(cursor + n, 1);
+    einc[eptr[n] + slot] = e * 16 + a;
+}
+
+// In-place insertion sort of each node's (short) incidence segment: ascending element id.
+__global__ void k_sort_incidence(int64_t nnode, const int32_t* __restrict__ eptr, int32_t* __restrict__ einc) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nnode) return;
+    const int lo = eptr[n], hi = eptr[n + 1];
+    for (int i = lo + 1; i < hi; ++i) {
+        const int v = einc[i];
+        int j = i;
+        while (j > lo && einc[j - 1] > v) {
+            einc[j] = einc[j - 1];
+            --j;
+        }
+        einc[j] = v;
+    }
+}
+
+// Sorted, distinct neighbour list of node n in thread-local storage.  Returns the count, or -1 when
+// more than kMaxAdj distinct neighbours exist.
+__device__ __forceinline__ int build_adjacency(int nnpe, const int32_t* __restrict__ conn,
+                                               const int32_t* __restrict__ einc, int k0, int k1, int* list) {
+    int cnt = 0;
+    for (int k = k0; k < k1; ++k) {
+        const int64_t e = einc[k] >> 4;
+        for (int b = 0; b < nnpe; ++b) {
+            const int v = conn[e * nnpe + b];
+            int j = cnt;
+            while (j > 0 && list[j - 1] > v) --j;
+            if (j > 0 && list[j - 1] == v) continue;
+            if (cnt == kMaxAdj) return -1;
+            for (int i = cnt; i > j; --i) list[i] = list[i - 1];
+            list[j] = v;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, int nnpe, const int32_t* __restrict__ conn,
+                                                         const int32_t* __restrict__ eptr,
+                                                         const int32_t* __restrict__ einc, int32_t* __restrict__ ndeg,
+                                                         int32_t* __restrict__ status) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n > nnode) return;
+    if (n == nnode) {  // slot for the grand total after the scan
+        ndeg[n] = 0;
+        return;
+    }
+    int list[kMaxAdj];
+    int cnt = build_adjacency(nnpe, conn, einc, eptr[n], eptr[n + 1], list);
+    if (cnt < 0) {
+        atomicMax(status, 1);
+        cnt = 0;
+    }
+    ndeg[n] = cnt;
+}
+
+__global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, int nnpe, const int32_t* __restrict__ conn,
+                                                        const int32_t* __restrict__ eptr,
+                                                        const int32_t* __restrict__ einc,
+                                                        const int32_t* __restrict__ nptr, int32_t* __restrict__ nadj,
+                                                        uint8_t* __restrict__ epos) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nnode) return;
+    int list[kMaxAdj];
+    const int k0 = eptr[n], k1 = eptr[n + 1];
+    const int cnt = build_adjacency(nnpe, conn, einc, k0, k1, list);
+    if (cnt < 0) return;
+    const int p0 = nptr[n];
+    for (int i = 0; i < cnt; ++i) nadj[p0 + i] = list[i];
+    for (int k = k0; k < k1; ++k) {
+        const int64_t e = einc[k] >> 4;
+        for (int b = 0; b < nnpe; ++b) {
+            const int v = conn[e * nnpe + b];
+            int lo = 0, hi = cnt - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (list[mid] < v) lo = mid + 1;
+                else hi = mid;
+            }
+            epos[(int64_t)k * nnpe + b] = (uint8_t)lo;
+        }
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256) k_csr_expand(int64_t nnode, int ndof, const int32_t* __restrict__ nptr,
+                                                    const int32_t* __restrict__ nadj, IdxT* __restrict__ row_ptr,
+                                                    int32_t* __restrict__ col_idx) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nrows = nnode * ndof;
+    if (r > nrows) return;
+    if (r == nrows) {
+        row_ptr[r] = (IdxT)((int64_t)ndof * ndof * nptr[nnode]);
+        return;
+    }
+    const int64_t n = r / ndof;
+    const int c = (int)(r - n * ndof);
+    const int p0 = nptr[n];
+    const int deg = nptr[n + 1] - p0;
+    const int64_t start = (int64_t)ndof * ndof * p0 + (int64_t)c * ndof * deg;
+    row_ptr[r] = (IdxT)start;
+    for (int p = 0; p < deg; ++p) {
+        const int m = nadj[p0 + p];
+        for (int d = 0; d < ndof; ++d) col_idx[start + (int64_t)ndof * p + d] = ndof * m + d;
+    }
+}
+
+}  // namespace fe
+
+extern "C" {
+
+int fe_incidence_count(int elem_type, int64_t nelem, int64_t nnode, const int32_t* conn, int32_t* eptr, void* scan_ws,
+                       void* stream) {
+    using namespace fe;
+    const int nnpe = nnpe_of(elem_type);
+    if (!nnpe) {
+        set_error("fe_incidence_count: Invalid elemType %d", elem_type);
+        return FE_ERR_UNSUPPORTED;
+    }
+    FE_REQUIRE(nelem >= 0 && nnode >= 0 && conn && eptr && scan_ws, "null pointer or negative size");
+    FE_REQUIRE(nelem < ((int64_t)1 << 27) && nelem * nnpe * nnpe < ((int64_t)1 << 31),
+               "element count exceeds the packed (element*16+a) / int32 slot range");
+    cudaStream_t st = as_stream(stream);
+    k_zero_i32<<<grid_for(nnode + 1, 256), 256, 0, st>>>(eptr, nnode + 1);
+    FE_CHECK_LAUNCH("k_zero_i32");
+    if (nelem > 0) {
+        k_count_incidence<<<grid_for(nelem * nnpe, 256), 256, 0, st>>>(nelem * nnpe, conn, eptr);
+        FE_CHECK_LAUNCH("k_count_incidence");
+    }
+    return exclusive_scan_i32(eptr, eptr, nnode + 1, scan_ws, st);
+}
+
+int fe_incidence_fill(int elem_type, int64_t nelem, int64_t nnode, const int32_t* conn, const int32_t* eptr,
+                      int32_t* cursor, int32_t* einc, void* stream) {
+    using namespace fe;
+    const int nnpe = nnpe_of(elem_type);
+    if (!nnpe) {
+        set_error("fe_incidence_fill: Invalid elemType %d", elem_type);
+        return FE_ERR_UNSUPPORTED;
+    }
+    FE_REQUIRE(nelem >= 0 && nnode >= 0 && conn && eptr && cursor && einc, "null pointer or negative size");
+    if (nelem == 0 || nnode == 0) return FE_OK;
+    cudaStream_t st = as_stream(stream);
+    k_zero_i32<<<grid_for(nnode, 256), 256, 0, st>>>(cursor, nnode);
+    FE_CHECK_LAUNCH("k_zero_i32");
+    k_fill_incidence<<<grid_for(nelem * nnpe, 256), 256, 0, st>>>(nelem * nnpe, nnpe, conn, eptr, cursor, einc);
+    FE_CHECK_LAUNCH("k_fill_incidence");
+    k_sort_incidence<<<grid_for(nnode, 256), 256, 0, st>>>(nnode, eptr, einc);
+    FE_CHECK_LAUNCH("k_sort_incidence");
+    return FE_OK;
+}
+
+int fe_adjacency_count(int elem_type, int64_t nnode, const int32_t* conn, const int32_t* eptr, const int32_t* einc,
+                       int32_t* nptr, int32_t* status, void* scan_ws, void* stream) {
+    using namespace fe;
+    const int nnpe = nnpe_of(elem_type);
+    if (!nnpe) {
+        set_error("fe_adjacency_count: Invalid elemType %d", elem_type);
+        return FE_ERR_UNSUPPORTED;
+    }
+    FE_REQUIRE(nnode >= 0 && conn && eptr && einc && nptr && status && scan_ws, "null pointer or negative size");
+    cudaStream_t st = as_stream(stream);
+    k_zero_i32<<<1, 32, 0, st>>>(status, 1);
+    FE_CHECK_LAUNCH("k_zero_i32");
+    k_adjacency_count<<<grid_for(nnode + 1, 128), 128, 0, st>>>(nnode, nnpe, conn, eptr, einc, nptr, status);
+    FE_CHECK_LAUNCH("k_adjacency_count");
+    return exclusive_scan_i32(nptr, nptr, nnode + 1, scan_ws, st);
+}
+
+int fe_adjacency_fill(int elem_type, int64_t nnode, const int32_t* conn, const int32_t* eptr, const int32_t* einc,
+                      const int32_t* nptr, int32_t* nadj, uint8_t* epos, void* stream) {
+    using namespace fe;
+    const int nnpe = nnpe_of(elem_type);
+    if (!nnpe) {
+        set_error("fe_adjacency_fill: Invalid elemType %d", elem_type);
+        return FE_ERR_UNSUPPORTED;
+    }
+    FE_REQUIRE(nnode >= 0 && conn && eptr && einc && nptr && nadj && epos, "null pointer or negative size");
+    if (nnode == 0) return FE_OK;
+    k_adjacency_fill<<<grid_for(nnode, 128), 128, 0, as_stream(stream)>>>(nnode, nnpe, conn, eptr, einc, nptr, nadj,
+                                                                         epos);
+    FE_CHECK_LAUNCH("k_adjacency_fill");
+    return FE_OK;
+}
+
+int fe_csr_expand(int ndof, int64_t nnode, const int32_t* nptr, const int32_t* nadj, int idx64, void* row_ptr,
+                  int32_t* col_idx, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(ndof >= 1 && ndof <= 3 && nnode >= 0 && nptr && nadj && row_ptr && col_idx,
+               "null pointer, negative size or ndof out of range");
+    cudaStream_t st = as_stream(stream);
+    const int64_t nrows = nnode * ndof;
+    if (idx64)
+        k_csr_expand<int64_t><<<grid_for(nrows + 1, 256), 256, 0, st>>>(nnode, ndof, nptr, nadj,
+                                                                        static_cast<int64_t*>(row_ptr), col_idx);
+    else
+        k_csr_expand<int32_t><<<grid_for(nrows + 1, 256), 256, 0, st>>>(nnode, ndof, nptr, nadj,
+                                                                        static_cast<int32_t*>(row_ptr), col_idx);
+    FE_CHECK_LAUNCH("k_csr_expand");
+    return FE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+"""Drop-in for the reference's ``elements`` module on the hot path (B200 / CUDA only).
+
+Same classes, method names, argument meaning and call order as /root/reference/elements.py
+(``Elem`` :9-38, ``FemProblem`` :40-243) as driven by main.py:17-40::
+
+    fem = FemProblem(conectivity, coordinates)      # 1-based tags, (nnode,2) fp64 coordinates
+    fem.setMatrix()
+    fem.setBoundaryConditions(bcNodeTags)
+    fem.assemble()                                  # GPU: symbolic (once per mesh) + numeric assembly + BCs
+    U = fem.solveProblem()                          # GPU: Jacobi-PCG; returns ndarray (2*nnode,)
+
+What differs, deliberately:
+  * the arithmetic runs in hand-written sm_100a kernels behind the C ABI (include/feprogram_b200.h)
+    via torch custom ops (feprogram_b200/ops.py); without a CUDA device every hot call raises;
+  * ``K`` / ``brhs`` live on the GPU; the ``scipy.sparse`` objects the reference exposes
+    (``fem.K`` csc_matrix, ``fem.brhs`` csc (2N x 1)) are materialised lazily on attribute access;
+  * ``solveProblem`` is Jacobi-PCG on the SPD system equivalent to the reference's row-only
+    Dirichlet treatment instead of SuperLU (agreement <= 1e-8 relative L2; tests/test_gpu_parity.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from .tools.interpFunctions import funH4, funH9, funHrs4, funHrs9
+
+__all__ = ["Elem", "FemProblem"]
+
+
+class Elem:
+    """Element descriptor (elements.py:9-38).  Host-side helpers kept for API parity; the per-element
+    arithmetic the assembly uses is csrc/fe_element.cuh."""
+
+    def __init__(self, nodes, elemType):
+        self.elemType = elemType
+        self.nnodesloc = nodes
+
+    def _gradients(self, dHrs, J):
+        return np.linalg.inv(J) * dHrs
+
+    def funB(self, dHrs, J):
+        """4 x 2n strain operator: rows [dx on u, dy on v, dy on u + dx on v, 0] (elements.py:15-23)."""
+        n = self.nnodesloc
+        Dh = np.asarray(self._gradients(np.asmatrix(dHrs), np.asmatrix(J)))
+        B = np.zeros((4, 2 * n))
+        B[0, 0::2] = Dh[0]
+        B[1, 1::2] = Dh[1]
+        B[2, 0::2] = Dh[1]
+        B[2, 1::2] = Dh[0]
+        return np.matrix(B)
+
+    def getHgrad(self, dHrs, J):
+        """4 x 2n velocity-gradient operator (elements.py:25-32); unused by the hot path."""
+        n = self.nnodesloc
+        Dh = np.asarray(self._gradients(np.asmatrix(dHrs), np.asmatrix(J)))
+        G = np.zeros((4, 2 * n))
+        G[0:2, 0::2] = Dh
+        G[2:4, 1::2] = Dh
+        return np.matrix(G)
+
+    def getpos(self, nodesTagList, coordinates):
+        """n x 2 matrix of the element's node coordinates, 0-based tags (elements.py:34-38)."""
+        idx = np.asarray(nodesTagList, dtype=np.int64)
+        return np.matrix(np.asarray(coordinates)[idx, :2])
+
+
+_ELEM_CODES = {"Quad4": 4, "Quad9": 9}
+
+
+class FemProblem:
+    def __init__(self, conectivity, coordinates, *, device=None, operator="reference"):
+        """conectivity: sequence of equal-length 1-D integer arrays of 1-BASED node tags (or a 2-D
+        ndarray); coordinates: float64 (nnode, >=2), row i <-> tag i+1 (elements.py:41-58).
+
+        Keyword-only extensions: ``device`` (torch device, default current CUDA device) and
+        ``operator`` ("reference" = un-weighted B^T B detJ as elements.py:162, "weighted" = times gpWei).
+        """
+        self.nnode = coordinates.shape[0]
+        self.nelem = len(conectivity)
+        self.elem = Elem(4, "Quad4") if len(conectivity[0]) == 4 else Elem(9, "Quad9")  # elements.py:55
+        self.conectivity = conectivity
+        self.coordinates = coordinates
+        self._device = device
+        self._operator = {"reference": 0, "weighted": 1}[operator]
+        self._dev = None        # device-side state, created on first assemble()
+        self._K_host = None
+        self._brhs_host = None
+        self._assembled = False
+        self.solver_info = None
+        self.rtol = 1e-10
+        self.maxit = None
+
+    # ------------------------------------------------------------------ setMatrix (elements.py:60-92)
+    def setMatrix(self):
+        et = self.elem.elemType
+        if et == "Quad9":
+            gpsList = [-0.774, 0, 0.774]
+            gpsWei = [0.55555, 0.88888, 0.55555]
+            self.H = self.quadH(gpsList, funH9, gpsWei)
+            self.Hrs = self.quadHrs(gpsList, funHrs9, gpsWei)
+        elif et == "Quad4":
+            gpsList = [-0.5773, 0.5773]
+            gpsWei = [1, 1]
+            self.H = self.quadH(gpsList, funH4, gpsWei)
+            self.Hrs = self.quadHrs(gpsList, funHrs4, gpsWei)
+        else:
+            raise Exception("Invalid elemType defined you must use Quad4 or Quad9")
+        # reset, like the reference's fresh empty lil K / brhs
+        self._K_host = None
+        self._brhs_host = None
+        self._assembled = False
+        if self._dev is not None:
+            self._dev.pop("rhs", None)
+
+    def quadH(self, gpoints, formFunction, gpweights=None):
+        """Shape values on the tensor Gauss grid, r outer / s inner (elements.py:94-113)."""
+        return [formFunction(r, s) for r in gpoints for s in gpoints]
+
+    def quadHrs(self, gpoints, formFunction, gpweights=None):
+        """Shape derivatives on the tensor Gauss grid + self.gpWei (elements.py:115-140)."""
+        self.gpWei = [wr * ws for wr in gpweights for ws in gpweights]
+        return [formFunction(r, s) for r in gpoints for s in gpoints]
+
+    # ------------------------------------------------------- boundary conditions (elements.py:202-229)
+    def setBoundaryConditions(self, bcNodesList, *, verbose=True):
+        """bcNodesList = 4 iterables of 1-based tags [bottom, right, top, left]; bottom -> Dirichlet
+        x,y; left -> nodal load ("Neumann") x,y.  Prints both dof sets like the reference unless
+        ``verbose=False``."""
+        dofSetDir = [[0, 1], [], [], []]
+        dofSetNeu = [[], [], [], [0, 1]]
+        dirDof, neuDof = set(), set()
+        for enu, nodes in enumerate(bcNodesList):
+            tags = np.fromiter((int(t) for t in nodes), dtype=np.int64)
+            for k in dofSetDir[enu]:
+                dirDof.update(((tags - 1) * 2 + k).tolist())
+            for m in dofSetNeu[enu]:
+                neuDof.update(((tags - 1) * 2 + m).tolist())
+        if verbose:
+            print(dirDof)
+            print(neuDof)
+        self.dofDir = list(dirDof)
+        self.dofNeu = list(neuDof)
+
+    # --------------------------------------------------------------- small helpers (elements.py:143-163)
+    def getRowData(self, elemNodesTag):
+        dofs = [(int(x) - 1) * 2 + y for x in elemNodesTag for y in (0, 1)]
+        m = len(dofs)
+        return [d for d in dofs for _ in range(m)], dofs * m
+
+    def getKe(self, elemNodeTags):
+        """Element matrix of one element from 0-based tags, computed by the CUDA kernel (fe_element_matrices)."""
+        import torch
+        dev = self._torch_device()
+        tags = torch.as_tensor(np.asarray(elemNodeTags, dtype=np.int64).astype(np.int32)[None, :], device=dev)
+        st = self._state()
+        ke = torch.ops.feprogram.element_matrices(tags.contiguous(), st["coords"], _ELEM_CODES[self.elem.elemType],
+                                                  self._operator)
+        return np.matrix(ke[0].cpu().numpy())
+
+    def getLocalVec(self, ind, Vec):
+        return Vec[ind].reshape((2, 4))
+
+    def initialVector(self):
+        return np.ones(self.nnode * 2)
+
+    def assembleMatrix(self, vec):
+        return 0
+
+    # ------------------------------------------------------------------------------- device state
+    def _torch_device(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("feprogram_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        return torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _state(self):
+        """Uploads connectivity (int32, 0-based) and coordinates once."""
+        if self._dev is not None:
+            return self._dev
+        import torch
+        from . import ops  # noqa: F401  (registers torch.ops.feprogram.*)
+        dev = self._torch_device()
+        conn = self.conectivity
+        if not isinstance(conn, np.ndarray) or conn.ndim != 2:
+            conn = np.stack([np.asarray(c) for c in conn])
+        conn0 = (conn.astype(np.int64, copy=False) - 1).astype(np.int32)       # elements.py:172 `elem-1`
+        xy = np.ascontiguousarray(np.asarray(self.coordinates, dtype=np.float64)[:, :2])
+        self._dev = {
+            "conn": torch.from_numpy(np.ascontiguousarray(conn0)).to(dev, non_blocking=False),
+            "coords": torch.from_numpy(xy).to(dev, non_blocking=False),
+        }
+        return self._dev
+
+    # ---------------------------------------------------------------------- assemble (elements.py:165-200)
+    def assemble(self):
+        import torch
+        from . import ops
+        st = self._state()
+        et = _ELEM_CODES[self.elem.elemType]
+        if "pattern" not in st:   # one-time symbolic phase for this mesh
+            st["pattern"] = ops.symbolic(st["conn"], self.nnode, et, 2)
+        pat = st["pattern"]
+        dev = st["conn"].device
+        if "vals" not in st:
+            st["vals"] = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
+        torch.ops.feprogram.assemble(st["conn"], st["coords"], pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg,
+                                     st["vals"], et, self._operator)
+        # boundary conditions: rhs + Dirichlet mask (matrix itself stays un-modified on the device)
+        if "rhs" not in st:
+            st["rhs"] = torch.empty(pat.nrows, dtype=torch.float64, device=dev)
+            st["dirmask"] = torch.empty(pat.nrows, dtype=torch.uint8, device=dev)
+        dir_d = torch.as_tensor(np.asarray(self.dofDir, dtype=np.int64), device=dev)
+        neu_d = torch.as_tensor(np.asarray(self.dofNeu, dtype=np.int64), device=dev)
+        torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
+        self._K_host = None
+        self._brhs_host = None
+        self._assembled = True
+
+    # --------------------------------------------------------------- lazily materialised scipy views
+    def csr_prebc(self):
+        """Pre-BC K as scipy CSR (indptr/indices bit-identical to the reference's fem.K.tocsr())."""
+        pat = self._dev["pattern"]
+        return sp.csr_matrix((self._dev["vals"].cpu().numpy(), pat.col_idx.cpu().numpy(),
+                              pat.row_ptr.cpu().numpy()), shape=(pat.nrows, pat.nrows))
+
+    @property
+    def K(self):
+        if not self._assembled:
+            n = self.nnode * 2
+            return sp.lil_matrix((n, n))
+        if self._K_host is None:
+            import torch
+            st = self._dev
+            pat = st["pattern"]
+            vals = st["vals"].clone()
+            torch.ops.feprogram.apply_bc(0, pat.row_ptr, pat.col_idx, vals, st["rhs"], st["dirmask"])
+            K = sp.csr_matrix((vals.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
+                              shape=(pat.nrows, pat.nrows))
+            # Dirichlet rows keep only their unit diagonal (canonical form of the LIL deletes, elements.py:187-191)
+            mask = st["dirmask"].cpu().numpy().astype(bool)
+            rows = np.repeat(np.arange(pat.nrows), np.diff(K.indptr))
+            keep = ~mask[rows] | (K.indices == rows)
+            counts = np.bincount(rows[keep], minlength=pat.nrows)
+            K = sp.csr_matrix((K.data[keep], K.indices[keep], np.concatenate([[0], np.cumsum(counts)])),
+                              shape=K.shape)
+            self._K_host = K.tocsc()
+        return self._K_host
+
+    @K.setter
+    def K(self, value):
+        self._K_host = value
+
+    @property
+    def brhs(self):
+        if not self._assembled:
+            return sp.lil_matrix((self.nnode * 2, 1))
+        if self._brhs_host is None:
+            self._brhs_host = sp.csc_matrix(self._dev["rhs"].cpu().numpy()[:, None])
+        return self._brhs_host
+
+    @brhs.setter
+    def brhs(self, value):
+        self._brhs_host = value
+
+    # ------------------------------------------------------------------ solve (elements.py:241-243)
+    def solveProblem(self):
+        import torch
+        st = self._dev
+        if st is None or not self._assembled:
+            raise RuntimeError("assemble() must be called before solveProblem()")
+        pat = st["pattern"]
+        x = torch.empty(pat.nrows, dtype=torch.float64, device=st["vals"].device)
+        maxit = self.maxit if self.maxit is not None else 20 * pat.nrows + 100
+        info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, st["vals"], st["rhs"], st["dirmask"], x,
+                                       self.rtol, 0.0, maxit, 50)
+        self.solver_info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]),
+                                converged=bool(info[3]))
+        st["x"] = x
+        return x.cpu().numpy()

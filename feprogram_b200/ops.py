@@ -1,0 +1,251 @@
+"""PyTorch custom ops over the C ABI (include/feprogram_b200.h).
+
+PyTorch is plumbing here: device memory, streams and (for multi-GPU) torch.distributed.  Every op
+launches hand-written sm_100a kernels from libfeprogram_b200.so on torch's current CUDA stream;
+nothing falls back to torch or the CPU.
+
+    torch.ops.feprogram.element_matrices / symbolic pieces / assemble / bc_rhs / apply_bc /
+    spmv / csr_diagonal / pcg
+
+plus thin Python helpers (``symbolic``, ``Pattern``) that chain the one-time symbolic steps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FE_BC_ROWS, FE_BC_SYMMETRIC, FE_OP_REFERENCE, FE_OP_WEIGHTED, FE_QUAD4, FE_QUAD9, FE_TRI3  # noqa: F401
+
+Tensor = torch.Tensor
+
+
+def _ptr(t: Optional[Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _chk_dev(*ts: Tensor):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("feprogram_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
+        if not t.is_contiguous():
+            raise RuntimeError("feprogram_b200 ops need contiguous tensors")
+
+
+def _want(t: Tensor, dtype, name: str):
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+# --------------------------------------------------------------------------------------------
+# host: tables
+# --------------------------------------------------------------------------------------------
+def tables(elem_type: int):
+    """(dH[ng2,2,nnpe], H[ng2,nnpe], w[ng2]) from the library's host-side fe_tables."""
+    nnpe, ng2 = C.c_int32(0), C.c_int32(0)
+    _lib.check(_lib.lib().fe_tables(elem_type, None, None, None, C.byref(nnpe), C.byref(ng2)))
+    dH = np.empty((ng2.value, 2, nnpe.value))
+    H = np.empty((ng2.value, nnpe.value))
+    w = np.empty(ng2.value)
+    _lib.check(_lib.lib().fe_tables(elem_type, dH.ctypes.data_as(C.c_void_p), H.ctypes.data_as(C.c_void_p),
+                                    w.ctypes.data_as(C.c_void_p), None, None))
+    return dH, H, w
+
+
+# --------------------------------------------------------------------------------------------
+# custom ops
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("feprogram::element_matrices", mutates_args=())
+def element_matrices(conn: Tensor, coords: Tensor, elem_type: int, op: int) -> Tensor:
+    """Dense Ke per element, (nelem, 2*nnpe, 2*nnpe) fp64.  fe_element_matrices."""
+    _chk_dev(conn, coords)
+    _want(conn, torch.int32, "conn")
+    _want(coords, torch.float64, "coords")
+    nelem, nnpe = conn.shape
+    with torch.cuda.device(conn.device):
+        ke = torch.empty((nelem, 2 * nnpe, 2 * nnpe), dtype=torch.float64, device=conn.device)
+        _lib.check(_lib.lib().fe_element_matrices(elem_type, op, nelem, _ptr(conn), _ptr(coords), _ptr(ke),
+                                                  _stream(conn)))
+    return ke
+
+
+@torch.library.custom_op("feprogram::incidence", mutates_args=())
+def incidence(conn: Tensor, nnode: int, elem_type: int) -> Tuple[Tensor, Tensor]:
+    """node -> (element*16 + local node) incidence: (eptr[nnode+1], einc[nelem*nnpe]) int32."""
+    _chk_dev(conn)
+    _want(conn, torch.int32, "conn")
+    nelem, nnpe = conn.shape
+    dev = conn.device
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        eptr = torch.empty(nnode + 1, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(1, L.fe_scan_workspace_bytes(nnode + 1)), dtype=torch.uint8, device=dev)
+        _lib.check(L.fe_incidence_count(elem_type, nelem, nnode, _ptr(conn), _ptr(eptr), _ptr(ws), _stream(conn)))
+        einc = torch.empty(nelem * nnpe, dtype=torch.int32, device=dev)
+        cursor = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
+        _lib.check(L.fe_incidence_fill(elem_type, nelem, nnode, _ptr(conn), _ptr(eptr), _ptr(cursor), _ptr(einc),
+                                       _stream(conn)))
+    return eptr, einc
+
+
+@torch.library.custom_op("feprogram::adjacency", mutates_args=())
+def adjacency(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """(nptr[nnode+1] int32, nadj[nnzN] int32, epos[nelem*nnpe*nnpe] uint8).  Syncs once to size nadj."""
+    _chk_dev(conn, eptr, einc)
+    nelem, nnpe = conn.shape
+    nnode = eptr.numel() - 1
+    dev = conn.device
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        nptr = torch.empty(nnode + 1, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(1, L.fe_scan_workspace_bytes(nnode + 1)), dtype=torch.uint8, device=dev)
+        _lib.check(L.fe_adjacency_count(elem_type, nnode, _ptr(conn), _ptr(eptr), _ptr(einc), _ptr(nptr),
+                                        _ptr(status), _ptr(ws), _stream(conn)))
+        tail = torch.stack([nptr[nnode], status[0]]).cpu()  # the one host sync of the symbolic phase
+        if int(tail[1]) != 0:
+            raise _lib.FeError(-4, "a node has more than %d distinct neighbours" % _lib.limits()["max_adj"])
+        nnz_n = int(tail[0])
+        nadj = torch.empty(max(1, nnz_n), dtype=torch.int32, device=dev)[:nnz_n]
+        epos = torch.empty(max(1, nelem * nnpe * nnpe), dtype=torch.uint8, device=dev)[: nelem * nnpe * nnpe]
+        _lib.check(L.fe_adjacency_fill(elem_type, nnode, _ptr(conn), _ptr(eptr), _ptr(einc), _ptr(nptr), _ptr(nadj),
+                                       _ptr(epos), _stream(conn)))
+    return nptr, nadj, epos
+
+
+@torch.library.custom_op("feprogram::csr_expand", mutates_args=())
+def csr_expand(nptr: Tensor, nadj: Tensor, ndof: int, idx64: bool) -> Tuple[Tensor, Tensor]:
+    """(row_ptr[ndof*nnode+1] int32|int64, col_idx[nnz] int32): the scipy-compatible CSR pattern."""
+    _chk_dev(nptr, nadj)
+    nnode = nptr.numel() - 1
+    dev = nptr.device
+    with torch.cuda.device(dev):
+        nnz = ndof * ndof * nadj.numel()
+        row_ptr = torch.empty(ndof * nnode + 1, dtype=torch.int64 if idx64 else torch.int32, device=dev)
+        col_idx = torch.empty(max(1, nnz), dtype=torch.int32, device=dev)[:nnz]
+        _lib.check(_lib.lib().fe_csr_expand(ndof, nnode, _ptr(nptr), _ptr(nadj), int(idx64), _ptr(row_ptr),
+                                            _ptr(col_idx), _stream(nptr)))
+    return row_ptr, col_idx
+
+
+@torch.library.custom_op("feprogram::assemble", mutates_args=("vals",))
+def assemble(conn: Tensor, coords: Tensor, eptr: Tensor, einc: Tensor, epos: Tensor, nptr: Tensor, max_deg: int,
+             vals: Tensor, elem_type: int, op: int) -> None:
+    """Numeric assembly into vals (every entry written once, deterministic).  fe_assemble."""
+    _chk_dev(conn, coords, eptr, einc, epos, nptr, vals)
+    _want(conn, torch.int32, "conn")
+    _want(coords, torch.float64, "coords")
+    _want(vals, torch.float64, "vals")
+    nelem = conn.shape[0]
+    nnode = nptr.numel() - 1
+    with torch.cuda.device(conn.device):
+        _lib.check(_lib.lib().fe_assemble(elem_type, op, nelem, nnode, _ptr(conn), _ptr(coords), _ptr(eptr),
+                                          _ptr(einc), _ptr(epos), _ptr(nptr), max_deg, _ptr(vals), _stream(conn)))
+
+
+@torch.library.custom_op("feprogram::bc_rhs", mutates_args=("rhs", "dirmask"))
+def bc_rhs(dir_dofs: Tensor, neu_dofs: Tensor, neu_value: float, rhs: Tensor, dirmask: Tensor) -> None:
+    """rhs <- 0; rhs[dir] <- 0; rhs[neu] <- value (Neumann last); dirmask <- 1 on Dirichlet dofs."""
+    _chk_dev(dir_dofs, neu_dofs, rhs, dirmask)
+    _want(dir_dofs, torch.int64, "dir_dofs")
+    _want(neu_dofs, torch.int64, "neu_dofs")
+    _want(dirmask, torch.uint8, "dirmask")
+    with torch.cuda.device(rhs.device):
+        _lib.check(_lib.lib().fe_bc_rhs(rhs.numel(), _ptr(dir_dofs), dir_dofs.numel(), _ptr(neu_dofs),
+                                        neu_dofs.numel(), float(neu_value), _ptr(rhs), _ptr(dirmask), _stream(rhs)))
+
+
+@torch.library.custom_op("feprogram::apply_bc", mutates_args=("vals", "rhs"))
+def apply_bc(mode: int, row_ptr: Tensor, col_idx: Tensor, vals: Tensor, rhs: Tensor, dirmask: Tensor) -> None:
+    """In-place Dirichlet treatment of the matrix: FE_BC_ROWS (reference) or FE_BC_SYMMETRIC (lift)."""
+    _chk_dev(row_ptr, col_idx, vals, rhs, dirmask)
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().fe_apply_bc(mode, row_ptr.numel() - 1, int(row_ptr.dtype == torch.int64), _ptr(row_ptr),
+                                          _ptr(col_idx), _ptr(vals), _ptr(rhs), _ptr(dirmask), _stream(vals)))
+
+
+@torch.library.custom_op("feprogram::spmv", mutates_args=("y",))
+def spmv(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, x: Tensor, y: Tensor, rowmask: Optional[Tensor]) -> None:
+    """y <- A x (rows with rowmask != 0 give 0).  fe_spmv."""
+    _chk_dev(row_ptr, col_idx, vals, x, y, rowmask)
+    _want(vals, torch.float64, "vals")
+    _want(x, torch.float64, "x")
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().fe_spmv(row_ptr.numel() - 1, int(row_ptr.dtype == torch.int64), _ptr(row_ptr),
+                                      _ptr(col_idx), _ptr(vals), _ptr(x), _ptr(y), _ptr(rowmask), _stream(vals)))
+
+
+@torch.library.custom_op("feprogram::csr_diagonal", mutates_args=())
+def csr_diagonal(row_ptr: Tensor, col_idx: Tensor, vals: Tensor) -> Tensor:
+    _chk_dev(row_ptr, col_idx, vals)
+    n = row_ptr.numel() - 1
+    with torch.cuda.device(vals.device):
+        d = torch.empty(n, dtype=torch.float64, device=vals.device)
+        _lib.check(_lib.lib().fe_csr_diagonal(n, int(row_ptr.dtype == torch.int64), _ptr(row_ptr), _ptr(col_idx),
+                                              _ptr(vals), _ptr(d), _stream(vals)))
+    return d
+
+
+@torch.library.custom_op("feprogram::pcg", mutates_args=("x",))
+def pcg(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, rhs: Tensor, dirmask: Optional[Tensor], x: Tensor,
+        rtol: float, atol: float, maxit: int, check_every: int) -> Tensor:
+    """Jacobi-PCG with Dirichlet dofs held at rhs[D]; returns CPU tensor [iters, relres, ||r0||, converged]."""
+    _chk_dev(row_ptr, col_idx, vals, rhs, dirmask, x)
+    n = row_ptr.numel() - 1
+    info = np.zeros(4, dtype=np.float64)
+    with torch.cuda.device(vals.device):
+        L = _lib.lib()
+        work = torch.empty(L.fe_pcg_workspace_bytes(n), dtype=torch.uint8, device=vals.device)
+        _lib.check(L.fe_pcg(n, int(row_ptr.dtype == torch.int64), _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(rhs),
+                            _ptr(dirmask), _ptr(x), float(rtol), float(atol), int(maxit), int(check_every), _ptr(work),
+                            info.ctypes.data_as(C.c_void_p), _stream(vals)))
+    return torch.from_numpy(info)
+
+
+# --------------------------------------------------------------------------------------------
+# symbolic phase driver
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Pattern:
+    """Everything the one-time symbolic phase produces (device tensors, reference numbering)."""
+    elem_type: int
+    ndof: int
+    nnode: int
+    nelem: int
+    eptr: Tensor
+    einc: Tensor
+    nptr: Tensor
+    nadj: Tensor
+    epos: Tensor
+    row_ptr: Tensor
+    col_idx: Tensor
+    max_deg: int
+
+    @property
+    def nnz(self) -> int:
+        return self.col_idx.numel()
+
+    @property
+    def nrows(self) -> int:
+        return self.ndof * self.nnode
+
+
+def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern:
+    """CSR pattern + element->slot map for a mesh (conn int32 0-based on the device)."""
+    nelem = conn.shape[0]
+    eptr, einc = torch.ops.feprogram.incidence(conn, nnode, elem_type)
+    nptr, nadj, epos = torch.ops.feprogram.adjacency(conn, eptr, einc, elem_type)
+    nnz = ndof * ndof * nadj.numel()
+    row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
+    max_deg = int((nptr[1:] - nptr[:-1]).max().item()) if nnode > 0 else 0
+    return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx, max_deg)

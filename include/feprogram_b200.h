@@ -1,0 +1,172 @@
+/*
+ * feprogram_b200 -- C ABI of the B200-native FEM hot path
+ * (element matrices -> deterministic CSR assembly -> Jacobi-PCG).
+ *
+ * The reference (ibejarano/feprogram) is pure Python and has no FFI layer: its boundary for this
+ * path is the FemProblem/Elem class API driven by main.py:17-40.  This header is the native
+ * layer placed directly beneath that API; every entry point cites the reference lines it
+ * replaces.  feprogram_b200/elements.py (same class/method names as the reference's
+ * elements.py) calls these through feprogram_b200/ops.py (PyTorch custom ops over ctypes).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  No C++ types, no exceptions cross the boundary.
+ *   - Every function returns FE_OK (0) or a negative FE_ERR_* code; fe_last_error() gives the
+ *     thread-local message of the last failure.
+ *   - All array arguments are CALLER-OWNED DEVICE pointers (contiguous; fp64 / int32 / int64 /
+ *     uint8 as declared) unless the parameter is documented "host".  The library allocates no
+ *     device memory: scratch arrays are explicit caller-provided arguments.
+ *   - Every device function takes a stream (a cudaStream_t passed as void*) and is stream-ordered:
+ *     no hidden synchronisation, no hidden host<->device copies except where documented
+ *     (fe_pcg polls one 64-byte status block every `check_every` iterations).
+ *   - Thread-safe for distinct streams.  Multi-GPU = one host process per GPU; communicators
+ *     are passed in as ncclComm_t (void*).
+ *   - Connectivity on the device is int32, 0-BASED, row-major (nelem x nnpe).  The host facade
+ *     converts the reference's 1-based tags (elements.py:172 `elem-1`).  Coordinates are fp64
+ *     (nnode x 2), interleaved x,y (elements.py:34-38).
+ *   - DOF numbering is the reference's: dof = ndof*node + c (elements.py:148), ndof = 2.
+ *
+ * Storage produced by the symbolic phase (all index arrays in the reference's numbering)
+ *   eptr[nnode+1] int32, einc[nelem*nnpe] int32 : node -> incident (element,local node) pairs,
+ *        einc = element*16 + a, ascending element id inside each node (the summation order).
+ *   nptr[nnode+1] int32, nadj[nnzN] int32       : node adjacency (sorted, self included) --
+ *        the CSR pattern at node granularity; the dof-level pattern is its ndof x ndof blow-up.
+ *   epos[nelem*nnpe*nnpe] uint8                 : for incidence entry k and local node b, the
+ *        position of node conn[e][b] inside nadj[nptr[n]..): the element -> CSR-slot map.
+ *   row_ptr[ndof*nnode+1] int32|int64, col_idx[nnz] int32 : scipy-compatible CSR pattern,
+ *        bit-identical to FemProblem.K.tocsr() of the reference before BCs (elements.py:183).
+ *   vals[nnz] fp64 : CSR values; value of (row ndof*n+c, col ndof*nadj[nptr[n]+p]+d) lives at
+ *        ndof*ndof*nptr[n] + c*ndof*deg(n) + ndof*p + d.
+ */
+#ifndef FEPROGRAM_B200_H
+#define FEPROGRAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define FE_OK 0
+#define FE_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unknown enum)      */
+#define FE_ERR_UNSUPPORTED (-2) /* element type / operator / ndof combination not implemented    */
+#define FE_ERR_CUDA (-3)        /* a CUDA runtime call or kernel launch failed                    */
+#define FE_ERR_CAPACITY (-4)    /* a documented per-node capacity was exceeded (see fe_limits)    */
+#define FE_ERR_NCCL (-5)        /* an NCCL call failed                                            */
+
+/* ---- element types (elements.py:55: Quad4 if len(conectivity[0])==4 else Quad9) --------- */
+#define FE_QUAD4 4
+#define FE_QUAD9 9
+#define FE_TRI3 3 /* extension, not in the reference */
+
+/* ---- operators -------------------------------------------------------------------------- */
+#define FE_OP_REFERENCE 0 /* Ke = sum_g B^T B detJ, 2 dof/node, no weights (elements.py:153-163) */
+#define FE_OP_WEIGHTED 1  /* same, each Gauss term times gpWei[g] (elements.py:137; extension)   */
+
+/* Copies the thread-local message of the last failing call into buf (NUL-terminated). */
+void fe_last_error(char* buf, size_t len);
+
+/* Library / build identification: "feprogram_b200 <version> sm_100a". */
+const char* fe_version(void);
+
+/* Compile-time capacities: out[0] = max distinct neighbours per node, out[1] = max incident
+ * elements per node, out[2] = max nnpe, out[3] = max Gauss points. */
+void fe_limits(int32_t out[4]);
+
+/* ---- T1-T4: tables (host) ------------------------------------------------------------------
+ * Replaces funH4/funH9/funHrs4/funHrs9 (tools/interpFunctions.py:3-84) evaluated on the tensor
+ * Gauss grid by quadH/quadHrs (elements.py:94-140), same expression order => bit-identical.
+ * HOST pointers: dH[ng2*2*nnpe] (g-major, then r/s row, then node), H[ng2*nnpe], w[ng2].
+ * Any of the outputs may be NULL.  *nnpe_out / *ng2_out may be NULL. */
+int fe_tables(int elem_type, double* dH, double* H, double* w, int32_t* nnpe_out, int32_t* ng2_out);
+
+/* ---- E1-E3: stand-alone element matrices -----------------------------------------------------
+ * Replaces Elem.getpos / Elem.funB / FemProblem.getKe (elements.py:34-38, 15-23, 153-163) for a
+ * batch: Ke[e] is the dense row-major (ndof*nnpe)^2 block of element e.  Debug / parity entry;
+ * the assembly path never materialises Ke in HBM. */
+int fe_element_matrices(int elem_type, int op, int64_t nelem, const int32_t* conn, const double* coords,
+                        double* Ke, void* stream);
+
+/* ---- A1/A3 symbolic phase (one-time per mesh) ---------------------------------------------
+ * Replaces getRowData (elements.py:143-151) and the pattern half of
+ * coo_matrix(...).tolil() (elements.py:183).  Steps, in order; the caller allocates between
+ * steps from the counts the previous step produced (read back eptr[nnode] / nptr[nnode]):
+ *
+ *  1. fe_incidence_count : eptr[0..nnode] <- exclusive scan of per-node element counts.
+ *                          scratch: scan_ws (fe_scan_workspace_bytes(nnode+1) bytes).
+ *  2. fe_incidence_fill  : einc <- (element*16 + a), ascending inside each node.
+ *                          scratch: cursor[nnode] int32.
+ *  3. fe_adjacency_count : nptr[0..nnode] <- exclusive scan of distinct-neighbour counts;
+ *                          status[0] != 0 afterwards means FE_ERR_CAPACITY on some node.
+ *  4. fe_adjacency_fill  : nadj, epos.
+ *  5. fe_csr_expand      : row_ptr (int32 if idx64 == 0 else int64), col_idx.
+ */
+size_t fe_scan_workspace_bytes(int64_t n);
+int fe_incidence_count(int elem_type, int64_t nelem, int64_t nnode, const int32_t* conn, int32_t* eptr,
+                       void* scan_ws, void* stream);
+int fe_incidence_fill(int elem_type, int64_t nelem, int64_t nnode, const int32_t* conn, const int32_t* eptr,
+                      int32_t* cursor, int32_t* einc, void* stream);
+int fe_adjacency_count(int elem_type, int64_t nnode, const int32_t* conn, const int32_t* eptr,
+                       const int32_t* einc, int32_t* nptr, int32_t* status, void* scan_ws, void* stream);
+int fe_adjacency_fill(int elem_type, int64_t nnode, const int32_t* conn, const int32_t* eptr,
+                      const int32_t* einc, const int32_t* nptr, int32_t* nadj, uint8_t* epos, void* stream);
+int fe_csr_expand(int ndof, int64_t nnode, const int32_t* nptr, const int32_t* nadj, int idx64, void* row_ptr,
+                  int32_t* col_idx, void* stream);
+
+/* ---- A2/A3 numeric assembly -------------------------------------------------------------------
+ * Replaces the element loop + duplicate-summing COO->CSR conversion of FemProblem.assemble
+ * (elements.py:165-183): evaluates every element matrix on the fly (never stored) and reduces
+ * the contributions of each CSR slot in ascending element order -- no atomics, bit-identical
+ * from run to run.  Writes every entry of vals exactly once.
+ * max_deg = max_n (nptr[n+1]-nptr[n]) (sizes the shared-memory row tile; caller computed). */
+int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32_t* conn, const double* coords,
+                const int32_t* eptr, const int32_t* einc, const uint8_t* epos, const int32_t* nptr,
+                int32_t max_deg, double* vals, void* stream);
+
+/* ---- B1-B3: boundary conditions ---------------------------------------------------------------
+ * fe_bc_rhs replaces the brhs writes of elements.py:185-197: rhs <- 0; rhs[dir] <- 0;
+ * rhs[neu] <- neu_value (Neumann written last, so it wins on shared dofs); dirmask[d] <- 1 on
+ * Dirichlet dofs, 0 elsewhere.  dofs are int64 device arrays.
+ *
+ * fe_apply_bc modifies vals in place.  mode FE_BC_ROWS is the reference's row-only treatment
+ * (elements.py:185-193): Dirichlet rows -> 0 with unit diagonal, columns untouched, rhs untouched.
+ * mode FE_BC_SYMMETRIC additionally eliminates Dirichlet columns, moving them to the right-hand
+ * side: rhs[j] -= K[j,d]*rhs[d] (the SPD system equivalent to the reference's).
+ * row_ptr is int32 (idx64 == 0) or int64. */
+#define FE_BC_ROWS 0
+#define FE_BC_SYMMETRIC 1
+int fe_bc_rhs(int64_t nrows, const int64_t* dir_dofs, int64_t n_dir, const int64_t* neu_dofs, int64_t n_neu,
+              double neu_value, double* rhs, uint8_t* dirmask, void* stream);
+int fe_apply_bc(int mode, int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, double* vals,
+                double* rhs, const uint8_t* dirmask, void* stream);
+
+/* ---- S: solve -----------------------------------------------------------------------------------
+ * Replaces spsolve(K, brhs) (elements.py:241-243) by Jacobi-preconditioned CG on the SPD system
+ * the reference's Dirichlet treatment is equivalent to.
+ *
+ * fe_spmv: y <- A x with A in CSR.  If rowmask != NULL rows with rowmask[r] != 0 give y[r] = 0.
+ *
+ * fe_csr_diagonal: diag[r] <- A[r,r] (0 if not stored).
+ *
+ * fe_pcg: solves the Dirichlet-constrained system in place on the UNMODIFIED (pre-BC) matrix:
+ *   x_D = rhs_D, and CG runs on the remaining dofs with the Dirichlet columns moved to the
+ *   right-hand side (dirmask may be NULL: plain SPD solve).  x is the output (initial guess
+ *   ignored: starts from 0 / the Dirichlet lift).  Converged when ||r||_2 <= rtol*||r0||_2 or
+ *   ||r||_2 <= atol.  work: 4*nrows doubles + FE_PCG_SCALAR_DOUBLES doubles + 2*fe_pcg_blocks(nrows)
+ *   doubles of scratch, see fe_pcg_workspace_bytes.  info (HOST, 4 doubles): iterations, final
+ *   ||r||/||r0||, ||r0||, converged flag.  check_every: iterations between host polls (>=1).
+ */
+int fe_spmv(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+            const double* x, double* y, const uint8_t* rowmask, void* stream);
+int fe_csr_diagonal(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+                    double* diag, void* stream);
+size_t fe_pcg_workspace_bytes(int64_t nrows);
+int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+           const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit,
+           int32_t check_every, void* work, double* info, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEPROGRAM_B200_H */

@@ -1,0 +1,312 @@
+"""Parity of the CUDA path (through the C ABI / torch custom ops / FemProblem facade) with the oracle
+and with the frozen outputs of the unmodified reference (tests/golden).  Tolerances (north_star):
+CSR structure bit-exact; values <= 1e-12 relative (norm-wise); solution <= 1e-8 rel-L2."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import FULL_CASES, bc_sets_of
+from oracle import fe_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+VAL_TOL = 1e-12
+SOL_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    from feprogram_b200 import build
+    build.build()
+    from feprogram_b200 import ops  # noqa: F401
+    assert torch.cuda.is_available()
+    return torch
+
+
+def rel_max(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max()
+
+
+def dev_mesh(torch, conn1, coords):
+    conn0 = torch.from_numpy((np.asarray(conn1, dtype=np.int64) - 1).astype(np.int32)).cuda()
+    xy = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).cuda()
+    return conn0, xy
+
+
+def test_single_element_matrices_against_reference(torch_cuda, golden):
+    torch = torch_cuda
+    z = golden("tables_and_single")
+    c4, x4 = dev_mesh(torch, np.arange(1, 5)[None, :], z["X4"])
+    ke4 = torch.ops.feprogram.element_matrices(c4, x4, 4, 0).cpu().numpy()[0]
+    assert rel_max(ke4, z["ke4"]) < 1e-13
+    c9, x9 = dev_mesh(torch, z["conn9"], z["X9"])
+    ke9 = torch.ops.feprogram.element_matrices(c9, x9, 9, 0).cpu().numpy()[0]
+    assert rel_max(ke9, z["ke9"]) < 1e-13
+    assert abs(np.trace(ke4) - 7.238136187218806) < 1e-12
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_element_matrices_batch(torch_cuda, golden, name):
+    torch = torch_cuda
+    z = golden(name)
+    conn0, xy = dev_mesh(torch, z["conn"], z["coords"])
+    et = z["conn"].shape[1]
+    ke = torch.ops.feprogram.element_matrices(conn0, xy, et, 0).cpu().numpy()
+    assert rel_max(ke[: len(z["ke"])], z["ke"]) < 1e-13                       # the reference's getKe
+    assert rel_max(ke, orc.element_matrices(z["conn"] - 1, z["coords"])) < 1e-13  # the oracle, all elements
+    kw = torch.ops.feprogram.element_matrices(conn0, xy, et, 1).cpu().numpy()
+    assert rel_max(kw, orc.element_matrices(z["conn"] - 1, z["coords"], weighted=True)) < 1e-13
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_symbolic_structures_bit_exact(torch_cuda, golden, name):
+    torch = torch_cuda
+    from feprogram_b200 import ops
+    z = golden(name)
+    conn0, _ = dev_mesh(torch, z["conn"], z["coords"])
+    nnode = z["coords"].shape[0]
+    pat = ops.symbolic(conn0, nnode, z["conn"].shape[1], 2)
+    eptr, einc = orc.node_incidence(z["conn"] - 1, nnode)
+    assert np.array_equal(pat.eptr.cpu().numpy(), eptr)
+    assert np.array_equal(pat.einc.cpu().numpy(), einc)
+    nptr, nadj = orc.node_adjacency(z["conn"] - 1, nnode)
+    assert np.array_equal(pat.nptr.cpu().numpy(), nptr)
+    assert np.array_equal(pat.nadj.cpu().numpy(), nadj)
+    # the reference's own CSR structure, bit for bit (int32 like scipy's)
+    assert pat.row_ptr.dtype == torch.int32 and pat.col_idx.dtype == torch.int32
+    assert np.array_equal(pat.row_ptr.cpu().numpy(), z["k0_indptr"])
+    assert np.array_equal(pat.col_idx.cpu().numpy(), z["k0_indices"])
+    # slot map: position of every element node inside the owner's adjacency list
+    epos = pat.epos.cpu().numpy().reshape(-1, z["conn"].shape[1])
+    conn0h = z["conn"] - 1
+    owner = np.repeat(np.arange(nnode), np.diff(eptr))
+    for k in range(0, len(einc), max(1, len(einc) // 97)):
+        e = einc[k] // 16
+        seg = nadj[nptr[owner[k]]:nptr[owner[k] + 1]]
+        assert np.array_equal(seg[epos[k]], conn0h[e])
+    # 64-bit row pointers are the same numbers
+    rp64, ci64 = torch.ops.feprogram.csr_expand(pat.nptr, pat.nadj, 2, True)
+    assert rp64.dtype == torch.int64 and np.array_equal(rp64.cpu().numpy(), z["k0_indptr"])
+    assert np.array_equal(ci64.cpu().numpy(), z["k0_indices"])
+
+
+def run_facade(z, **kw):
+    from feprogram_b200.elements import FemProblem
+    fem = FemProblem(z["conn"], z["coords"], **kw)
+    fem.setMatrix()
+    fem.setBoundaryConditions(bc_sets_of(z), verbose=False)
+    fem.assemble()
+    return fem
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_facade_assembly_bc_and_solution_against_reference(torch_cuda, golden, name):
+    z = golden(name)
+    fem = run_facade(z)
+    K0 = fem.csr_prebc()
+    assert K0.indices.dtype == np.int32
+    assert np.array_equal(K0.indptr, z["k0_indptr"]) and np.array_equal(K0.indices, z["k0_indices"])
+    assert rel_max(K0.data, z["k0_data"]) < VAL_TOL
+    # post-BC system in the reference's own types
+    K = fem.K
+    assert sp.issparse(K) and K.format == "csc" and K.shape == (2 * fem.nnode, 2 * fem.nnode)
+    b = np.asarray(fem.brhs.todense()).ravel()
+    assert fem.brhs.format == "csc" and np.array_equal(b, z["brhs"])
+    Kref = sp.csr_matrix((z["k_data"], z["k_indices"], z["k_indptr"]), shape=K.shape)
+    assert rel_max(K.toarray(), Kref.toarray()) < VAL_TOL
+    # reference pattern ⊇ ours, extras are stored zeros in Dirichlet rows
+    Kc = K.tocsr()
+    Kc.sort_indices()
+    ours = set(zip(np.repeat(np.arange(K.shape[0]), np.diff(Kc.indptr)).tolist(), Kc.indices.tolist()))
+    isdir = np.zeros(K.shape[0], bool)
+    isdir[z["dofDir"]] = True
+    rr = np.repeat(np.arange(K.shape[0]), np.diff(Kref.indptr))
+    extras = [(r, c, v) for r, c, v in zip(rr.tolist(), Kref.indices.tolist(), Kref.data.tolist())
+              if (r, c) not in ours]
+    assert all(v == 0.0 and isdir[r] for r, c, v in extras)
+    assert len(ours) + len(extras) == Kref.nnz
+    # solution
+    U = fem.solveProblem()
+    assert U.shape == (2 * fem.nnode,) and U.dtype == np.float64
+    assert fem.solver_info["converged"]
+    assert np.linalg.norm(U - z["U"]) / np.linalg.norm(z["U"]) < SOL_TOL
+    assert np.array_equal(U[z["dofDir"]], b[z["dofDir"]])          # Dirichlet values exact (corner dofs = 1)
+
+
+def test_getke_and_weighted_operator(torch_cuda, golden):
+    z = golden("q4_16x16_pert")
+    fem = run_facade(z)
+    for e in range(3):
+        ke = fem.getKe(z["conn"][e] - 1)
+        assert isinstance(ke, np.matrix) and ke.shape == (8, 8)
+        assert rel_max(ke, z["ke"][e]) < 1e-13
+    z9 = golden("q9_6x6_pert_shuf")
+    femw = run_facade(z9, operator="weighted")
+    Kw = orc.assemble_csr(z9["conn"] - 1, z9["coords"], weighted=True)
+    assert rel_max(femw.csr_prebc().data, Kw.data) < VAL_TOL
+
+
+def test_determinism_bit_identical_reruns(torch_cuda, golden):
+    torch = torch_cuda
+    z = golden("q9_6x6_pert_shuf")
+    fem = run_facade(z)
+    v1 = fem._dev["vals"].clone()
+    u1 = fem.solveProblem()
+    fem.setMatrix()
+    fem.assemble()
+    assert torch.equal(v1, fem._dev["vals"])
+    assert np.array_equal(u1, fem.solveProblem())
+    from feprogram_b200 import mesh
+    conn, coords, bc = mesh.structured_quad4(96)
+    coords = mesh.perturb_interior(coords, 96, 96)
+    z2 = dict(conn=conn, coords=coords, **{"bc%d" % i: np.array(sorted(s)) for i, s in enumerate(bc)})
+    f1, f2 = run_facade(z2), run_facade(z2)
+    assert torch.equal(f1._dev["vals"], f2._dev["vals"])
+
+
+def test_spmv_and_bc_modes_against_scipy(torch_cuda, golden):
+    torch = torch_cuda
+    z = golden("q4_12x12_pert_shuf")
+    fem = run_facade(z)
+    st, pat = fem._dev, fem._dev["pattern"]
+    K0 = fem.csr_prebc()
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(pat.nrows)
+    xd = torch.from_numpy(x).cuda()
+    y = torch.empty_like(xd)
+    torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, st["vals"], xd, y, None)
+    assert rel_max(y.cpu().numpy(), K0 @ x) < 1e-13
+    torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, st["vals"], xd, y, st["dirmask"])
+    ref = K0 @ x
+    ref[z["dofDir"]] = 0.0
+    assert rel_max(y.cpu().numpy(), ref) < 1e-13
+    d = torch.ops.feprogram.csr_diagonal(pat.row_ptr, pat.col_idx, st["vals"]).cpu().numpy()
+    assert np.array_equal(d, K0.diagonal())
+    # symmetric lift in place == oracle's lifted system
+    vals = st["vals"].clone()
+    rhs = st["rhs"].clone()
+    torch.ops.feprogram.apply_bc(1, pat.row_ptr, pat.col_idx, vals, rhs, st["dirmask"])
+    A, b = orc.lifted_system(K0, z["dofDir"], z["brhs"])
+    assert rel_max(vals.cpu().numpy(), A.data) < 1e-14
+    assert rel_max(rhs.cpu().numpy(), b) < 1e-13
+    # plain SPD solve on the lifted matrix (no mask) gives the same solution
+    xs = torch.empty_like(rhs)
+    info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, None, xs, 1e-11, 0.0, 100000, 25)
+    assert info[3] == 1.0
+    assert np.linalg.norm(xs.cpu().numpy() - z["U"]) / np.linalg.norm(z["U"]) < SOL_TOL
+
+
+def test_cfg1_quad4_64_known_answers(torch_cuda, golden):
+    """BASELINE config 1 (2-D Quad4 64x64): scalars frozen from the reference."""
+    from feprogram_b200 import mesh
+    g = golden("scalars")["q4_64"]
+    conn, coords, bc = mesh.structured_quad4(64)
+    z = dict(conn=conn, coords=coords, **{"bc%d" % i: np.array(sorted(s)) for i, s in enumerate(bc)})
+    fem = run_facade(z)
+    K0 = fem.csr_prebc()
+    assert K0.nnz == 148996 == int(g[0])
+    assert abs(np.sqrt((K0.data ** 2).sum()) - g[1]) < 1e-11 * g[1]
+    assert abs(K0.diagonal().sum() - g[2]) < 1e-11 * g[2]
+    U = fem.solveProblem()
+    assert abs(U.min() - g[6]) < 1e-6 and abs(U.max() - g[7]) < 1e-6
+    assert abs(np.linalg.norm(U) - g[8]) < 1e-8 * g[8]
+    Ko, Kbc, b, Uo = orc.solve_reference_path(conn - 1, coords, bc)
+    assert np.linalg.norm(U - Uo) / np.linalg.norm(Uo) < SOL_TOL
+
+
+@pytest.mark.parametrize("kind,n", [(4, 300), (9, 120)])
+def test_medium_mesh_against_oracle(torch_cuda, kind, n):
+    """Perturbed geometry + shuffled numbering at a size only the vectorised oracle reaches quickly."""
+    from feprogram_b200 import mesh
+    gen = mesh.structured_quad4 if kind == 4 else mesh.structured_quad9
+    conn, coords, bc = gen(n)
+    mx = n if kind == 4 else 2 * n
+    coords = mesh.perturb_interior(coords, mx, mx, 0.2, seed=0)
+    conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=1)
+    z = dict(conn=conn, coords=coords, **{"bc%d" % i: np.array(sorted(s)) for i, s in enumerate(bc)})
+    fem = run_facade(z)
+    K0 = fem.csr_prebc()
+    Ko = orc.assemble_csr(conn - 1, coords)
+    assert np.array_equal(K0.indptr, Ko.indptr) and np.array_equal(K0.indices, Ko.indices)
+    assert rel_max(K0.data, Ko.data) < VAL_TOL
+    fem.rtol = 1e-11
+    U = fem.solveProblem()
+    d, nn = orc.boundary_dofs(bc)
+    Kbc, b = orc.apply_bc_reference(Ko, d, nn)
+    Uo = orc.solve_direct(Kbc, b)
+    assert np.linalg.norm(U - Uo) / np.linalg.norm(Uo) < SOL_TOL
+
+
+def test_empty_and_degenerate_inputs(torch_cuda):
+    torch = torch_cuda
+    from feprogram_b200 import ops
+    # mesh with an isolated (unused) node: its rows are empty, like the reference's
+    conn = np.array([[1, 2, 4, 3]])
+    coords = np.array([[0, 0], [1, 0], [0, 1], [1, 1], [5, 5.0]])
+    conn0, xy = dev_mesh(torch, conn, coords)
+    pat = ops.symbolic(conn0, 5, 4, 2)
+    rp = pat.row_ptr.cpu().numpy()
+    assert rp[-1] == 64 and rp[8] == rp[9] == rp[10] == 64
+    vals = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    torch.ops.feprogram.assemble(conn0, xy, pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg, vals, 4, 0)
+    K = sp.csr_matrix((vals.cpu().numpy(), pat.col_idx.cpu().numpy(), rp), shape=(10, 10))
+    Ko = orc.assemble_csr(conn - 1, coords)
+    assert rel_max(K.toarray(), Ko.toarray()) < VAL_TOL
+    # zero elements
+    ke = torch.ops.feprogram.element_matrices(conn0[:0].contiguous(), xy, 4, 0)
+    assert ke.shape == (0, 8, 8)
+    # unsupported operator code is reported, not ignored
+    from feprogram_b200._lib import FeError
+    with pytest.raises(FeError):
+        torch.ops.feprogram.element_matrices(conn0, xy, 4, 7)
+
+
+def test_full_size_cfg2_properties(torch_cuda):
+    """BASELINE config 2 (Quad4 4096x4096, 16.8 M elements): size-independent properties of K --
+    closed-form nnz, rigid-body null space (2 translations + rotation), symmetry via SpMV, exact
+    agreement of a window of rows with the oracle on the sub-mesh that determines them."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    n = 4096
+    conn, coords, _ = mesh.structured_quad4(n, dtype=np.int32)
+    conn0 = torch.from_numpy(conn - 1).cuda()
+    xy = torch.from_numpy(coords).cuda()
+    nnode = coords.shape[0]
+    pat = ops.symbolic(conn0, nnode, 4, 2)
+    assert pat.nnz == 4 * (3 * n + 1) ** 2 == 604078084
+    vals = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    torch.ops.feprogram.assemble(conn0, xy, pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg, vals, 4, 0)
+    y = torch.empty(pat.nrows, dtype=torch.float64, device="cuda")
+    scale = float(vals.abs().max())
+    modes = []
+    tx = torch.zeros(pat.nrows, dtype=torch.float64, device="cuda"); tx[0::2] = 1.0
+    ty = torch.zeros(pat.nrows, dtype=torch.float64, device="cuda"); ty[1::2] = 1.0
+    rot = torch.empty(pat.nrows, dtype=torch.float64, device="cuda"); rot[0::2] = -xy[:, 1]; rot[1::2] = xy[:, 0]
+    for m in (tx, ty, rot):
+        torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, vals, m, y, None)
+        assert float(y.abs().max()) < 1e-12 * scale * 10
+        modes.append(m)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(pat.nrows, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn(pat.nrows, dtype=torch.float64, device="cuda", generator=g)
+    Ka, Kb = torch.empty_like(a), torch.empty_like(b)
+    torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, vals, a, Ka, None)
+    torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, vals, b, Kb, None)
+    lhs, rhs_ = float(b @ Ka), float(a @ Kb)
+    assert abs(lhs - rhs_) < 1e-10 * max(abs(lhs), 1.0)
+    # rows of the nodes in mesh rows 1000..1001 depend only on element rows 999..1001: oracle on that strip
+    j0 = 999
+    sub_conn, sub_coords, _ = mesh.structured_quad4(n, 3)
+    sub_coords = sub_coords.copy()
+    sub_coords[:, 1] = np.linspace(0, 1, n + 1)[j0 + (np.arange(sub_coords.shape[0]) // (n + 1))]
+    Ko = orc.assemble_csr(sub_conn - 1, sub_coords)
+    w = n + 1
+    r0, r1 = 2 * (1000 * w), 2 * (1002 * w)              # global rows of mesh rows 1000, 1001
+    rp = pat.row_ptr[r0:r1 + 1].cpu().numpy().astype(np.int64)
+    got = vals[rp[0]:rp[-1]].cpu().numpy()
+    s0, s1 = 2 * (1 * w), 2 * (3 * w)                    # the same nodes inside the strip
+    want = Ko.data[Ko.indptr[s0]:Ko.indptr[s1]]
+    assert got.shape == want.shape and rel_max(got, want) < VAL_TOL
+    cols = pat.col_idx[rp[0]:rp[-1]].cpu().numpy().astype(np.int64)
+    assert np.array_equal(cols - 2 * (j0 * w), Ko.indices[Ko.indptr[s0]:Ko.indptr[s1]])
