@@ -28,6 +28,7 @@ PROTOTYPES = {
     "fe_version": (C.c_char_p, []),
     "fe_limits": (None, [C.POINTER(_i32)]),
     "fe_tables": (_i, [_i, _p, _p, _p, C.POINTER(_i32), C.POINTER(_i32)]),
+    "fe_tags_to_conn": (_i, [_i, _i64, _p, _p, _p]),
     "fe_element_matrices": (_i, [_i, _i, _i64, _p, _p, _p, _p]),
     "fe_scan_workspace_bytes": (_sz, [_i64]),
     "fe_incidence_count": (_i, [_i, _i64, _i64, _p, _p, _p, _p]),
@@ -36,6 +37,14 @@ PROTOTYPES = {
     "fe_adjacency_fill": (_i, [_i, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_csr_expand": (_i, [_i, _i64, _p, _p, _i, _p, _p, _p]),
     "fe_assemble": (_i, [_i, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+    "fe_tile_params": (None, [_i, C.POINTER(_i32)]),
+    "fe_exclusive_scan_i32": (_i, [_p, _p, _i64, _p, _p]),
+    "fe_morton_keys": (_i, [_i, _i64, _p, _p, _f64, _f64, _f64, _f64, _p, _p]),
+    "fe_invert_permutation": (_i, [_i64, _p, _p, _p]),
+    "fe_tile_owner": (_i, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "fe_tile_nodes": (_i, [_i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fe_tile_items": (_i, [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fe_assemble_tiled": (_i, [_i, _i, _i64, _i64] + [_p] * 13 + [_i32, _p, _p]),
     "fe_bc_rhs": (_i, [_i64, _p, _i64, _p, _i64, _f64, _p, _p, _p]),
     "fe_apply_bc": (_i, [_i, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "fe_spmv": (_i, [_i64, _i, _p, _p, _p, _p, _p, _p, _p]),
@@ -86,6 +95,12 @@ def check(code: int) -> None:
 
 def version() -> str:
     return lib().fe_version().decode()
+
+
+def tile_params(elem_type: int):
+    out = (_i32 * 4)()
+    lib().fe_tile_params(elem_type, out)
+    return dict(tile_elems=out[0], halo_cap=out[1], local_range=out[2], threads=out[3])
 
 
 def limits():

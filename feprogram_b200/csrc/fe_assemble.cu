@@ -89,6 +89,13 @@ __global__ void __launch_bounds__(128) k_assemble_rows(int64_t nnode, int R, con
     for (int i = threadIdx.x; i < len; i += blockDim.x) out[i] = acc[i];
 }
 
+// 1-based node tags of any integer width -> int32 0-based connectivity (elements.py:172 `elem-1`).
+template <typename T>
+__global__ void k_tags_to_conn(int64_t n, const T* __restrict__ tags, int32_t* __restrict__ conn) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) conn[i] = (int32_t)(tags[i] - 1);
+}
+
 template <int ET>
 static int launch_assemble_rows(int64_t nnode, const int32_t* conn, const double* coords, const int32_t* eptr,
                                 const int32_t* einc, const uint8_t* epos, const int32_t* nptr, int32_t max_deg,
@@ -114,15 +121,31 @@ static int launch_assemble_rows(int64_t nnode, const int32_t* conn, const double
 
 extern "C" {
 
+int fe_tags_to_conn(int tag_bytes, int64_t n, const void* tags, int32_t* conn, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(n >= 0, "negative size");
+    FE_REQUIRE(tag_bytes == 4 || tag_bytes == 8, "tags must be 4- or 8-byte integers");
+    if (n == 0) return FE_OK;
+    FE_REQUIRE(tags && conn, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (tag_bytes == 4)
+        k_tags_to_conn<int32_t><<<grid_for(n, 256), 256, 0, st>>>(n, static_cast<const int32_t*>(tags), conn);
+    else
+        k_tags_to_conn<int64_t><<<grid_for(n, 256), 256, 0, st>>>(n, static_cast<const int64_t*>(tags), conn);
+    FE_CHECK_LAUNCH("k_tags_to_conn");
+    return FE_OK;
+}
+
 int fe_element_matrices(int elem_type, int op, int64_t nelem, const int32_t* conn, const double* coords, double* Ke,
                         void* stream) {
     using namespace fe;
-    FE_REQUIRE(nelem >= 0 && conn && coords && Ke, "null pointer or negative size");
+    FE_REQUIRE(nelem >= 0, "negative size");
     if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED) {
         set_error("fe_element_matrices: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
     if (nelem == 0) return FE_OK;
+    FE_REQUIRE(conn && coords && Ke, "null pointer");
     cudaStream_t st = as_stream(stream);
     int rc = ensure_tables_tu(st);
     if (rc != FE_OK) return rc;

@@ -82,12 +82,13 @@ __device__ __forceinline__ void load_element(const int32_t* __restrict__ conn, c
     }
 }
 
-// Adjugate gradients at Gauss point g:  Ax_b = J11 dHr_b - J01 dHs_b, Ay_b = -J10 dHr_b + J00 dHs_b,
-// returns 1/det (times the Gauss weight when weighted).
+// Adjugate gradients at Gauss point g:  ax_b = J11 dHr_b - J01 dHs_b, ay_b = J00 dHs_b - J10 dHr_b and
+// their scaled copies sx_b = ax_b / det, sy_b = ay_b / det (times the Gauss weight when weighted).
 template <int ET>
-__device__ __forceinline__ double gauss_point(int g, const double (&x)[Elem<ET>::NNPE],
-                                              const double (&y)[Elem<ET>::NNPE], bool weighted,
-                                              double (&ax)[Elem<ET>::NNPE], double (&ay)[Elem<ET>::NNPE]) {
+__device__ __forceinline__ void gauss_point(int g, const double (&x)[Elem<ET>::NNPE],
+                                            const double (&y)[Elem<ET>::NNPE], bool weighted,
+                                            double (&ax)[Elem<ET>::NNPE], double (&ay)[Elem<ET>::NNPE],
+                                            double (&sx)[Elem<ET>::NNPE], double (&sy)[Elem<ET>::NNPE]) {
     using E = Elem<ET>;
     double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
 #pragma unroll
@@ -98,18 +99,81 @@ __device__ __forceinline__ double gauss_point(int g, const double (&x)[Elem<ET>:
         j11 = fma(E::dHs(g, b), y[b], j11);
     }
     const double det = j00 * j11 - j01 * j10;
+    double s = 1.0 / det;
+    if (weighted) s *= E::w(g);
 #pragma unroll
     for (int b = 0; b < E::NNPE; ++b) {
         ax[b] = j11 * E::dHr(g, b) - j01 * E::dHs(g, b);
         ay[b] = j00 * E::dHs(g, b) - j10 * E::dHr(g, b);
+        sx[b] = ax[b] * s;
+        sy[b] = ay[b] * s;
     }
-    double s = 1.0 / det;
-    if (weighted) s *= E::w(g);
-    return s;
 }
 
-// Row pair of local node a:  L[b], P[b], Q[b] for all b (see file header).  `a` is a run-time
-// value; the own-node gradients are picked with selects so everything stays in registers.
+// Canonical pair arithmetic.  For a node pair lo <= hi and Gauss point g
+//     L(lo,hi) += sx_lo ax_hi + sy_lo ay_hi,   P(lo,hi) += sy_lo ax_hi,   Q(lo,hi) += sx_lo ay_hi
+// and the mirrored block is its transpose: L(hi,lo) = L(lo,hi), P(hi,lo) = Q(lo,hi), Q(hi,lo) = P(lo,hi).
+// Every code path (full symmetric element, single row pair) evaluates a pair with exactly these
+// operations in this order, so a matrix entry has the same bits no matter which path produced it and
+// the assembled K is bit-wise symmetric.
+
+// Symmetric-compressed element matrix: diagonal pairs (a,a) store [L, P] at 2a (Q == P there);
+// off-diagonal pairs a < b store [L, P, Q] at 2N + 3*pair_index(a,b).
+template <int N> struct SymLayout {
+    static constexpr int kSize = 2 * N + 3 * (N * (N - 1) / 2);
+    __host__ __device__ static constexpr int pair_index(int a, int b) { return a * (2 * N - a - 1) / 2 + (b - a - 1); }
+    __host__ __device__ static constexpr int offdiag(int a, int b) { return 2 * N + 3 * pair_index(a, b); }
+};
+
+template <int ET>
+__device__ __forceinline__ void element_sym(const double (&x)[Elem<ET>::NNPE], const double (&y)[Elem<ET>::NNPE],
+                                            bool weighted, double (&out)[SymLayout<Elem<ET>::NNPE>::kSize]) {
+    using E = Elem<ET>;
+    using S = SymLayout<E::NNPE>;
+#pragma unroll
+    for (int i = 0; i < S::kSize; ++i) out[i] = 0.0;
+#pragma unroll
+    for (int g = 0; g < E::NG; ++g) {
+        double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
+        gauss_point<ET>(g, x, y, weighted, ax, ay, sx, sy);
+#pragma unroll
+        for (int a = 0; a < E::NNPE; ++a) {
+            out[2 * a] = fma(sx[a], ax[a], fma(sy[a], ay[a], out[2 * a]));
+            out[2 * a + 1] = fma(sy[a], ax[a], out[2 * a + 1]);
+#pragma unroll
+            for (int b = a + 1; b < E::NNPE; ++b) {
+                const int o = S::offdiag(a, b);
+                out[o] = fma(sx[a], ax[b], fma(sy[a], ay[b], out[o]));
+                out[o + 1] = fma(sy[a], ax[b], out[o + 1]);
+                out[o + 2] = fma(sx[a], ay[b], out[o + 2]);
+            }
+        }
+    }
+}
+
+// (L, P, Q) of block (a, b) out of a symmetric-compressed element matrix (run-time a, b).
+template <int N>
+__device__ __forceinline__ void sym_block(const double* __restrict__ s, int a, int b, double& L, double& P, double& Q) {
+    using S = SymLayout<N>;
+    if (a == b) {
+        L = s[2 * a];
+        P = s[2 * a + 1];
+        Q = P;
+    } else if (a < b) {
+        const int o = S::offdiag(a, b);
+        L = s[o];
+        P = s[o + 1];
+        Q = s[o + 2];
+    } else {
+        const int o = S::offdiag(b, a);
+        L = s[o];
+        P = s[o + 2];
+        Q = s[o + 1];
+    }
+}
+
+// Row pair of local node a:  L[b], P[b], Q[b] for all b.  `a` is a run-time value; operands are picked
+// with selects so everything stays in registers.  Same pair arithmetic as element_sym.
 template <int ET>
 __device__ __forceinline__ void element_row_pair(const double (&x)[Elem<ET>::NNPE],
                                                  const double (&y)[Elem<ET>::NNPE], int a, bool weighted,
@@ -120,23 +184,30 @@ __device__ __forceinline__ void element_row_pair(const double (&x)[Elem<ET>::NNP
     for (int b = 0; b < E::NNPE; ++b) L[b] = P[b] = Q[b] = 0.0;
 #pragma unroll
     for (int g = 0; g < E::NG; ++g) {
-        double ax[E::NNPE], ay[E::NNPE];
-        const double s = gauss_point<ET>(g, x, y, weighted, ax, ay);
-        double axa = 0.0, aya = 0.0;
+        double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
+        gauss_point<ET>(g, x, y, weighted, ax, ay, sx, sy);
+        double axa = 0.0, aya = 0.0, sxa = 0.0, sya = 0.0;
 #pragma unroll
         for (int b = 0; b < E::NNPE; ++b) {
             axa = (b == a) ? ax[b] : axa;
             aya = (b == a) ? ay[b] : aya;
+            sxa = (b == a) ? sx[b] : sxa;
+            sya = (b == a) ? sy[b] : sya;
         }
-        axa *= s;
-        aya *= s;
 #pragma unroll
         for (int b = 0; b < E::NNPE; ++b) {
-            L[b] = fma(axa, ax[b], fma(aya, ay[b], L[b]));
-            P[b] = fma(aya, ax[b], P[b]);
-            Q[b] = fma(axa, ay[b], Q[b]);
+            const bool lo = a <= b;  // the lower-numbered local node carries the 1/det scaling
+            const double ux = lo ? sxa : sx[b], uy = lo ? sya : sy[b];   // scaled (lo) operands
+            const double vx = lo ? ax[b] : axa, vy = lo ? ay[b] : aya;   // plain (hi) operands
+            L[b] = fma(ux, vx, fma(uy, vy, L[b]));
+            // lo == a: P = sy_a ax_b, Q = sx_a ay_b.   lo == b: P(a,b) = Q(b,a) = sx_b ay_a, Q(a,b) = P(b,a) = sy_b ax_a
+            P[b] = fma(lo ? uy : ux, lo ? vx : vy, P[b]);
+            Q[b] = fma(lo ? ux : uy, lo ? vy : vx, Q[b]);
         }
     }
+    // diagonal pair: Q(a,a) == P(a,a) mathematically; use the one stored value (as element_sym does)
+#pragma unroll
+    for (int b = 0; b < E::NNPE; ++b) Q[b] = (b == a) ? P[b] : Q[b];
 }
 
 }  // namespace fe

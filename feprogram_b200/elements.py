@@ -183,11 +183,17 @@ class FemProblem:
         conn = self.conectivity
         if not isinstance(conn, np.ndarray) or conn.ndim != 2:
             conn = np.stack([np.asarray(c) for c in conn])
-        conn0 = (conn.astype(np.int64, copy=False) - 1).astype(np.int32)       # elements.py:172 `elem-1`
-        xy = np.ascontiguousarray(np.asarray(self.coordinates, dtype=np.float64)[:, :2])
+        if conn.dtype.kind not in "iu" or conn.dtype.itemsize not in (4, 8):
+            conn = conn.astype(np.int64)
+        if conn.dtype.kind == "u":                       # gmsh hands out uint64 tags; same bits as int64
+            conn = conn.view(np.int64 if conn.dtype.itemsize == 8 else np.int32)
+        tags = torch.from_numpy(np.ascontiguousarray(conn)).to(dev, non_blocking=True)
+        xy = np.asarray(self.coordinates, dtype=np.float64)
+        if xy.shape[1] != 2 or not xy.flags.c_contiguous:
+            xy = np.ascontiguousarray(xy[:, :2])
         self._dev = {
-            "conn": torch.from_numpy(np.ascontiguousarray(conn0)).to(dev, non_blocking=False),
-            "coords": torch.from_numpy(xy).to(dev, non_blocking=False),
+            "conn": torch.ops.feprogram.tags_to_conn(tags),                       # elements.py:172 `elem-1`
+            "coords": torch.from_numpy(xy).to(dev, non_blocking=True),
         }
         return self._dev
 
@@ -197,14 +203,14 @@ class FemProblem:
         from . import ops
         st = self._state()
         et = _ELEM_CODES[self.elem.elemType]
-        if "pattern" not in st:   # one-time symbolic phase for this mesh
+        if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
             st["pattern"] = ops.symbolic(st["conn"], self.nnode, et, 2)
+            st["plan"] = ops.tile_plan(st["conn"], st["coords"], st["pattern"])
         pat = st["pattern"]
         dev = st["conn"].device
         if "vals" not in st:
             st["vals"] = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
-        torch.ops.feprogram.assemble(st["conn"], st["coords"], pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg,
-                                     st["vals"], et, self._operator)
+        ops.assemble_values(st["conn"], st["coords"], pat, st["plan"], st["vals"], self._operator)
         # boundary conditions: rhs + Dirichlet mask (matrix itself stays un-modified on the device)
         if "rhs" not in st:
             st["rhs"] = torch.empty(pat.nrows, dtype=torch.float64, device=dev)

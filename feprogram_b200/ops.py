@@ -65,6 +65,19 @@ def tables(elem_type: int):
 # --------------------------------------------------------------------------------------------
 # custom ops
 # --------------------------------------------------------------------------------------------
+@torch.library.custom_op("feprogram::tags_to_conn", mutates_args=())
+def tags_to_conn(tags: Tensor) -> Tensor:
+    """1-based integer tags (int32 / int64 / uint64 bit pattern) -> int32 0-based connectivity."""
+    _chk_dev(tags)
+    if tags.element_size() not in (4, 8) or tags.dtype.is_floating_point:
+        raise TypeError("tags must be 4- or 8-byte integers, got %s" % tags.dtype)
+    with torch.cuda.device(tags.device):
+        conn = torch.empty(tags.shape, dtype=torch.int32, device=tags.device)
+        _lib.check(_lib.lib().fe_tags_to_conn(tags.element_size(), tags.numel(), _ptr(tags), _ptr(conn),
+                                              _stream(tags)))
+    return conn
+
+
 @torch.library.custom_op("feprogram::element_matrices", mutates_args=())
 def element_matrices(conn: Tensor, coords: Tensor, elem_type: int, op: int) -> Tensor:
     """Dense Ke per element, (nelem, 2*nnpe, 2*nnpe) fp64.  fe_element_matrices."""
@@ -249,3 +262,107 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern
     row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
     max_deg = int((nptr[1:] - nptr[:-1]).max().item()) if nnode > 0 else 0
     return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx, max_deg)
+
+
+# --------------------------------------------------------------------------------------------
+# tile plan for the fast assembly kernel
+# --------------------------------------------------------------------------------------------
+@dataclass
+class TilePlan:
+    """One-time plan of fe_assemble_tiled (device tensors)."""
+    eperm: Optional[Tensor]
+    tile_nptr: Tensor
+    tile_nodes: Tensor
+    tile_hptr: Tensor
+    hitems: Tensor
+    iloc: Tensor
+    ntiles: int
+    max_halo: int
+    max_nodes: int
+
+
+def _scan_i32(t: Tensor) -> Tensor:
+    L = _lib.lib()
+    out = torch.empty_like(t)
+    ws = torch.empty(max(1, L.fe_scan_workspace_bytes(t.numel())), dtype=torch.uint8, device=t.device)
+    _lib.check(L.fe_exclusive_scan_i32(_ptr(t), _ptr(out), t.numel(), _ptr(ws), _stream(t)))
+    return out
+
+
+def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -> Optional[TilePlan]:
+    """Builds the tile plan; returns None when the mesh does not fit the tiled kernel's capacities
+    (the caller then uses the row-tile kernel fe_assemble, which has none)."""
+    L = _lib.lib()
+    params = _lib.tile_params(pat.elem_type)
+    if params["halo_cap"] == 0 or pat.nelem == 0:
+        return None
+    dev = conn.device
+    te = params["tile_elems"]
+    nelem, nnode = pat.nelem, pat.nnode
+    ntiles = (nelem + te - 1) // te
+    with torch.cuda.device(dev):
+        st = _stream(conn)
+        eperm = einv = None
+        if morton:
+            lo = coords.amin(dim=0).tolist()
+            hi = coords.amax(dim=0).tolist()
+            keys = torch.empty(nelem, dtype=torch.int32, device=dev)
+            _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo[0], lo[1], hi[0], hi[1],
+                                        _ptr(keys), st))
+            # ordering the elements is input preparation of the one-time plan: torch's stable sort
+            eperm = torch.sort(keys, stable=True).indices.to(torch.int32)
+            del keys
+            einv = torch.empty(nelem, dtype=torch.int32, device=dev)
+            _lib.check(L.fe_invert_permutation(nelem, _ptr(eperm), _ptr(einv), st))
+        owner = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
+        tile_ncount = torch.empty(ntiles + 1, dtype=torch.int32, device=dev)
+        node_hcount = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
+        _lib.check(L.fe_tile_owner(nnode, nelem, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner),
+                                   _ptr(tile_ncount), _ptr(node_hcount), st))
+        tile_nptr = _scan_i32(tile_ncount)
+        cursor = torch.empty(ntiles, dtype=torch.int32, device=dev)
+        tile_nodes = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
+        node_hoff = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
+        tile_hcount = torch.empty(ntiles + 1, dtype=torch.int32, device=dev)
+        stats = torch.empty(2, dtype=torch.int32, device=dev)
+        _lib.check(L.fe_tile_nodes(nnode, nelem, _ptr(owner), _ptr(tile_nptr), _ptr(node_hcount), _ptr(cursor),
+                                   _ptr(tile_nodes), _ptr(node_hoff), _ptr(tile_hcount), _ptr(stats), st))
+        tile_hptr = _scan_i32(tile_hcount)
+        tail = torch.cat([tile_hptr[ntiles:ntiles + 1], stats]).cpu().tolist()   # one host sync
+        total_halo, max_halo, max_nodes = int(tail[0]), int(tail[1]), int(tail[2])
+        if max_halo > params["halo_cap"]:
+            return None
+        iloc = torch.empty(max(1, pat.einc.numel()), dtype=torch.uint16, device=dev)
+        hitems = torch.empty(max(1, total_halo), dtype=torch.int32, device=dev)
+        _lib.check(L.fe_tile_items(nnode, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner), _ptr(node_hoff),
+                                   _ptr(tile_hptr), _ptr(iloc), _ptr(hitems), st))
+    return TilePlan(eperm, tile_nptr, tile_nodes, tile_hptr, hitems, iloc, ntiles, max_halo, max_nodes)
+
+
+@torch.library.custom_op("feprogram::assemble_tiled", mutates_args=("vals",))
+def assemble_tiled(conn: Tensor, coords: Tensor, eperm: Optional[Tensor], eptr: Tensor, einc: Tensor, epos: Tensor,
+                   nptr: Tensor, tile_nptr: Tensor, tile_nodes: Tensor, tile_hptr: Tensor, hitems: Tensor,
+                   iloc: Tensor, max_deg: int, vals: Tensor, elem_type: int, op: int) -> None:
+    """Numeric assembly, tiled kernel (same results as feprogram::assemble, bit for bit)."""
+    _chk_dev(conn, coords, eperm, eptr, einc, epos, nptr, tile_nptr, tile_nodes, tile_hptr, hitems, iloc, vals)
+    _want(conn, torch.int32, "conn")
+    _want(coords, torch.float64, "coords")
+    _want(vals, torch.float64, "vals")
+    nelem = conn.shape[0]
+    nnode = nptr.numel() - 1
+    with torch.cuda.device(conn.device):
+        _lib.check(_lib.lib().fe_assemble_tiled(elem_type, op, nelem, nnode, _ptr(conn), _ptr(coords), _ptr(eperm),
+                                                _ptr(eptr), _ptr(einc), _ptr(epos), _ptr(nptr), _ptr(tile_nptr),
+                                                _ptr(tile_nodes), _ptr(tile_hptr), _ptr(hitems), _ptr(iloc),
+                                                max_deg, _ptr(vals), _stream(conn)))
+
+
+def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):
+    """Numeric assembly with whichever kernel the plan allows."""
+    if plan is not None:
+        torch.ops.feprogram.assemble_tiled(conn, coords, plan.eperm, pat.eptr, pat.einc, pat.epos, pat.nptr,
+                                           plan.tile_nptr, plan.tile_nodes, plan.tile_hptr, plan.hitems, plan.iloc,
+                                           pat.max_deg, vals, pat.elem_type, op)
+    else:
+        torch.ops.feprogram.assemble(conn, coords, pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg, vals,
+                                     pat.elem_type, op)

@@ -310,3 +310,32 @@ def test_full_size_cfg2_properties(torch_cuda):
     assert got.shape == want.shape and rel_max(got, want) < VAL_TOL
     cols = pat.col_idx[rp[0]:rp[-1]].cpu().numpy().astype(np.int64)
     assert np.array_equal(cols - 2 * (j0 * w), Ko.indices[Ko.indptr[s0]:Ko.indptr[s1]])
+
+
+@pytest.mark.parametrize("kind,n,shuffle", [(4, 70, False), (4, 45, True), (3, 40, False), (3, 33, True)])
+def test_tiled_and_row_kernels_agree_bitwise(torch_cuda, kind, n, shuffle):
+    """The tiled kernel (Morton tiles and input-order tiles) and the row-tile kernel produce the same
+    bits: same per-pair arithmetic, same ascending-element summation order; and K is bit-wise symmetric."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    gen = mesh.structured_quad4 if kind == 4 else mesh.structured_tri3
+    conn, coords, bc = gen(n, n + 3)
+    coords = mesh.perturb_interior(coords, n, n + 3, 0.2, seed=2)
+    if shuffle:
+        conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=4)
+    conn0, xy = dev_mesh(torch, conn, coords)
+    pat = ops.symbolic(conn0, coords.shape[0], kind, 2)
+    v_rows = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v_rows)
+    for morton in (True, False):
+        plan = ops.tile_plan(conn0, xy, pat, morton=morton)
+        assert plan is not None
+        v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        ops.assemble_values(conn0, xy, pat, plan, v)
+        assert torch.equal(v, v_rows)
+    K = sp.csr_matrix((v_rows.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
+                      shape=(pat.nrows, pat.nrows))
+    assert abs(K - K.T).max() == 0.0
+    Ko = orc.assemble_csr(conn - 1, coords, kind)
+    assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices)
+    assert rel_max(K.data, Ko.data) < VAL_TOL
