@@ -269,24 +269,19 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern
 # --------------------------------------------------------------------------------------------
 @dataclass
 class TilePlan:
-    """One-time plan of fe_assemble_tiled (device tensors)."""
+    """One-time plan of fe_assemble_tiled (device tensors, tile-major)."""
     eperm: Optional[Tensor]
-    tile_nptr: Tensor
-    tile_nodes: Tensor
-    tile_hptr: Tensor
-    hitems: Tensor
-    iloc: Tensor
+    tile_ptr: Tensor        # int32 [4, ntiles+1]: nodes / items / halo items / work items prefix sums
+    tnode: Tensor           # int32 [nslots, 2]
+    tloc: Tensor            # uint16 [items]
+    thalo: Tensor           # int32 [halo items]
+    twork: Tensor           # int32 (uint32 bit pattern) [work items]
     ntiles: int
-    max_halo: int
-    max_nodes: int
+    stats: dict
 
 
-def _scan_i32(t: Tensor) -> Tensor:
-    L = _lib.lib()
-    out = torch.empty_like(t)
-    ws = torch.empty(max(1, L.fe_scan_workspace_bytes(t.numel())), dtype=torch.uint8, device=t.device)
-    _lib.check(L.fe_exclusive_scan_i32(_ptr(t), _ptr(out), t.numel(), _ptr(ws), _stream(t)))
-    return out
+def _scan_into(src: Tensor, dst: Tensor, ws: Tensor):
+    _lib.check(_lib.lib().fe_exclusive_scan_i32(_ptr(src), _ptr(dst), src.numel(), _ptr(ws), _stream(src)))
 
 
 def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -> Optional[TilePlan]:
@@ -294,12 +289,13 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
     (the caller then uses the row-tile kernel fe_assemble, which has none)."""
     L = _lib.lib()
     params = _lib.tile_params(pat.elem_type)
-    if params["halo_cap"] == 0 or pat.nelem == 0:
+    if params["halo_cap"] == 0 or pat.nelem == 0 or pat.nnode == 0:
         return None
     dev = conn.device
     te = params["tile_elems"]
     nelem, nnode = pat.nelem, pat.nnode
     ntiles = (nelem + te - 1) // te
+    s = ntiles + 1
     with torch.cuda.device(dev):
         st = _stream(conn)
         eperm = einv = None
@@ -314,55 +310,62 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
             del keys
             einv = torch.empty(nelem, dtype=torch.int32, device=dev)
             _lib.check(L.fe_invert_permutation(nelem, _ptr(eperm), _ptr(einv), st))
-        owner = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
-        tile_ncount = torch.empty(ntiles + 1, dtype=torch.int32, device=dev)
-        node_hcount = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
+        ws = torch.empty(max(1, L.fe_scan_workspace_bytes(s)), dtype=torch.uint8, device=dev)
+        owner = torch.empty(nnode, dtype=torch.int32, device=dev)
+        tile_ncount = torch.empty(s, dtype=torch.int32, device=dev)
         _lib.check(L.fe_tile_owner(nnode, nelem, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner),
-                                   _ptr(tile_ncount), _ptr(node_hcount), st))
-        tile_nptr = _scan_i32(tile_ncount)
+                                   _ptr(tile_ncount), st))
+        tile_ptr = torch.empty((4, s), dtype=torch.int32, device=dev)
+        _scan_into(tile_ncount, tile_ptr[0], ws)
         cursor = torch.empty(ntiles, dtype=torch.int32, device=dev)
-        tile_nodes = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
-        node_hoff = torch.empty(max(1, nnode), dtype=torch.int32, device=dev)
-        tile_hcount = torch.empty(ntiles + 1, dtype=torch.int32, device=dev)
-        stats = torch.empty(2, dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_nodes(nnode, nelem, _ptr(owner), _ptr(tile_nptr), _ptr(node_hcount), _ptr(cursor),
-                                   _ptr(tile_nodes), _ptr(node_hoff), _ptr(tile_hcount), _ptr(stats), st))
-        tile_hptr = _scan_i32(tile_hcount)
-        tail = torch.cat([tile_hptr[ntiles:ntiles + 1], stats]).cpu().tolist()   # one host sync
-        total_halo, max_halo, max_nodes = int(tail[0]), int(tail[1]), int(tail[2])
-        if max_halo > params["halo_cap"]:
+        tile_nodes = torch.empty(nnode, dtype=torch.int32, device=dev)
+        noff = torch.empty(3 * nnode, dtype=torch.int32, device=dev)
+        counts = torch.empty((3, s), dtype=torch.int32, device=dev)
+        stats = torch.empty(8, dtype=torch.int32, device=dev)
+        _lib.check(L.fe_tile_layout(nnode, nelem, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
+                                    _ptr(einv), _ptr(pat.nptr), _ptr(cursor), _ptr(tile_nodes), _ptr(noff),
+                                    _ptr(counts), _ptr(stats), st))
+        for r in range(3):
+            _scan_into(counts[r], tile_ptr[r + 1], ws)
+        tail = torch.cat([tile_ptr[:, ntiles], stats]).cpu().tolist()       # one host sync
+        nslots, n_items, n_halo, n_work = (int(v) for v in tail[:4])
+        max_nodes, max_items, max_halo, max_cnt = (int(v) for v in tail[4:8])
+        info = dict(max_nodes=max_nodes, max_items=max_items, max_halo=max_halo, max_cnt=max_cnt,
+                    items=n_items, halo_items=n_halo, work_items=n_work, morton=morton)
+        if max_nodes > params["max_nodes"] or max_items >= params["max_items"] - 1 or max_halo > params["halo_cap"]:
             return None
-        iloc = torch.empty(max(1, pat.einc.numel()), dtype=torch.uint16, device=dev)
-        hitems = torch.empty(max(1, total_halo), dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_items(nnode, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner), _ptr(node_hoff),
-                                   _ptr(tile_hptr), _ptr(iloc), _ptr(hitems), st))
-    return TilePlan(eperm, tile_nptr, tile_nodes, tile_hptr, hitems, iloc, ntiles, max_halo, max_nodes)
+        tnode = torch.empty((max(1, nslots), 2), dtype=torch.int32, device=dev)
+        tloc = torch.zeros(max(2, n_items), dtype=torch.uint16, device=dev)
+        thalo = torch.empty(max(1, n_halo), dtype=torch.int32, device=dev)
+        twork = torch.empty(max(1, n_work), dtype=torch.int32, device=dev)
+        _lib.check(L.fe_tile_records(pat.elem_type, nslots, _ptr(tile_nodes), _ptr(owner), _ptr(tile_ptr), ntiles,
+                                     _ptr(noff), _ptr(pat.eptr), _ptr(pat.einc), _ptr(pat.epos), _ptr(einv),
+                                     _ptr(pat.nptr), _ptr(pat.nadj), _ptr(tnode), _ptr(tloc), _ptr(thalo),
+                                     _ptr(twork), _ptr(stats), st))
+        if int(stats[4].item()) != 0:
+            return None
+    return TilePlan(eperm, tile_ptr, tnode, tloc, thalo, twork, ntiles, info)
 
 
 @torch.library.custom_op("feprogram::assemble_tiled", mutates_args=("vals",))
-def assemble_tiled(conn: Tensor, coords: Tensor, eperm: Optional[Tensor], eptr: Tensor, einc: Tensor, epos: Tensor,
-                   nptr: Tensor, tile_nptr: Tensor, tile_nodes: Tensor, tile_hptr: Tensor, hitems: Tensor,
-                   iloc: Tensor, max_deg: int, vals: Tensor, elem_type: int, op: int) -> None:
+def assemble_tiled(conn: Tensor, coords: Tensor, eperm: Optional[Tensor], tile_ptr: Tensor, tnode: Tensor,
+                   tloc: Tensor, thalo: Tensor, twork: Tensor, vals: Tensor, elem_type: int, op: int) -> None:
     """Numeric assembly, tiled kernel (same results as feprogram::assemble, bit for bit)."""
-    _chk_dev(conn, coords, eperm, eptr, einc, epos, nptr, tile_nptr, tile_nodes, tile_hptr, hitems, iloc, vals)
+    _chk_dev(conn, coords, eperm, tile_ptr, tnode, tloc, thalo, twork, vals)
     _want(conn, torch.int32, "conn")
     _want(coords, torch.float64, "coords")
     _want(vals, torch.float64, "vals")
-    nelem = conn.shape[0]
-    nnode = nptr.numel() - 1
     with torch.cuda.device(conn.device):
-        _lib.check(_lib.lib().fe_assemble_tiled(elem_type, op, nelem, nnode, _ptr(conn), _ptr(coords), _ptr(eperm),
-                                                _ptr(eptr), _ptr(einc), _ptr(epos), _ptr(nptr), _ptr(tile_nptr),
-                                                _ptr(tile_nodes), _ptr(tile_hptr), _ptr(hitems), _ptr(iloc),
-                                                max_deg, _ptr(vals), _stream(conn)))
+        _lib.check(_lib.lib().fe_assemble_tiled(elem_type, op, conn.shape[0], _ptr(conn), _ptr(coords), _ptr(eperm),
+                                                _ptr(tile_ptr), _ptr(tnode), _ptr(tloc), _ptr(thalo), _ptr(twork),
+                                                _ptr(vals), _stream(conn)))
 
 
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):
     """Numeric assembly with whichever kernel the plan allows."""
     if plan is not None:
-        torch.ops.feprogram.assemble_tiled(conn, coords, plan.eperm, pat.eptr, pat.einc, pat.epos, pat.nptr,
-                                           plan.tile_nptr, plan.tile_nodes, plan.tile_hptr, plan.hitems, plan.iloc,
-                                           pat.max_deg, vals, pat.elem_type, op)
+        torch.ops.feprogram.assemble_tiled(conn, coords, plan.eperm, plan.tile_ptr, plan.tnode, plan.tloc,
+                                           plan.thalo, plan.twork, vals, pat.elem_type, op)
     else:
         torch.ops.feprogram.assemble(conn, coords, pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg, vals,
                                      pat.elem_type, op)

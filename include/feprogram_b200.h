@@ -133,43 +133,48 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
 /* ---- A2/A3 numeric assembly, tiled form (the fast path) ------------------------------------------
  * Same contract and bit-identical results as fe_assemble, ~3x fewer fp64 operations: a tile is
  * TE = out[0] of fe_tile_params consecutive elements of a spatially compact element order; each
- * element matrix is evaluated once per tile into shared memory (symmetric-compressed), every node
- * (CSR row block) is owned by the tile of its first incident element, and elements of neighbouring
- * tiles that touch an owned node ("halo items") contribute just that node's row pair.
+ * element matrix is evaluated once per tile into shared memory (upper-triangular block form), every
+ * node (CSR row block) is owned by the tile of its first incident element, and elements of
+ * neighbouring tiles that touch an owned node ("halo items") contribute just that node's row pair.
  *
- * One-time plan, in order (ntiles = ceil(nelem / TE)):
+ * One-time plan, in order (ntiles = ceil(nelem / TE), s = ntiles + 1):
  *  1. fe_morton_keys        : 30-bit Morton key of each element centroid inside the bounding box;
  *                             the caller sorts elements by key (stable) -> eperm, and inverts it
  *                             with fe_invert_permutation -> einv.  eperm/einv may be NULL
  *                             everywhere below (= identity: tiles are runs of the input order).
  *  2. fe_tile_owner         : owner[nnode] (tile id, -1 if the node has no element),
- *                             tile_ncount[ntiles+1] (owned nodes per tile), node_hcount[nnode].
- *  3. fe_exclusive_scan_i32 : tile_nptr <- scan(tile_ncount)          (ntiles+1 entries)
- *  4. fe_tile_nodes         : tile_nodes (ascending node id inside each tile), node_hoff[nnode],
- *                             tile_hcount[ntiles+1], stats[0] = max halo items of a tile (must be
- *                             <= out[1] of fe_tile_params, else use fe_assemble), stats[1] = max
- *                             owned nodes of a tile.  scratch: cursor[ntiles].
- *  5. fe_exclusive_scan_i32 : tile_hptr <- scan(tile_hcount)
- *  6. fe_tile_items         : iloc[nelem*nnpe] (uint16 locator per incidence entry),
- *                             hitems[tile_hptr[ntiles]] (incidence entry of each halo item). */
+ *                             tile_ncount[s] (owned nodes per tile, last entry 0).
+ *  3. fe_exclusive_scan_i32 : tile_ptr[0..s) <- scan(tile_ncount)
+ *  4. fe_tile_layout        : tile_nodes (ascending node id inside each tile), noff[3*nslots]
+ *                             (item / halo / work offset of each tile-node slot inside its tile),
+ *                             tile_counts[3*s] (items (even), halo items, work items per tile),
+ *                             stats[8]: [0] max owned nodes, [1] max items, [2] max halo items of a
+ *                             tile, [3] max incident elements of a node.  scratch: cursor[ntiles].
+ *  5. fe_exclusive_scan_i32 x3 : tile_ptr[s..2s), [2s..3s), [3s..4s) <- scans of tile_counts rows
+ *  6. fe_tile_records       : tnode (int2 per slot), tloc (uint16 per item), thalo (int32 per halo
+ *                             item), twork (uint32 per work item); stats[4] != 0 afterwards means the
+ *                             mesh is not representable (use fe_assemble).
+ * The plan is usable iff stats[0] <= out[2], stats[1] < out[3], stats[2] <= out[1] of fe_tile_params
+ * and stats[4] == 0. */
 void fe_tile_params(int elem_type, int32_t out[4]);
 int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan_ws, void* stream);
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin,
                    double ymin, double xmax, double ymax, int32_t* keys, void* stream);
 int fe_invert_permutation(int64_t n, const int32_t* perm, int32_t* inv, void* stream);
 int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32_t* einc, const int32_t* einv,
-                  int32_t* owner, int32_t* tile_ncount, int32_t* node_hcount, void* stream);
-int fe_tile_nodes(int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr,
-                  const int32_t* node_hcount, int32_t* cursor, int32_t* tile_nodes, int32_t* node_hoff,
-                  int32_t* tile_hcount, int32_t* stats, void* stream);
-int fe_tile_items(int64_t nnode, const int32_t* eptr, const int32_t* einc, const int32_t* einv,
-                  const int32_t* owner, const int32_t* node_hoff, const int32_t* tile_hptr, uint16_t* iloc,
-                  int32_t* hitems, void* stream);
-int fe_assemble_tiled(int elem_type, int op, int64_t nelem, int64_t nnode, const int32_t* conn,
-                      const double* coords, const int32_t* eperm, const int32_t* eptr, const int32_t* einc,
-                      const uint8_t* epos, const int32_t* nptr, const int32_t* tile_nptr,
-                      const int32_t* tile_nodes, const int32_t* tile_hptr, const int32_t* hitems,
-                      const uint16_t* iloc, int32_t max_deg, double* vals, void* stream);
+                  int32_t* owner, int32_t* tile_ncount, void* stream);
+int fe_tile_layout(int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr,
+                   const int32_t* eptr, const int32_t* einc, const int32_t* einv, const int32_t* nptr,
+                   int32_t* cursor, int32_t* tile_nodes, int32_t* noff, int32_t* tile_counts, int32_t* stats,
+                   void* stream);
+int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, const int32_t* owner,
+                    const int32_t* tile_ptr, int64_t ntiles, const int32_t* noff, const int32_t* eptr,
+                    const int32_t* einc, const uint8_t* epos, const int32_t* einv, const int32_t* nptr,
+                    const int32_t* nadj, void* tnode, uint16_t* tloc, int32_t* thalo, uint32_t* twork,
+                    int32_t* stats, void* stream);
+int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* conn, const double* coords,
+                      const int32_t* eperm, const int32_t* tile_ptr, const void* tnode, const uint16_t* tloc,
+                      const int32_t* thalo, const uint32_t* twork, double* vals, void* stream);
 
 /* ---- B1-B3: boundary conditions ---------------------------------------------------------------
  * fe_bc_rhs replaces the brhs writes of elements.py:185-197: rhs <- 0; rhs[dir] <- 0;

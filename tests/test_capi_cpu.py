@@ -109,3 +109,26 @@ def test_hot_path_fails_loudly_without_cuda(golden):
     fem.setBoundaryConditions([set(z["bc%d" % i].tolist()) for i in range(4)], verbose=False)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         fem.assemble()
+
+
+def test_ctypes_prototypes_match_header_arity_and_kinds(lib):
+    """Each ctypes prototype has the parameter count and pointer/scalar kinds the header declares."""
+    import ctypes as C
+    from feprogram_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "feprogram_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = re.findall(r"\b(fe_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) == len(_lib.PROTOTYPES)
+    for name, params in decls:
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        _, argtypes = _lib.PROTOTYPES[name]
+        assert len(plist) == len(argtypes), "%s: header has %d parameters, ctypes %d" % (name, len(plist), len(argtypes))
+        for p, a in zip(plist, argtypes):
+            is_ptr = "*" in p or "[" in p
+            a_ptr = a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents")
+            assert is_ptr == a_ptr, "%s: parameter '%s' vs ctypes %s" % (name, p, a)
+            if not is_ptr:
+                want = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double,
+                        "size_t": C.c_size_t}[p.split()[-2] if len(p.split()) > 1 else p]
+                assert a is want or (want is C.c_int and a is C.c_int32), "%s: '%s' vs %s" % (name, p, a)
