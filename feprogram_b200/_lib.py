@@ -42,9 +42,10 @@ PROTOTYPES = {
     "fe_morton_keys": (_i, [_i, _i64, _p, _p, _f64, _f64, _f64, _f64, _p, _p]),
     "fe_invert_permutation": (_i, [_i64, _p, _p, _p]),
     "fe_tile_owner": (_i, [_i64, _i64, _p, _p, _p, _p, _p, _p]),
-    "fe_tile_layout": (_i, [_i64, _i64] + [_p] * 12),
-    "fe_tile_records": (_i, [_i, _i64, _p, _p, _p, _i64] + [_p] * 13),
-    "fe_assemble_tiled": (_i, [_i, _i, _i64] + [_p] * 10),
+    "fe_tile_layout": (_i, [_i64, _i64] + [_p] * 13),
+    "fe_tile_records": (_i, [_i, _i64, _p, _p, _p, _i64] + [_p] * 14),
+    "fe_tile_conn": (_i, [_i, _i64] + [_p] * 6),
+    "fe_assemble_tiled": (_i, [_i, _i, _i64] + [_p] * 9),
     "fe_bc_rhs": (_i, [_i64, _p, _i64, _p, _i64, _f64, _p, _p, _p]),
     "fe_apply_bc": (_i, [_i, _i64, _i, _p, _p, _p, _p, _p, _p]),
     "fe_spmv": (_i, [_i64, _i, _p, _p, _p, _p, _p, _p, _p]),
@@ -98,9 +99,10 @@ def version() -> str:
 
 
 def tile_params(elem_type: int):
-    out = (_i32 * 4)()
+    out = (_i32 * 6)()
     lib().fe_tile_params(elem_type, out)
-    return dict(tile_elems=out[0], halo_cap=out[1], max_nodes=out[2], max_items=out[3])
+    return dict(tile_elems=out[0], halo_cap=out[1], max_nodes=out[2], max_items=out[3], max_work=out[4],
+                tile_rows=out[5])
 
 
 def limits():

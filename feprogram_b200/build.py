@@ -75,6 +75,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     inc, nccl_lib = _nccl_paths()
     extra_inc = ["-I", inc] if inc else []
+    if os.environ.get("FE_EXTRA_DEFS"):       # tuning experiments: extra -D flags, space separated
+        extra_inc += os.environ["FE_EXTRA_DEFS"].split()
+    if os.environ.get("FE_TILE_CONFIG"):      # tuning experiments: "TE,HE,CTAS"
+        te, he, ctas = os.environ["FE_TILE_CONFIG"].split(",")
+        extra_inc += ["-DFE_TILE_ELEMS=" + te, "-DFE_HALO_ELEMS=" + he, "-DFE_TILE_CTAS=" + ctas]
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")

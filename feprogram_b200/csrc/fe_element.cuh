@@ -82,21 +82,96 @@ __device__ __forceinline__ void load_element(const int32_t* __restrict__ conn, c
     }
 }
 
+// Per-element geometry state shared by all Gauss points.
+//
+// Generic elements keep the node coordinates; every Gauss point evaluates J = dH_g X from the tables and
+// its own reciprocal determinant.
+//
+// Quad4 uses the structure of the bilinear tables: with p = (1+t)/4, m = (1-t)/4 (t = the Gauss abscissa;
+// both values are read from the reference-exact table, so the truncated abscissae are honoured)
+//     dH/dr = [ps, -ps, -ms, ms],   dH/ds = [pr, mr, -mr, -pr]
+// so J only needs four coordinate differences per axis and two table values, the adjugate gradients are
+// sums/differences of eight products, and the four reciprocal determinants come from ONE division:
+//     1/det_g = (prod_{h != g} det_h) / (det_0 det_1 det_2 det_3).
+// Same mathematics as the table-driven path (differences are a few ulp); roughly 35 % fewer fp64
+// instructions and three divisions less per element.
+template <int ET> struct ElemGeom {
+    double x[Elem<ET>::NNPE], y[Elem<ET>::NNPE];
+};
+template <> struct ElemGeom<FE_QUAD4> {
+    double dx01, dx32, dx03, dx12, dy01, dy32, dy03, dy12;  // coordinate differences
+    double s[4];                                            // weight_g / det_g
+};
+
+template <int ET>
+__device__ __forceinline__ void geom_init(ElemGeom<ET>& G, const double (&x)[Elem<ET>::NNPE],
+                                          const double (&y)[Elem<ET>::NNPE], bool weighted) {
+#pragma unroll
+    for (int a = 0; a < Elem<ET>::NNPE; ++a) {
+        G.x[a] = x[a];
+        G.y[a] = y[a];
+    }
+}
+
+// (p, m) table values of Gauss point g along s (is = g & 1) and r (ir = g >> 1)
+__device__ __forceinline__ void q4_table(int g, double& ps, double& ms, double& pr, double& mr) {
+    const double al = c_q4.dH[3][0][0];  // (1 + gamma) / 4
+    const double be = c_q4.dH[0][0][0];  // (1 - gamma) / 4
+    ps = (g & 1) ? al : be;
+    ms = (g & 1) ? be : al;
+    pr = (g >> 1) ? al : be;
+    mr = (g >> 1) ? be : al;
+}
+
+__device__ __forceinline__ void q4_jacobian(int g, const ElemGeom<FE_QUAD4>& G, double& j00, double& j01, double& j10,
+                                            double& j11) {
+    double ps, ms, pr, mr;
+    q4_table(g, ps, ms, pr, mr);
+    j00 = fma(ps, G.dx01, ms * G.dx32);
+    j01 = fma(ps, G.dy01, ms * G.dy32);
+    j10 = fma(pr, G.dx03, mr * G.dx12);
+    j11 = fma(pr, G.dy03, mr * G.dy12);
+}
+
+template <>
+__device__ __forceinline__ void geom_init<FE_QUAD4>(ElemGeom<FE_QUAD4>& G, const double (&x)[4], const double (&y)[4],
+                                                    bool weighted) {
+    G.dx01 = x[0] - x[1]; G.dx32 = x[3] - x[2]; G.dx03 = x[0] - x[3]; G.dx12 = x[1] - x[2];
+    G.dy01 = y[0] - y[1]; G.dy32 = y[3] - y[2]; G.dy03 = y[0] - y[3]; G.dy12 = y[1] - y[2];
+    double d[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        double j00, j01, j10, j11;
+        q4_jacobian(g, G, j00, j01, j10, j11);
+        d[g] = j00 * j11 - j01 * j10;
+    }
+    const double d01 = d[0] * d[1], d23 = d[2] * d[3];
+    const double inv = 1.0 / (d01 * d23);
+    const double i01 = inv * d23, i23 = inv * d01;   // 1/(d0 d1), 1/(d2 d3)
+    G.s[0] = i01 * d[1];
+    G.s[1] = i01 * d[0];
+    G.s[2] = i23 * d[3];
+    G.s[3] = i23 * d[2];
+    if (weighted) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) G.s[g] *= c_q4.w[g];
+    }
+}
+
 // Adjugate gradients at Gauss point g:  ax_b = J11 dHr_b - J01 dHs_b, ay_b = J00 dHs_b - J10 dHr_b and
 // their scaled copies sx_b = ax_b / det, sy_b = ay_b / det (times the Gauss weight when weighted).
 template <int ET>
-__device__ __forceinline__ void gauss_point(int g, const double (&x)[Elem<ET>::NNPE],
-                                            const double (&y)[Elem<ET>::NNPE], bool weighted,
+__device__ __forceinline__ void gauss_point(int g, const ElemGeom<ET>& G, bool weighted,
                                             double (&ax)[Elem<ET>::NNPE], double (&ay)[Elem<ET>::NNPE],
                                             double (&sx)[Elem<ET>::NNPE], double (&sy)[Elem<ET>::NNPE]) {
     using E = Elem<ET>;
     double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
 #pragma unroll
     for (int b = 0; b < E::NNPE; ++b) {
-        j00 = fma(E::dHr(g, b), x[b], j00);
-        j01 = fma(E::dHr(g, b), y[b], j01);
-        j10 = fma(E::dHs(g, b), x[b], j10);
-        j11 = fma(E::dHs(g, b), y[b], j11);
+        j00 = fma(E::dHr(g, b), G.x[b], j00);
+        j01 = fma(E::dHr(g, b), G.y[b], j01);
+        j10 = fma(E::dHs(g, b), G.x[b], j10);
+        j11 = fma(E::dHs(g, b), G.y[b], j11);
     }
     const double det = j00 * j11 - j01 * j10;
     double s = 1.0 / det;
@@ -105,6 +180,25 @@ __device__ __forceinline__ void gauss_point(int g, const double (&x)[Elem<ET>::N
     for (int b = 0; b < E::NNPE; ++b) {
         ax[b] = j11 * E::dHr(g, b) - j01 * E::dHs(g, b);
         ay[b] = j00 * E::dHs(g, b) - j10 * E::dHr(g, b);
+        sx[b] = ax[b] * s;
+        sy[b] = ay[b] * s;
+    }
+}
+
+template <>
+__device__ __forceinline__ void gauss_point<FE_QUAD4>(int g, const ElemGeom<FE_QUAD4>& G, bool weighted,
+                                                      double (&ax)[4], double (&ay)[4], double (&sx)[4],
+                                                      double (&sy)[4]) {
+    double ps, ms, pr, mr, j00, j01, j10, j11;
+    q4_table(g, ps, ms, pr, mr);
+    q4_jacobian(g, G, j00, j01, j10, j11);
+    const double u1 = j11 * ps, u2 = j11 * ms, v1 = j01 * pr, v2 = j01 * mr;
+    const double w1 = j00 * pr, w2 = j00 * mr, z1 = j10 * ps, z2 = j10 * ms;
+    ax[0] = u1 - v1; ax[1] = -(u1 + v2); ax[2] = v2 - u2; ax[3] = u2 + v1;
+    ay[0] = w1 - z1; ay[1] = w2 + z1;    ay[2] = z2 - w2; ay[3] = -(w1 + z2);
+    const double s = G.s[g];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
         sx[b] = ax[b] * s;
         sy[b] = ay[b] * s;
     }
@@ -132,10 +226,12 @@ __device__ __forceinline__ void element_sym(const double (&x)[Elem<ET>::NNPE], c
     using S = SymLayout<E::NNPE>;
 #pragma unroll
     for (int i = 0; i < S::kSize; ++i) out[i] = 0.0;
+    ElemGeom<ET> G;
+    geom_init<ET>(G, x, y, weighted);
 #pragma unroll
     for (int g = 0; g < E::NG; ++g) {
         double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
-        gauss_point<ET>(g, x, y, weighted, ax, ay, sx, sy);
+        gauss_point<ET>(g, G, weighted, ax, ay, sx, sy);
 #pragma unroll
         for (int a = 0; a < E::NNPE; ++a) {
             out[2 * a] = fma(sx[a], ax[a], fma(sy[a], ay[a], out[2 * a]));
@@ -182,10 +278,12 @@ __device__ __forceinline__ void element_row_pair(const double (&x)[Elem<ET>::NNP
     using E = Elem<ET>;
 #pragma unroll
     for (int b = 0; b < E::NNPE; ++b) L[b] = P[b] = Q[b] = 0.0;
+    ElemGeom<ET> G;
+    geom_init<ET>(G, x, y, weighted);
 #pragma unroll
     for (int g = 0; g < E::NG; ++g) {
         double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
-        gauss_point<ET>(g, x, y, weighted, ax, ay, sx, sy);
+        gauss_point<ET>(g, G, weighted, ax, ay, sx, sy);
         double axa = 0.0, aya = 0.0, sxa = 0.0, sya = 0.0;
 #pragma unroll
         for (int b = 0; b < E::NNPE; ++b) {

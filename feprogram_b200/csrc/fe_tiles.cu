@@ -2,44 +2,58 @@
 //
 // A tile is TE consecutive elements of a spatially compact element order (Morton order of the element
 // centroids, computed once per mesh).  Every node is owned by the tile of its first incident element in
-// that order, so each CSR row block belongs to exactly one tile.  The numeric kernel runs one CTA per
-// tile:
+// that order, so each CSR row block belongs to exactly one tile.  Elements of other tiles that touch an
+// owned node are the tile's halo elements (deduplicated, <= HE per tile) and are simply recomputed.
+// The numeric kernel runs one CTA of TE + HE threads per tile:
 //   phase 0   cp.async the tile's node descriptors and item locators into shared memory
-//   phase 1a  one thread per own element: symmetric (upper-triangular, block) element matrix -> smem
-//   phase 1b  one thread per halo item (an incident element of an owned node that lives in another
-//             tile): only the owned node's row pair -> smem
-//   phase 2   one thread per work item = (owned node, neighbour position): the plan lists, for every
-//             work item, which (incident element, local node) pairs contribute, in ascending element id;
-//             the thread sums them straight out of shared memory and writes the 2x2 CSR block once.
+//   phase 1   one thread per own / halo element: upper-triangular block element matrix -> smem slab
+//   phase 2a  one thread per work item = (owned node, neighbour position != self): the plan gives the
+//             (at most two) slab blocks that contribute, in ascending element id; sum, write the 2x2
+//             CSR block once (both rows, 16-byte streaming stores)
+//   phase 2b  one thread per owned node: its diagonal block = sum over all its incident elements
 // No atomics, fixed summation order => bit-identical reruns; element matrices never touch HBM.
-// Per element ~350 fp64 ops (vs ~1000 for the row-tile kernel) so the kernel is HBM- not fp64-bound.
 //
 // Plan storage (tile-major, contiguous per tile => every kernel read is a coalesced stream):
-//   tile_ptr[4][ntiles+1]   prefix sums: owned nodes / items / halo items / work items per tile
-//   tnode[]   int2 per owned node  {nptr[n], deg | cnt << 8 | item_offset << 16}
-//   tloc[]    uint16 per item      own: a << 11 | local element;  halo: 0x8000 | a << 11 | halo index
-//   thalo[]   int32 per halo item  element << 4 | a
-//   twork[]   uint32 per work item src0 | src1 << 8 | local node << 16 | p << 25, src = item << 4 | b,
-//             0xFF = none, src0 == 0xFE marks the node's own (diagonal) block: sum over all its items.
+//   tile_ptr[4][ntiles+1]  prefix sums per tile: owned nodes / items (even) / halo elements / work items (x32)
+//   tnode[]   int2 per owned node   {nptr[n], deg | self_pos << 7 | cnt << 14 | item_offset << 18}
+//   tloc[]    uint16 per item       slab row << 4 | a          (items of a node: ascending element id)
+//   thalo[]   int32, HE per tile    halo element ids (ascending)
+//   twork[]   uint32 per work item  src0 | src1 << 13 | first_of_node << 26 | is_self << 27,
+//             src = slab row << 5 | block(lo,hi) << 1 | transposed;  absent src1 points at a zero block
+//   tchunk[]  uint32 per 32 work items  (local node of the chunk's first item, +1, -1 if that item starts a
+//             node) << 7 | p of that item: lanes rebuild (node, p) with one ballot
+#include <stdlib.h>
+
 #include "fe_element.cuh"
 
 namespace fe {
 
-constexpr int kTileThreads = 256;
-constexpr int kTileElems = 128;      // TE: own elements per tile (threads 0..TE-1 in phase 1a)
-constexpr int kTileMaxNodes = 512;   // owned nodes per tile (9-bit local node index)
-constexpr int kTileMaxItems = 2048;  // incidence items of owned nodes per tile
-constexpr int kHaloBytes = 16 * 1024 + 512;
-constexpr unsigned kHaloFlag = 0x8000u;
-constexpr unsigned kSrcNone = 0xFFu, kSrcSelf = 0xFEu;
+#ifndef FE_TILE_ELEMS
+#define FE_TILE_ELEMS 128
+#define FE_HALO_ELEMS 32
+#define FE_TILE_CTAS 3
+#endif
+constexpr int kTileElems = FE_TILE_ELEMS;   // TE: own elements per tile
+constexpr int kHaloElems = FE_HALO_ELEMS;   // HE: halo element capacity per tile
+constexpr int kTileThreads = kTileElems + kHaloElems;
+constexpr int kZeroRow = kTileElems + kHaloElems;  // slab row of zeros (target of absent sources)
+constexpr int kTileMaxNodes = 2 * kTileElems;    // owned nodes per tile
+constexpr int kTileMaxItems = 8 * kTileElems;    // incidence items of owned nodes per tile
+constexpr int kTileMaxWork = 12 * kTileElems;    // work items (node-level non-zeros of owned nodes) per tile, x32
+constexpr int kTileCtasPerSm = FE_TILE_CTAS;     // persistent grid = SMs x this
+constexpr unsigned kWorkFirst = 1u << 26, kWorkSelf = 1u << 27;
 
 template <int N> struct TileLayout {
     static constexpr int kBlocks = N * (N + 1) / 2;            // upper-triangular node pairs incl. diagonal
-    static constexpr int kSlabStride = (3 * kBlocks) | 1;      // odd stride: conflict-free 64-bit rows
-    static constexpr int kHaloStride = (3 * N) | 1;
-    static constexpr int kHaloCap = kHaloBytes / (kHaloStride * 8);
-    static constexpr size_t kSmem = (size_t)(kTileElems * kSlabStride + kHaloCap * kHaloStride) * sizeof(double) +
-                                    (size_t)kTileMaxNodes * sizeof(int2) + (size_t)kTileMaxItems * sizeof(uint16_t);
+#ifndef FE_SLAB_PAD
+#define FE_SLAB_PAD 0
+#endif
+    static constexpr int kSlabStride = ((3 * kBlocks) | 1) + FE_SLAB_PAD;   // odd stride: conflict-free 64-bit rows
+    static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
+    // one set of staged plan records (16-byte aligned size); the kernel double-buffers it
+    static constexpr size_t kRecBytes = (size_t)kTileMaxWork * 4 + (size_t)kTileMaxNodes * 8 +
+                                        (size_t)(kTileMaxWork / 32) * 4 + (size_t)kTileMaxItems * 2;
+    static constexpr size_t kSmem = (size_t)kSlabDoubles * sizeof(double) + 2 * kRecBytes;
     // block index of the pair lo <= hi in the upper triangle (row-major)
     __host__ __device__ static constexpr int tri(int lo, int hi) { return lo * N - lo * (lo - 1) / 2 + (hi - lo); }
 };
@@ -115,14 +129,15 @@ __global__ void k_tile_bucket(int64_t nnode, const int32_t* __restrict__ owner, 
 }
 
 // One thread per tile: sort the tile's node list ascending (deterministic order after the atomic bucket
-// fill) and lay out the tile's items / halo items / work items: per-node offsets and per-tile counts.
-// noff[3*i + {0,1,2}] = item / halo / work offset of tile-node slot i inside its tile.
-__global__ void k_tile_layout(int64_t ntiles, const int32_t* __restrict__ tile_nptr, int32_t* __restrict__ tile_nodes,
-                              const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc,
-                              const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr,
-                              int32_t* __restrict__ noff, int32_t* __restrict__ tile_icount,
-                              int32_t* __restrict__ tile_hcount, int32_t* __restrict__ tile_wcount,
-                              int32_t* __restrict__ stats) {
+// fill); lay out items and work items (noff[2i], noff[2i+1] = item / work offset of tile-node slot i
+// inside its tile); collect the sorted, distinct halo elements.
+__global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_t* __restrict__ tile_nptr,
+                                                    int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ eptr,
+                                                    const int32_t* __restrict__ einc, const int32_t* __restrict__ einv,
+                                                    const int32_t* __restrict__ nptr, int32_t* __restrict__ noff,
+                                                    int32_t* __restrict__ thalo, int32_t* __restrict__ tile_icount,
+                                                    int32_t* __restrict__ tile_hcount, int32_t* __restrict__ tile_wcount,
+                                                    int32_t* __restrict__ stats) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
     if (t == ntiles) {
@@ -139,83 +154,124 @@ __global__ void k_tile_layout(int64_t ntiles, const int32_t* __restrict__ tile_n
         }
         tile_nodes[j] = v;
     }
+    int hl[kHaloElems];
     int ni = 0, nh = 0, nw = 0, maxcnt = 0;
+    bool overflow = false;
     for (int i = lo; i < hi; ++i) {
         const int n = tile_nodes[i];
-        noff[3 * (int64_t)i] = ni;
-        noff[3 * (int64_t)i + 1] = nh;
-        noff[3 * (int64_t)i + 2] = nw;
+        noff[2 * (int64_t)i] = ni;
+        noff[2 * (int64_t)i + 1] = nw;
         const int k0 = eptr[n], k1 = eptr[n + 1];
         ni += k1 - k0;
         maxcnt = (k1 - k0) > maxcnt ? (k1 - k0) : maxcnt;
-        for (int k = k0; k < k1; ++k) nh += tile_of(einv, einc[k] >> 4) != (int)t;
         nw += nptr[n + 1] - nptr[n];
+        for (int k = k0; k < k1; ++k) {
+            const int e = einc[k] >> 4;
+            if (tile_of(einv, e) == (int)t) continue;
+            int j = nh;
+            while (j > 0 && hl[j - 1] > e) --j;
+            if (j > 0 && hl[j - 1] == e) continue;
+            if (nh == kHaloElems) {
+                overflow = true;
+                continue;
+            }
+            for (int q = nh; q > j; --q) hl[q] = hl[q - 1];
+            hl[j] = e;
+            ++nh;
+        }
     }
-    tile_icount[t] = (ni + 1) & ~1;  // even: item locators are staged with 4-byte cp.async
+    for (int j = 0; j < nh; ++j) thalo[t * kHaloElems + j] = hl[j];
+    tile_icount[t] = (ni + 1) & ~1;    // even: item locators are staged with 4-byte cp.async
     tile_hcount[t] = nh;
-    tile_wcount[t] = nw;
+    tile_wcount[t] = (nw + 31) & ~31;  // chunks of 32 work items never straddle tiles
     atomicMax(stats + 0, hi - lo);
     atomicMax(stats + 1, ni);
-    atomicMax(stats + 2, nh);
+    atomicMax(stats + 2, overflow ? kHaloElems + 1 : nh);
     atomicMax(stats + 3, maxcnt);
+    atomicMax(stats + 5, nw);
 }
 
-// One thread per tile-node slot: node descriptor, item locators, halo item list, work records.
+// Tile-ordered copy of the connectivity: row r of tile t = own element r (r < TE) or halo element r - TE.
+__global__ void k_tile_conn(int64_t nrows, int64_t nelem, int nnpe, const int32_t* __restrict__ conn,
+                            const int32_t* __restrict__ eperm, const int32_t* __restrict__ thalo,
+                            const int32_t* __restrict__ tile_hptr, int32_t* __restrict__ tconn) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int64_t t = i / kTileThreads;
+    const int r = (int)(i - t * kTileThreads);
+    int64_t e = -1;
+    if (r < kTileElems) {
+        const int64_t k = t * kTileElems + r;
+        if (k < nelem) e = eperm ? eperm[k] : k;
+    } else if (r - kTileElems < tile_hptr[t + 1] - tile_hptr[t]) {
+        e = thalo[t * kHaloElems + (r - kTileElems)];
+    }
+    for (int a = 0; a < nnpe; ++a) tconn[i * nnpe + a] = e >= 0 ? conn[e * nnpe + a] : -1;
+}
+
+// One thread per tile-node slot: node descriptor, item locators, work records, chunk headers.
 __global__ void __launch_bounds__(128) k_tile_records(
     int64_t nslots, int nnpe, const int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ owner,
     const int32_t* __restrict__ tile_nptr, const int32_t* __restrict__ tile_iptr,
     const int32_t* __restrict__ tile_hptr, const int32_t* __restrict__ tile_wptr, const int32_t* __restrict__ noff,
-    const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc, const uint8_t* __restrict__ epos,
-    const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr, const int32_t* __restrict__ nadj,
-    int2* __restrict__ tnode, uint16_t* __restrict__ tloc, int32_t* __restrict__ thalo, uint32_t* __restrict__ twork,
-    int32_t* __restrict__ stats) {
+    const int32_t* __restrict__ thalo, const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc,
+    const uint8_t* __restrict__ epos, const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr,
+    const int32_t* __restrict__ nadj, int2* __restrict__ tnode, uint16_t* __restrict__ tloc,
+    uint32_t* __restrict__ twork, uint32_t* __restrict__ tchunk, int32_t* __restrict__ stats) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     const int n = tile_nodes[i];
     const int t = owner[n];
     const int ln = (int)(i - tile_nptr[t]);
-    const int ioff = noff[3 * i], hoff = noff[3 * i + 1], woff = noff[3 * i + 2];
+    const int ioff = noff[2 * i], woff = noff[2 * i + 1];
     const int k0 = eptr[n], cnt = eptr[n + 1] - k0;
     const int p0 = nptr[n], deg = nptr[n + 1] - p0;
-    tnode[i] = make_int2(p0, deg | (cnt << 8) | (ioff << 16));
-    if (cnt > 14 || deg > 127 || ioff > 0xFFFF) atomicMax(stats + 4, 1);  // not representable: use fe_assemble
-
-    unsigned char src[kMaxAdj][2];
-    for (int p = 0; p < deg; ++p) src[p][0] = src[p][1] = (unsigned char)kSrcNone;
-    // position of the node itself inside its own adjacency list
+    const int nh = tile_hptr[t + 1] - tile_hptr[t];
+    const int32_t* hl = thalo + (int64_t)t * kHaloElems;
     int self = 0;
     for (int p = 0; p < deg; ++p) self = (nadj[p0 + p] == n) ? p : self;
-    int h = hoff;
+    if (cnt > 15 || deg > 127 || deg > kMaxAdj || ioff > 0x3FFF) {  // not representable: caller uses fe_assemble
+        atomicMax(stats + 4, 1);
+        return;
+    }
+    tnode[i] = make_int2(p0, deg | (self << 7) | (cnt << 14) | (ioff << 18));
+
+    constexpr unsigned kZeroSrc = (unsigned)kZeroRow << 5;
+    unsigned short src[kMaxAdj][2];
+    for (int p = 0; p < deg; ++p) src[p][0] = src[p][1] = (unsigned short)kZeroSrc;
     for (int j = 0; j < cnt; ++j) {
         const int item = einc[k0 + j];
         const int e = item >> 4, a = item & 15;
         const int pos = einv ? einv[e] : e;
-        unsigned loc;
+        int row;
         if (pos / kTileElems == t) {
-            loc = (unsigned)(a << 11) | (unsigned)(pos - t * kTileElems);
-        } else {
-            const int hl = h;  // halo index inside the tile
-            loc = kHaloFlag | (unsigned)(a << 11) | (unsigned)hl;
-            thalo[tile_hptr[t] + hl] = item;
-            if (hl > 0x7FF) atomicMax(stats + 4, 1);
-            ++h;
-        }
-        tloc[tile_iptr[t] + ioff + j] = (uint16_t)loc;
-        if (j < 15) {
-            for (int b = 0; b < nnpe; ++b) {
-                const int p = epos[(int64_t)(k0 + j) * nnpe + b];
-                if (p == self) continue;
-                const unsigned char s = (unsigned char)((j << 4) | b);
-                if (src[p][0] == kSrcNone) src[p][0] = s;
-                else if (src[p][1] == kSrcNone) src[p][1] = s;
-                else atomicMax(stats + 4, 1);  // an edge shared by more than two elements
+            row = pos - t * kTileElems;
+        } else {  // position inside the tile's sorted halo list
+            int lo = 0, hi = nh - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (hl[mid] < e) lo = mid + 1;
+                else hi = mid;
             }
+            row = kTileElems + lo;
+        }
+        tloc[tile_iptr[t] + ioff + j] = (uint16_t)((row << 4) | a);
+        for (int b = 0; b < nnpe; ++b) {
+            const int p = epos[(int64_t)(k0 + j) * nnpe + b];
+            if (p == self) continue;
+            const int blo = a < b ? a : b, bhi = a < b ? b : a;
+            const int tri = blo * nnpe - blo * (blo - 1) / 2 + (bhi - blo);
+            const unsigned short s = (unsigned short)((row << 5) | (tri << 1) | (a > b ? 1 : 0));
+            if (src[p][0] == kZeroSrc) src[p][0] = s;
+            else if (src[p][1] == kZeroSrc) src[p][1] = s;
+            else atomicMax(stats + 4, 1);  // a node pair shared by more than two elements
         }
     }
+    const int64_t wbase = (int64_t)tile_wptr[t] + woff;
     for (int p = 0; p < deg; ++p) {
-        const unsigned s0 = (p == self) ? kSrcSelf : src[p][0];
-        const unsigned s1 = (p == self) ? kSrcNone : src[p][1];
-        twork[tile_wptr[t] + woff + p] = s0 | (s1 << 8) | ((unsigned)ln << 16) | ((unsigned)p << 25);
+        twork[wbase + p] = (unsigned)src[p][0] | ((unsigned)src[p][1] << 13) | (p == 0 ? kWorkFirst : 0u) |
+                           (p == self ? kWorkSelf : 0u);
+        if (((woff + p) & 31) == 0) tchunk[(wbase + p) >> 5] = ((unsigned)(ln + (p == 0 ? 0 : 1)) << 7) | (unsigned)p;
     }
 }
 
@@ -227,6 +283,9 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -241,10 +300,12 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
     using T = TileLayout<E::NNPE>;
 #pragma unroll
     for (int i = 0; i < 3 * T::kBlocks; ++i) out[i] = 0.0;
+    ElemGeom<ET> G;
+    geom_init<ET>(G, x, y, weighted);
 #pragma unroll
     for (int g = 0; g < E::NG; ++g) {
         double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
-        gauss_point<ET>(g, x, y, weighted, ax, ay, sx, sy);
+        gauss_point<ET>(g, G, weighted, ax, ay, sx, sy);
 #pragma unroll
         for (int a = 0; a < E::NNPE; ++a) {
 #pragma unroll
@@ -260,118 +321,192 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
     for (int a = 0; a < E::NNPE; ++a) out[3 * T::tri(a, a) + 2] = out[3 * T::tri(a, a) + 1];
 }
 
+// Persistent kernel: CTA c processes tiles c, c + G, c + 2G, ...  While tile t is computed, the plan
+// records of tile t + G stream into the other shared-memory buffer (cp.async) and its connectivity row
+// and coordinates are prefetched into registers, so no global-memory latency is exposed per tile.
 template <int ET>
-__global__ void __launch_bounds__(kTileThreads, 2) k_assemble_tiled(
-    int64_t nelem, const int32_t* __restrict__ conn, const double2* __restrict__ coords,
-    const int32_t* __restrict__ eperm, const int32_t* __restrict__ tile_nptr, const int32_t* __restrict__ tile_iptr,
-    const int32_t* __restrict__ tile_hptr, const int32_t* __restrict__ tile_wptr, const int2* __restrict__ tnode,
-    const uint16_t* __restrict__ tloc, const int32_t* __restrict__ thalo, const uint32_t* __restrict__ twork,
-    double* __restrict__ vals, int weighted) {
+__global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) k_assemble_tiled(
+    int64_t ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords,
+    const int4* __restrict__ tdesc, const int2* __restrict__ tnode, const uint16_t* __restrict__ tloc,
+    const uint32_t* __restrict__ twork, const uint32_t* __restrict__ tchunk, double* __restrict__ vals, int weighted,
+    int dbg) {
     using E = Elem<ET>;
     constexpr int N = E::NNPE;
     using T = TileLayout<N>;
-    extern __shared__ double smem[];
-    double* slab = smem;
-    double* halo = smem + kTileElems * T::kSlabStride;
-    int2* s_node = reinterpret_cast<int2*>(halo + T::kHaloCap * T::kHaloStride);
-    uint16_t* s_loc = reinterpret_cast<uint16_t*>(s_node + kTileMaxNodes);
+    constexpr int SS = T::kSlabStride;
+    extern __shared__ __align__(16) double slab[];
+    unsigned char* rec_base = reinterpret_cast<unsigned char*>(slab + T::kSlabDoubles);
 
-    const int64_t t = blockIdx.x;
     const int tid = threadIdx.x;
-    const int64_t e0 = t * kTileElems;
+    const unsigned lane = tid & 31u;
+    const unsigned le_mask = 0xFFFFFFFFu >> (31u - lane);
+    if (tid < 3) slab[kZeroRow * SS + tid] = 0.0;
 
-    // ---- phase 0: asynchronous staging of the tile's descriptors -----------------------------------
-    const int n0 = __ldg(tile_nptr + t), nn = __ldg(tile_nptr + t + 1) - n0;
-    const int i0 = __ldg(tile_iptr + t), ni = __ldg(tile_iptr + t + 1) - i0;  // even, i0 even
-    const int w0 = __ldg(tile_wptr + t), nw = __ldg(tile_wptr + t + 1) - w0;
-    for (int i = tid; i < nn; i += kTileThreads) cp_async_8(s_node + i, tnode + n0 + i);
-    for (int i = tid; 2 * i < ni; i += kTileThreads) cp_async_4(s_loc + 2 * i, tloc + i0 + 2 * i);
-    unsigned rec = (tid < nw) ? __ldg(twork + w0 + tid) : 0u;  // first work record, prefetched
+    // staged record views of buffer b
+    auto s_work = [&](int b) { return reinterpret_cast<uint32_t*>(rec_base + b * T::kRecBytes); };
+    auto s_node = [&](int b) { return reinterpret_cast<int2*>(s_work(b) + kTileMaxWork); };
+    auto s_chunk = [&](int b) { return reinterpret_cast<uint32_t*>(s_node(b) + kTileMaxNodes); };
+    auto s_loc = [&](int b) { return reinterpret_cast<uint16_t*>(s_chunk(b) + kTileMaxWork / 32); };
+    // tdesc[2t] = {n0, nn, i0, ni}, tdesc[2t+1] = {w0, nw, -, -}
+    auto stage = [&](int b, const int4 d0, const int4 d1) {
+        const int n0 = d0.x, nn = d0.y, i0 = d0.z, ni = d0.w, w0 = d1.x, nw = d1.y;
+        for (int i = tid; 4 * i < nw; i += kTileThreads) cp_async_16(s_work(b) + 4 * i, twork + w0 + 4 * i);
+        for (int i = tid; 32 * i < nw; i += kTileThreads) cp_async_4(s_chunk(b) + i, tchunk + (w0 >> 5) + i);
+        for (int i = tid; i < nn; i += kTileThreads) cp_async_8(s_node(b) + i, tnode + n0 + i);
+        for (int i = tid; 2 * i < ni; i += kTileThreads) cp_async_4(s_loc(b) + 2 * i, tloc + i0 + 2 * i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_row = [&](int64_t t, int (&tg)[N]) {
+        const int32_t* row = tconn + (t * kTileThreads + tid) * N;
+        if constexpr (N == 4) {
+            const int4 c = __ldg(reinterpret_cast<const int4*>(row));
+            tg[0] = c.x; tg[1] = c.y; tg[2] = c.z; tg[3] = c.w;
+        } else {
+#pragma unroll
+            for (int a = 0; a < N; ++a) tg[a] = __ldg(row + a);
+        }
+    };
+    auto load_xy = [&](const int (&tg)[N], double (&x)[N], double (&y)[N]) {
+        if (tg[0] < 0) return;
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            const double2 p = __ldg(coords + tg[a]);
+            x[a] = p.x;
+            y[a] = p.y;
+        }
+    };
 
-    if (tid < kTileElems) {
-        // ---- phase 1a: own elements --------------------------------------------------------------
-        if (e0 + tid < nelem) {
-            const int64_t e = eperm ? (int64_t)__ldg(eperm + e0 + tid) : e0 + tid;
-            int tg[N];
-            double x[N], y[N], ke[3 * T::kBlocks];
-            load_element<ET>(conn, coords, e, tg, x, y);
+    auto prefetch_xy = [&](const int (&tg_)[N]) {   // pull the nodes' coordinates into L2
+        if (tg_[0] < 0) return;
+#pragma unroll
+        for (int a = 0; a < N; ++a) asm volatile("prefetch.global.L2 [%0];" ::"l"(coords + tg_[a]));
+    };
+
+    // ---- prologue: first tile of this CTA --------------------------------------------------------------
+    int64_t t = blockIdx.x;
+    if (t >= ntiles) return;
+    int4 d0 = __ldg(tdesc + 2 * t), d1 = __ldg(tdesc + 2 * t + 1);
+    int tg[N], tgn[N];
+    double x[N], y[N];
+    load_row(t, tg);
+    tgn[0] = -1;
+    if (t + gridDim.x < ntiles) load_row(t + gridDim.x, tgn);
+    stage(0, d0, d1);
+    load_xy(tg, x, y);
+    int buf = 0;
+
+    for (; t < ntiles; t += gridDim.x) {
+        const int64_t tn = t + gridDim.x, tn2 = tn + gridDim.x;
+        const bool more = tn < ntiles;
+        // next tile: descriptor; its connectivity row arrived during the previous iteration, so its
+        // coordinates can be pulled into L2 now; the row after that is requested two tiles ahead.
+        int4 e0 = d0, e1 = d1;
+        int tgn2[N];
+        tgn2[0] = -1;
+        if (more) {
+            e0 = __ldg(tdesc + 2 * tn);
+            e1 = __ldg(tdesc + 2 * tn + 1);
+#ifdef FE_L2_PREFETCH
+            prefetch_xy(tgn);
+#endif
+            if (tn2 < ntiles) load_row(tn2, tgn2);
+        }
+        // ---- phase 1: own and halo elements -> slab --------------------------------------------------
+        const bool active = tg[0] >= 0;
+        if (active && dbg != 2) {
+            double ke[3 * T::kBlocks];
             element_tri<ET>(x, y, weighted != 0, ke);
-            double* dst = slab + tid * T::kSlabStride;
+            double* dst = slab + tid * SS;
 #pragma unroll
             for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
         }
-    } else {
-        // ---- phase 1b: halo items (row pairs of elements owned by other tiles) -------------------
-        const int h0 = __ldg(tile_hptr + t);
-        const int nh = __ldg(tile_hptr + t + 1) - h0;
-        for (int h = tid - kTileElems; h < nh; h += kTileThreads - kTileElems) {
-            const int item = __ldg(thalo + h0 + h);
-            int tg[N];
-            double x[N], y[N], L[N], P[N], Q[N];
-            load_element<ET>(conn, coords, item >> 4, tg, x, y);
-            element_row_pair<ET>(x, y, item & 15, weighted != 0, L, P, Q);
-            double* dst = halo + h * T::kHaloStride;
+        // records of the next tile start streaming into the other buffer
+        if (more) stage(buf ^ 1, e0, e1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's records have landed
+        __syncthreads();
+        // coordinates of the next tile (L2-resident by now): in flight during phase 2
+        if (more) {
 #pragma unroll
-            for (int b = 0; b < N; ++b) {
-                dst[3 * b] = L[b];
-                dst[3 * b + 1] = P[b];
-                dst[3 * b + 2] = Q[b];
+            for (int a = 0; a < N; ++a) {
+                tg[a] = tgn[a];
+                tgn[a] = tgn2[a];
+            }
+            load_xy(tg, x, y);
+        }
+        if (dbg != 1) {
+            const int nn = d0.y, nw = d1.y;
+            const uint32_t* work = s_work(buf);
+            const uint32_t* chunk = s_chunk(buf);
+            const int2* node = s_node(buf);
+            const uint16_t* locs = s_loc(buf);
+            // ---- phase 2a: off-diagonal work items ---------------------------------------------------
+            for (int q = tid; q < nw; q += kTileThreads) {
+                const unsigned rec = work[q];
+                const unsigned ch = chunk[q >> 5];
+                const unsigned before = __ballot_sync(0xFFFFFFFFu, (rec & kWorkFirst) != 0) & le_mask;
+                const int ln = (int)(ch >> 7) - 1 + __popc(before);
+                const int p = before ? (int)lane - (31 - __clz(before)) : (int)(ch & 127u) + (int)lane;
+                if (rec == 0u || (rec & kWorkSelf)) continue;   // padding or diagonal block
+                const int2 nd = node[ln];
+                const int deg = nd.y & 127;
+                const unsigned s0 = rec & 0x1FFFu, s1 = (rec >> 13) & 0x1FFFu;
+                const double* b0 = slab + (s0 >> 5) * SS + 3 * ((s0 >> 1) & 15);
+                const int f0 = s0 & 1;                          // transposed block: P and Q trade places
+                double L = b0[0], P = b0[1 + f0], Q = b0[2 - f0];
+                if ((s1 >> 5) != (unsigned)kZeroRow) {          // second contributing element (higher id)
+                    const double* b1 = slab + (s1 >> 5) * SS + 3 * ((s1 >> 1) & 15);
+                    const int f1 = s1 & 1;
+                    L += b1[0];
+                    P += b1[1 + f1];
+                    Q += b1[2 - f1];
+                }
+                double* out = vals + 4 * (int64_t)nd.x + 2 * p;
+                __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
+                __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(Q, L));
+            }
+            // ---- phase 2b: diagonal blocks, one thread per owned node ---------------------------------
+            for (int ln = tid; ln < nn; ln += kTileThreads) {
+                const int2 nd = node[ln];
+                const int deg = nd.y & 127, self = (nd.y >> 7) & 127, cnt = (nd.y >> 14) & 15;
+                const int ioff = (unsigned)nd.y >> 18;
+                double L = 0.0, P = 0.0;
+                for (int j = 0; j < cnt; ++j) {
+                    const unsigned loc = locs[ioff + j];
+                    const int a = loc & 15;
+                    const double* b = slab + (loc >> 4) * SS + 3 * (a * N - ((a * (a - 1)) >> 1));
+                    L += b[0];
+                    P += b[1];
+                }
+                double* out = vals + 4 * (int64_t)nd.x + 2 * self;
+                __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
+                __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(P, L));
             }
         }
+        __syncthreads();   // slab and this record buffer are free again
+        d0 = e0;
+        d1 = e1;
+        buf ^= 1;
     }
-    cp_async_wait_all();
-    __syncthreads();
-
-    // ---- phase 2: one thread per work item ----------------------------------------------------------
-    for (int q = tid; q < nw; q += kTileThreads) {
-        if (q != tid) rec = __ldg(twork + w0 + q);
-        const unsigned s0 = rec & 0xFFu, s1 = (rec >> 8) & 0xFFu;
-        const int ln = (rec >> 16) & 0x1FF, p = rec >> 25;
-        const int2 nd = s_node[ln];
-        const int deg = nd.y & 0xFF, cnt = (nd.y >> 8) & 0xFF, ioff = (unsigned)nd.y >> 16;
-        double L = 0.0, P = 0.0, Q = 0.0;
-        // contribution of item j, block (a_item, b): own -> slab (transposed when a > b), halo -> row pair
-        auto add = [&](int j, int b, bool diag) {
-            const unsigned loc = s_loc[ioff + j];
-            const int a = (loc >> 11) & 15;
-            if (diag) b = a;
-            const double* src;
-            bool swap = false;
-            if (loc & kHaloFlag) {
-                src = halo + (loc & 0x7FFu) * T::kHaloStride + 3 * b;
-            } else {
-                const int lo = a < b ? a : b, hi = a < b ? b : a;
-                swap = a > b;
-                src = slab + (loc & 0x7FFu) * T::kSlabStride + 3 * (lo * N - ((lo * (lo - 1)) >> 1) + (hi - lo));
-            }
-            const double l = src[0], u = src[1], v = src[2];
-            L += l;
-            P += swap ? v : u;
-            Q += swap ? u : v;
-        };
-        if (s0 == kSrcSelf) {
-            for (int j = 0; j < cnt; ++j) add(j, 0, true);
-        } else {
-            if (s0 != kSrcNone) add(s0 >> 4, s0 & 15, false);
-            if (s1 != kSrcNone) add(s1 >> 4, s1 & 15, false);
-        }
-        double* out = vals + 4 * (int64_t)nd.x;
-        __stcs(reinterpret_cast<double2*>(out + 2 * p), make_double2(L, P));
-        __stcs(reinterpret_cast<double2*>(out + 2 * deg + 2 * p), make_double2(Q, L));
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <int ET>
-static int launch_tiled(int64_t nelem, const int32_t* conn, const double* coords, const int32_t* eperm,
-                        const int32_t* tile_ptr, const int2* tnode, const uint16_t* tloc, const int32_t* thalo,
-                        const uint32_t* twork, double* vals, int weighted, cudaStream_t st) {
+static int launch_tiled(int64_t nelem, const int32_t* tconn, const double* coords, const int32_t* tdesc,
+                        const int2* tnode, const uint16_t* tloc, const uint32_t* twork, const uint32_t* tchunk,
+                        double* vals, int weighted, cudaStream_t st) {
     using T = TileLayout<Elem<ET>::NNPE>;
     const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
-    const int64_t s = ntiles + 1;
+    const int dbg = getenv("FE_TILED_DBG") ? atoi(getenv("FE_TILED_DBG")) : 0;  // phase isolation for profiling
+    int dev = 0, sms = 0;
+    FE_CUDA_TRY(cudaGetDevice(&dev));
+    FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t grid = (int64_t)sms * kTileCtasPerSm;
+    if (grid > ntiles) grid = ntiles;
     FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
-    k_assemble_tiled<ET><<<(unsigned)ntiles, kTileThreads, T::kSmem, st>>>(
-        nelem, conn, reinterpret_cast<const double2*>(coords), eperm, tile_ptr, tile_ptr + s, tile_ptr + 2 * s,
-        tile_ptr + 3 * s, tnode, tloc, thalo, twork, vals, weighted);
+    k_assemble_tiled<ET><<<(unsigned)grid, kTileThreads, T::kSmem, st>>>(
+        ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc), tnode, tloc,
+        twork, tchunk, vals, weighted, dbg);
     FE_CHECK_LAUNCH("k_assemble_tiled");
     return FE_OK;
 }
@@ -388,13 +523,14 @@ int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan
     return exclusive_scan_i32(in, out, n, scan_ws, as_stream(stream));
 }
 
-void fe_tile_params(int elem_type, int32_t out[4]) {
+void fe_tile_params(int elem_type, int32_t out[6]) {
     using namespace fe;
     out[0] = kTileElems;
-    out[1] = elem_type == FE_QUAD4 ? TileLayout<4>::kHaloCap
-             : elem_type == FE_TRI3 ? TileLayout<3>::kHaloCap : 0;   // 0: tiled kernel not available
+    out[1] = (elem_type == FE_QUAD4 || elem_type == FE_TRI3) ? kHaloElems : 0;   // 0: no tiled kernel
     out[2] = kTileMaxNodes;
     out[3] = kTileMaxItems;
+    out[4] = kTileMaxWork;
+    out[5] = kTileThreads;   // rows per tile of the tile-ordered connectivity (fe_tile_conn)
 }
 
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin, double ymin,
@@ -443,11 +579,12 @@ int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32
 
 int fe_tile_layout(int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr, const int32_t* eptr,
                    const int32_t* einc, const int32_t* einv, const int32_t* nptr, int32_t* cursor,
-                   int32_t* tile_nodes, int32_t* noff, int32_t* tile_counts, int32_t* stats, void* stream) {
+                   int32_t* tile_nodes, int32_t* noff, int32_t* thalo, int32_t* tile_counts, int32_t* stats,
+                   void* stream) {
     using namespace fe;
     FE_REQUIRE(nnode >= 0 && nelem >= 0, "negative size");
     const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
-    FE_REQUIRE(tile_nptr && cursor && tile_counts && stats, "null pointer");
+    FE_REQUIRE(tile_nptr && cursor && tile_counts && stats && thalo, "null pointer");
     cudaStream_t st = as_stream(stream);
     FE_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)(ntiles > 0 ? ntiles : 1) * sizeof(int32_t), st));
     FE_CUDA_TRY(cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
@@ -457,18 +594,18 @@ int fe_tile_layout(int64_t nnode, int64_t nelem, const int32_t* owner, const int
         FE_CHECK_LAUNCH("k_tile_bucket");
     }
     const int64_t s = ntiles + 1;
-    k_tile_layout<<<grid_for(ntiles + 1, 128), 128, 0, st>>>(ntiles, tile_nptr, tile_nodes, eptr, einc, einv, nptr,
-                                                            noff, tile_counts, tile_counts + s, tile_counts + 2 * s,
-                                                            stats);
+    k_tile_layout<<<grid_for(ntiles + 1, 64), 64, 0, st>>>(ntiles, tile_nptr, tile_nodes, eptr, einc, einv, nptr, noff,
+                                                          thalo, tile_counts, tile_counts + s, tile_counts + 2 * s,
+                                                          stats);
     FE_CHECK_LAUNCH("k_tile_layout");
     return FE_OK;
 }
 
 int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, const int32_t* owner,
-                    const int32_t* tile_ptr, int64_t ntiles, const int32_t* noff, const int32_t* eptr,
-                    const int32_t* einc, const uint8_t* epos, const int32_t* einv, const int32_t* nptr,
-                    const int32_t* nadj, void* tnode, uint16_t* tloc, int32_t* thalo, uint32_t* twork, int32_t* stats,
-                    void* stream) {
+                    const int32_t* tile_ptr, int64_t ntiles, const int32_t* noff, const int32_t* thalo,
+                    const int32_t* eptr, const int32_t* einc, const uint8_t* epos, const int32_t* einv,
+                    const int32_t* nptr, const int32_t* nadj, void* tnode, uint16_t* tloc, uint32_t* twork,
+                    uint32_t* tchunk, int32_t* stats, void* stream) {
     using namespace fe;
     const int nnpe = nnpe_of(elem_type);
     if (!nnpe) {
@@ -477,20 +614,39 @@ int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, co
     }
     FE_REQUIRE(nslots >= 0 && ntiles >= 0, "negative size");
     if (nslots == 0) return FE_OK;
-    FE_REQUIRE(tile_nodes && owner && tile_ptr && noff && eptr && einc && epos && nptr && nadj && tnode && tloc &&
-                   thalo && twork && stats,
+    FE_REQUIRE(tile_nodes && owner && tile_ptr && noff && thalo && eptr && einc && epos && nptr && nadj && tnode &&
+                   tloc && twork && tchunk && stats,
                "null pointer");
     const int64_t s = ntiles + 1;
     k_tile_records<<<grid_for(nslots, 128), 128, 0, as_stream(stream)>>>(
-        nslots, nnpe, tile_nodes, owner, tile_ptr, tile_ptr + s, tile_ptr + 2 * s, tile_ptr + 3 * s, noff, eptr, einc,
-        epos, einv, nptr, nadj, static_cast<int2*>(tnode), tloc, thalo, twork, stats);
+        nslots, nnpe, tile_nodes, owner, tile_ptr, tile_ptr + s, tile_ptr + 2 * s, tile_ptr + 3 * s, noff, thalo, eptr,
+        einc, epos, einv, nptr, nadj, static_cast<int2*>(tnode), tloc, twork, tchunk, stats);
     FE_CHECK_LAUNCH("k_tile_records");
     return FE_OK;
 }
 
-int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* conn, const double* coords,
-                      const int32_t* eperm, const int32_t* tile_ptr, const void* tnode, const uint16_t* tloc,
-                      const int32_t* thalo, const uint32_t* twork, double* vals, void* stream) {
+int fe_tile_conn(int elem_type, int64_t nelem, const int32_t* conn, const int32_t* eperm, const int32_t* thalo,
+                 const int32_t* tile_ptr, int32_t* tconn, void* stream) {
+    using namespace fe;
+    const int nnpe = nnpe_of(elem_type);
+    if (!nnpe) {
+        set_error("fe_tile_conn: Invalid elemType %d", elem_type);
+        return FE_ERR_UNSUPPORTED;
+    }
+    FE_REQUIRE(nelem >= 0, "negative size");
+    if (nelem == 0) return FE_OK;
+    FE_REQUIRE(conn && thalo && tile_ptr && tconn, "null pointer");
+    const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
+    const int64_t nrows = ntiles * kTileThreads;
+    k_tile_conn<<<grid_for(nrows, 256), 256, 0, as_stream(stream)>>>(nrows, nelem, nnpe, conn, eperm, thalo,
+                                                                    tile_ptr + 2 * (ntiles + 1), tconn);
+    FE_CHECK_LAUNCH("k_tile_conn");
+    return FE_OK;
+}
+
+int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* tconn, const double* coords,
+                      const int32_t* tdesc, const void* tnode, const uint16_t* tloc, const uint32_t* twork,
+                      const uint32_t* tchunk, double* vals, void* stream) {
     using namespace fe;
     FE_REQUIRE(nelem >= 0, "negative size");
     if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED) {
@@ -498,7 +654,7 @@ int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* conn,
         return FE_ERR_UNSUPPORTED;
     }
     if (nelem == 0) return FE_OK;
-    FE_REQUIRE(conn && coords && tile_ptr && tnode && tloc && thalo && twork && vals, "null pointer");
+    FE_REQUIRE(tconn && coords && tdesc && tnode && tloc && twork && tchunk && vals, "null pointer");
     cudaStream_t st = as_stream(stream);
     int rc = ensure_tables_tu(st);
     if (rc != FE_OK) return rc;
@@ -506,9 +662,9 @@ int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* conn,
     const int2* nd = static_cast<const int2*>(tnode);
     switch (elem_type) {
         case FE_QUAD4:
-            return launch_tiled<FE_QUAD4>(nelem, conn, coords, eperm, tile_ptr, nd, tloc, thalo, twork, vals, w, st);
+            return launch_tiled<FE_QUAD4>(nelem, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
         case FE_TRI3:
-            return launch_tiled<FE_TRI3>(nelem, conn, coords, eperm, tile_ptr, nd, tloc, thalo, twork, vals, w, st);
+            return launch_tiled<FE_TRI3>(nelem, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
         default:
             set_error("fe_assemble_tiled: element type %d has no tiled kernel (use fe_assemble)", elem_type);
             return FE_ERR_UNSUPPORTED;

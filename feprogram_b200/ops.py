@@ -269,13 +269,13 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern
 # --------------------------------------------------------------------------------------------
 @dataclass
 class TilePlan:
-    """One-time plan of fe_assemble_tiled (device tensors, tile-major)."""
-    eperm: Optional[Tensor]
-    tile_ptr: Tensor        # int32 [4, ntiles+1]: nodes / items / halo items / work items prefix sums
+    """One-time plan of fe_assemble_tiled (device tensors, tile-major; formats in csrc/fe_tiles.cu)."""
+    tconn: Tensor           # int32 [ntiles, tile_rows, nnpe]: connectivity in tile order (own + halo rows)
+    tdesc: Tensor           # int32 [ntiles, 8]: node offset/count, item offset/count, work offset/count, 0, 0
     tnode: Tensor           # int32 [nslots, 2]
     tloc: Tensor            # uint16 [items]
-    thalo: Tensor           # int32 [halo items]
-    twork: Tensor           # int32 (uint32 bit pattern) [work items]
+    twork: Tensor           # int32 (uint32 bit pattern) [work items, padded to 32 per tile]
+    tchunk: Tensor          # int32 (uint32 bit pattern) [work items / 32]
     ntiles: int
     stats: dict
 
@@ -292,7 +292,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
     if params["halo_cap"] == 0 or pat.nelem == 0 or pat.nnode == 0:
         return None
     dev = conn.device
-    te = params["tile_elems"]
+    te, hcap = params["tile_elems"], params["halo_cap"]
     nelem, nnode = pat.nelem, pat.nnode
     ntiles = (nelem + te - 1) // te
     s = ntiles + 1
@@ -319,53 +319,63 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
         _scan_into(tile_ncount, tile_ptr[0], ws)
         cursor = torch.empty(ntiles, dtype=torch.int32, device=dev)
         tile_nodes = torch.empty(nnode, dtype=torch.int32, device=dev)
-        noff = torch.empty(3 * nnode, dtype=torch.int32, device=dev)
+        noff = torch.empty(2 * nnode, dtype=torch.int32, device=dev)
+        thalo = torch.empty((ntiles, hcap), dtype=torch.int32, device=dev)
         counts = torch.empty((3, s), dtype=torch.int32, device=dev)
         stats = torch.empty(8, dtype=torch.int32, device=dev)
         _lib.check(L.fe_tile_layout(nnode, nelem, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
                                     _ptr(einv), _ptr(pat.nptr), _ptr(cursor), _ptr(tile_nodes), _ptr(noff),
-                                    _ptr(counts), _ptr(stats), st))
+                                    _ptr(thalo), _ptr(counts), _ptr(stats), st))
         for r in range(3):
             _scan_into(counts[r], tile_ptr[r + 1], ws)
         tail = torch.cat([tile_ptr[:, ntiles], stats]).cpu().tolist()       # one host sync
         nslots, n_items, n_halo, n_work = (int(v) for v in tail[:4])
         max_nodes, max_items, max_halo, max_cnt = (int(v) for v in tail[4:8])
-        info = dict(max_nodes=max_nodes, max_items=max_items, max_halo=max_halo, max_cnt=max_cnt,
-                    items=n_items, halo_items=n_halo, work_items=n_work, morton=morton)
-        if max_nodes > params["max_nodes"] or max_items >= params["max_items"] - 1 or max_halo > params["halo_cap"]:
+        max_work = int(tail[9])
+        info = dict(max_nodes=max_nodes, max_items=max_items, max_halo=max_halo, max_cnt=max_cnt, max_work=max_work,
+                    items=n_items, halo_elems=n_halo, work_items=n_work, morton=morton)
+        if (max_nodes > params["max_nodes"] or max_items >= params["max_items"] - 1 or max_halo > hcap
+                or max_work > params["max_work"]):
             return None
         tnode = torch.empty((max(1, nslots), 2), dtype=torch.int32, device=dev)
         tloc = torch.zeros(max(2, n_items), dtype=torch.uint16, device=dev)
-        thalo = torch.empty(max(1, n_halo), dtype=torch.int32, device=dev)
-        twork = torch.empty(max(1, n_work), dtype=torch.int32, device=dev)
+        twork = torch.zeros(max(32, n_work), dtype=torch.int32, device=dev)
+        tchunk = torch.zeros(max(1, n_work // 32), dtype=torch.int32, device=dev)
         _lib.check(L.fe_tile_records(pat.elem_type, nslots, _ptr(tile_nodes), _ptr(owner), _ptr(tile_ptr), ntiles,
-                                     _ptr(noff), _ptr(pat.eptr), _ptr(pat.einc), _ptr(pat.epos), _ptr(einv),
-                                     _ptr(pat.nptr), _ptr(pat.nadj), _ptr(tnode), _ptr(tloc), _ptr(thalo),
-                                     _ptr(twork), _ptr(stats), st))
+                                     _ptr(noff), _ptr(thalo), _ptr(pat.eptr), _ptr(pat.einc), _ptr(pat.epos),
+                                     _ptr(einv), _ptr(pat.nptr), _ptr(pat.nadj), _ptr(tnode), _ptr(tloc),
+                                     _ptr(twork), _ptr(tchunk), _ptr(stats), st))
         if int(stats[4].item()) != 0:
             return None
-    return TilePlan(eperm, tile_ptr, tnode, tloc, thalo, twork, ntiles, info)
+        tconn = torch.empty((ntiles, params["tile_rows"], conn.shape[1]), dtype=torch.int32, device=dev)
+        _lib.check(L.fe_tile_conn(pat.elem_type, nelem, _ptr(conn), _ptr(eperm), _ptr(thalo), _ptr(tile_ptr),
+                                  _ptr(tconn), st))
+        z = torch.zeros(ntiles, dtype=torch.int32, device=dev)
+        tdesc = torch.stack([tile_ptr[0, :-1], tile_ptr[0, 1:] - tile_ptr[0, :-1],
+                             tile_ptr[1, :-1], tile_ptr[1, 1:] - tile_ptr[1, :-1],
+                             tile_ptr[3, :-1], tile_ptr[3, 1:] - tile_ptr[3, :-1], z, z], dim=1).contiguous()
+    return TilePlan(tconn, tdesc, tnode, tloc, twork, tchunk, ntiles, info)
 
 
 @torch.library.custom_op("feprogram::assemble_tiled", mutates_args=("vals",))
-def assemble_tiled(conn: Tensor, coords: Tensor, eperm: Optional[Tensor], tile_ptr: Tensor, tnode: Tensor,
-                   tloc: Tensor, thalo: Tensor, twork: Tensor, vals: Tensor, elem_type: int, op: int) -> None:
+def assemble_tiled(tconn: Tensor, coords: Tensor, nelem: int, tdesc: Tensor, tnode: Tensor, tloc: Tensor,
+                   twork: Tensor, tchunk: Tensor, vals: Tensor, elem_type: int, op: int) -> None:
     """Numeric assembly, tiled kernel (same results as feprogram::assemble, bit for bit)."""
-    _chk_dev(conn, coords, eperm, tile_ptr, tnode, tloc, thalo, twork, vals)
-    _want(conn, torch.int32, "conn")
+    _chk_dev(tconn, coords, tdesc, tnode, tloc, twork, tchunk, vals)
+    _want(tconn, torch.int32, "tconn")
     _want(coords, torch.float64, "coords")
     _want(vals, torch.float64, "vals")
-    with torch.cuda.device(conn.device):
-        _lib.check(_lib.lib().fe_assemble_tiled(elem_type, op, conn.shape[0], _ptr(conn), _ptr(coords), _ptr(eperm),
-                                                _ptr(tile_ptr), _ptr(tnode), _ptr(tloc), _ptr(thalo), _ptr(twork),
-                                                _ptr(vals), _stream(conn)))
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().fe_assemble_tiled(elem_type, op, nelem, _ptr(tconn), _ptr(coords), _ptr(tdesc),
+                                                _ptr(tnode), _ptr(tloc), _ptr(twork), _ptr(tchunk), _ptr(vals),
+                                                _stream(vals)))
 
 
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):
     """Numeric assembly with whichever kernel the plan allows."""
     if plan is not None:
-        torch.ops.feprogram.assemble_tiled(conn, coords, plan.eperm, plan.tile_ptr, plan.tnode, plan.tloc,
-                                           plan.thalo, plan.twork, vals, pat.elem_type, op)
+        torch.ops.feprogram.assemble_tiled(plan.tconn, coords, pat.nelem, plan.tdesc, plan.tnode, plan.tloc,
+                                           plan.twork, plan.tchunk, vals, pat.elem_type, op)
     else:
         torch.ops.feprogram.assemble(conn, coords, pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg, vals,
                                      pat.elem_type, op)

@@ -145,18 +145,21 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
  *  2. fe_tile_owner         : owner[nnode] (tile id, -1 if the node has no element),
  *                             tile_ncount[s] (owned nodes per tile, last entry 0).
  *  3. fe_exclusive_scan_i32 : tile_ptr[0..s) <- scan(tile_ncount)
- *  4. fe_tile_layout        : tile_nodes (ascending node id inside each tile), noff[3*nslots]
- *                             (item / halo / work offset of each tile-node slot inside its tile),
- *                             tile_counts[3*s] (items (even), halo items, work items per tile),
- *                             stats[8]: [0] max owned nodes, [1] max items, [2] max halo items of a
- *                             tile, [3] max incident elements of a node.  scratch: cursor[ntiles].
+ *  4. fe_tile_layout        : tile_nodes (ascending node id inside each tile), noff[2*nslots]
+ *                             (item / work offset of each tile-node slot inside its tile),
+ *                             thalo[ntiles*out[1]] (sorted distinct halo elements of each tile),
+ *                             tile_counts[3*s] (items (even), halo elements, work items (x32) per
+ *                             tile), stats[8]: [0] max owned nodes, [1] max items, [2] max halo
+ *                             elements of a tile, [3] max incident elements of a node.
+ *                             scratch: cursor[ntiles].
  *  5. fe_exclusive_scan_i32 x3 : tile_ptr[s..2s), [2s..3s), [3s..4s) <- scans of tile_counts rows
- *  6. fe_tile_records       : tnode (int2 per slot), tloc (uint16 per item), thalo (int32 per halo
- *                             item), twork (uint32 per work item); stats[4] != 0 afterwards means the
- *                             mesh is not representable (use fe_assemble).
- * The plan is usable iff stats[0] <= out[2], stats[1] < out[3], stats[2] <= out[1] of fe_tile_params
- * and stats[4] == 0. */
-void fe_tile_params(int elem_type, int32_t out[4]);
+ *  6. fe_tile_records       : tnode (int2 per slot), tloc (uint16 per item), twork (uint32 per work
+ *                             item, ZERO-INITIALISED by the caller), tchunk (uint32 per 32 work
+ *                             items); stats[4] != 0 afterwards means the mesh is not representable
+ *                             (use fe_assemble).
+ * The plan is usable iff stats[0] <= out[2], stats[1] < out[3], stats[2] <= out[1], stats[5] <= out[4]
+ * of fe_tile_params and stats[4] == 0.  Record formats are documented in feprogram_b200/csrc/fe_tiles.cu. */
+void fe_tile_params(int elem_type, int32_t out[6]);
 int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan_ws, void* stream);
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin,
                    double ymin, double xmax, double ymax, int32_t* keys, void* stream);
@@ -165,16 +168,22 @@ int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32
                   int32_t* owner, int32_t* tile_ncount, void* stream);
 int fe_tile_layout(int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr,
                    const int32_t* eptr, const int32_t* einc, const int32_t* einv, const int32_t* nptr,
-                   int32_t* cursor, int32_t* tile_nodes, int32_t* noff, int32_t* tile_counts, int32_t* stats,
-                   void* stream);
+                   int32_t* cursor, int32_t* tile_nodes, int32_t* noff, int32_t* thalo, int32_t* tile_counts,
+                   int32_t* stats, void* stream);
 int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, const int32_t* owner,
-                    const int32_t* tile_ptr, int64_t ntiles, const int32_t* noff, const int32_t* eptr,
-                    const int32_t* einc, const uint8_t* epos, const int32_t* einv, const int32_t* nptr,
-                    const int32_t* nadj, void* tnode, uint16_t* tloc, int32_t* thalo, uint32_t* twork,
-                    int32_t* stats, void* stream);
-int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* conn, const double* coords,
-                      const int32_t* eperm, const int32_t* tile_ptr, const void* tnode, const uint16_t* tloc,
-                      const int32_t* thalo, const uint32_t* twork, double* vals, void* stream);
+                    const int32_t* tile_ptr, int64_t ntiles, const int32_t* noff, const int32_t* thalo,
+                    const int32_t* eptr, const int32_t* einc, const uint8_t* epos, const int32_t* einv,
+                    const int32_t* nptr, const int32_t* nadj, void* tnode, uint16_t* tloc, uint32_t* twork,
+                    uint32_t* tchunk, int32_t* stats, void* stream);
+/*  7. fe_tile_conn : tconn[ntiles * out[5] * nnpe] <- connectivity in tile order (own elements then halo
+ *                     elements of each tile, -1 rows unused), so the numeric kernel streams it. */
+int fe_tile_conn(int elem_type, int64_t nelem, const int32_t* conn, const int32_t* eperm, const int32_t* thalo,
+                 const int32_t* tile_ptr, int32_t* tconn, void* stream);
+/* tdesc[8*t..] = {node offset, node count, item offset, item count, work offset, work count, 0, 0} of tile t
+ * (from tile_ptr rows 0, 1, 3), 32 bytes per tile, 16-byte aligned. */
+int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* tconn, const double* coords,
+                      const int32_t* tdesc, const void* tnode, const uint16_t* tloc, const uint32_t* twork,
+                      const uint32_t* tchunk, double* vals, void* stream);
 
 /* ---- B1-B3: boundary conditions ---------------------------------------------------------------
  * fe_bc_rhs replaces the brhs writes of elements.py:185-197: rhs <- 0; rhs[dir] <- 0;
