@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
     inc, nccl_lib = _nccl_paths()
-    extra_inc = ["-I", inc] if inc else []
+    extra_inc = ["-I", inc, "-DFE_WITH_NCCL"] if inc else []
     if os.environ.get("FE_EXTRA_DEFS"):       # tuning experiments: extra -D flags, space separated
         extra_inc += os.environ["FE_EXTRA_DEFS"].split()
     if os.environ.get("FE_TILE_CONFIG"):      # tuning experiments: "TE,HE,CTAS"
@@ -96,9 +96,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
-    if any("dist" in s for s in srcs) and nccl_lib:
-        # resolved at load time against the libnccl torch has already loaded
-        link += ["-Xlinker", "--allow-shlib-undefined"]
+    if inc and nccl_lib:
+        # NCCL symbols resolve at load time against the libnccl.so.2 torch has already loaded (same soname);
+        # the rpath covers a process that loads this library before torch.
+        so = os.path.join(nccl_lib, "libnccl.so.2")
+        link += ["-L", nccl_lib, "-l:libnccl.so.2" if os.path.exists(so) else "-lnccl",
+                 "-Xlinker", "-rpath", "-Xlinker", nccl_lib]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -148,11 +148,13 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init2(int64_t n, const doub
     }
 }
 
+// `g` (optional): globally reduced scalars of a multi-GPU solve; when given they replace the local sums.
 __global__ void __launch_bounds__(kVecThreads) k_pcg_init3(int nb, const double* __restrict__ partB, double rtol,
-                                                           double atol, double* __restrict__ scal) {
+                                                           double atol, double* __restrict__ scal,
+                                                           const double* __restrict__ g) {
     __shared__ double sm[kVecThreads / 32];
-    const double rz = sum_partials(partB, nb, 2, sm);
-    const double rr = sum_partials(partB + 1, nb, 2, sm);
+    const double rz = g ? g[0] : sum_partials(partB, nb, 2, sm);
+    const double rr = g ? g[1] : sum_partials(partB + 1, nb, 2, sm);
     if (threadIdx.x == 0) {
         scal[S_RZ_CUR] = rz;
         scal[S_RZ_PREV] = rz;
@@ -173,12 +175,12 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_update(int64_t n, int nbA, 
                                                             const double* __restrict__ Ap,
                                                             const double* __restrict__ minv, double* __restrict__ x,
                                                             double* __restrict__ r, double* __restrict__ partB,
-                                                            double* __restrict__ scal) {
+                                                            double* __restrict__ scal, const double* __restrict__ g) {
     __shared__ double sm[kVecThreads / 32];
     const bool done = scal[S_DONE_C] != 0.0;
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE_B] = done ? 1.0 : 0.0;
     if (done) return;
-    const double pAp = sum_partials(partA, nbA, 1, sm);
+    const double pAp = g ? g[0] : sum_partials(partA, nbA, 1, sm);
     const double rz_cur = scal[S_RZ_CUR];
     const double alpha = rz_cur / pAp;
     double rz = 0.0, rr = 0.0;
@@ -206,11 +208,12 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_update(int64_t n, int nbA, 
 __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int64_t n, int nbB, const double* __restrict__ partB,
                                                                const double* __restrict__ r,
                                                                const double* __restrict__ minv,
-                                                               double* __restrict__ p, double* __restrict__ scal) {
+                                                               double* __restrict__ p, double* __restrict__ scal,
+                                                               const double* __restrict__ g) {
     __shared__ double sm[kVecThreads / 32];
     if (scal[S_DONE_B] != 0.0) return;
-    const double rz_new = sum_partials(partB, nbB, 2, sm);
-    const double rr = sum_partials(partB + 1, nbB, 2, sm);
+    const double rz_new = g ? g[0] : sum_partials(partB, nbB, 2, sm);
+    const double rr = g ? g[1] : sum_partials(partB + 1, nbB, 2, sm);
     const double beta = rz_new / scal[S_RZ_PREV];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = fma(beta, p[i], minv[i] * r[i]);
@@ -325,7 +328,7 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
         return rc;
     k_pcg_init2<<<gv, kVecThreads, 0, st>>>(nrows, rhs, mask, w.Ap, w.minv, w.r, w.p, w.partB);
     FE_CHECK_LAUNCH("k_pcg_init2");
-    k_pcg_init3<<<1, kVecThreads, 0, st>>>(gv, w.partB, rtol, atol, w.scal);
+    k_pcg_init3<<<1, kVecThreads, 0, st>>>(gv, w.partB, rtol, atol, w.scal, nullptr);
     FE_CHECK_LAUNCH("k_pcg_init3");
 
     double hs[kScalarDoubles];
@@ -341,8 +344,9 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
             if ((rc = launch_spmv<IdxT, true>(lpr, nrows, row_ptr, col_idx, vals, w.p, w.Ap, mask, w.partA, w.scal, &ga,
                                               st)) != FE_OK)
                 return rc;
-            k_pcg_update<<<gv, kVecThreads, 0, st>>>(nrows, ga, w.partA, w.p, w.Ap, w.minv, x, w.r, w.partB, w.scal);
-            k_pcg_direction<<<gv, kVecThreads, 0, st>>>(nrows, gv, w.partB, w.r, w.minv, w.p, w.scal);
+            k_pcg_update<<<gv, kVecThreads, 0, st>>>(nrows, ga, w.partA, w.p, w.Ap, w.minv, x, w.r, w.partB, w.scal,
+                                                     nullptr);
+            k_pcg_direction<<<gv, kVecThreads, 0, st>>>(nrows, gv, w.partB, w.r, w.minv, w.p, w.scal, nullptr);
         }
         FE_CHECK_LAUNCH("pcg iteration");
         launched += batch;
@@ -427,3 +431,5 @@ int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx
 }
 
 }  // extern "C"
+
+#include "fe_dist.cuh"

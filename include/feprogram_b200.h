@@ -227,6 +227,39 @@ int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx
            const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit,
            int32_t check_every, void* work, double* info, void* stream);
 
+/* ---- multi-GPU (one host process per GPU, NCCL over NVLink) ------------------------------------------
+ * The reference has no distributed code; this is the north_star's scale-out of the solve.  Elements are
+ * partitioned into contiguous blocks; rank r owns the nodes whose first incident element it holds and
+ * assembles exactly those rows from its own elements plus one layer of recomputed ghost elements (no
+ * communication during assembly; fe_assemble* on the local mesh).  Local dof numbering: owned dofs
+ * first, then ghost dofs grouped by owning rank (ascending rank, ascending global id inside a rank), so a
+ * neighbour's contribution is received straight into a contiguous segment of the vector.
+ *
+ * fe_dist_available      : 1 when the library was built with NCCL.
+ * fe_dist_unique_id      : HOST, 128-byte ncclUniqueId (rank 0 creates it, the caller broadcasts it).
+ * fe_dist_comm_init      : HOST, collective; *comm_out is an ncclComm_t.
+ * fe_dist_halo_exchange  : vec[ghost segments] <- owners' values.  nbr_rank[n_nbr], send_off[n_nbr+1],
+ *                          recv_off[n_nbr+1] are HOST arrays; send_idx (owned dof indices, neighbour-major)
+ *                          and sendbuf[send_off[n_nbr]] are DEVICE arrays; recv_off are offsets into vec.
+ * fe_dist_pcg            : fe_pcg over all ranks: rows [0, nrows_owned) of the local CSR matrix (columns
+ *                          are local dof ids < nrows_local), one halo exchange + two scalar all-reduces
+ *                          per iteration; every rank returns the same iteration count and residual.
+ *                          x, rhs, dirmask have nrows_local entries; on return x is valid on owned AND
+ *                          ghost dofs.  work: fe_dist_pcg_workspace_bytes(nrows_local). */
+int fe_dist_available(void);
+int fe_dist_unique_id(uint8_t* out128);
+int fe_dist_comm_init(const uint8_t* id128, int rank, int nranks, void** comm_out);
+int fe_dist_comm_destroy(void* comm);
+int fe_dist_halo_exchange(void* comm, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_off,
+                          const int32_t* send_idx, double* sendbuf, const int64_t* recv_off, double* vec,
+                          void* stream);
+size_t fe_dist_pcg_workspace_bytes(int64_t nrows_local);
+int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void* row_ptr, const int32_t* col_idx,
+                const double* vals, const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol,
+                int64_t maxit, int32_t check_every, void* work, double* info, void* comm, int32_t n_nbr,
+                const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx, double* sendbuf,
+                const int64_t* recv_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
