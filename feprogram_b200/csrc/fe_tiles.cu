@@ -34,9 +34,11 @@ namespace fe {
 #define FE_TILE_CTAS 3
 #endif
 constexpr int kTileElems = FE_TILE_ELEMS;   // TE: own elements per tile
-constexpr int kHaloElems = FE_HALO_ELEMS;   // HE: halo element capacity per tile
-constexpr int kTileThreads = kTileElems + kHaloElems;
-constexpr int kZeroRow = kTileElems + kHaloElems;  // slab row of zeros (target of absent sources)
+constexpr int kHaloElemsMax = 64;           // largest halo capacity of any element type (plan scratch)
+// HE: halo element capacity per tile.  Quad4 threads need ~124 registers, so its CTA is kept at 5 warps
+// (128 + 32 threads, 15 warps per SM => 128 registers available); Tri3 is register-light and its tiles
+// have more halo elements per owned node, so it takes 64.
+__host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS : 64; }
 constexpr int kTileMaxNodes = 2 * kTileElems;    // owned nodes per tile
 constexpr int kTileMaxItems = 8 * kTileElems;    // incidence items of owned nodes per tile
 constexpr int kTileMaxWork = 12 * kTileElems;    // work items (node-level non-zeros of owned nodes) per tile, x32
@@ -49,6 +51,9 @@ template <int N> struct TileLayout {
 #define FE_SLAB_PAD 0
 #endif
     static constexpr int kSlabStride = ((3 * kBlocks) | 1) + FE_SLAB_PAD;   // odd stride: conflict-free 64-bit rows
+    static constexpr int kHalo = halo_cap(N);
+    static constexpr int kThreads = kTileElems + kHalo;        // one thread per slab row
+    static constexpr int kZeroRow = kTileElems + kHalo;        // slab row of zeros (target of absent sources)
     static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
     // one set of staged plan records (16-byte aligned size); the kernel double-buffers it
     static constexpr size_t kRecBytes = (size_t)kTileMaxWork * 4 + (size_t)kTileMaxNodes * 8 +
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_
                                                     const int32_t* __restrict__ nptr, int32_t* __restrict__ noff,
                                                     int32_t* __restrict__ thalo, int32_t* __restrict__ tile_icount,
                                                     int32_t* __restrict__ tile_hcount, int32_t* __restrict__ tile_wcount,
-                                                    int32_t* __restrict__ stats) {
+                                                    int32_t* __restrict__ stats, int he) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntiles) return;
     if (t == ntiles) {
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_
         }
         tile_nodes[j] = v;
     }
-    int hl[kHaloElems];
+    int hl[kHaloElemsMax];
     int ni = 0, nh = 0, nw = 0, maxcnt = 0;
     bool overflow = false;
     for (int i = lo; i < hi; ++i) {
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_
             int j = nh;
             while (j > 0 && hl[j - 1] > e) --j;
             if (j > 0 && hl[j - 1] == e) continue;
-            if (nh == kHaloElems) {
+            if (nh == he) {
                 overflow = true;
                 continue;
             }
@@ -180,13 +185,13 @@ __global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_
             ++nh;
         }
     }
-    for (int j = 0; j < nh; ++j) thalo[t * kHaloElems + j] = hl[j];
+    for (int j = 0; j < nh; ++j) thalo[t * he + j] = hl[j];
     tile_icount[t] = (ni + 1) & ~1;    // even: item locators are staged with 4-byte cp.async
     tile_hcount[t] = nh;
     tile_wcount[t] = (nw + 31) & ~31;  // chunks of 32 work items never straddle tiles
     atomicMax(stats + 0, hi - lo);
     atomicMax(stats + 1, ni);
-    atomicMax(stats + 2, overflow ? kHaloElems + 1 : nh);
+    atomicMax(stats + 2, overflow ? he + 1 : nh);
     atomicMax(stats + 3, maxcnt);
     atomicMax(stats + 5, nw);
 }
@@ -194,17 +199,18 @@ __global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_
 // Tile-ordered copy of the connectivity: row r of tile t = own element r (r < TE) or halo element r - TE.
 __global__ void k_tile_conn(int64_t nrows, int64_t nelem, int nnpe, const int32_t* __restrict__ conn,
                             const int32_t* __restrict__ eperm, const int32_t* __restrict__ thalo,
-                            const int32_t* __restrict__ tile_hptr, int32_t* __restrict__ tconn) {
+                            const int32_t* __restrict__ tile_hptr, int32_t* __restrict__ tconn, int he) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
-    const int64_t t = i / kTileThreads;
-    const int r = (int)(i - t * kTileThreads);
+    const int rows = kTileElems + he;
+    const int64_t t = i / rows;
+    const int r = (int)(i - t * rows);
     int64_t e = -1;
     if (r < kTileElems) {
         const int64_t k = t * kTileElems + r;
         if (k < nelem) e = eperm ? eperm[k] : k;
     } else if (r - kTileElems < tile_hptr[t + 1] - tile_hptr[t]) {
-        e = thalo[t * kHaloElems + (r - kTileElems)];
+        e = thalo[t * he + (r - kTileElems)];
     }
     for (int a = 0; a < nnpe; ++a) tconn[i * nnpe + a] = e >= 0 ? conn[e * nnpe + a] : -1;
 }
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
     const int32_t* __restrict__ thalo, const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc,
     const uint8_t* __restrict__ epos, const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr,
     const int32_t* __restrict__ nadj, int2* __restrict__ tnode, uint16_t* __restrict__ tloc,
-    uint32_t* __restrict__ twork, uint32_t* __restrict__ tchunk, int32_t* __restrict__ stats) {
+    uint32_t* __restrict__ twork, uint32_t* __restrict__ tchunk, int32_t* __restrict__ stats, int he) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     const int n = tile_nodes[i];
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
     const int k0 = eptr[n], cnt = eptr[n + 1] - k0;
     const int p0 = nptr[n], deg = nptr[n + 1] - p0;
     const int nh = tile_hptr[t + 1] - tile_hptr[t];
-    const int32_t* hl = thalo + (int64_t)t * kHaloElems;
+    const int32_t* hl = thalo + (int64_t)t * he;
     int self = 0;
     for (int p = 0; p < deg; ++p) self = (nadj[p0 + p] == n) ? p : self;
     if (cnt > 15 || deg > 127 || deg > kMaxAdj || ioff > 0x3FFF) {  // not representable: caller uses fe_assemble
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
     }
     tnode[i] = make_int2(p0, deg | (self << 7) | (cnt << 14) | (ioff << 18));
 
-    constexpr unsigned kZeroSrc = (unsigned)kZeroRow << 5;
+    const unsigned kZeroSrc = (unsigned)(kTileElems + he) << 5;
     unsigned short src[kMaxAdj][2];
     for (int p = 0; p < deg; ++p) src[p][0] = src[p][1] = (unsigned short)kZeroSrc;
     for (int j = 0; j < cnt; ++j) {
@@ -325,7 +331,7 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
 // records of tile t + G stream into the other shared-memory buffer (cp.async) and its connectivity row
 // and coordinates are prefetched into registers, so no global-memory latency is exposed per tile.
 template <int ET>
-__global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) k_assemble_tiled(
+__global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCtasPerSm) k_assemble_tiled(
     int64_t ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords,
     const int4* __restrict__ tdesc, const int2* __restrict__ tnode, const uint16_t* __restrict__ tloc,
     const uint32_t* __restrict__ twork, const uint32_t* __restrict__ tchunk, double* __restrict__ vals, int weighted,
@@ -334,6 +340,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) k_assemble_tiled
     constexpr int N = E::NNPE;
     using T = TileLayout<N>;
     constexpr int SS = T::kSlabStride;
+    constexpr int kTileThreads = T::kThreads, kZeroRow = T::kZeroRow;
     extern __shared__ __align__(16) double slab[];
     unsigned char* rec_base = reinterpret_cast<unsigned char*>(slab + T::kSlabDoubles);
 
@@ -504,7 +511,7 @@ static int launch_tiled(int64_t nelem, const int32_t* tconn, const double* coord
     int64_t grid = (int64_t)sms * kTileCtasPerSm;
     if (grid > ntiles) grid = ntiles;
     FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
-    k_assemble_tiled<ET><<<(unsigned)grid, kTileThreads, T::kSmem, st>>>(
+    k_assemble_tiled<ET><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
         ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc), tnode, tloc,
         twork, tchunk, vals, weighted, dbg);
     FE_CHECK_LAUNCH("k_assemble_tiled");
@@ -526,11 +533,11 @@ int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan
 void fe_tile_params(int elem_type, int32_t out[6]) {
     using namespace fe;
     out[0] = kTileElems;
-    out[1] = (elem_type == FE_QUAD4 || elem_type == FE_TRI3) ? kHaloElems : 0;   // 0: no tiled kernel
+    out[1] = (elem_type == FE_QUAD4 || elem_type == FE_TRI3) ? halo_cap(elem_type) : 0;   // 0: no tiled kernel
     out[2] = kTileMaxNodes;
     out[3] = kTileMaxItems;
     out[4] = kTileMaxWork;
-    out[5] = kTileThreads;   // rows per tile of the tile-ordered connectivity (fe_tile_conn)
+    out[5] = kTileElems + halo_cap(elem_type);   // rows per tile of the tile-ordered connectivity
 }
 
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin, double ymin,
@@ -577,7 +584,7 @@ int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32
     return FE_OK;
 }
 
-int fe_tile_layout(int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr, const int32_t* eptr,
+int fe_tile_layout(int elem_type, int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr, const int32_t* eptr,
                    const int32_t* einc, const int32_t* einv, const int32_t* nptr, int32_t* cursor,
                    int32_t* tile_nodes, int32_t* noff, int32_t* thalo, int32_t* tile_counts, int32_t* stats,
                    void* stream) {
@@ -596,7 +603,7 @@ int fe_tile_layout(int64_t nnode, int64_t nelem, const int32_t* owner, const int
     const int64_t s = ntiles + 1;
     k_tile_layout<<<grid_for(ntiles + 1, 64), 64, 0, st>>>(ntiles, tile_nptr, tile_nodes, eptr, einc, einv, nptr, noff,
                                                           thalo, tile_counts, tile_counts + s, tile_counts + 2 * s,
-                                                          stats);
+                                                          stats, halo_cap(nnpe_of(elem_type)));
     FE_CHECK_LAUNCH("k_tile_layout");
     return FE_OK;
 }
@@ -620,7 +627,7 @@ int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, co
     const int64_t s = ntiles + 1;
     k_tile_records<<<grid_for(nslots, 128), 128, 0, as_stream(stream)>>>(
         nslots, nnpe, tile_nodes, owner, tile_ptr, tile_ptr + s, tile_ptr + 2 * s, tile_ptr + 3 * s, noff, thalo, eptr,
-        einc, epos, einv, nptr, nadj, static_cast<int2*>(tnode), tloc, twork, tchunk, stats);
+        einc, epos, einv, nptr, nadj, static_cast<int2*>(tnode), tloc, twork, tchunk, stats, halo_cap(nnpe));
     FE_CHECK_LAUNCH("k_tile_records");
     return FE_OK;
 }
@@ -637,9 +644,10 @@ int fe_tile_conn(int elem_type, int64_t nelem, const int32_t* conn, const int32_
     if (nelem == 0) return FE_OK;
     FE_REQUIRE(conn && thalo && tile_ptr && tconn, "null pointer");
     const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
-    const int64_t nrows = ntiles * kTileThreads;
+    const int he = halo_cap(nnpe);
+    const int64_t nrows = ntiles * (kTileElems + he);
     k_tile_conn<<<grid_for(nrows, 256), 256, 0, as_stream(stream)>>>(nrows, nelem, nnpe, conn, eperm, thalo,
-                                                                    tile_ptr + 2 * (ntiles + 1), tconn);
+                                                                    tile_ptr + 2 * (ntiles + 1), tconn, he);
     FE_CHECK_LAUNCH("k_tile_conn");
     return FE_OK;
 }

@@ -323,7 +323,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
         thalo = torch.empty((ntiles, hcap), dtype=torch.int32, device=dev)
         counts = torch.empty((3, s), dtype=torch.int32, device=dev)
         stats = torch.empty(8, dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_layout(nnode, nelem, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
+        _lib.check(L.fe_tile_layout(pat.elem_type, nnode, nelem, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
                                     _ptr(einv), _ptr(pat.nptr), _ptr(cursor), _ptr(tile_nodes), _ptr(noff),
                                     _ptr(thalo), _ptr(counts), _ptr(stats), st))
         for r in range(3):

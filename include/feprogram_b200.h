@@ -166,7 +166,7 @@ int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const doub
 int fe_invert_permutation(int64_t n, const int32_t* perm, int32_t* inv, void* stream);
 int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32_t* einc, const int32_t* einv,
                   int32_t* owner, int32_t* tile_ncount, void* stream);
-int fe_tile_layout(int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr,
+int fe_tile_layout(int elem_type, int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr,
                    const int32_t* eptr, const int32_t* einc, const int32_t* einv, const int32_t* nptr,
                    int32_t* cursor, int32_t* tile_nodes, int32_t* noff, int32_t* thalo, int32_t* tile_counts,
                    int32_t* stats, void* stream);
