@@ -77,7 +77,7 @@ __device__ __forceinline__ unsigned spread15(unsigned v) {
 
 // 30-bit Morton key of the element centroid inside the mesh bounding box (15 bits per axis).
 __global__ void k_morton_keys(int64_t nelem, int nnpe, const int32_t* __restrict__ conn,
-                              const double2* __restrict__ coords, double x0, double y0, double sx, double sy,
+                              const double2* __restrict__ coords, double x0, double y0, double inv_cell,
                               int32_t* __restrict__ keys) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nelem) return;
@@ -89,7 +89,7 @@ __global__ void k_morton_keys(int64_t nelem, int nnpe, const int32_t* __restrict
     }
     cx /= nnpe;
     cy /= nnpe;
-    int ix = (int)((cx - x0) * sx), iy = (int)((cy - y0) * sy);
+    int ix = (int)((cx - x0) * inv_cell), iy = (int)((cy - y0) * inv_cell);
     ix = ix < 0 ? 0 : (ix > 32767 ? 32767 : ix);
     iy = iy < 0 ? 0 : (iy > 32767 ? 32767 : iy);
     keys[e] = (int32_t)(spread15((unsigned)ix) | (spread15((unsigned)iy) << 1));
@@ -100,8 +100,9 @@ __global__ void k_invert_perm(int64_t n, const int32_t* __restrict__ perm, int32
     if (i < n) inv[perm[i]] = (int32_t)i;
 }
 
-__device__ __forceinline__ int tile_of(const int32_t* __restrict__ einv, int e) {
-    return (einv ? einv[e] : e) / kTileElems;
+// eloc[e] = tile << 8 | row: the tile an element belongs to and its row inside that tile
+__device__ __forceinline__ int tile_of(const int32_t* __restrict__ eloc, int e) {
+    return eloc[e] >> 8;
 }
 
 // owner tile of each node (-1: no incident element); per-tile owned-node count
@@ -196,10 +197,12 @@ __global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_
     atomicMax(stats + 5, nw);
 }
 
-// Tile-ordered copy of the connectivity: row r of tile t = own element r (r < TE) or halo element r - TE.
-__global__ void k_tile_conn(int64_t nrows, int64_t nelem, int nnpe, const int32_t* __restrict__ conn,
-                            const int32_t* __restrict__ eperm, const int32_t* __restrict__ thalo,
-                            const int32_t* __restrict__ tile_hptr, int32_t* __restrict__ tconn, int he) {
+// Tile-ordered copy of the connectivity: row r of tile t = own element r (r < own count) or halo element
+// r - TE; unused rows are -1.
+__global__ void k_tile_conn(int64_t nrows, int nnpe, const int32_t* __restrict__ conn,
+                            const int32_t* __restrict__ eperm, const int32_t* __restrict__ tile_estart,
+                            const int32_t* __restrict__ thalo, const int32_t* __restrict__ tile_hptr,
+                            int32_t* __restrict__ tconn, int he) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     const int rows = kTileElems + he;
@@ -207,8 +210,7 @@ __global__ void k_tile_conn(int64_t nrows, int64_t nelem, int nnpe, const int32_
     const int r = (int)(i - t * rows);
     int64_t e = -1;
     if (r < kTileElems) {
-        const int64_t k = t * kTileElems + r;
-        if (k < nelem) e = eperm ? eperm[k] : k;
+        if (r < tile_estart[t + 1] - tile_estart[t]) e = eperm[tile_estart[t] + r];
     } else if (r - kTileElems < tile_hptr[t + 1] - tile_hptr[t]) {
         e = thalo[t * he + (r - kTileElems)];
     }
@@ -248,10 +250,10 @@ __global__ void __launch_bounds__(128) k_tile_records(
     for (int j = 0; j < cnt; ++j) {
         const int item = einc[k0 + j];
         const int e = item >> 4, a = item & 15;
-        const int pos = einv ? einv[e] : e;
+        const int pos = einv[e];
         int row;
-        if (pos / kTileElems == t) {
-            row = pos - t * kTileElems;
+        if ((pos >> 8) == t) {
+            row = pos & 255;
         } else {  // position inside the tile's sorted halo list
             int lo = 0, hi = nh - 1;
             while (lo < hi) {
@@ -499,11 +501,10 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
 }
 
 template <int ET>
-static int launch_tiled(int64_t nelem, const int32_t* tconn, const double* coords, const int32_t* tdesc,
+static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coords, const int32_t* tdesc,
                         const int2* tnode, const uint16_t* tloc, const uint32_t* twork, const uint32_t* tchunk,
                         double* vals, int weighted, cudaStream_t st) {
     using T = TileLayout<Elem<ET>::NNPE>;
-    const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
     const int dbg = getenv("FE_TILED_DBG") ? atoi(getenv("FE_TILED_DBG")) : 0;  // phase isolation for profiling
     int dev = 0, sms = 0;
     FE_CUDA_TRY(cudaGetDevice(&dev));
@@ -541,7 +542,7 @@ void fe_tile_params(int elem_type, int32_t out[6]) {
 }
 
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin, double ymin,
-                   double xmax, double ymax, int32_t* keys, void* stream) {
+                   double cell, int32_t* keys, void* stream) {
     using namespace fe;
     const int nnpe = nnpe_of(elem_type);
     if (!nnpe) {
@@ -551,10 +552,9 @@ int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const doub
     FE_REQUIRE(nelem >= 0, "negative size");
     if (nelem == 0) return FE_OK;
     FE_REQUIRE(conn && coords && keys, "null pointer");
-    const double sx = xmax > xmin ? 32768.0 / (xmax - xmin) : 0.0;
-    const double sy = ymax > ymin ? 32768.0 / (ymax - ymin) : 0.0;
+    FE_REQUIRE(cell > 0.0, "cell size must be positive");
     k_morton_keys<<<grid_for(nelem, 256), 256, 0, as_stream(stream)>>>(
-        nelem, nnpe, conn, reinterpret_cast<const double2*>(coords), xmin, ymin, sx, sy, keys);
+        nelem, nnpe, conn, reinterpret_cast<const double2*>(coords), xmin, ymin, 1.0 / cell, keys);
     FE_CHECK_LAUNCH("k_morton_keys");
     return FE_OK;
 }
@@ -569,12 +569,11 @@ int fe_invert_permutation(int64_t n, const int32_t* perm, int32_t* inv, void* st
     return FE_OK;
 }
 
-int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32_t* einc, const int32_t* einv,
+int fe_tile_owner(int64_t nnode, int64_t ntiles, const int32_t* eptr, const int32_t* einc, const int32_t* einv,
                   int32_t* owner, int32_t* tile_ncount, void* stream) {
     using namespace fe;
-    FE_REQUIRE(nnode >= 0 && nelem >= 0, "negative size");
-    const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
-    FE_REQUIRE(tile_ncount, "null pointer");
+    FE_REQUIRE(nnode >= 0 && ntiles >= 0, "negative size");
+    FE_REQUIRE(tile_ncount && einv, "null pointer");
     cudaStream_t st = as_stream(stream);
     FE_CUDA_TRY(cudaMemsetAsync(tile_ncount, 0, (size_t)(ntiles + 1) * sizeof(int32_t), st));
     if (nnode == 0) return FE_OK;
@@ -584,14 +583,13 @@ int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32
     return FE_OK;
 }
 
-int fe_tile_layout(int elem_type, int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr, const int32_t* eptr,
+int fe_tile_layout(int elem_type, int64_t nnode, int64_t ntiles, const int32_t* owner, const int32_t* tile_nptr, const int32_t* eptr,
                    const int32_t* einc, const int32_t* einv, const int32_t* nptr, int32_t* cursor,
                    int32_t* tile_nodes, int32_t* noff, int32_t* thalo, int32_t* tile_counts, int32_t* stats,
                    void* stream) {
     using namespace fe;
-    FE_REQUIRE(nnode >= 0 && nelem >= 0, "negative size");
-    const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
-    FE_REQUIRE(tile_nptr && cursor && tile_counts && stats && thalo, "null pointer");
+    FE_REQUIRE(nnode >= 0 && ntiles >= 0, "negative size");
+    FE_REQUIRE(tile_nptr && cursor && tile_counts && stats && thalo && einv, "null pointer");
     cudaStream_t st = as_stream(stream);
     FE_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)(ntiles > 0 ? ntiles : 1) * sizeof(int32_t), st));
     FE_CUDA_TRY(cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
@@ -632,36 +630,35 @@ int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, co
     return FE_OK;
 }
 
-int fe_tile_conn(int elem_type, int64_t nelem, const int32_t* conn, const int32_t* eperm, const int32_t* thalo,
-                 const int32_t* tile_ptr, int32_t* tconn, void* stream) {
+int fe_tile_conn(int elem_type, int64_t ntiles, const int32_t* conn, const int32_t* eperm, const int32_t* tile_estart,
+                 const int32_t* thalo, const int32_t* tile_ptr, int32_t* tconn, void* stream) {
     using namespace fe;
     const int nnpe = nnpe_of(elem_type);
     if (!nnpe) {
         set_error("fe_tile_conn: Invalid elemType %d", elem_type);
         return FE_ERR_UNSUPPORTED;
     }
-    FE_REQUIRE(nelem >= 0, "negative size");
-    if (nelem == 0) return FE_OK;
-    FE_REQUIRE(conn && thalo && tile_ptr && tconn, "null pointer");
-    const int64_t ntiles = (nelem + kTileElems - 1) / kTileElems;
+    FE_REQUIRE(ntiles >= 0, "negative size");
+    if (ntiles == 0) return FE_OK;
+    FE_REQUIRE(conn && eperm && tile_estart && thalo && tile_ptr && tconn, "null pointer");
     const int he = halo_cap(nnpe);
     const int64_t nrows = ntiles * (kTileElems + he);
-    k_tile_conn<<<grid_for(nrows, 256), 256, 0, as_stream(stream)>>>(nrows, nelem, nnpe, conn, eperm, thalo,
+    k_tile_conn<<<grid_for(nrows, 256), 256, 0, as_stream(stream)>>>(nrows, nnpe, conn, eperm, tile_estart, thalo,
                                                                     tile_ptr + 2 * (ntiles + 1), tconn, he);
     FE_CHECK_LAUNCH("k_tile_conn");
     return FE_OK;
 }
 
-int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* tconn, const double* coords,
+int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tconn, const double* coords,
                       const int32_t* tdesc, const void* tnode, const uint16_t* tloc, const uint32_t* twork,
                       const uint32_t* tchunk, double* vals, void* stream) {
     using namespace fe;
-    FE_REQUIRE(nelem >= 0, "negative size");
+    FE_REQUIRE(ntiles >= 0, "negative size");
     if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED) {
         set_error("fe_assemble_tiled: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
-    if (nelem == 0) return FE_OK;
+    if (ntiles == 0) return FE_OK;
     FE_REQUIRE(tconn && coords && tdesc && tnode && tloc && twork && tchunk && vals, "null pointer");
     cudaStream_t st = as_stream(stream);
     int rc = ensure_tables_tu(st);
@@ -670,9 +667,9 @@ int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* tconn
     const int2* nd = static_cast<const int2*>(tnode);
     switch (elem_type) {
         case FE_QUAD4:
-            return launch_tiled<FE_QUAD4>(nelem, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
+            return launch_tiled<FE_QUAD4>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
         case FE_TRI3:
-            return launch_tiled<FE_TRI3>(nelem, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
+            return launch_tiled<FE_TRI3>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
         default:
             set_error("fe_assemble_tiled: element type %d has no tiled kernel (use fe_assemble)", elem_type);
             return FE_ERR_UNSUPPORTED;

@@ -294,26 +294,47 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
     dev = conn.device
     te, hcap = params["tile_elems"], params["halo_cap"]
     nelem, nnode = pat.nelem, pat.nnode
-    ntiles = (nelem + te - 1) // te
-    s = ntiles + 1
     with torch.cuda.device(dev):
         st = _stream(conn)
-        eperm = einv = None
+        # ---- element order and tile boundaries (input preparation of the one-time plan; torch sort/scan) ----
+        idx = torch.arange(nelem, dtype=torch.int64, device=dev)
         if morton:
-            lo = coords.amin(dim=0).tolist()
-            hi = coords.amax(dim=0).tolist()
+            lo = coords.amin(dim=0)
+            hi = coords.amax(dim=0)
+            ext = (hi - lo).clamp_min(1e-300)
+            cell = float(torch.sqrt(ext[0] * ext[1] / nelem).item())          # ~ one element per cell
+            cell = max(cell, float(ext.max().item()) / 32767.0)               # 15 bits per axis
             keys = torch.empty(nelem, dtype=torch.int32, device=dev)
-            _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo[0], lo[1], hi[0], hi[1],
+            lo_h = lo.tolist()
+            _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo_h[0], lo_h[1], cell,
                                         _ptr(keys), st))
-            # ordering the elements is input preparation of the one-time plan: torch's stable sort
-            eperm = torch.sort(keys, stable=True).indices.to(torch.int32)
-            del keys
-            einv = torch.empty(nelem, dtype=torch.int32, device=dev)
-            _lib.check(L.fe_invert_permutation(nelem, _ptr(eperm), _ptr(einv), st))
+            skeys, order = torch.sort(keys, stable=True)
+            eperm = order.to(torch.int32)
+            block = skeys >> 7                                                # aligned Z-blocks of 128 cells
+            del keys, skeys, order
+        else:
+            eperm = idx.to(torch.int32)
+            block = idx // te
+        flag = torch.ones(nelem, dtype=torch.bool, device=dev)
+        flag[1:] = block[1:] != block[:-1]
+        seg_start = torch.cummax(torch.where(flag, idx, torch.zeros_like(idx)), dim=0).values
+        flag |= ((idx - seg_start) % te) == 0                                 # at most TE elements per tile
+        tid = torch.cumsum(flag.to(torch.int32), dim=0, dtype=torch.int32) - 1
+        ntiles = int(tid[-1].item()) + 1
+        starts = torch.nonzero(flag).flatten()
+        row = (idx - starts[tid.long()]).to(torch.int32)
+        tile_estart = torch.cat([starts, torch.tensor([nelem], device=dev)]).to(torch.int32)
+        eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
+        eloc[eperm.long()] = (tid << 8) | row
+        del block, flag, seg_start, tid, starts, row, idx
+        if ntiles >= (1 << 23):
+            return None
+        s = ntiles + 1
+        einv = eloc
         ws = torch.empty(max(1, L.fe_scan_workspace_bytes(s)), dtype=torch.uint8, device=dev)
         owner = torch.empty(nnode, dtype=torch.int32, device=dev)
         tile_ncount = torch.empty(s, dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_owner(nnode, nelem, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner),
+        _lib.check(L.fe_tile_owner(nnode, ntiles, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner),
                                    _ptr(tile_ncount), st))
         tile_ptr = torch.empty((4, s), dtype=torch.int32, device=dev)
         _scan_into(tile_ncount, tile_ptr[0], ws)
@@ -323,7 +344,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
         thalo = torch.empty((ntiles, hcap), dtype=torch.int32, device=dev)
         counts = torch.empty((3, s), dtype=torch.int32, device=dev)
         stats = torch.empty(8, dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_layout(pat.elem_type, nnode, nelem, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
+        _lib.check(L.fe_tile_layout(pat.elem_type, nnode, ntiles, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
                                     _ptr(einv), _ptr(pat.nptr), _ptr(cursor), _ptr(tile_nodes), _ptr(noff),
                                     _ptr(thalo), _ptr(counts), _ptr(stats), st))
         for r in range(3):
@@ -348,8 +369,8 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
         if int(stats[4].item()) != 0:
             return None
         tconn = torch.empty((ntiles, params["tile_rows"], conn.shape[1]), dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_conn(pat.elem_type, nelem, _ptr(conn), _ptr(eperm), _ptr(thalo), _ptr(tile_ptr),
-                                  _ptr(tconn), st))
+        _lib.check(L.fe_tile_conn(pat.elem_type, ntiles, _ptr(conn), _ptr(eperm), _ptr(tile_estart), _ptr(thalo),
+                                  _ptr(tile_ptr), _ptr(tconn), st))
         z = torch.zeros(ntiles, dtype=torch.int32, device=dev)
         tdesc = torch.stack([tile_ptr[0, :-1], tile_ptr[0, 1:] - tile_ptr[0, :-1],
                              tile_ptr[1, :-1], tile_ptr[1, 1:] - tile_ptr[1, :-1],
@@ -358,7 +379,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
 
 
 @torch.library.custom_op("feprogram::assemble_tiled", mutates_args=("vals",))
-def assemble_tiled(tconn: Tensor, coords: Tensor, nelem: int, tdesc: Tensor, tnode: Tensor, tloc: Tensor,
+def assemble_tiled(tconn: Tensor, coords: Tensor, ntiles: int, tdesc: Tensor, tnode: Tensor, tloc: Tensor,
                    twork: Tensor, tchunk: Tensor, vals: Tensor, elem_type: int, op: int) -> None:
     """Numeric assembly, tiled kernel (same results as feprogram::assemble, bit for bit)."""
     _chk_dev(tconn, coords, tdesc, tnode, tloc, twork, tchunk, vals)
@@ -366,7 +387,7 @@ def assemble_tiled(tconn: Tensor, coords: Tensor, nelem: int, tdesc: Tensor, tno
     _want(coords, torch.float64, "coords")
     _want(vals, torch.float64, "vals")
     with torch.cuda.device(vals.device):
-        _lib.check(_lib.lib().fe_assemble_tiled(elem_type, op, nelem, _ptr(tconn), _ptr(coords), _ptr(tdesc),
+        _lib.check(_lib.lib().fe_assemble_tiled(elem_type, op, ntiles, _ptr(tconn), _ptr(coords), _ptr(tdesc),
                                                 _ptr(tnode), _ptr(tloc), _ptr(twork), _ptr(tchunk), _ptr(vals),
                                                 _stream(vals)))
 
@@ -374,7 +395,7 @@ def assemble_tiled(tconn: Tensor, coords: Tensor, nelem: int, tdesc: Tensor, tno
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):
     """Numeric assembly with whichever kernel the plan allows."""
     if plan is not None:
-        torch.ops.feprogram.assemble_tiled(plan.tconn, coords, pat.nelem, plan.tdesc, plan.tnode, plan.tloc,
+        torch.ops.feprogram.assemble_tiled(plan.tconn, coords, plan.ntiles, plan.tdesc, plan.tnode, plan.tloc,
                                            plan.twork, plan.tchunk, vals, pat.elem_type, op)
     else:
         torch.ops.feprogram.assemble(conn, coords, pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg, vals,

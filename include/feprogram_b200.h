@@ -137,12 +137,16 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
  * node (CSR row block) is owned by the tile of its first incident element, and elements of
  * neighbouring tiles that touch an owned node ("halo items") contribute just that node's row pair.
  *
- * One-time plan, in order (ntiles = ceil(nelem / TE), s = ntiles + 1):
- *  1. fe_morton_keys        : 30-bit Morton key of each element centroid inside the bounding box;
- *                             the caller sorts elements by key (stable) -> eperm, and inverts it
- *                             with fe_invert_permutation -> einv.  eperm/einv may be NULL
- *                             everywhere below (= identity: tiles are runs of the input order).
- *  2. fe_tile_owner         : owner[nnode] (tile id, -1 if the node has no element),
+ * One-time plan, in order (s = ntiles + 1):
+ *  1. fe_morton_keys        : 30-bit Morton key of each element centroid on a grid of `cell`-sized
+ *                             squares anchored at (xmin, ymin) (cell ~ one element).  The caller sorts
+ *                             elements by key (stable) -> eperm and cuts the sorted list into tiles:
+ *                             a tile = the elements of one aligned Z-block of 2^7 cells, split further
+ *                             when it holds more than TE elements.  That yields ntiles,
+ *                             tile_estart[s] (offsets into eperm) and eloc[nelem] = tile << 8 | row.
+ *                             (Any other tiling with <= TE elements per tile is equally valid, e.g.
+ *                             runs of the input order.)
+ *  2. fe_tile_owner         : owner[nnode] (smallest tile id among the node's elements, -1 if none),
  *                             tile_ncount[s] (owned nodes per tile, last entry 0).
  *  3. fe_exclusive_scan_i32 : tile_ptr[0..s) <- scan(tile_ncount)
  *  4. fe_tile_layout        : tile_nodes (ascending node id inside each tile), noff[2*nslots]
@@ -162,26 +166,27 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
 void fe_tile_params(int elem_type, int32_t out[6]);
 int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan_ws, void* stream);
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin,
-                   double ymin, double xmax, double ymax, int32_t* keys, void* stream);
+                   double ymin, double cell, int32_t* keys, void* stream);
 int fe_invert_permutation(int64_t n, const int32_t* perm, int32_t* inv, void* stream);
-int fe_tile_owner(int64_t nnode, int64_t nelem, const int32_t* eptr, const int32_t* einc, const int32_t* einv,
+int fe_tile_owner(int64_t nnode, int64_t ntiles, const int32_t* eptr, const int32_t* einc, const int32_t* eloc,
                   int32_t* owner, int32_t* tile_ncount, void* stream);
-int fe_tile_layout(int elem_type, int64_t nnode, int64_t nelem, const int32_t* owner, const int32_t* tile_nptr,
-                   const int32_t* eptr, const int32_t* einc, const int32_t* einv, const int32_t* nptr,
+int fe_tile_layout(int elem_type, int64_t nnode, int64_t ntiles, const int32_t* owner, const int32_t* tile_nptr,
+                   const int32_t* eptr, const int32_t* einc, const int32_t* eloc, const int32_t* nptr,
                    int32_t* cursor, int32_t* tile_nodes, int32_t* noff, int32_t* thalo, int32_t* tile_counts,
                    int32_t* stats, void* stream);
 int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, const int32_t* owner,
                     const int32_t* tile_ptr, int64_t ntiles, const int32_t* noff, const int32_t* thalo,
-                    const int32_t* eptr, const int32_t* einc, const uint8_t* epos, const int32_t* einv,
+                    const int32_t* eptr, const int32_t* einc, const uint8_t* epos, const int32_t* eloc,
                     const int32_t* nptr, const int32_t* nadj, void* tnode, uint16_t* tloc, uint32_t* twork,
                     uint32_t* tchunk, int32_t* stats, void* stream);
 /*  7. fe_tile_conn : tconn[ntiles * out[5] * nnpe] <- connectivity in tile order (own elements then halo
  *                     elements of each tile, -1 rows unused), so the numeric kernel streams it. */
-int fe_tile_conn(int elem_type, int64_t nelem, const int32_t* conn, const int32_t* eperm, const int32_t* thalo,
-                 const int32_t* tile_ptr, int32_t* tconn, void* stream);
+int fe_tile_conn(int elem_type, int64_t ntiles, const int32_t* conn, const int32_t* eperm,
+                 const int32_t* tile_estart, const int32_t* thalo, const int32_t* tile_ptr, int32_t* tconn,
+                 void* stream);
 /* tdesc[8*t..] = {node offset, node count, item offset, item count, work offset, work count, 0, 0} of tile t
  * (from tile_ptr rows 0, 1, 3), 32 bytes per tile, 16-byte aligned. */
-int fe_assemble_tiled(int elem_type, int op, int64_t nelem, const int32_t* tconn, const double* coords,
+int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tconn, const double* coords,
                       const int32_t* tdesc, const void* tnode, const uint16_t* tloc, const uint32_t* twork,
                       const uint32_t* tchunk, double* vals, void* stream);
 
