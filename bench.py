@@ -145,6 +145,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: anything libraries print there (NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -342,7 +345,8 @@ def run_ours(args):
                                 "algorithmic_bytes_per_launch": spmv_bytes_total / world}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * K, "clocks": clk.summary(),
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

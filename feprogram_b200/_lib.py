@@ -39,7 +39,7 @@ PROTOTYPES = {
     "fe_assemble": (_i, [_i, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "fe_tile_params": (None, [_i, C.POINTER(_i32)]),
     "fe_exclusive_scan_i32": (_i, [_p, _p, _i64, _p, _p]),
-    "fe_morton_keys": (_i, [_i, _i64, _p, _p, _f64, _f64, _f64, _p, _p]),
+    "fe_morton_keys": (_i, [_i, _i64, _p, _p, _f64, _f64, _f64, _f64, _p, _p]),
     "fe_invert_permutation": (_i, [_i64, _p, _p, _p]),
     "fe_tile_owner": (_i, [_i64, _i64, _p, _p, _p, _p, _p, _p]),
     "fe_tile_layout": (_i, [_i, _i64, _i64] + [_p] * 13),

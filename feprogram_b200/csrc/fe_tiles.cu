@@ -77,8 +77,8 @@ __device__ __forceinline__ unsigned spread15(unsigned v) {
 
 // 30-bit Morton key of the element centroid inside the mesh bounding box (15 bits per axis).
 __global__ void k_morton_keys(int64_t nelem, int nnpe, const int32_t* __restrict__ conn,
-                              const double2* __restrict__ coords, double x0, double y0, double inv_cell,
-                              int32_t* __restrict__ keys) {
+                              const double2* __restrict__ coords, double x0, double y0, double inv_cx,
+                              double inv_cy, int32_t* __restrict__ keys) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nelem) return;
     double cx = 0.0, cy = 0.0;
@@ -89,7 +89,7 @@ __global__ void k_morton_keys(int64_t nelem, int nnpe, const int32_t* __restrict
     }
     cx /= nnpe;
     cy /= nnpe;
-    int ix = (int)((cx - x0) * inv_cell), iy = (int)((cy - y0) * inv_cell);
+    int ix = (int)((cx - x0) * inv_cx), iy = (int)((cy - y0) * inv_cy);
     ix = ix < 0 ? 0 : (ix > 32767 ? 32767 : ix);
     iy = iy < 0 ? 0 : (iy > 32767 ? 32767 : iy);
     keys[e] = (int32_t)(spread15((unsigned)ix) | (spread15((unsigned)iy) << 1));
@@ -542,7 +542,7 @@ void fe_tile_params(int elem_type, int32_t out[6]) {
 }
 
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin, double ymin,
-                   double cell, int32_t* keys, void* stream) {
+                   double cell_x, double cell_y, int32_t* keys, void* stream) {
     using namespace fe;
     const int nnpe = nnpe_of(elem_type);
     if (!nnpe) {
@@ -552,9 +552,10 @@ int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const doub
     FE_REQUIRE(nelem >= 0, "negative size");
     if (nelem == 0) return FE_OK;
     FE_REQUIRE(conn && coords && keys, "null pointer");
-    FE_REQUIRE(cell > 0.0, "cell size must be positive");
+    FE_REQUIRE(cell_x > 0.0 && cell_y > 0.0, "cell size must be positive");
     k_morton_keys<<<grid_for(nelem, 256), 256, 0, as_stream(stream)>>>(
-        nelem, nnpe, conn, reinterpret_cast<const double2*>(coords), xmin, ymin, 1.0 / cell, keys);
+        nelem, nnpe, conn, reinterpret_cast<const double2*>(coords), xmin, ymin, 1.0 / cell_x,
+        1.0 / cell_y, keys);
     FE_CHECK_LAUNCH("k_morton_keys");
     return FE_OK;
 }

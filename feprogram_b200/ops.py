@@ -302,12 +302,17 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
             lo = coords.amin(dim=0)
             hi = coords.amax(dim=0)
             ext = (hi - lo).clamp_min(1e-300)
-            cell = float(torch.sqrt(ext[0] * ext[1] / nelem).item())          # ~ one element per cell
-            cell = max(cell, float(ext.max().item()) / 32767.0)               # 15 bits per axis
+            # cell = typical element extent per axis (sampled), so that one cell holds ~ one element
+            sample = conn[:: max(1, nelem // 65536)][:65536].long()
+            xy = coords[sample]                                               # (m, nnpe, 2)
+            size = (xy.amax(dim=1) - xy.amin(dim=1)).mean(dim=0)
+            if pat.elem_type == FE_TRI3:
+                size = size * 0.7071                                          # two triangles share a quad cell
+            cell = torch.maximum(size, ext / 32767.0).clamp_min(1e-300).tolist()  # 15 bits per axis
             keys = torch.empty(nelem, dtype=torch.int32, device=dev)
             lo_h = lo.tolist()
-            _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo_h[0], lo_h[1], cell,
-                                        _ptr(keys), st))
+            _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo_h[0], lo_h[1], cell[0],
+                                        cell[1], _ptr(keys), st))
             skeys, order = torch.sort(keys, stable=True)
             eperm = order.to(torch.int32)
             block = skeys >> 7                                                # aligned Z-blocks of 128 cells

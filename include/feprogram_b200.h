@@ -138,8 +138,8 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
  * neighbouring tiles that touch an owned node ("halo items") contribute just that node's row pair.
  *
  * One-time plan, in order (s = ntiles + 1):
- *  1. fe_morton_keys        : 30-bit Morton key of each element centroid on a grid of `cell`-sized
- *                             squares anchored at (xmin, ymin) (cell ~ one element).  The caller sorts
+ *  1. fe_morton_keys        : 30-bit Morton key of each element centroid on a grid of cell_x x cell_y
+ *                             cells anchored at (xmin, ymin) (a cell ~ one element).  The caller sorts
  *                             elements by key (stable) -> eperm and cuts the sorted list into tiles:
  *                             a tile = the elements of one aligned Z-block of 2^7 cells, split further
  *                             when it holds more than TE elements.  That yields ntiles,
@@ -166,7 +166,7 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
 void fe_tile_params(int elem_type, int32_t out[6]);
 int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan_ws, void* stream);
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin,
-                   double ymin, double cell, int32_t* keys, void* stream);
+                   double ymin, double cell_x, double cell_y, int32_t* keys, void* stream);
 int fe_invert_permutation(int64_t n, const int32_t* perm, int32_t* inv, void* stream);
 int fe_tile_owner(int64_t nnode, int64_t ntiles, const int32_t* eptr, const int32_t* einc, const int32_t* eloc,
                   int32_t* owner, int32_t* tile_ncount, void* stream);
