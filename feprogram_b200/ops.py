@@ -322,7 +322,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
             block = idx // te
         flag = torch.ones(nelem, dtype=torch.bool, device=dev)
         flag[1:] = block[1:] != block[:-1]
-        seg_start = torch.cummax(torch.where(flag, idx, torch.zeros_like(idx)), dim=0).values
+        seg_start = torch.nonzero(flag).flatten()[torch.cumsum(flag, dim=0) - 1]   # start of each element's block
         flag |= ((idx - seg_start) % te) == 0                                 # at most TE elements per tile
         tid = torch.cumsum(flag.to(torch.int32), dim=0, dtype=torch.int32) - 1
         ntiles = int(tid[-1].item()) + 1
