@@ -365,24 +365,23 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
         for (int i = tid; 2 * i < ni; i += kTileThreads) cp_async_4(s_loc(b) + 2 * i, tloc + i0 + 2 * i);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // Prefetching loads are volatile asm so that the compiler keeps them where they are written (well
+    // ahead of their first use, on the far side of the barriers) instead of sinking them to the use.
     auto load_row = [&](int64_t t, int (&tg)[N]) {
         const int32_t* row = tconn + (t * kTileThreads + tid) * N;
         if constexpr (N == 4) {
-            const int4 c = __ldg(reinterpret_cast<const int4*>(row));
-            tg[0] = c.x; tg[1] = c.y; tg[2] = c.z; tg[3] = c.w;
+            asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(tg[0]), "=r"(tg[1]), "=r"(tg[2]), "=r"(tg[3]) : "l"(row));
         } else {
 #pragma unroll
-            for (int a = 0; a < N; ++a) tg[a] = __ldg(row + a);
+            for (int a = 0; a < N; ++a) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(tg[a]) : "l"(row + a));
         }
     };
     auto load_xy = [&](const int (&tg)[N], double (&x)[N], double (&y)[N]) {
         if (tg[0] < 0) return;
 #pragma unroll
-        for (int a = 0; a < N; ++a) {
-            const double2 p = __ldg(coords + tg[a]);
-            x[a] = p.x;
-            y[a] = p.y;
-        }
+        for (int a = 0; a < N; ++a)
+            asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(x[a]), "=d"(y[a]) : "l"(coords + tg[a]));
     };
 
     auto prefetch_xy = [&](const int (&tg_)[N]) {   // pull the nodes' coordinates into L2
@@ -461,15 +460,11 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
                 const int deg = nd.y & 127;
                 const unsigned s0 = rec & 0x1FFFu, s1 = (rec >> 13) & 0x1FFFu;
                 const double* b0 = slab + (s0 >> 5) * SS + 3 * ((s0 >> 1) & 15);
-                const int f0 = s0 & 1;                          // transposed block: P and Q trade places
-                double L = b0[0], P = b0[1 + f0], Q = b0[2 - f0];
-                if ((s1 >> 5) != (unsigned)kZeroRow) {          // second contributing element (higher id)
-                    const double* b1 = slab + (s1 >> 5) * SS + 3 * ((s1 >> 1) & 15);
-                    const int f1 = s1 & 1;
-                    L += b1[0];
-                    P += b1[1 + f1];
-                    Q += b1[2 - f1];
-                }
+                const double* b1 = slab + (s1 >> 5) * SS + 3 * ((s1 >> 1) & 15);   // zero block when absent
+                const int f0 = s0 & 1, f1 = s1 & 1;            // transposed block: P and Q trade places
+                const double L = b0[0] + b1[0];
+                const double P = b0[1 + f0] + b1[1 + f1];
+                const double Q = b0[2 - f0] + b1[2 - f1];
                 double* out = vals + 4 * (int64_t)nd.x + 2 * p;
                 __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
                 __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(Q, L));
