@@ -267,6 +267,10 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern
 # --------------------------------------------------------------------------------------------
 # tile plan for the fast assembly kernel
 # --------------------------------------------------------------------------------------------
+import os as _os
+FE_TILE_SORT_BY_ID = _os.environ.get("FE_TILE_SORT_BY_ID", "1") == "1"   # tuning knob
+
+
 @dataclass
 class TilePlan:
     """One-time plan of fe_assemble_tiled (device tensors, tile-major; formats in csrc/fe_tiles.cu)."""
@@ -329,8 +333,14 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
         starts = torch.nonzero(flag).flatten()
         row = (idx - starts[tid.long()]).to(torch.int32)
         tile_estart = torch.cat([starts, torch.tensor([nelem], device=dev)]).to(torch.int32)
+        if FE_TILE_SORT_BY_ID:
+            # inside a tile order the elements by element id
+            etile = torch.empty(nelem, dtype=torch.int32, device=dev)
+            etile[eperm.long()] = tid
+            eperm = torch.sort(etile, stable=True).indices.to(torch.int32)
+            del etile
         eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
-        eloc[eperm.long()] = (tid << 8) | row
+        eloc[eperm.long()] = (tid << 8) | row          # tid / row are per sorted position
         del block, flag, seg_start, tid, starts, row, idx
         if ntiles >= (1 << 23):
             return None
