@@ -38,7 +38,11 @@ constexpr int kHaloElemsMax = 64;           // largest halo capacity of any elem
 // HE: halo element capacity per tile.  Quad4 threads need ~124 registers, so its CTA is kept at 5 warps
 // (128 + 32 threads, 15 warps per SM => 128 registers available); Tri3 is register-light and its tiles
 // have more halo elements per owned node, so it takes 64.
-__host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS : 64; }
+__host__ __device__ constexpr int halo_threads(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS : 64; }
+// Slab rows for halo elements.  Quad4 tiles may carry up to 16 more halo elements than the CTA has halo
+// threads (irregular tiles of perturbed / unstructured meshes); those rows are evaluated in a short second
+// pass by the halo warp, so regular tiles pay nothing.
+__host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS + 16 : 64; }
 constexpr int kTileMaxNodes = 2 * kTileElems;    // owned nodes per tile
 constexpr int kTileMaxItems = 8 * kTileElems;    // incidence items of owned nodes per tile
 constexpr int kTileMaxWork = 12 * kTileElems;    // work items (node-level non-zeros of owned nodes) per tile, x32
@@ -52,7 +56,8 @@ template <int N> struct TileLayout {
 #endif
     static constexpr int kSlabStride = ((3 * kBlocks) | 1) + FE_SLAB_PAD;   // odd stride: conflict-free 64-bit rows
     static constexpr int kHalo = halo_cap(N);
-    static constexpr int kThreads = kTileElems + kHalo;        // one thread per slab row
+    static constexpr int kThreads = kTileElems + halo_threads(N);   // one thread per slab row (+ overflow pass)
+    static constexpr int kRows = kTileElems + kHalo;           // rows per tile of tconn / the slab
     static constexpr int kZeroRow = kTileElems + kHalo;        // slab row of zeros (target of absent sources)
     static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
     // one set of staged plan records (16-byte aligned size); the kernel double-buffers it
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
     // Prefetching loads are volatile asm so that the compiler keeps them where they are written (well
     // ahead of their first use, on the far side of the barriers) instead of sinking them to the use.
     auto load_row = [&](int64_t t, int (&tg)[N]) {
-        const int32_t* row = tconn + (t * kTileThreads + tid) * N;
+        const int32_t* row = tconn + (t * T::kRows + tid) * N;
         if constexpr (N == 4) {
             asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
                          : "=r"(tg[0]), "=r"(tg[1]), "=r"(tg[2]), "=r"(tg[3]) : "l"(row));
@@ -427,6 +432,28 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
             double* dst = slab + tid * SS;
 #pragma unroll
             for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+        }
+        if constexpr (T::kRows > T::kThreads) {
+            // overflow halo rows (irregular tiles only): second pass of the halo warp, not prefetched
+            const int nh = d1.z;
+            const int row = tid + (T::kThreads - kTileElems);          // rows kThreads.. for threads TE..
+            if (nh > T::kThreads - kTileElems && tid >= kTileElems && row < kTileElems + nh && dbg != 2) {
+                const int32_t* rp = tconn + (t * T::kRows + row) * N;
+                int tq[N];
+                double xq[N], yq[N], ke[3 * T::kBlocks];
+#pragma unroll
+                for (int a = 0; a < N; ++a) tq[a] = __ldg(rp + a);
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    const double2 pq = __ldg(coords + tq[a]);
+                    xq[a] = pq.x;
+                    yq[a] = pq.y;
+                }
+                element_tri<ET>(xq, yq, weighted != 0, ke);
+                double* dst = slab + row * SS;
+#pragma unroll
+                for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+            }
         }
         // records of the next tile start streaming into the other buffer
         if (more) stage(buf ^ 1, e0, e1);

@@ -290,7 +290,33 @@ def _scan_into(src: Tensor, dst: Tensor, ws: Tensor):
 
 def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -> Optional[TilePlan]:
     """Builds the tile plan; returns None when the mesh does not fit the tiled kernel's capacities
-    (the caller then uses the row-tile kernel fe_assemble, which has none)."""
+    (the caller then uses the row-tile kernel fe_assemble, which has none).
+
+    Elements are ordered along the Morton curve of a grid of one-element cells.  Strategy 1 ("blocks"): a
+    tile = one aligned Z-block of 128 cells (exact 8x16 patches on structured meshes).  If that needs many
+    more tiles than nelem/TE (irregular meshes: blocks with > TE elements get split, others are underfull)
+    or overflows a capacity, strategy 2 ("pack") fills tiles with consecutive 16-cell sub-blocks up to TE
+    elements; coarser cells are the last resort."""
+    if not morton:
+        return _tile_plan(conn, coords, pat, False, 1.0, "blocks")
+    te = _lib.tile_params(pat.elem_type)["tile_elems"]
+    if te == 0 or pat.nelem == 0:
+        return None
+    ideal = (pat.nelem + te - 1) // te
+    best = _tile_plan(conn, coords, pat, True, 1.0, "blocks")
+    if best is not None and best.ntiles <= 1.12 * ideal + 8:
+        return best
+    for scale in (1.0, 1.25, 1.6):
+        plan = _tile_plan(conn, coords, pat, True, scale, "pack")
+        if plan is not None and (best is None or plan.ntiles < best.ntiles):
+            best = plan
+        if best is not None:
+            break
+    return best
+
+
+def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_scale: float,
+               mode: str) -> Optional[TilePlan]:
     L = _lib.lib()
     params = _lib.tile_params(pat.elem_type)
     if params["halo_cap"] == 0 or pat.nelem == 0 or pat.nnode == 0:
@@ -312,6 +338,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
             size = (xy.amax(dim=1) - xy.amin(dim=1)).mean(dim=0)
             if pat.elem_type == FE_TRI3:
                 size = size * 0.7071                                          # two triangles share a quad cell
+            size = size * cell_scale
             cell = torch.maximum(size, ext / 32767.0).clamp_min(1e-300).tolist()  # 15 bits per axis
             keys = torch.empty(nelem, dtype=torch.int32, device=dev)
             lo_h = lo.tolist()
@@ -319,7 +346,20 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
                                         cell[1], _ptr(keys), st))
             skeys, order = torch.sort(keys, stable=True)
             eperm = order.to(torch.int32)
-            block = skeys >> 7                                                # aligned Z-blocks of 128 cells
+            if mode == "pack":
+                # consecutive 16-cell sub-blocks are packed into tiles of at most TE elements
+                sub = skeys >> 4
+                sflag = torch.ones(nelem, dtype=torch.bool, device=dev)
+                sflag[1:] = sub[1:] != sub[:-1]
+                sstart = torch.nonzero(sflag).flatten()
+                ssize = torch.diff(torch.cat([sstart, torch.tensor([nelem], device=dev)]))
+                m = int(ssize.max().item())
+                if m > te // 2:
+                    return None
+                block = sstart[torch.cumsum(sflag, dim=0) - 1] // (te - m + 1)
+                del sub, sflag, sstart, ssize
+            else:
+                block = skeys >> 7                                            # aligned Z-blocks of 128 cells
             del keys, skeys, order
         else:
             eperm = idx.to(torch.int32)
@@ -369,7 +409,8 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
         max_nodes, max_items, max_halo, max_cnt = (int(v) for v in tail[4:8])
         max_work = int(tail[9])
         info = dict(max_nodes=max_nodes, max_items=max_items, max_halo=max_halo, max_cnt=max_cnt, max_work=max_work,
-                    items=n_items, halo_elems=n_halo, work_items=n_work, morton=morton)
+                    items=n_items, halo_elems=n_halo, work_items=n_work, morton=morton, cell_scale=cell_scale,
+                    mode=mode, ntiles=ntiles)
         if (max_nodes > params["max_nodes"] or max_items >= params["max_items"] - 1 or max_halo > hcap
                 or max_work > params["max_work"]):
             return None
@@ -389,7 +430,8 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
         z = torch.zeros(ntiles, dtype=torch.int32, device=dev)
         tdesc = torch.stack([tile_ptr[0, :-1], tile_ptr[0, 1:] - tile_ptr[0, :-1],
                              tile_ptr[1, :-1], tile_ptr[1, 1:] - tile_ptr[1, :-1],
-                             tile_ptr[3, :-1], tile_ptr[3, 1:] - tile_ptr[3, :-1], z, z], dim=1).contiguous()
+                             tile_ptr[3, :-1], tile_ptr[3, 1:] - tile_ptr[3, :-1],
+                             tile_ptr[2, 1:] - tile_ptr[2, :-1], z], dim=1).contiguous()
     return TilePlan(tconn, tdesc, tnode, tloc, twork, tchunk, ntiles, info)
 
 

@@ -184,8 +184,8 @@ int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, co
 int fe_tile_conn(int elem_type, int64_t ntiles, const int32_t* conn, const int32_t* eperm,
                  const int32_t* tile_estart, const int32_t* thalo, const int32_t* tile_ptr, int32_t* tconn,
                  void* stream);
-/* tdesc[8*t..] = {node offset, node count, item offset, item count, work offset, work count, 0, 0} of tile t
- * (from tile_ptr rows 0, 1, 3), 32 bytes per tile, 16-byte aligned. */
+/* tdesc[8*t..] = {node offset, node count, item offset, item count, work offset, work count, halo element
+ * count, 0} of tile t (from tile_ptr rows 0, 1, 3, 2), 32 bytes per tile, 16-byte aligned. */
 int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tconn, const double* coords,
                       const int32_t* tdesc, const void* tnode, const uint16_t* tloc, const uint32_t* twork,
                       const uint32_t* tchunk, double* vals, void* stream);
