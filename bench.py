@@ -206,7 +206,7 @@ def run_ours(args):
         spmv_bytes = 12 * pat.nnz + 20 * pat.nrows
     else:
         from feprogram_b200 import dist as fdist
-        part = fdist.build_structured_block(n, rank, world, dev)
+        part = fdist.build_structured_block(n, rank, world, dev, args.ny_per_rank or n)
         symbolic_s = part.symbolic_s
         nelem_local = part.nelem_owned
         step = part.assemble_step
@@ -332,7 +332,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "quad4_%dx%d_2dof_reference_operator%s" % (n, n * world, "" if world == 1 else "_row_blocks"),
+            "config": {"workload": "quad4_%dx%d_2dof_reference_operator%s" % (n, (args.ny_per_rank or n) * world if world > 1 else n,
+                                                                              "" if world == 1 else "_row_blocks"),
                        "elements": int(nelem_total), "l2": "inputs exceed L2 (no flush needed)" if nelem_total / world > 2e6 else "inputs fit L2",
                        "symbolic_phase_s": symbolic_s, "partition": "dp%d element row blocks, owned-row assembly with ghost elements" % world},
             "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak,
@@ -362,6 +363,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024, help="side of the CPU-baseline sample block")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "rows"], help="numeric assembly kernel")
+    ap.add_argument("--ny-per-rank", type=int, default=0,
+                    help="element rows per rank for N > 1 (default --n: weak scaling; 8192/N with --n 8192 = cfg4 strong scaling)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

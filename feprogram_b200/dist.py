@@ -293,10 +293,10 @@ class DistFemProblem:
 # bench.py support: weak-scaling workload, rank r = one n x n element block of the n x (world*n) mesh
 # ----------------------------------------------------------------------------------------------------
 class _BenchPart:
-    def __init__(self, n: int, rank: int, world: int, dev):
+    def __init__(self, n: int, rank: int, world: int, dev, ny_per_rank: int):
         import torch
         self.torch = torch
-        self.m, self.bc = structured_quad4_block(n, n, rank, world)
+        self.m, self.bc = structured_quad4_block(n, ny_per_rank, rank, world)
         self.comm = DistFemProblem.make_comm(rank, world, dev)
         self.p = DistFemProblem(self.m, dev, 4, self.comm)
         self.p = DistFemProblem(self.m, dev, 4, self.comm)        # second build: excludes context / module load
@@ -384,5 +384,5 @@ class _BenchPart:
                 "includes": "per rank: H2D, symbolic phase, numeric assembly, BCs, D2H rhs + checksum", "checksum": chk}
 
 
-def build_structured_block(n: int, rank: int, world: int, dev):
-    return _BenchPart(n, rank, world, dev)
+def build_structured_block(n: int, rank: int, world: int, dev, ny_per_rank: int = 0):
+    return _BenchPart(n, rank, world, dev, ny_per_rank or n)
