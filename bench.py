@@ -358,7 +358,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=4096, help="elements per side of each rank's block")
+    ap.add_argument("--n", "--nx", dest="n", type=int, default=4096, help="elements per side of each rank's block")
     ap.add_argument("--cg-iters", type=int, default=200)
     ap.add_argument("--cpu-sample", type=int, default=1024, help="side of the CPU-baseline sample block")
     ap.add_argument("--no-cpu", action="store_true")
