@@ -1,0 +1,57 @@
+"""ASCII .vtu writer with the reference's file format (next-row f-3 of SURVEY.md §8; not on the hot path).
+
+``writeXML_nodeData(coords, conect, nodedata, nameFile)`` produces byte for byte what
+/root/reference/python_to_xml.py:74-141 writes -- PointData vector "Velocidad" (2 components), Points with
+a 0.0 z, 0-based connectivity, offsets, VTK cell types 9 (quad) / 28 (biquadratic quad) -- but builds each
+section with vectorised string operations and one write per section instead of one ``write`` per number.
+"""
+import numpy as np
+
+__all__ = ["writeXML_nodeData"]
+
+
+def _s(a):
+    """Shortest round-trip decimal strings, identical to ``str(np.float64)`` / ``'{}'.format``."""
+    return np.asarray(a).astype(str)
+
+
+def writeXML_nodeData(coords, conect, nodedata, nameFile):
+    coords = np.asarray(coords)
+    nnode = coords.shape[0]
+    nelem = len(conect)
+    conn = np.asarray(conect)
+    if conn.dtype == object:
+        conn = np.stack([np.asarray(c) for c in conect])
+    nnpe = conn.shape[1]
+    cellType = 9 if nnpe == 4 else 28
+    data = np.asarray(nodedata)
+    with open(nameFile.split(".")[0] + ".vtu", "w") as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian">\n')
+        f.write(" <UnstructuredGrid>\n")
+        f.write('  <Piece NumberOfPoints="{}" NumberOfCells="{}">\n'.format(nnode, nelem))
+        f.write('   <PointData Vectors="Tensiones">\n')
+        f.write('    <DataArray Name="Velocidad" NumberOfComponents="2" type="Float32" format="ascii">\n    ')
+        d = _s(data[:, :2])
+        f.write("".join(np.char.add(np.char.add(np.char.add(" ", d[:, 0]), np.char.add(" ", d[:, 1])), "\n").tolist()))
+        f.write("\n    </DataArray>")
+        f.write("\n   </PointData>\n")
+        f.write("   <Points>\n")
+        f.write('    <DataArray NumberOfComponents="3" type="Float32"  format="ascii">\n    ')
+        c = _s(coords[:, :2])
+        f.write("".join(np.char.add(np.char.add(np.char.add(" ", c[:, 0]), np.char.add(" ", c[:, 1])), " 0.0").tolist()))
+        f.write("\n    </DataArray>")
+        f.write("\n   </Points>\n")
+        f.write("   <Cells>\n")
+        f.write('    <DataArray type="Int32" Name="connectivity" format="ascii" RangeMin="" RangeMax="">\n')
+        f.write("".join(np.char.add(" ", (conn.astype(np.int64) - 1).ravel().astype(str)).tolist()))
+        f.write("\n    </DataArray>\n")
+        f.write('    <DataArray type="Int32" Name="offsets" format="ascii" RangeMin="" RangeMax="">\n')
+        f.write("".join(np.char.add(" ", (nnpe * np.arange(1, nelem + 1, dtype=np.int64)).astype(str)).tolist()))
+        f.write("\n    </DataArray>\n")
+        f.write('    <DataArray type="Int32" Name="types" format="ascii" RangeMin="" RangeMax="">\n')
+        f.write((" " + str(cellType)) * nelem)
+        f.write("\n    </DataArray>")
+        f.write("\n   </Cells>\n")
+        f.write("  </Piece>\n")
+        f.write(" </UnstructuredGrid>\n")
+        f.write("</VTKFile>\n")

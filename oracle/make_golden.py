@@ -97,6 +97,16 @@ def main():
                         q4_64=scalar_case(4, 64), q9_32=scalar_case(9, 32), q4_4=scalar_case(4, 4),
                         q9_4=scalar_case(9, 4),
                         versions=np.array([np.__version__, scipy.__version__]))
+    # .vtu writer (python_to_xml.py:74-141): the reference's own output on two tiny meshes
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_writer", os.path.join(ref_runner.REF_ROOT, "python_to_xml.py"))
+    writer = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(writer)
+    rng = np.random.default_rng(0)
+    for k, gen in enumerate((mesh.structured_quad4, mesh.structured_quad9)):
+        conn, coords, _ = gen(3, 2)
+        U = rng.standard_normal((coords.shape[0], 2)) * 1e3
+        writer.writeXML_nodeData(coords * np.array([2.0, 10.0]), conn, U, os.path.join(OUT, "writer_case%d" % k))
     print("golden fixtures written to", OUT)
 
 
