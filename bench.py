@@ -258,11 +258,12 @@ def run_ours(args):
         barrier()
         ms_spmv = s0.elapsed_time(s1) / reps
         sol = torch.empty(pat.nrows, dtype=torch.float64, device=dev)
-        torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, dirmask, sol, 0.0, 0.0, 10, 10)  # warm-up
+        torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, dirmask, sol, 0.0, 0.0, 10, 10, pat.nptr, pat.nadj)
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
-        info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, dirmask, sol, 0.0, 0.0, cg_iters, cg_iters)
+        info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, dirmask, sol, 0.0, 0.0, cg_iters, cg_iters,
+                                       pat.nptr, pat.nadj)
         p1.record()
         barrier()
         ms_pcg = p0.elapsed_time(p1)

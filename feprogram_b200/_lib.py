@@ -51,7 +51,8 @@ PROTOTYPES = {
     "fe_spmv": (_i, [_i64, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fe_csr_diagonal": (_i, [_i64, _i, _p, _p, _p, _p, _p]),
     "fe_pcg_workspace_bytes": (_sz, [_i64]),
-    "fe_pcg": (_i, [_i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p]),
+    "fe_pcg": (_i, [_i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _p, _p]),
+    "fe_spmv_nodal": (_i, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_dist_available": (_i, []),
     "fe_dist_unique_id": (_i, [_p]),
     "fe_dist_comm_init": (_i, [_p, _i, _i, C.POINTER(C.c_void_p)]),
@@ -59,7 +60,7 @@ PROTOTYPES = {
     "fe_dist_halo_exchange": (_i, [_p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "fe_dist_pcg_workspace_bytes": (_sz, [_i64]),
     "fe_dist_pcg": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _i32,
-                         _p, _p, _p, _p, _p, _p]),
+                         _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

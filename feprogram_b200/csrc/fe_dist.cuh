@@ -63,13 +63,15 @@ static int halo_exchange(const Halo& h, double* vec, cudaStream_t st) {
 template <typename IdxT>
 static int dist_pcg_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, const int32_t* col_idx, const double* vals,
                          const double* rhs, const uint8_t* mask, double* x, double rtol, double atol, int64_t maxit,
-                         int check_every, void* work, double* info, const Halo& h, cudaStream_t st) {
+                         int check_every, void* work, double* info, const Halo& h, const int32_t* nptr,
+                         const int32_t* nadj, cudaStream_t st) {
     PcgWork w = carve(work, nloc);
     double* g = w.partB + 2 * kMaxPartials;  // 8 doubles of globally reduced scalars
     IdxT last;
     FE_CUDA_TRY(cudaMemcpyAsync(&last, row_ptr + nown, sizeof(IdxT), cudaMemcpyDeviceToHost, st));
     FE_CUDA_TRY(cudaStreamSynchronize(st));
     const int lpr = pick_lpr(nown, (int64_t)last);
+    const Mat<IdxT> A{nown, row_ptr, col_idx, vals, nptr, nadj, lpr};
     int gv = 0, rc;
     if ((rc = persistent_grid((const void*)k_pcg_update, kVecThreads, &gv)) != FE_OK) return rc;
     const int64_t need = (nown + kVecThreads - 1) / kVecThreads;
@@ -82,9 +84,7 @@ static int dist_pcg_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, const 
     k_pcg_init1<<<gv, kVecThreads, 0, st>>>(nown, rhs, mask, x, w.minv);
     FE_CHECK_LAUNCH("k_pcg_init1");
     if ((rc = halo_exchange(h, x, st)) != FE_OK) return rc;   // Dirichlet values of ghost dofs
-    if ((rc = launch_spmv<IdxT, false>(lpr, nown, row_ptr, col_idx, vals, x, w.Ap, mask, nullptr, nullptr, nullptr,
-                                       st)) != FE_OK)
-        return rc;
+    if ((rc = mat_spmv<IdxT, false>(A, x, w.Ap, mask, nullptr, nullptr, nullptr, st)) != FE_OK) return rc;
     k_pcg_init2<<<gv, kVecThreads, 0, st>>>(nown, rhs, mask, w.Ap, w.minv, w.r, w.p, w.partB);
     FE_CHECK_LAUNCH("k_pcg_init2");
     k_reduce_partials<<<1, kVecThreads, 0, st>>>(gv, w.partB, 2, 2, g);
@@ -103,9 +103,7 @@ static int dist_pcg_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, const 
         for (int64_t k = 0; k < batch; ++k) {
             int ga = 0;
             if ((rc = halo_exchange(h, w.p, st)) != FE_OK) return rc;
-            if ((rc = launch_spmv<IdxT, true>(lpr, nown, row_ptr, col_idx, vals, w.p, w.Ap, mask, w.partA, w.scal, &ga,
-                                              st)) != FE_OK)
-                return rc;
+            if ((rc = mat_spmv<IdxT, true>(A, w.p, w.Ap, mask, w.partA, w.scal, &ga, st)) != FE_OK) return rc;
             k_reduce_partials<<<1, kVecThreads, 0, st>>>(ga, w.partA, 1, 1, g + 2);
             FE_NCCL_TRY(ncclAllReduce(g + 2, g + 2, 1, ncclDouble, ncclSum, h.comm, st));
             k_pcg_update<<<gv, kVecThreads, 0, st>>>(nown, ga, w.partA, w.p, w.Ap, w.minv, x, w.r, w.partB, w.scal,
@@ -203,7 +201,7 @@ int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void*
                 const double* vals, const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol,
                 int64_t maxit, int32_t check_every, void* work, double* info, void* comm, int32_t n_nbr,
                 const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx, double* sendbuf,
-                const int64_t* recv_off, void* stream) {
+                const int64_t* recv_off, const int32_t* nptr, const int32_t* nadj, void* stream) {
     using namespace fe;
     FE_REQUIRE(nrows_owned >= 0 && nrows_local >= nrows_owned && row_ptr && col_idx && vals && rhs && x && work && comm,
                "null pointer or bad size");
@@ -216,9 +214,9 @@ int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void*
     cudaStream_t st = as_stream(stream);
     if (idx64)
         return dist_pcg_impl<int64_t>(nrows_owned, nrows_local, static_cast<const int64_t*>(row_ptr), col_idx, vals,
-                                      rhs, dirmask, x, rtol, atol, maxit, check_every, work, info, h, st);
+                                      rhs, dirmask, x, rtol, atol, maxit, check_every, work, info, h, nptr, nadj, st);
     return dist_pcg_impl<int32_t>(nrows_owned, nrows_local, static_cast<const int32_t*>(row_ptr), col_idx, vals, rhs,
-                                  dirmask, x, rtol, atol, maxit, check_every, work, info, h, st);
+                                  dirmask, x, rtol, atol, maxit, check_every, work, info, h, nptr, nadj, st);
 #else
     set_error("built without NCCL");
     return FE_ERR_NCCL;

@@ -284,7 +284,8 @@ class DistFemProblem:
                                      C.c_void_p(self.vals.data_ptr()), C.c_void_p(self.rhs.data_ptr()),
                                      C.c_void_p(self.dirmask.data_ptr()), C.c_void_p(x.data_ptr()), float(rtol), 0.0,
                                      int(maxit), int(check_every), C.c_void_p(work.data_ptr()),
-                                     info.ctypes.data_as(C.c_void_p), self.comm, n, nbr, soff, sidx, sbuf, roff, st))
+                                     info.ctypes.data_as(C.c_void_p), self.comm, n, nbr, soff, sidx, sbuf, roff,
+                                     C.c_void_p(pat.nptr.data_ptr()), C.c_void_p(pat.nadj.data_ptr()), st))
         self.info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]), converged=bool(info[3]))
         return x
 

@@ -278,7 +278,7 @@ class FemProblem:
         x = torch.empty(pat.nrows, dtype=torch.float64, device=st["vals"].device)
         maxit = self.maxit if self.maxit is not None else 20 * pat.nrows + 100
         info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, st["vals"], st["rhs"], st["dirmask"], x,
-                                       self.rtol, 0.0, maxit, 50)
+                                       self.rtol, 0.0, maxit, 50, pat.nptr, pat.nadj)
         self.solver_info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]),
                                 converged=bool(info[3]))
         st["x"] = x

@@ -198,6 +198,15 @@ def spmv(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, x: Tensor, y: Tensor, r
                                       _ptr(col_idx), _ptr(vals), _ptr(x), _ptr(y), _ptr(rowmask), _stream(vals)))
 
 
+@torch.library.custom_op("feprogram::spmv_nodal", mutates_args=("y",))
+def spmv_nodal(nptr: Tensor, nadj: Tensor, vals: Tensor, x: Tensor, y: Tensor, rowmask: Optional[Tensor]) -> None:
+    """y <- A x through the node-level pattern (2-dof matrices in this library's value layout).  fe_spmv_nodal."""
+    _chk_dev(nptr, nadj, vals, x, y, rowmask)
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().fe_spmv_nodal(nptr.numel() - 1, _ptr(nptr), _ptr(nadj), _ptr(vals), _ptr(x), _ptr(y),
+                                            _ptr(rowmask), _stream(vals)))
+
+
 @torch.library.custom_op("feprogram::csr_diagonal", mutates_args=())
 def csr_diagonal(row_ptr: Tensor, col_idx: Tensor, vals: Tensor) -> Tensor:
     _chk_dev(row_ptr, col_idx, vals)
@@ -211,9 +220,11 @@ def csr_diagonal(row_ptr: Tensor, col_idx: Tensor, vals: Tensor) -> Tensor:
 
 @torch.library.custom_op("feprogram::pcg", mutates_args=("x",))
 def pcg(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, rhs: Tensor, dirmask: Optional[Tensor], x: Tensor,
-        rtol: float, atol: float, maxit: int, check_every: int) -> Tensor:
-    """Jacobi-PCG with Dirichlet dofs held at rhs[D]; returns CPU tensor [iters, relres, ||r0||, converged]."""
-    _chk_dev(row_ptr, col_idx, vals, rhs, dirmask, x)
+        rtol: float, atol: float, maxit: int, check_every: int, nptr: Optional[Tensor] = None,
+        nadj: Optional[Tensor] = None) -> Tensor:
+    """Jacobi-PCG with Dirichlet dofs held at rhs[D]; returns CPU tensor [iters, relres, ||r0||, converged].
+    nptr/nadj: node-level pattern of a 2-dof matrix (node-block SpMV inside the iteration)."""
+    _chk_dev(row_ptr, col_idx, vals, rhs, dirmask, x, nptr, nadj)
     n = row_ptr.numel() - 1
     info = np.zeros(4, dtype=np.float64)
     with torch.cuda.device(vals.device):
@@ -221,7 +232,7 @@ def pcg(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, rhs: Tensor, dirmask: Op
         work = torch.empty(L.fe_pcg_workspace_bytes(n), dtype=torch.uint8, device=vals.device)
         _lib.check(L.fe_pcg(n, int(row_ptr.dtype == torch.int64), _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(rhs),
                             _ptr(dirmask), _ptr(x), float(rtol), float(atol), int(maxit), int(check_every), _ptr(work),
-                            info.ctypes.data_as(C.c_void_p), _stream(vals)))
+                            info.ctypes.data_as(C.c_void_p), _ptr(nptr), _ptr(nadj), _stream(vals)))
     return torch.from_numpy(info)
 
 

@@ -222,15 +222,20 @@ int fe_apply_bc(int mode, int64_t nrows, int idx64, const void* row_ptr, const i
  *   ||r||_2 <= atol.  work: 4*nrows doubles + FE_PCG_SCALAR_DOUBLES doubles + 2*fe_pcg_blocks(nrows)
  *   doubles of scratch, see fe_pcg_workspace_bytes.  info (HOST, 4 doubles): iterations, final
  *   ||r||/||r0||, ||r0||, converged flag.  check_every: iterations between host polls (>=1).
+ *   nptr/nadj (optional, may be NULL): node-level pattern of a 2-dof matrix -> node-block SpMV.
  */
 int fe_spmv(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
             const double* x, double* y, const uint8_t* rowmask, void* stream);
+/* Same product read through the node-level pattern of a 2-dof matrix in this library's value layout (one
+ * column index per 2x2 block): 24 % fewer bytes.  fe_pcg / fe_dist_pcg use it when nptr/nadj are given. */
+int fe_spmv_nodal(int64_t nnode, const int32_t* nptr, const int32_t* nadj, const double* vals, const double* x,
+                  double* y, const uint8_t* rowmask, void* stream);
 int fe_csr_diagonal(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
                     double* diag, void* stream);
 size_t fe_pcg_workspace_bytes(int64_t nrows);
 int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
            const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit,
-           int32_t check_every, void* work, double* info, void* stream);
+           int32_t check_every, void* work, double* info, const int32_t* nptr, const int32_t* nadj, void* stream);
 
 /* ---- multi-GPU (one host process per GPU, NCCL over NVLink) ------------------------------------------
  * The reference has no distributed code; this is the north_star's scale-out of the solve.  Elements are
@@ -263,7 +268,7 @@ int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void*
                 const double* vals, const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol,
                 int64_t maxit, int32_t check_every, void* work, double* info, void* comm, int32_t n_nbr,
                 const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx, double* sendbuf,
-                const int64_t* recv_off, void* stream);
+                const int64_t* recv_off, const int32_t* nptr, const int32_t* nadj, void* stream);
 
 #ifdef __cplusplus
 }

@@ -181,6 +181,12 @@ def test_spmv_and_bc_modes_against_scipy(torch_cuda, golden):
     ref = K0 @ x
     ref[z["dofDir"]] = 0.0
     assert rel_max(y.cpu().numpy(), ref) < 1e-13
+    # node-block form of the same product (with and without the Dirichlet row mask)
+    yn = torch.empty_like(xd)
+    torch.ops.feprogram.spmv_nodal(pat.nptr, pat.nadj, st["vals"], xd, yn, None)
+    assert rel_max(yn.cpu().numpy(), K0 @ x) < 1e-13
+    torch.ops.feprogram.spmv_nodal(pat.nptr, pat.nadj, st["vals"], xd, yn, st["dirmask"])
+    assert rel_max(yn.cpu().numpy(), ref) < 1e-13
     d = torch.ops.feprogram.csr_diagonal(pat.row_ptr, pat.col_idx, st["vals"]).cpu().numpy()
     assert np.array_equal(d, K0.diagonal())
     # symmetric lift in place == oracle's lifted system
