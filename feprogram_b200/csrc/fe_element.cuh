@@ -127,34 +127,36 @@ __device__ __forceinline__ void q4_jacobian(int g, const ElemGeom<FE_QUAD4>& G, 
                                             double& j11) {
     double ps, ms, pr, mr;
     q4_table(g, ps, ms, pr, mr);
-    j00 = fma(ps, G.dx01, ms * G.dx32);
-    j01 = fma(ps, G.dy01, ms * G.dy32);
-    j10 = fma(pr, G.dx03, mr * G.dx12);
-    j11 = fma(pr, G.dy03, mr * G.dy12);
+    j00 = fma(ps, G.dx01, __dmul_rn(ms, G.dx32));
+    j01 = fma(ps, G.dy01, __dmul_rn(ms, G.dy32));
+    j10 = fma(pr, G.dx03, __dmul_rn(mr, G.dx12));
+    j11 = fma(pr, G.dy03, __dmul_rn(mr, G.dy12));
 }
 
 template <>
 __device__ __forceinline__ void geom_init<FE_QUAD4>(ElemGeom<FE_QUAD4>& G, const double (&x)[4], const double (&y)[4],
                                                     bool weighted) {
-    G.dx01 = x[0] - x[1]; G.dx32 = x[3] - x[2]; G.dx03 = x[0] - x[3]; G.dx12 = x[1] - x[2];
-    G.dy01 = y[0] - y[1]; G.dy32 = y[3] - y[2]; G.dy03 = y[0] - y[3]; G.dy12 = y[1] - y[2];
+    G.dx01 = __dsub_rn(x[0], x[1]); G.dx32 = __dsub_rn(x[3], x[2]);
+    G.dx03 = __dsub_rn(x[0], x[3]); G.dx12 = __dsub_rn(x[1], x[2]);
+    G.dy01 = __dsub_rn(y[0], y[1]); G.dy32 = __dsub_rn(y[3], y[2]);
+    G.dy03 = __dsub_rn(y[0], y[3]); G.dy12 = __dsub_rn(y[1], y[2]);
     double d[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         double j00, j01, j10, j11;
         q4_jacobian(g, G, j00, j01, j10, j11);
-        d[g] = j00 * j11 - j01 * j10;
+        d[g] = fma(j00, j11, -__dmul_rn(j01, j10));
     }
-    const double d01 = d[0] * d[1], d23 = d[2] * d[3];
-    const double inv = 1.0 / (d01 * d23);
-    const double i01 = inv * d23, i23 = inv * d01;   // 1/(d0 d1), 1/(d2 d3)
-    G.s[0] = i01 * d[1];
-    G.s[1] = i01 * d[0];
-    G.s[2] = i23 * d[3];
-    G.s[3] = i23 * d[2];
+    const double d01 = __dmul_rn(d[0], d[1]), d23 = __dmul_rn(d[2], d[3]);
+    const double inv = 1.0 / __dmul_rn(d01, d23);
+    const double i01 = __dmul_rn(inv, d23), i23 = __dmul_rn(inv, d01);   // 1/(d0 d1), 1/(d2 d3)
+    G.s[0] = __dmul_rn(i01, d[1]);
+    G.s[1] = __dmul_rn(i01, d[0]);
+    G.s[2] = __dmul_rn(i23, d[3]);
+    G.s[3] = __dmul_rn(i23, d[2]);
     if (weighted) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) G.s[g] *= c_q4.w[g];
+        for (int g = 0; g < 4; ++g) G.s[g] = __dmul_rn(G.s[g], c_q4.w[g]);
     }
 }
 
@@ -173,15 +175,17 @@ __device__ __forceinline__ void gauss_point(int g, const ElemGeom<ET>& G, bool w
         j10 = fma(E::dHs(g, b), G.x[b], j10);
         j11 = fma(E::dHs(g, b), G.y[b], j11);
     }
-    const double det = j00 * j11 - j01 * j10;
+    // every product / sum below is written with explicit roundings so that all kernels that evaluate an
+    // element (tiled, row-tile, multi-thread Quad9) produce the same bits regardless of FMA contraction
+    const double det = fma(j00, j11, -__dmul_rn(j01, j10));
     double s = 1.0 / det;
-    if (weighted) s *= E::w(g);
+    if (weighted) s = __dmul_rn(s, E::w(g));
 #pragma unroll
     for (int b = 0; b < E::NNPE; ++b) {
-        ax[b] = j11 * E::dHr(g, b) - j01 * E::dHs(g, b);
-        ay[b] = j00 * E::dHs(g, b) - j10 * E::dHr(g, b);
-        sx[b] = ax[b] * s;
-        sy[b] = ay[b] * s;
+        ax[b] = fma(j11, E::dHr(g, b), -__dmul_rn(j01, E::dHs(g, b)));
+        ay[b] = fma(j00, E::dHs(g, b), -__dmul_rn(j10, E::dHr(g, b)));
+        sx[b] = __dmul_rn(ax[b], s);
+        sy[b] = __dmul_rn(ay[b], s);
     }
 }
 
@@ -192,15 +196,15 @@ __device__ __forceinline__ void gauss_point<FE_QUAD4>(int g, const ElemGeom<FE_Q
     double ps, ms, pr, mr, j00, j01, j10, j11;
     q4_table(g, ps, ms, pr, mr);
     q4_jacobian(g, G, j00, j01, j10, j11);
-    const double u1 = j11 * ps, u2 = j11 * ms, v1 = j01 * pr, v2 = j01 * mr;
-    const double w1 = j00 * pr, w2 = j00 * mr, z1 = j10 * ps, z2 = j10 * ms;
-    ax[0] = u1 - v1; ax[1] = -(u1 + v2); ax[2] = v2 - u2; ax[3] = u2 + v1;
-    ay[0] = w1 - z1; ay[1] = w2 + z1;    ay[2] = z2 - w2; ay[3] = -(w1 + z2);
+    const double u1 = __dmul_rn(j11, ps), u2 = __dmul_rn(j11, ms), v1 = __dmul_rn(j01, pr), v2 = __dmul_rn(j01, mr);
+    const double w1 = __dmul_rn(j00, pr), w2 = __dmul_rn(j00, mr), z1 = __dmul_rn(j10, ps), z2 = __dmul_rn(j10, ms);
+    ax[0] = __dsub_rn(u1, v1); ax[1] = -__dadd_rn(u1, v2); ax[2] = __dsub_rn(v2, u2); ax[3] = __dadd_rn(u2, v1);
+    ay[0] = __dsub_rn(w1, z1); ay[1] = __dadd_rn(w2, z1);  ay[2] = __dsub_rn(z2, w2); ay[3] = -__dadd_rn(w1, z2);
     const double s = G.s[g];
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        sx[b] = ax[b] * s;
-        sy[b] = ay[b] * s;
+        sx[b] = __dmul_rn(ax[b], s);
+        sy[b] = __dmul_rn(ay[b], s);
     }
 }
 

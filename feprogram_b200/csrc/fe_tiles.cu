@@ -33,19 +33,23 @@ namespace fe {
 #define FE_HALO_ELEMS 32
 #define FE_TILE_CTAS 3
 #endif
-constexpr int kTileElems = FE_TILE_ELEMS;   // TE: own elements per tile
 constexpr int kHaloElemsMax = 64;           // largest halo capacity of any element type (plan scratch)
-// HE: halo element capacity per tile.  Quad4 threads need ~124 registers, so its CTA is kept at 5 warps
-// (128 + 32 threads, 15 warps per SM => 128 registers available); Tri3 is register-light and its tiles
-// have more halo elements per owned node, so it takes 64.
-__host__ __device__ constexpr int halo_threads(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS : 64; }
+// ---- per-element-type tile configuration ------------------------------------------------------------
+// TE own elements per tile.  Quad4 / Tri3: 128 (one thread per element).  Quad9: 32 elements, FIVE threads
+// per element (its 45 node-pair blocks = 135 accumulators do not fit one thread).
+__host__ __device__ constexpr int tile_elems(int nnpe) { return nnpe == 9 ? 32 : FE_TILE_ELEMS; }
+// halo element threads per CTA.  Quad4 threads need ~124 registers, so its CTA is kept at 5 warps
+// (128 + 32 threads, 15 warps per SM => 128 registers available); Tri3 is register-light.
+__host__ __device__ constexpr int halo_threads(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS : nnpe == 9 ? 32 : 64; }
 // Slab rows for halo elements.  Quad4 tiles may carry up to 16 more halo elements than the CTA has halo
 // threads (irregular tiles of perturbed / unstructured meshes); those rows are evaluated in a short second
 // pass by the halo warp, so regular tiles pay nothing.
-__host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS + 16 : 64; }
-constexpr int kTileMaxNodes = 2 * kTileElems;    // owned nodes per tile
-constexpr int kTileMaxItems = 8 * kTileElems;    // incidence items of owned nodes per tile
-constexpr int kTileMaxWork = 12 * kTileElems;    // work items (node-level non-zeros of owned nodes) per tile, x32
+__host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS + 16 : nnpe == 9 ? 16 : 64; }
+__host__ __device__ constexpr int tile_parts(int nnpe) { return nnpe == 9 ? 5 : 1; }      // threads per element
+__host__ __device__ constexpr int tri_bits(int nnpe) { return nnpe == 9 ? 6 : 4; }        // bits of a block index
+__host__ __device__ constexpr int max_nodes(int nnpe) { return nnpe == 9 ? 192 : 2 * tile_elems(nnpe); }
+__host__ __device__ constexpr int max_items(int nnpe) { return nnpe == 9 ? 640 : 8 * tile_elems(nnpe); }
+__host__ __device__ constexpr int max_work(int nnpe) { return nnpe == 9 ? 3072 : 12 * tile_elems(nnpe); }   // x32
 constexpr int kTileCtasPerSm = FE_TILE_CTAS;     // persistent grid = SMs x this
 constexpr unsigned kWorkFirst = 1u << 26, kWorkSelf = 1u << 27;
 
@@ -55,15 +59,24 @@ template <int N> struct TileLayout {
 #define FE_SLAB_PAD 0
 #endif
     static constexpr int kSlabStride = ((3 * kBlocks) | 1) + FE_SLAB_PAD;   // odd stride: conflict-free 64-bit rows
+    static constexpr int kTE = tile_elems(N);
     static constexpr int kHalo = halo_cap(N);
-    static constexpr int kThreads = kTileElems + halo_threads(N);   // one thread per slab row (+ overflow pass)
-    static constexpr int kRows = kTileElems + kHalo;           // rows per tile of tconn / the slab
-    static constexpr int kZeroRow = kTileElems + kHalo;        // slab row of zeros (target of absent sources)
+    static constexpr int kParts = tile_parts(N);
+    static constexpr int kRowThreads = kTE + halo_threads(N);  // threads per part: one per slab row
+    static constexpr int kThreads = kRowThreads * kParts;
+    static constexpr int kRows = kTE + kHalo;                  // rows per tile of tconn / the slab
+    static constexpr int kZeroRow = kTE + kHalo;               // slab row of zeros (target of absent sources)
+    static constexpr int kMaxNodes = max_nodes(N), kMaxItems = max_items(N), kMaxWork = max_work(N);
+    static constexpr int kCtas = kParts > 1 ? 2 : kTileCtasPerSm;   // persistent CTAs per SM
+    static constexpr int kTriBits = tri_bits(N);
+    static constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
     static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
+    // shared copy of the rows' node coordinates (multi-thread-per-element types only)
+    static constexpr size_t kXyBytes = kParts > 1 ? (size_t)kRows * N * 16 : 0;
     // one set of staged plan records (16-byte aligned size); the kernel double-buffers it
-    static constexpr size_t kRecBytes = (size_t)kTileMaxWork * 4 + (size_t)kTileMaxNodes * 8 +
-                                        (size_t)(kTileMaxWork / 32) * 4 + (size_t)kTileMaxItems * 2;
-    static constexpr size_t kSmem = (size_t)kSlabDoubles * sizeof(double) + 2 * kRecBytes;
+    static constexpr size_t kRecBytes = (size_t)kMaxWork * 4 + (size_t)kMaxNodes * 8 + (size_t)(kMaxWork / 32) * 4 +
+                                        (size_t)kMaxItems * 2;
+    static constexpr size_t kSmem = (size_t)kSlabDoubles * sizeof(double) + 2 * kRecBytes + kXyBytes;
     // block index of the pair lo <= hi in the upper triangle (row-major)
     __host__ __device__ static constexpr int tri(int lo, int hi) { return lo * N - lo * (lo - 1) / 2 + (hi - lo); }
 };
@@ -207,17 +220,17 @@ __global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_
 __global__ void k_tile_conn(int64_t nrows, int nnpe, const int32_t* __restrict__ conn,
                             const int32_t* __restrict__ eperm, const int32_t* __restrict__ tile_estart,
                             const int32_t* __restrict__ thalo, const int32_t* __restrict__ tile_hptr,
-                            int32_t* __restrict__ tconn, int he) {
+                            int32_t* __restrict__ tconn, int te, int he) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
-    const int rows = kTileElems + he;
+    const int rows = te + he;
     const int64_t t = i / rows;
     const int r = (int)(i - t * rows);
     int64_t e = -1;
-    if (r < kTileElems) {
+    if (r < te) {
         if (r < tile_estart[t + 1] - tile_estart[t]) e = eperm[tile_estart[t] + r];
-    } else if (r - kTileElems < tile_hptr[t + 1] - tile_hptr[t]) {
-        e = thalo[t * he + (r - kTileElems)];
+    } else if (r - te < tile_hptr[t + 1] - tile_hptr[t]) {
+        e = thalo[t * he + (r - te)];
     }
     for (int a = 0; a < nnpe; ++a) tconn[i * nnpe + a] = e >= 0 ? conn[e * nnpe + a] : -1;
 }
@@ -230,7 +243,8 @@ __global__ void __launch_bounds__(128) k_tile_records(
     const int32_t* __restrict__ thalo, const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc,
     const uint8_t* __restrict__ epos, const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr,
     const int32_t* __restrict__ nadj, int2* __restrict__ tnode, uint16_t* __restrict__ tloc,
-    uint32_t* __restrict__ twork, uint32_t* __restrict__ tchunk, int32_t* __restrict__ stats, int he) {
+    uint32_t* __restrict__ twork, uint32_t* __restrict__ tchunk, int32_t* __restrict__ stats, int te, int he,
+    int tribits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     const int n = tile_nodes[i];
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
     }
     tnode[i] = make_int2(p0, deg | (self << 7) | (cnt << 14) | (ioff << 18));
 
-    const unsigned kZeroSrc = (unsigned)(kTileElems + he) << 5;
+    const unsigned kZeroSrc = (unsigned)(te + he) << (tribits + 1);
     unsigned short src[kMaxAdj][2];
     for (int p = 0; p < deg; ++p) src[p][0] = src[p][1] = (unsigned short)kZeroSrc;
     for (int j = 0; j < cnt; ++j) {
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
                 if (hl[mid] < e) lo = mid + 1;
                 else hi = mid;
             }
-            row = kTileElems + lo;
+            row = te + lo;
         }
         tloc[tile_iptr[t] + ioff + j] = (uint16_t)((row << 4) | a);
         for (int b = 0; b < nnpe; ++b) {
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
             if (p == self) continue;
             const int blo = a < b ? a : b, bhi = a < b ? b : a;
             const int tri = blo * nnpe - blo * (blo - 1) / 2 + (bhi - blo);
-            const unsigned short s = (unsigned short)((row << 5) | (tri << 1) | (a > b ? 1 : 0));
+            const unsigned short s = (unsigned short)((row << (tribits + 1)) | (tri << 1) | (a > b ? 1 : 0));
             if (src[p][0] == kZeroSrc) src[p][0] = s;
             else if (src[p][1] == kZeroSrc) src[p][1] = s;
             else atomicMax(stats + 4, 1);  // a node pair shared by more than two elements
@@ -334,11 +348,87 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
     for (int a = 0; a < E::NNPE; ++a) out[3 * T::tri(a, a) + 2] = out[3 * T::tri(a, a) + 1];
 }
 
+// Quad9: one of five threads of an element evaluates the block rows A1 (and A2) of the upper triangle --
+// {0}, {1,8}, {2,7}, {3,6}, {4,5}: nine blocks = 27 accumulators each -- reading the element's node
+// coordinates from shared memory.  Same pair arithmetic (and therefore the same bits) as element_row_pair.
+template <int A1, int A2>
+__device__ __forceinline__ void q9_block_rows(const double2* __restrict__ xy, bool weighted, double* __restrict__ dst) {
+    constexpr int N = 9;
+    using T = TileLayout<N>;
+    constexpr int N1 = N - A1, N2 = A2 >= 0 ? N - A2 : 1;
+    double acc1[3 * N1], acc2[3 * N2];
+#pragma unroll
+    for (int i = 0; i < 3 * N1; ++i) acc1[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3 * N2; ++i) acc2[i] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < 9; ++g) {
+        double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
+#pragma unroll
+        for (int b = 0; b < N; ++b) {
+            const double2 p = xy[b];
+            const double hr = c_q9.dH[g][0][b], hs = c_q9.dH[g][1][b];
+            j00 = fma(hr, p.x, j00);
+            j01 = fma(hr, p.y, j01);
+            j10 = fma(hs, p.x, j10);
+            j11 = fma(hs, p.y, j11);
+        }
+        const double det = fma(j00, j11, -__dmul_rn(j01, j10));
+        double s = 1.0 / det;
+        if (weighted) s = __dmul_rn(s, c_q9.w[g]);
+        double sx1 = 0.0, sy1 = 0.0, sx2 = 0.0, sy2 = 0.0;
+#pragma unroll
+        for (int b = A1; b < N; ++b) {
+            const double hr = c_q9.dH[g][0][b], hs = c_q9.dH[g][1][b];
+            const double ax = fma(j11, hr, -__dmul_rn(j01, hs));
+            const double ay = fma(j00, hs, -__dmul_rn(j10, hr));
+            if (b == A1) {
+                sx1 = __dmul_rn(ax, s);
+                sy1 = __dmul_rn(ay, s);
+            }
+            {
+                const int o = 3 * (b - A1);
+                acc1[o] = fma(sx1, ax, fma(sy1, ay, acc1[o]));
+                acc1[o + 1] = fma(sy1, ax, acc1[o + 1]);
+                if (b > A1) acc1[o + 2] = fma(sx1, ay, acc1[o + 2]);
+            }
+            if (A2 >= 0 && b >= A2) {
+                if (b == A2) {
+                    sx2 = __dmul_rn(ax, s);
+                    sy2 = __dmul_rn(ay, s);
+                }
+                const int o = 3 * (b - A2);
+                acc2[o] = fma(sx2, ax, fma(sy2, ay, acc2[o]));
+                acc2[o + 1] = fma(sy2, ax, acc2[o + 1]);
+                if (b > A2) acc2[o + 2] = fma(sx2, ay, acc2[o + 2]);
+            }
+        }
+    }
+    acc1[2] = acc1[1];   // diagonal block: Q == P
+#pragma unroll
+    for (int b = A1; b < N; ++b) {
+        double* d = dst + 3 * T::tri(A1, b);
+        d[0] = acc1[3 * (b - A1)];
+        d[1] = acc1[3 * (b - A1) + 1];
+        d[2] = acc1[3 * (b - A1) + 2];
+    }
+    if (A2 >= 0) {
+        acc2[2] = acc2[1];
+#pragma unroll
+        for (int b = A2 >= 0 ? A2 : N; b < N; ++b) {
+            double* d = dst + 3 * T::tri(A2 >= 0 ? A2 : 0, b);
+            d[0] = acc2[3 * (b - (A2 >= 0 ? A2 : 0))];
+            d[1] = acc2[3 * (b - (A2 >= 0 ? A2 : 0)) + 1];
+            d[2] = acc2[3 * (b - (A2 >= 0 ? A2 : 0)) + 2];
+        }
+    }
+}
+
 // Persistent kernel: CTA c processes tiles c, c + G, c + 2G, ...  While tile t is computed, the plan
 // records of tile t + G stream into the other shared-memory buffer (cp.async) and its connectivity row
 // and coordinates are prefetched into registers, so no global-memory latency is exposed per tile.
 template <int ET>
-__global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCtasPerSm) k_assemble_tiled(
+__global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayout<Elem<ET>::NNPE>::kCtas) k_assemble_tiled(
     int64_t ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords,
     const int4* __restrict__ tdesc, const int2* __restrict__ tnode, const uint16_t* __restrict__ tloc,
     const uint32_t* __restrict__ twork, const uint32_t* __restrict__ tchunk, double* __restrict__ vals, int weighted,
@@ -347,7 +437,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
     constexpr int N = E::NNPE;
     using T = TileLayout<N>;
     constexpr int SS = T::kSlabStride;
-    constexpr int kTileThreads = T::kThreads, kZeroRow = T::kZeroRow;
+    constexpr int kTileThreads = T::kThreads, kZeroRow = T::kZeroRow, kTileElems = T::kTE;
     extern __shared__ __align__(16) double slab[];
     unsigned char* rec_base = reinterpret_cast<unsigned char*>(slab + T::kSlabDoubles);
 
@@ -358,9 +448,9 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
 
     // staged record views of buffer b
     auto s_work = [&](int b) { return reinterpret_cast<uint32_t*>(rec_base + b * T::kRecBytes); };
-    auto s_node = [&](int b) { return reinterpret_cast<int2*>(s_work(b) + kTileMaxWork); };
-    auto s_chunk = [&](int b) { return reinterpret_cast<uint32_t*>(s_node(b) + kTileMaxNodes); };
-    auto s_loc = [&](int b) { return reinterpret_cast<uint16_t*>(s_chunk(b) + kTileMaxWork / 32); };
+    auto s_node = [&](int b) { return reinterpret_cast<int2*>(s_work(b) + T::kMaxWork); };
+    auto s_chunk = [&](int b) { return reinterpret_cast<uint32_t*>(s_node(b) + T::kMaxNodes); };
+    auto s_loc = [&](int b) { return reinterpret_cast<uint16_t*>(s_chunk(b) + T::kMaxWork / 32); };
     // tdesc[2t] = {n0, nn, i0, ni}, tdesc[2t+1] = {w0, nw, -, -}
     auto stage = [&](int b, const int4 d0, const int4 d1) {
         const int n0 = d0.x, nn = d0.y, i0 = d0.z, ni = d0.w, w0 = d1.x, nw = d1.y;
@@ -396,17 +486,23 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
     };
 
     // ---- prologue: first tile of this CTA --------------------------------------------------------------
+    constexpr bool kSingle = T::kParts == 1;          // one thread per element (Quad4 / Tri3)
+    constexpr int NR = kSingle ? N : 1;               // register prefetch buffers exist only in that case
     int64_t t = blockIdx.x;
     if (t >= ntiles) return;
     int4 d0 = __ldg(tdesc + 2 * t), d1 = __ldg(tdesc + 2 * t + 1);
     int tg[N], tgn[N];
     double x[N], y[N];
-    load_row(t, tg);
-    tgn[0] = -1;
-    if (t + gridDim.x < ntiles) load_row(t + gridDim.x, tgn);
+    (void)NR;
+    if constexpr (kSingle) {
+        load_row(t, tg);
+        tgn[0] = -1;
+        if (t + gridDim.x < ntiles) load_row(t + gridDim.x, tgn);
+    }
     stage(0, d0, d1);
-    load_xy(tg, x, y);
+    if constexpr (kSingle) load_xy(tg, x, y);
     int buf = 0;
+    double2* s_xy = reinterpret_cast<double2*>(rec_base + 2 * T::kRecBytes);   // Quad9 only
 
     for (; t < ntiles; t += gridDim.x) {
         const int64_t tn = t + gridDim.x, tn2 = tn + gridDim.x;
@@ -419,19 +515,43 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
         if (more) {
             e0 = __ldg(tdesc + 2 * tn);
             e1 = __ldg(tdesc + 2 * tn + 1);
+            if constexpr (kSingle) {
 #ifdef FE_L2_PREFETCH
-            prefetch_xy(tgn);
+                prefetch_xy(tgn);
 #endif
-            if (tn2 < ntiles) load_row(tn2, tgn2);
+                if (tn2 < ntiles) load_row(tn2, tgn2);
+            }
         }
         // ---- phase 1: own and halo elements -> slab --------------------------------------------------
-        const bool active = tg[0] >= 0;
-        if (active && dbg != 2) {
-            double ke[3 * T::kBlocks];
-            element_tri<ET>(x, y, weighted != 0, ke);
-            double* dst = slab + tid * SS;
+        if constexpr (kSingle) {
+            const bool active = tg[0] >= 0;
+            if (active && dbg != 2) {
+                double ke[3 * T::kBlocks];
+                element_tri<ET>(x, y, weighted != 0, ke);
+                double* dst = slab + tid * SS;
 #pragma unroll
-            for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+                for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+            }
+        } else if (dbg != 2) {
+            // Quad9: stage the rows' node coordinates, then five threads per row evaluate block rows
+            const int32_t* rows = tconn + t * T::kRows * N;
+            for (int i = tid; i < T::kRows * N; i += kTileThreads) {
+                const int node = __ldg(rows + i);
+                if (node >= 0) s_xy[i] = __ldg(coords + node);
+            }
+            __syncthreads();
+            const int part = tid / T::kRowThreads, row = tid - part * T::kRowThreads;
+            if (row < T::kRows && __ldg(rows + row * N) >= 0) {
+                const double2* xy = s_xy + row * N;
+                double* dst = slab + row * SS;
+                switch (part) {          // warp-uniform: kRowThreads is a multiple of 32
+                    case 0: q9_block_rows<0, -1>(xy, weighted != 0, dst); break;
+                    case 1: q9_block_rows<1, 8>(xy, weighted != 0, dst); break;
+                    case 2: q9_block_rows<2, 7>(xy, weighted != 0, dst); break;
+                    case 3: q9_block_rows<3, 6>(xy, weighted != 0, dst); break;
+                    default: q9_block_rows<4, 5>(xy, weighted != 0, dst); break;
+                }
+            }
         }
         if constexpr (T::kRows > T::kThreads) {
             // overflow halo rows (irregular tiles only): second pass of the halo warp, not prefetched
@@ -460,14 +580,16 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
         else asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's records have landed
         __syncthreads();
-        // coordinates of the next tile (L2-resident by now): in flight during phase 2
-        if (more) {
+        // coordinates of the next tile: in flight during phase 2
+        if constexpr (kSingle) {
+            if (more) {
 #pragma unroll
-            for (int a = 0; a < N; ++a) {
-                tg[a] = tgn[a];
-                tgn[a] = tgn2[a];
+                for (int a = 0; a < N; ++a) {
+                    tg[a] = tgn[a];
+                    tgn[a] = tgn2[a];
+                }
+                load_xy(tg, x, y);
             }
-            load_xy(tg, x, y);
         }
         if (dbg != 1) {
             const int nn = d0.y, nw = d1.y;
@@ -486,8 +608,8 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, kTileCta
                 const int2 nd = node[ln];
                 const int deg = nd.y & 127;
                 const unsigned s0 = rec & 0x1FFFu, s1 = (rec >> 13) & 0x1FFFu;
-                const double* b0 = slab + (s0 >> 5) * SS + 3 * ((s0 >> 1) & 15);
-                const double* b1 = slab + (s1 >> 5) * SS + 3 * ((s1 >> 1) & 15);   // zero block when absent
+                const double* b0 = slab + (s0 >> (T::kTriBits + 1)) * SS + 3 * ((s0 >> 1) & T::kTriMask);
+                const double* b1 = slab + (s1 >> (T::kTriBits + 1)) * SS + 3 * ((s1 >> 1) & T::kTriMask);   // zeros if absent
                 const int f0 = s0 & 1, f1 = s1 & 1;            // transposed block: P and Q trade places
                 const double L = b0[0] + b1[0];
                 const double P = b0[1 + f0] + b1[1 + f1];
@@ -531,7 +653,7 @@ static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coor
     int dev = 0, sms = 0;
     FE_CUDA_TRY(cudaGetDevice(&dev));
     FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int64_t grid = (int64_t)sms * kTileCtasPerSm;
+    int64_t grid = (int64_t)sms * T::kCtas;
     if (grid > ntiles) grid = ntiles;
     FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
     k_assemble_tiled<ET><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
@@ -555,12 +677,13 @@ int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan
 
 void fe_tile_params(int elem_type, int32_t out[6]) {
     using namespace fe;
-    out[0] = kTileElems;
-    out[1] = (elem_type == FE_QUAD4 || elem_type == FE_TRI3) ? halo_cap(elem_type) : 0;   // 0: no tiled kernel
-    out[2] = kTileMaxNodes;
-    out[3] = kTileMaxItems;
-    out[4] = kTileMaxWork;
-    out[5] = kTileElems + halo_cap(elem_type);   // rows per tile of the tile-ordered connectivity
+    const int nn = nnpe_of(elem_type);
+    out[0] = tile_elems(nn);
+    out[1] = nn ? halo_cap(nn) : 0;   // 0: no tiled kernel
+    out[2] = max_nodes(nn);
+    out[3] = max_items(nn);
+    out[4] = max_work(nn);
+    out[5] = tile_elems(nn) + halo_cap(nn);   // rows per tile of the tile-ordered connectivity
 }
 
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin, double ymin,
@@ -648,7 +771,8 @@ int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, co
     const int64_t s = ntiles + 1;
     k_tile_records<<<grid_for(nslots, 128), 128, 0, as_stream(stream)>>>(
         nslots, nnpe, tile_nodes, owner, tile_ptr, tile_ptr + s, tile_ptr + 2 * s, tile_ptr + 3 * s, noff, thalo, eptr,
-        einc, epos, einv, nptr, nadj, static_cast<int2*>(tnode), tloc, twork, tchunk, stats, halo_cap(nnpe));
+        einc, epos, einv, nptr, nadj, static_cast<int2*>(tnode), tloc, twork, tchunk, stats, tile_elems(nnpe),
+        halo_cap(nnpe), tri_bits(nnpe));
     FE_CHECK_LAUNCH("k_tile_records");
     return FE_OK;
 }
@@ -665,9 +789,10 @@ int fe_tile_conn(int elem_type, int64_t ntiles, const int32_t* conn, const int32
     if (ntiles == 0) return FE_OK;
     FE_REQUIRE(conn && eperm && tile_estart && thalo && tile_ptr && tconn, "null pointer");
     const int he = halo_cap(nnpe);
-    const int64_t nrows = ntiles * (kTileElems + he);
+    const int te = tile_elems(nnpe);
+    const int64_t nrows = ntiles * (te + he);
     k_tile_conn<<<grid_for(nrows, 256), 256, 0, as_stream(stream)>>>(nrows, nnpe, conn, eperm, tile_estart, thalo,
-                                                                    tile_ptr + 2 * (ntiles + 1), tconn, he);
+                                                                    tile_ptr + 2 * (ntiles + 1), tconn, te, he);
     FE_CHECK_LAUNCH("k_tile_conn");
     return FE_OK;
 }
@@ -693,6 +818,8 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
             return launch_tiled<FE_QUAD4>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
         case FE_TRI3:
             return launch_tiled<FE_TRI3>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
+        case FE_QUAD9:
+            return launch_tiled<FE_QUAD9>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
         default:
             set_error("fe_assemble_tiled: element type %d has no tiled kernel (use fe_assemble)", elem_type);
             return FE_ERR_UNSUPPORTED;

@@ -359,7 +359,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
             eperm = order.to(torch.int32)
             if mode == "pack":
                 # consecutive 16-cell sub-blocks are packed into tiles of at most TE elements
-                sub = skeys >> 4
+                sub = skeys >> max(0, te.bit_length() - 1 - 3)                     # sub-blocks of TE/8 cells
                 sflag = torch.ones(nelem, dtype=torch.bool, device=dev)
                 sflag[1:] = sub[1:] != sub[:-1]
                 sstart = torch.nonzero(sflag).flatten()
@@ -370,7 +370,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                 block = sstart[torch.cumsum(sflag, dim=0) - 1] // (te - m + 1)
                 del sub, sflag, sstart, ssize
             else:
-                block = skeys >> 7                                            # aligned Z-blocks of 128 cells
+                block = skeys >> (te.bit_length() - 1)                        # aligned Z-blocks of TE cells
             del keys, skeys, order
         else:
             eperm = idx.to(torch.int32)

@@ -365,3 +365,31 @@ def test_tiled_and_row_kernels_agree_bitwise(torch_cuda, kind, n, shuffle):
     Ko = orc.assemble_csr(conn - 1, coords, kind)
     assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices)
     assert rel_max(K.data, Ko.data) < VAL_TOL
+
+
+@pytest.mark.parametrize("n,perturb,shuffle", [(16, False, False), (21, True, False), (13, True, True)])
+def test_quad9_tiled_kernel_matches_row_kernel_bitwise(torch_cuda, n, perturb, shuffle):
+    """Quad9 in the tiled kernel (five threads per element) == row-tile kernel, bit for bit, == oracle at 1e-12."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    conn, coords, bc = mesh.structured_quad9(n, n + 2)
+    if perturb:
+        coords = mesh.perturb_interior(coords, 2 * n, 2 * (n + 2), 0.15, seed=9)
+    if shuffle:
+        conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=10)
+    conn0, xy = dev_mesh(torch, conn, coords)
+    pat = ops.symbolic(conn0, coords.shape[0], 9, 2)
+    v_rows = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v_rows)
+    plan = ops.tile_plan(conn0, xy, pat)
+    assert plan is not None or shuffle or perturb
+    if plan is not None:
+        v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        ops.assemble_values(conn0, xy, pat, plan, v)
+        assert torch.equal(v, v_rows)
+    K = sp.csr_matrix((v_rows.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
+                      shape=(pat.nrows, pat.nrows))
+    Ko = orc.assemble_csr(conn - 1, coords, 9)
+    assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices)
+    assert rel_max(K.data, Ko.data) < VAL_TOL
+    assert abs(K - K.T).max() == 0.0
