@@ -303,12 +303,13 @@ static int pick_lpr(int64_t nrows, int64_t nnz) {
     }
     if (forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
-    // ~4-5 entries per lane keeps enough independent loads in flight per thread (measured on B200:
-    // 18 nnz/row -> 4 lanes: 6.26 TB/s, 8 lanes: 4.95 TB/s, 2 lanes: 5.16 TB/s)
-    if (avg < 10.0) return 2;
-    if (avg < 28.0) return 4;
-    if (avg < 56.0) return 8;
-    if (avg < 112.0) return 16;
+    // few lanes per row keep several independent loads in flight per thread (measured on B200:
+    // 18 nnz/row: 4 lanes 6.26 TB/s, 8 lanes 4.95, 2 lanes 5.16; 32 nnz/row: 4 lanes 4.64 TB/s, 8 lanes 4.14,
+    // 16 lanes 2.70; 14 nnz/row: 4 lanes 5.51 TB/s, 2 lanes 5.14)
+    if (avg < 8.0) return 2;
+    if (avg < 64.0) return 4;
+    if (avg < 128.0) return 8;
+    if (avg < 256.0) return 16;
     return 32;
 }
 

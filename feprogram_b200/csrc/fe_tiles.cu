@@ -33,6 +33,9 @@ namespace fe {
 #define FE_HALO_ELEMS 32
 #define FE_TILE_CTAS 3
 #endif
+#ifndef FE_Q9_CTAS
+#define FE_Q9_CTAS 2
+#endif
 constexpr int kHaloElemsMax = 64;           // largest halo capacity of any element type (plan scratch)
 // ---- per-element-type tile configuration ------------------------------------------------------------
 // TE own elements per tile.  Quad4 / Tri3: 128 (one thread per element).  Quad9: 32 elements, FIVE threads
@@ -67,7 +70,7 @@ template <int N> struct TileLayout {
     static constexpr int kRows = kTE + kHalo;                  // rows per tile of tconn / the slab
     static constexpr int kZeroRow = kTE + kHalo;               // slab row of zeros (target of absent sources)
     static constexpr int kMaxNodes = max_nodes(N), kMaxItems = max_items(N), kMaxWork = max_work(N);
-    static constexpr int kCtas = kParts > 1 ? 2 : kTileCtasPerSm;   // persistent CTAs per SM
+    static constexpr int kCtas = kParts > 1 ? FE_Q9_CTAS : kTileCtasPerSm;   // persistent CTAs per SM
     static constexpr int kTriBits = tri_bits(N);
     static constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
     static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
