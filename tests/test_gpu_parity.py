@@ -393,3 +393,48 @@ def test_quad9_tiled_kernel_matches_row_kernel_bitwise(torch_cuda, n, perturb, s
     assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices)
     assert rel_max(K.data, Ko.data) < VAL_TOL
     assert abs(K - K.T).max() == 0.0
+
+
+def test_gmsh_style_inputs_and_int64_row_pointers(torch_cuda, golden):
+    """(1) The reference's real input types: connectivity as a list of uint64 arrays, coordinates (nnode,3).
+    (2) The 64-bit row-pointer code path (used when nnz >= 2^31) gives the same SpMV / PCG results."""
+    torch = torch_cuda
+    from feprogram_b200.elements import FemProblem
+    z = golden("q4_16x16_pert")
+    conn_list = [np.asarray(r, dtype=np.uint64) for r in z["conn"]]
+    xyz = np.concatenate([z["coords"], np.zeros((z["coords"].shape[0], 1))], axis=1)
+    fem = FemProblem(conn_list, xyz)
+    fem.setMatrix()
+    fem.setBoundaryConditions(bc_sets_of(z), verbose=False)
+    fem.assemble()
+    K0 = fem.csr_prebc()
+    assert np.array_equal(K0.indptr, z["k0_indptr"]) and np.array_equal(K0.indices, z["k0_indices"])
+    assert rel_max(K0.data, z["k0_data"]) < VAL_TOL
+    U = fem.solveProblem()
+    assert np.linalg.norm(U - z["U"]) / np.linalg.norm(z["U"]) < SOL_TOL
+    st, pat = fem._dev, fem._dev["pattern"]
+    rp64, ci = torch.ops.feprogram.csr_expand(pat.nptr, pat.nadj, 2, True)
+    x = torch.randn(pat.nrows, dtype=torch.float64, device="cuda")
+    y32, y64 = torch.empty_like(x), torch.empty_like(x)
+    torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, st["vals"], x, y32, None)
+    torch.ops.feprogram.spmv(rp64, ci, st["vals"], x, y64, None)
+    assert torch.equal(y32, y64)
+    s32, s64 = torch.empty_like(x), torch.empty_like(x)
+    i32 = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, st["vals"], st["rhs"], st["dirmask"], s32, 1e-10, 0.0, 5000, 20)
+    i64 = torch.ops.feprogram.pcg(rp64, ci, st["vals"], st["rhs"], st["dirmask"], s64, 1e-10, 0.0, 5000, 20)
+    assert torch.equal(s32, s64) and i32[0] == i64[0] and i32[3] == 1.0
+    # CSR-walk PCG and node-block PCG reach the same solution (different summation grouping, same tolerance)
+    sn = torch.empty_like(x)
+    torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, st["vals"], st["rhs"], st["dirmask"], sn, 1e-10, 0.0, 5000, 20,
+                            pat.nptr, pat.nadj)
+    assert np.linalg.norm(sn.cpu().numpy() - z["U"]) / np.linalg.norm(z["U"]) < SOL_TOL
+    assert np.linalg.norm(s32.cpu().numpy() - z["U"]) / np.linalg.norm(z["U"]) < SOL_TOL
+
+
+def test_maxit_and_nonconvergence_are_reported(torch_cuda, golden):
+    z = golden("q9_4x4")
+    fem = run_facade(z)
+    fem.maxit = 3
+    U = fem.solveProblem()
+    assert fem.solver_info["iterations"] == 3 and not fem.solver_info["converged"]
+    assert np.all(np.isfinite(U))
