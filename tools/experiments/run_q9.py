@@ -1,0 +1,9 @@
+import sys, numpy as np, torch
+sys.path.insert(0, '/root/repo')
+from feprogram_b200 import mesh, ops
+conn_h, coords_h, bc = mesh.structured_quad9(1024, dtype=np.int32)
+conn = torch.from_numpy(conn_h - 1).cuda(); coords = torch.from_numpy(coords_h).cuda()
+pat = ops.symbolic(conn, coords_h.shape[0], 9, 2); plan = ops.tile_plan(conn, coords, pat)
+vals = torch.empty(pat.nnz, dtype=torch.float64, device='cuda')
+for _ in range(4): ops.assemble_values(conn, coords, pat, plan, vals)
+torch.cuda.synchronize()
