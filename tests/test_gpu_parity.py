@@ -438,3 +438,41 @@ def test_maxit_and_nonconvergence_are_reported(torch_cuda, golden):
     U = fem.solveProblem()
     assert fem.solver_info["iterations"] == 3 and not fem.solver_info["converged"]
     assert np.all(np.isfinite(U))
+
+
+@pytest.mark.parametrize("kind,n", [(4, 150), (3, 90), (9, 40)])
+def test_kernels_stay_inside_their_output_buffers(torch_cuda, kind, n):
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds stores are caught with guard
+    zones: the value array sits inside a larger buffer filled with a sentinel; both assembly kernels, SpMV
+    and PCG must leave the guards untouched and write every entry in between."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    gen = {4: mesh.structured_quad4, 3: mesh.structured_tri3, 9: mesh.structured_quad9}[kind]
+    conn, coords, bc = gen(n, n + 1)
+    mx = 2 * n if kind == 9 else n
+    coords = mesh.perturb_interior(coords, mx, mx + (2 if kind == 9 else 1), 0.15, seed=12)
+    conn0, xy = dev_mesh(torch, conn, coords)
+    pat = ops.symbolic(conn0, coords.shape[0], kind, 2)
+    plan = ops.tile_plan(conn0, xy, pat)
+    G, sentinel = 4096, -7.25e300
+
+    def guarded(n_):
+        big = torch.full((n_ + 2 * G,), sentinel, dtype=torch.float64, device="cuda")
+        return big, big[G:G + n_]
+
+    for p in ([plan, None] if plan is not None else [None]):
+        big, vals = guarded(pat.nnz)
+        ops.assemble_values(conn0, xy, pat, p, vals)
+        torch.cuda.synchronize()
+        assert bool((big[:G] == sentinel).all()) and bool((big[-G:] == sentinel).all())
+        assert not bool((vals == sentinel).any())
+    x = torch.randn(pat.nrows, dtype=torch.float64, device="cuda")
+    for op in ("csr", "nodal"):
+        big, y = guarded(pat.nrows)
+        if op == "csr":
+            torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, vals, x, y, None)
+        else:
+            torch.ops.feprogram.spmv_nodal(pat.nptr, pat.nadj, vals, x, y, None)
+        torch.cuda.synchronize()
+        assert bool((big[:G] == sentinel).all()) and bool((big[-G:] == sentinel).all())
+        assert not bool((y == sentinel).any())
