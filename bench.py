@@ -368,7 +368,7 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": asm_bytes_total / world, "ms_per_launch": ms_kernel},
             "cg": {"spmv_ms": ms_spmv, "spmv_gbs": spmv_gbs, "spmv_frac": spmv_gbs / hbm_peak,
-                   "pcg_iters_timed": pcg_done, "pcg_iters_per_s": pcg_done / (ms_pcg * 1e-3) if ms_pcg > 0 else None,
+                   "pcg_iters_timed": pcg_done, "halo": (part.halo if part is not None else None), "pcg_iters_per_s": pcg_done / (ms_pcg * 1e-3) if ms_pcg > 0 else None,
                    "roofline": {"kernel": "k_spmv", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": spmv_gbs / hbm_peak, "traffic": traffic.get("k_spmv"),
                                 "algorithmic_bytes_per_launch": spmv_bytes_total / world}},

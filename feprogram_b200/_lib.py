@@ -61,6 +61,8 @@ PROTOTYPES = {
     "fe_dist_pcg_workspace_bytes": (_sz, [_i64]),
     "fe_dist_pcg": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _i32,
                          _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fe_dist_pcg_p2p": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _i32,
+                             _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64, _p]),
 }
 
 _lib = None

@@ -23,7 +23,7 @@ constexpr int kScalarDoubles = 16;
 // Flags and scalars are double-buffered between kernels so that no kernel reads a location one of its
 // own blocks writes:  DONE_C / RZ_CUR are written by kernel C and read by A and B;  DONE_B / RZ_PREV
 // are written by kernel B and read by C.
-enum { S_RZ_CUR = 0, S_RZ_PREV = 1, S_RR = 2, S_RR0 = 3, S_TOL2 = 4, S_ITERS = 5, S_DONE_C = 6, S_PAP = 7, S_DONE_B = 8 };
+enum { S_RZ_CUR = 0, S_RZ_PREV = 1, S_RR = 2, S_RR0 = 3, S_TOL2 = 4, S_ITERS = 5, S_DONE_C = 6, S_PAP = 7, S_DONE_B = 8, S_ERR = 9 };
 
 // ---- deterministic block reduction (fixed shuffle tree, then warp 0 over the warp sums) ----------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -57,6 +57,56 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ part, 
     if (threadIdx.x == 0) bc = v;
     __syncthreads();
     return bc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer-memory all-reduce of the PCG scalars (multi-GPU, fe_dist_pcg_p2p).  Every rank owns a slot table
+// double[2][kMaxRanks][2] and a version array int64[kMaxRanks] in peer-mapped memory.  Reduction number
+// `seq` (0, 1, 2 ... over the life of the buffers): a rank stores its local sum into slot [seq & 1][rank] of
+// EVERY rank (itself included) and then release-stores seq + 1 into that rank's version[rank]; a consumer
+// waits until all `world` versions reach seq + 1 and adds the slots in rank order, so every rank (and
+// every CTA) gets the same bits.  Slot reuse at seq + 2 is safe: nobody can publish seq + 2 before it has
+// consumed seq + 1, which needs every rank's seq + 1, which each rank publishes after consuming seq.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+struct PeerRed {
+    double* const* slots;        // device array [world] of peer pointers
+    long long* const* versions;  // device array [world] of peer pointers
+    int rank, world;             // world == 0: not used
+};
+
+__device__ __forceinline__ long long ld_acquire_sys_s64(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_s64(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// all threads of the CTA call this; v[0..nv) <- the global sums of reduction `seq`; false on time-out
+__device__ __forceinline__ bool peer_reduced(const PeerRed& pr, long long seq, int nv, double* v) {
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < pr.world) {
+        const long long* ver = pr.versions[pr.rank] + threadIdx.x;
+        long long spins = 0;
+        while (ld_acquire_sys_s64(ver) < seq + 1) {
+            if (++spins > (1ll << 26)) {
+                timed_out = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const double* s = pr.slots[pr.rank] + (seq & 1) * (2 * kMaxRanks);
+    for (int k = 0; k < nv; ++k) {
+        double a = 0.0;
+        for (int q = 0; q < pr.world; ++q) a += __ldcg(s + 2 * q + k);   // L2: the slots are written by peers
+        v[k] = a;
+    }
+    return timed_out == 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -209,10 +259,13 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init2(int64_t n, const doub
 // `g` (optional): globally reduced scalars of a multi-GPU solve; when given they replace the local sums.
 __global__ void __launch_bounds__(kVecThreads) k_pcg_init3(int nb, const double* __restrict__ partB, double rtol,
                                                            double atol, double* __restrict__ scal,
-                                                           const double* __restrict__ g) {
+                                                           const double* __restrict__ g, PeerRed pr, long long seq) {
     __shared__ double sm[kVecThreads / 32];
-    const double rz = g ? g[0] : sum_partials(partB, nb, 2, sm);
-    const double rr = g ? g[1] : sum_partials(partB + 1, nb, 2, sm);
+    double gv[2];
+    bool ok = true;
+    if (pr.world) ok = peer_reduced(pr, seq, 2, gv);
+    const double rz = pr.world ? gv[0] : g ? g[0] : sum_partials(partB, nb, 2, sm);
+    const double rr = pr.world ? gv[1] : g ? g[1] : sum_partials(partB + 1, nb, 2, sm);
     if (threadIdx.x == 0) {
         scal[S_RZ_CUR] = rz;
         scal[S_RZ_PREV] = rz;
@@ -224,6 +277,7 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init3(int nb, const double*
         scal[S_DONE_C] = (rr <= t) ? 1.0 : 0.0;
         scal[S_DONE_B] = 0.0;
         scal[S_PAP] = 0.0;
+        scal[S_ERR] = ok ? 0.0 : 1.0;
     }
 }
 
@@ -233,12 +287,15 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_update(int64_t n, int nbA, 
                                                             const double* __restrict__ Ap,
                                                             const double* __restrict__ minv, double* __restrict__ x,
                                                             double* __restrict__ r, double* __restrict__ partB,
-                                                            double* __restrict__ scal, const double* __restrict__ g) {
+                                                            double* __restrict__ scal, const double* __restrict__ g,
+                                                            PeerRed pr, long long seq) {
     __shared__ double sm[kVecThreads / 32];
     const bool done = scal[S_DONE_C] != 0.0;
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE_B] = done ? 1.0 : 0.0;
     if (done) return;
-    const double pAp = g ? g[0] : sum_partials(partA, nbA, 1, sm);
+    double gv[1];
+    if (pr.world && !peer_reduced(pr, seq, 1, gv) && threadIdx.x == 0) scal[S_ERR] = 1.0;
+    const double pAp = pr.world ? gv[0] : g ? g[0] : sum_partials(partA, nbA, 1, sm);
     const double rz_cur = scal[S_RZ_CUR];
     const double alpha = rz_cur / pAp;
     double rz = 0.0, rr = 0.0;
@@ -266,15 +323,20 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_update(int64_t n, int nbA, 
 __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int64_t n, int nbB, const double* __restrict__ partB,
                                                                const double* __restrict__ r,
                                                                const double* __restrict__ minv,
-                                                               double* __restrict__ p, double* __restrict__ scal,
-                                                               const double* __restrict__ g) {
+                                                               const double* p_in, double* p_out,
+                                                               double* __restrict__ scal,
+                                                               const double* __restrict__ g, PeerRed pr,
+                                                               long long seq) {
+    // p_out may alias p_in (single GPU) or be the other half of a double-buffered direction vector (P2P halo)
     __shared__ double sm[kVecThreads / 32];
     if (scal[S_DONE_B] != 0.0) return;
-    const double rz_new = g ? g[0] : sum_partials(partB, nbB, 2, sm);
-    const double rr = g ? g[1] : sum_partials(partB + 1, nbB, 2, sm);
+    double gv[2];
+    if (pr.world && !peer_reduced(pr, seq, 2, gv) && threadIdx.x == 0) scal[S_ERR] = 1.0;
+    const double rz_new = pr.world ? gv[0] : g ? g[0] : sum_partials(partB, nbB, 2, sm);
+    const double rr = pr.world ? gv[1] : g ? g[1] : sum_partials(partB + 1, nbB, 2, sm);
     const double beta = rz_new / scal[S_RZ_PREV];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = fma(beta, p[i], minv[i] * r[i]);
+        p_out[i] = fma(beta, p_in[i], minv[i] * r[i]);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         scal[S_RZ_CUR] = rz_new;
         scal[S_RR] = rr;
@@ -442,7 +504,7 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
     if ((rc = mat_spmv<IdxT, false>(A, x, w.Ap, mask, nullptr, nullptr, nullptr, st)) != FE_OK) return rc;
     k_pcg_init2<<<gv, kVecThreads, 0, st>>>(nrows, rhs, mask, w.Ap, w.minv, w.r, w.p, w.partB);
     FE_CHECK_LAUNCH("k_pcg_init2");
-    k_pcg_init3<<<1, kVecThreads, 0, st>>>(gv, w.partB, rtol, atol, w.scal, nullptr);
+    k_pcg_init3<<<1, kVecThreads, 0, st>>>(gv, w.partB, rtol, atol, w.scal, nullptr, PeerRed{}, 0);
     FE_CHECK_LAUNCH("k_pcg_init3");
 
     double hs[kScalarDoubles];
@@ -457,8 +519,9 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
             int ga = 0;
             if ((rc = mat_spmv<IdxT, true>(A, w.p, w.Ap, mask, w.partA, w.scal, &ga, st)) != FE_OK) return rc;
             k_pcg_update<<<gv, kVecThreads, 0, st>>>(nrows, ga, w.partA, w.p, w.Ap, w.minv, x, w.r, w.partB, w.scal,
-                                                     nullptr);
-            k_pcg_direction<<<gv, kVecThreads, 0, st>>>(nrows, gv, w.partB, w.r, w.minv, w.p, w.scal, nullptr);
+                                                     nullptr, PeerRed{}, 0);
+            k_pcg_direction<<<gv, kVecThreads, 0, st>>>(nrows, gv, w.partB, w.r, w.minv, w.p, w.p, w.scal, nullptr,
+                                                        PeerRed{}, 0);
         }
         FE_CHECK_LAUNCH("pcg iteration");
         launched += batch;

@@ -16,6 +16,7 @@ that touches values runs in the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -268,11 +269,64 @@ class DistFemProblem:
                                           C.c_void_p(self.vals.data_ptr()), C.c_void_p(x.data_ptr()),
                                           C.c_void_p(y.data_ptr()), None, st))
 
-    def solve(self, rtol: float = 1e-10, maxit: int = 100000, check_every: int = 50):
+    def enable_p2p(self, group=None):
+        """Collective.  Sets up the peer-memory halo for solve(): a double-buffered direction vector and a flag
+        array per rank in CUDA symmetric memory (peer-mapped over NVLink), plus, for every ghost node, its
+        owner and its index inside the owner."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        m = self.m
+        group = group or dist.group.WORLD
+        sizes = [None] * m.world
+        dist.all_gather_object(sizes, self.nrows_local, group=group)
+        self._pstride = (max(sizes) + 15) // 16 * 16
+        self._pbuf = symm_mem.empty(2 * self._pstride, dtype=torch.float64, device=self.dev)
+        self._flags = symm_mem.empty(max(m.world, 8), dtype=torch.int64, device=self.dev)
+        self._red = symm_mem.empty(64, dtype=torch.float64, device=self.dev)      # double[2][16][2] slot table
+        self._rver = symm_mem.empty(16, dtype=torch.int64, device=self.dev)
+        for t in (self._pbuf, self._flags, self._red, self._rver):
+            t.zero_()
+        hp = symm_mem.rendezvous(self._pbuf, group)
+        hf = symm_mem.rendezvous(self._flags, group)
+        hr = symm_mem.rendezvous(self._red, group)
+        hv = symm_mem.rendezvous(self._rver, group)
+        self._symm_handles = (hp, hf, hr, hv)
+        self._peer_red = torch.tensor(list(hr.buffer_ptrs), dtype=torch.int64, device=self.dev)
+        self._peer_rver = torch.tensor(list(hv.buffer_ptrs), dtype=torch.int64, device=self.dev)
+        self._seq = 0
+        self._peer_p = torch.tensor(list(hp.buffer_ptrs), dtype=torch.int64, device=self.dev)
+        self._peer_flags = torch.tensor(list(hf.buffer_ptrs), dtype=torch.int64, device=self.dev)
+        # what every owner sends to whom (owner-local node indices, in the requester's ghost order)
+        lists = [None] * m.world
+        dist.all_gather_object(lists, {int(q): np.asarray(s).tolist() for q, s in zip(m.nbr, m.send_nodes)}, group=group)
+        n_ghost = m.nnode - m.n_owned
+        grank = np.zeros(max(1, n_ghost), dtype=np.int32)
+        gridx = np.zeros(max(1, n_ghost), dtype=np.int32)
+        for q, (a, b) in zip(m.nbr, m.recv_range):
+            if b > a:
+                theirs = np.asarray(lists[q][m.rank], dtype=np.int32)
+                assert theirs.size == b - a
+                grank[a - m.n_owned: b - m.n_owned] = q
+                gridx[a - m.n_owned: b - m.n_owned] = theirs
+        self._ghost_rank = torch.from_numpy(grank).to(self.dev)
+        self._ghost_ridx = torch.from_numpy(gridx).to(self.dev)
+        self._nbr_dev = torch.from_numpy(np.ascontiguousarray(self._nbr, dtype=np.int32)).to(self.dev) \
+            if len(self._nbr) else torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._epoch = 0
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=group)
+        self.p2p = True
+
+    def solve(self, rtol: float = 1e-10, maxit: int = 100000, check_every: int = 50, p2p=None):
         import torch
         from . import _lib
         L = _lib.lib()
         pat = self.pat
+        if p2p is None:
+            p2p = getattr(self, "p2p", False)
+        if p2p:
+            return self._solve_p2p(rtol, maxit, check_every)
         x = torch.zeros(self.nrows_local, dtype=torch.float64, device=self.dev)
         work = torch.empty(L.fe_dist_pcg_workspace_bytes(self.nrows_local), dtype=torch.uint8, device=self.dev)
         info = np.zeros(4)
@@ -290,6 +344,33 @@ class DistFemProblem:
         return x
 
 
+    def _solve_p2p(self, rtol, maxit, check_every):
+        import torch
+        from . import _lib
+        L = _lib.lib()
+        pat = self.pat
+        x = torch.zeros(self.nrows_local, dtype=torch.float64, device=self.dev)
+        work = torch.empty(L.fe_dist_pcg_workspace_bytes(self.nrows_local), dtype=torch.uint8, device=self.dev)
+        info = np.zeros(4)
+        n, nbr, soff, sidx, sbuf, roff = self._halo_args()
+        dp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        with torch.cuda.device(self.dev):
+            st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            epoch, seq = self._epoch, self._seq
+            self._epoch += int(maxit) + 2
+            self._seq += 2 * int(maxit) + 2
+            _lib.check(L.fe_dist_pcg_p2p(self.nrows_owned, self.nrows_local, int(pat.row_ptr.dtype == torch.int64),
+                                         dp(pat.row_ptr), dp(pat.col_idx), dp(self.vals), dp(self.rhs), dp(self.dirmask),
+                                         dp(x), float(rtol), 0.0, int(maxit), int(check_every), dp(work),
+                                         info.ctypes.data_as(C.c_void_p), self.comm, n, nbr, soff, sidx, sbuf, roff,
+                                         dp(pat.nptr), dp(pat.nadj), self.m.rank, self.m.world, dp(self._peer_p),
+                                         dp(self._peer_flags), dp(self._ghost_rank), dp(self._ghost_ridx),
+                                         dp(self._nbr_dev), self._pstride, dp(self._pbuf), epoch,
+                                         dp(self._peer_red), dp(self._peer_rver), seq, st))
+        self.info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]), converged=bool(info[3]))
+        return x
+
+
 # ----------------------------------------------------------------------------------------------------
 # bench.py support: weak-scaling workload, rank r = one n x n element block of the n x (world*n) mesh
 # ----------------------------------------------------------------------------------------------------
@@ -303,6 +384,10 @@ class _BenchPart:
         self.p = DistFemProblem(self.m, dev, 4, self.comm)        # second build: excludes context / module load
         self.p.set_bc(self.bc["dir"], self.bc["neu"])
         self.symbolic_s = self.p.symbolic_s
+        self.halo = "nccl"
+        if world > 1 and os.environ.get("FE_P2P", "1") != "0":
+            self.p.enable_p2p()
+            self.halo = "peer-memory (NVLink loads + flag-gated scalar exchange)"
         self.nelem_owned = self.m.n_own_elems
         self.tiled = self.p.plan is not None
         self.launches_per_step = 3

@@ -269,6 +269,30 @@ int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void*
                 int64_t maxit, int32_t check_every, void* work, double* info, void* comm, int32_t n_nbr,
                 const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx, double* sendbuf,
                 const int64_t* recv_off, const int32_t* nptr, const int32_t* nadj, void* stream);
+/* fe_dist_pcg with the per-iteration halo taken out of NCCL: the SpMV loads the ghost entries of the search
+ * direction directly from the owning GPU's memory over NVLink (peer pointers from CUDA IPC / torch symmetric
+ * memory), gated by per-neighbour version flags.  Same arithmetic, same iterates as fe_dist_pcg (bitwise).
+ *   peer_p     DEVICE array [world] of double*: every rank's direction buffer `pbuf` (2 * pstride doubles,
+ *              pstride >= nrows_local on every rank); pbuf is this rank's own entry.
+ *   peer_flags DEVICE array [world] of int64*: every rank's flag array (int64[world], zero-initialised once).
+ *   ghost_rank / ghost_ridx  DEVICE int32 [nnode_local - nnode_owned]: owner rank and node index inside the
+ *              owner for every ghost node;  nbr_dev DEVICE copy of nbr_rank.
+ *   epoch      version base; the call uses versions (epoch, epoch + maxit + 1], so the caller advances it
+ *              by maxit + 2 between calls (flags only ever grow).
+ *   peer_slots / peer_versions  DEVICE arrays [world] of peer pointers to every rank's reduction table
+ *              (double[64]) and version array (int64[16], zero-initialised once): the two scalar all-reduces
+ *              of an iteration are stores into every peer's table followed by a release-store of the version;
+ *              consumers add the `world` slots in rank order (same bits everywhere).  seq: reduction counter,
+ *              the call uses [seq, seq + 2 * maxit + 1); the caller advances it between calls.  world <= 16.
+ * Only the first / last exchange of x stay on NCCL. */
+int fe_dist_pcg_p2p(int64_t nrows_owned, int64_t nrows_local, int idx64, const void* row_ptr, const int32_t* col_idx,
+                    const double* vals, const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol,
+                    int64_t maxit, int32_t check_every, void* work, double* info, void* comm, int32_t n_nbr,
+                    const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx, double* sendbuf,
+                    const int64_t* recv_off, const int32_t* nptr, const int32_t* nadj, int32_t rank, int32_t world,
+                    const void* peer_p, const void* peer_flags, const int32_t* ghost_rank, const int32_t* ghost_ridx,
+                    const int32_t* nbr_dev, int64_t pstride, double* pbuf, int64_t epoch, const void* peer_slots,
+                    const void* peer_versions, int64_t seq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,12 @@ for case in ("general", "structured"):
     x = p.solve(rtol=1e-11)
     x2 = p.solve(rtol=1e-11)
     assert torch.equal(x, x2), "distributed solve is not reproducible"
+    it_nccl = p.info["iterations"]
+    p.enable_p2p()                      # ghost entries read from the owner's memory over NVLink
+    for _ in range(2):
+        x3 = p.solve(rtol=1e-11)
+        assert p.info["iterations"] == it_nccl and torch.equal(x, x3), "peer-memory halo changed the iterates"
+    x = p.solve(rtol=1e-11, p2p=False)
     # single-GPU reference on every rank
     fem = FemProblem(conn, coords, device=dev); fem.setMatrix(); fem.setBoundaryConditions(bc, verbose=False)
     fem.assemble(); fem.rtol = 1e-11; U = fem.solveProblem()
