@@ -58,6 +58,9 @@ PROTOTYPES = {
     "fe_dist_comm_init": (_i, [_p, _i, _i, C.POINTER(C.c_void_p)]),
     "fe_dist_comm_destroy": (_i, [_p]),
     "fe_dist_halo_exchange": (_i, [_p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "fe_edge_load": (_i, [_i, _i64, _p, _p, _f64, _f64, _p, _p, _p]),
+    "fe_gauss_gradients": (_i, [_i, _i64, _p, _p, _p, _p, _p]),
+    "fe_nodal_strain": (_i, [_i, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_dist_pcg_workspace_bytes": (_sz, [_i64]),
     "fe_dist_pcg": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _i32,
                          _p, _p, _p, _p, _p, _p, _p, _p]),

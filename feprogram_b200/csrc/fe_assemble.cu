@@ -7,7 +7,7 @@ namespace fe {
 // K1: dense Ke per element, one thread per (element, local node a) writing rows 2a and 2a+1.
 // Parity/debug entry (FemProblem.getKe); the assembly path below never stores Ke.
 // ------------------------------------------------------------------------------------------------
-template <int ET>
+template <int ET, bool MASS>
 __global__ void __launch_bounds__(128) k_element_matrices(int64_t nelem, const int32_t* __restrict__ conn,
                                                           const double2* __restrict__ coords,
                                                           double* __restrict__ Ke, int weighted) {
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128) k_element_matrices(int64_t nelem, const i
     int t[N];
     double x[N], y[N], L[N], P[N], Q[N];
     load_element<ET>(conn, coords, e, t, x, y);
-    element_row_pair<ET>(x, y, a, weighted != 0, L, P, Q);
+    element_row_pair<ET, MASS>(x, y, a, weighted != 0, L, P, Q);
     double* r0 = Ke + e * (M * M) + (2 * a) * M;
     double* r1 = r0 + M;
 #pragma unroll
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) k_element_matrices(int64_t nelem, const i
 // result is bit-identical from run to run.  The tile is then written once, fully coalesced.
 // Shared layout mirrors the global layout: value (row 2n+c, p, d) at 4*(nptr[n]-base) + 2*c*deg + 2p + d.
 // ------------------------------------------------------------------------------------------------
-template <int ET>
+template <int ET, bool MASS>
 __global__ void __launch_bounds__(128) k_assemble_rows(int64_t nnode, int R, const int32_t* __restrict__ eptr,
                                                        const int32_t* __restrict__ einc,
                                                        const uint8_t* __restrict__ epos,
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_assemble_rows(int64_t nnode, int R, con
             int t[N];
             double x[N], y[N], L[N], P[N], Q[N];
             load_element<ET>(conn, coords, e, t, x, y);
-            element_row_pair<ET>(x, y, a, weighted != 0, L, P, Q);
+            element_row_pair<ET, MASS>(x, y, a, weighted != 0, L, P, Q);
             const uint8_t* ps = epos + (int64_t)k * N;
 #pragma unroll
             for (int b = 0; b < N; ++b) {
@@ -96,7 +96,7 @@ __global__ void k_tags_to_conn(int64_t n, const T* __restrict__ tags, int32_t* _
     if (i < n) conn[i] = (int32_t)(tags[i] - 1);
 }
 
-template <int ET>
+template <int ET, bool MASS>
 static int launch_assemble_rows(int64_t nnode, const int32_t* conn, const double* coords, const int32_t* eptr,
                                 const int32_t* einc, const uint8_t* epos, const int32_t* nptr, int32_t max_deg,
                                 double* vals, int weighted, cudaStream_t stream) {
@@ -109,8 +109,8 @@ static int launch_assemble_rows(int64_t nnode, const int32_t* conn, const double
         return FE_ERR_CAPACITY;
     }
     const size_t smem = (size_t)R * per_node;
-    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_rows<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_assemble_rows<ET><<<grid_for(nnode, R), R, smem, stream>>>(nnode, R, eptr, einc, epos, nptr, conn,
+    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_rows<ET, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_assemble_rows<ET, MASS><<<grid_for(nnode, R), R, smem, stream>>>(nnode, R, eptr, einc, epos, nptr, conn,
                                                                  reinterpret_cast<const double2*>(coords), vals,
                                                                  weighted);
     FE_CHECK_LAUNCH("k_assemble_rows");
@@ -140,7 +140,7 @@ int fe_element_matrices(int elem_type, int op, int64_t nelem, const int32_t* con
                         void* stream) {
     using namespace fe;
     FE_REQUIRE(nelem >= 0, "negative size");
-    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED) {
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
         set_error("fe_element_matrices: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
@@ -151,16 +151,18 @@ int fe_element_matrices(int elem_type, int op, int64_t nelem, const int32_t* con
     if (rc != FE_OK) return rc;
     const double2* xy = reinterpret_cast<const double2*>(coords);
     const int w = op == FE_OP_WEIGHTED;
+#define FE_KE_CASE(ET, N)                                                                                       \
+    case ET:                                                                                                    \
+        if (op == FE_OP_MASS)                                                                                   \
+            k_element_matrices<ET, true><<<grid_for(nelem * N, 128), 128, 0, st>>>(nelem, conn, xy, Ke, 1);     \
+        else                                                                                                    \
+            k_element_matrices<ET, false><<<grid_for(nelem * N, 128), 128, 0, st>>>(nelem, conn, xy, Ke, w);    \
+        break;
     switch (elem_type) {
-        case FE_QUAD4:
-            k_element_matrices<FE_QUAD4><<<grid_for(nelem * 4, 128), 128, 0, st>>>(nelem, conn, xy, Ke, w);
-            break;
-        case FE_QUAD9:
-            k_element_matrices<FE_QUAD9><<<grid_for(nelem * 9, 128), 128, 0, st>>>(nelem, conn, xy, Ke, w);
-            break;
-        case FE_TRI3:
-            k_element_matrices<FE_TRI3><<<grid_for(nelem * 3, 128), 128, 0, st>>>(nelem, conn, xy, Ke, w);
-            break;
+        FE_KE_CASE(FE_QUAD4, 4)
+        FE_KE_CASE(FE_QUAD9, 9)
+        FE_KE_CASE(FE_TRI3, 3)
+#undef FE_KE_CASE
         default:
             set_error("fe_element_matrices: Invalid elemType %d", elem_type);
             return FE_ERR_UNSUPPORTED;
@@ -176,7 +178,7 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
     FE_REQUIRE(nelem >= 0 && nnode >= 0 && conn && coords && eptr && einc && epos && nptr && vals,
                "null pointer or negative size");
     FE_REQUIRE(max_deg > 0, "max_deg must be positive");
-    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED) {
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
         set_error("fe_assemble: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
@@ -185,13 +187,16 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
     int rc = ensure_tables_tu(st);
     if (rc != FE_OK) return rc;
     const int w = op == FE_OP_WEIGHTED;
+#define FE_ROWS_CASE(ET)                                                                                          \
+    case ET:                                                                                                      \
+        return op == FE_OP_MASS                                                                                   \
+                   ? launch_assemble_rows<ET, true>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, 1, st) \
+                   : launch_assemble_rows<ET, false>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, w, st);
     switch (elem_type) {
-        case FE_QUAD4:
-            return launch_assemble_rows<FE_QUAD4>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, w, st);
-        case FE_QUAD9:
-            return launch_assemble_rows<FE_QUAD9>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, w, st);
-        case FE_TRI3:
-            return launch_assemble_rows<FE_TRI3>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, w, st);
+        FE_ROWS_CASE(FE_QUAD4)
+        FE_ROWS_CASE(FE_QUAD9)
+        FE_ROWS_CASE(FE_TRI3)
+#undef FE_ROWS_CASE
         default:
             set_error("fe_assemble: Invalid elemType %d", elem_type);
             return FE_ERR_UNSUPPORTED;

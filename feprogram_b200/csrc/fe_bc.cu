@@ -45,9 +45,70 @@ __global__ void __launch_bounds__(256) k_apply_bc(int64_t nrows, const IdxT* __r
     if (any) rhs[r] -= lift;
 }
 
+// "Corrected" Neumann load (the reference writes a nodal 1.0 per dof regardless of the
+// mesh size, elements.py:195-197 FIXME): consistent load of a constant traction (tx, ty) on boundary edges,
+// rhs[2n+c] += t_c * int N_n |dx/dxi| dxi.  NEN = 2: straight 2-node edge (a, b); NEN = 3: quadratic edge
+// (a, b, mid), 3-point Gauss-Legendre.  A node receives at most two contributions, so the atomic adds
+// commute and the result does not depend on scheduling.  Dirichlet dofs (dirmask) are left at their value.
+template <int NEN>
+__global__ void k_edge_load(int64_t nedge, const int32_t* __restrict__ edges, const double2* __restrict__ coords,
+                            double tx, double ty, const uint8_t* __restrict__ dirmask, double* __restrict__ rhs) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nedge) return;
+    int n[NEN];
+    double2 p[NEN];
+    double w[NEN];
+#pragma unroll
+    for (int k = 0; k < NEN; ++k) {
+        n[k] = edges[e * NEN + k];
+        p[k] = coords[n[k]];
+        w[k] = 0.0;
+    }
+    if (NEN == 2) {
+        const double len = sqrt((p[1].x - p[0].x) * (p[1].x - p[0].x) + (p[1].y - p[0].y) * (p[1].y - p[0].y));
+        w[0] = w[1] = 0.5 * len;
+    } else {
+        const double gp[3] = {-0.7745966692414834, 0.0, 0.7745966692414834};
+        const double gw[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const double xi = gp[g];
+            const double N0 = 0.5 * xi * (xi - 1.0), N1 = 0.5 * xi * (xi + 1.0), N2 = 1.0 - xi * xi;
+            const double d0 = xi - 0.5, d1 = xi + 0.5, d2 = -2.0 * xi;
+            const double jx = d0 * p[0].x + d1 * p[1].x + d2 * p[NEN - 1].x;
+            const double jy = d0 * p[0].y + d1 * p[1].y + d2 * p[NEN - 1].y;
+            const double ds = sqrt(jx * jx + jy * jy) * gw[g];
+            w[0] = fma(N0, ds, w[0]);
+            w[1] = fma(N1, ds, w[1]);
+            w[NEN - 1] = fma(N2, ds, w[NEN - 1]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NEN; ++k) {
+        const int64_t d = 2 * (int64_t)n[k];
+        if (!dirmask || !dirmask[d]) atomicAdd(rhs + d, tx * w[k]);
+        if (!dirmask || !dirmask[d + 1]) atomicAdd(rhs + d + 1, ty * w[k]);
+    }
+}
+
 }  // namespace fe
 
 extern "C" {
+
+int fe_edge_load(int nodes_per_edge, int64_t nedge, const int32_t* edges, const double* coords, double tx, double ty,
+                 const uint8_t* dirmask, double* rhs, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(nedge >= 0, "negative size");
+    FE_REQUIRE(nodes_per_edge == 2 || nodes_per_edge == 3, "edges have 2 (linear) or 3 (quadratic: a, b, mid) nodes");
+    if (nedge == 0) return FE_OK;
+    FE_REQUIRE(edges && coords && rhs, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    const double2* xy = reinterpret_cast<const double2*>(coords);
+    if (nodes_per_edge == 2) k_edge_load<2><<<grid_for(nedge, 128), 128, 0, st>>>(nedge, edges, xy, tx, ty, dirmask, rhs);
+    else k_edge_load<3><<<grid_for(nedge, 128), 128, 0, st>>>(nedge, edges, xy, tx, ty, dirmask, rhs);
+    FE_CHECK_LAUNCH("k_edge_load");
+    return FE_OK;
+}
 
 int fe_bc_rhs(int64_t nrows, const int64_t* dir_dofs, int64_t n_dir, const int64_t* neu_dofs, int64_t n_neu,
               double neu_value, double* rhs, uint8_t* dirmask, void* stream) {

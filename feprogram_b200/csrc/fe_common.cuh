@@ -52,9 +52,9 @@ inline int ngauss_of(int elem_type) {
 // ---- element tables in constant memory --------------------------------------------------------
 // dH[g][0][a] = dN_a/dr, dH[g][1][a] = dN_a/ds at Gauss point g; w[g] = tensor weight.
 // One copy per element type so that fully unrolled kernels address them as c[bank][imm].
-struct TablesQ4 { double dH[4][2][4]; double w[4]; };
-struct TablesQ9 { double dH[9][2][9]; double w[9]; };
-struct TablesT3 { double dH[1][2][3]; double w[1]; };
+struct TablesQ4 { double dH[4][2][4]; double w[4]; double H[4][4]; };
+struct TablesQ9 { double dH[9][2][9]; double w[9]; double H[9][9]; };
+struct TablesT3 { double dH[1][2][3]; double w[1]; double H[1][3]; };
 
 // Uploads the tables for the current device once (idempotent, cheap afterwards).
 int ensure_tables(cudaStream_t stream);

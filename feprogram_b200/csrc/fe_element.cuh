@@ -8,6 +8,10 @@
 //     Ke[2a+1,2b  ] = sum_g Dx_a Dy_b det                                    ("Q")
 // evaluated through the adjugate A = det * J^-1 dH so that each Gauss point needs one division:
 //   (Dx_a Dx_b + ..) det = (Ax_a Ax_b + ..) / det.
+// Mass extension (FE_OP_MASS; the reference builds the shape-value tables H and the weights gpWei but never
+// uses them, elements.py:94-113): Me[2a+c, 2b+c] = sum_g gpWei_g H_g[a] H_g[b] det_g, zero across components.
+// It runs through the same (L, P, Q) pair arithmetic with "ax" = H_g, "sx" = H_g * gpWei_g * det_g and
+// ay = sy = 0, so every assembly kernel handles it unchanged and K and M share one CSR pattern.
 // fp64 throughout, no tensor cores (blocks are 8x8 / 18x18 and the kernel is HBM-bound).
 #pragma once
 
@@ -30,9 +34,9 @@ static int ensure_tables_tu(cudaStream_t stream) {
     TablesQ4 q4;
     TablesQ9 q9;
     TablesT3 t3;
-    fe_tables(FE_QUAD4, &q4.dH[0][0][0], nullptr, q4.w, nullptr, nullptr);
-    fe_tables(FE_QUAD9, &q9.dH[0][0][0], nullptr, q9.w, nullptr, nullptr);
-    fe_tables(FE_TRI3, &t3.dH[0][0][0], nullptr, t3.w, nullptr, nullptr);
+    fe_tables(FE_QUAD4, &q4.dH[0][0][0], &q4.H[0][0], q4.w, nullptr, nullptr);
+    fe_tables(FE_QUAD9, &q9.dH[0][0][0], &q9.H[0][0], q9.w, nullptr, nullptr);
+    fe_tables(FE_TRI3, &t3.dH[0][0][0], &t3.H[0][0], t3.w, nullptr, nullptr);
     FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_q4, &q4, sizeof(q4), 0, cudaMemcpyHostToDevice, stream));
     FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_q9, &q9, sizeof(q9), 0, cudaMemcpyHostToDevice, stream));
     FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_t3, &t3, sizeof(t3), 0, cudaMemcpyHostToDevice, stream));
@@ -47,18 +51,21 @@ template <> struct Elem<FE_QUAD4> {
     __device__ __forceinline__ static double dHr(int g, int a) { return c_q4.dH[g][0][a]; }
     __device__ __forceinline__ static double dHs(int g, int a) { return c_q4.dH[g][1][a]; }
     __device__ __forceinline__ static double w(int g) { return c_q4.w[g]; }
+    __device__ __forceinline__ static double H(int g, int a) { return c_q4.H[g][a]; }
 };
 template <> struct Elem<FE_QUAD9> {
     static constexpr int NNPE = 9, NG = 9;
     __device__ __forceinline__ static double dHr(int g, int a) { return c_q9.dH[g][0][a]; }
     __device__ __forceinline__ static double dHs(int g, int a) { return c_q9.dH[g][1][a]; }
     __device__ __forceinline__ static double w(int g) { return c_q9.w[g]; }
+    __device__ __forceinline__ static double H(int g, int a) { return c_q9.H[g][a]; }
 };
 template <> struct Elem<FE_TRI3> {
     static constexpr int NNPE = 3, NG = 1;
     __device__ __forceinline__ static double dHr(int g, int a) { return c_t3.dH[g][0][a]; }
     __device__ __forceinline__ static double dHs(int g, int a) { return c_t3.dH[g][1][a]; }
     __device__ __forceinline__ static double w(int g) { return c_t3.w[g]; }
+    __device__ __forceinline__ static double H(int g, int a) { return c_t3.H[g][a]; }
 };
 
 // Gathers the element's node ids and coordinates (Elem.getpos, elements.py:34-38).
@@ -103,7 +110,7 @@ template <> struct ElemGeom<FE_QUAD4> {
     double s[4];                                            // weight_g / det_g
 };
 
-template <int ET>
+template <int ET, bool MASS = false>
 __device__ __forceinline__ void geom_init(ElemGeom<ET>& G, const double (&x)[Elem<ET>::NNPE],
                                           const double (&y)[Elem<ET>::NNPE], bool weighted) {
 #pragma unroll
@@ -133,9 +140,9 @@ __device__ __forceinline__ void q4_jacobian(int g, const ElemGeom<FE_QUAD4>& G, 
     j11 = fma(pr, G.dy03, __dmul_rn(mr, G.dy12));
 }
 
-template <>
-__device__ __forceinline__ void geom_init<FE_QUAD4>(ElemGeom<FE_QUAD4>& G, const double (&x)[4], const double (&y)[4],
-                                                    bool weighted) {
+template <bool MASS>
+__device__ __forceinline__ void geom_init_q4(ElemGeom<FE_QUAD4>& G, const double (&x)[4], const double (&y)[4],
+                                             bool weighted) {
     G.dx01 = __dsub_rn(x[0], x[1]); G.dx32 = __dsub_rn(x[3], x[2]);
     G.dx03 = __dsub_rn(x[0], x[3]); G.dx12 = __dsub_rn(x[1], x[2]);
     G.dy01 = __dsub_rn(y[0], y[1]); G.dy32 = __dsub_rn(y[3], y[2]);
@@ -146,6 +153,11 @@ __device__ __forceinline__ void geom_init<FE_QUAD4>(ElemGeom<FE_QUAD4>& G, const
         double j00, j01, j10, j11;
         q4_jacobian(g, G, j00, j01, j10, j11);
         d[g] = fma(j00, j11, -__dmul_rn(j01, j10));
+    }
+    if constexpr (MASS) {   // the mass operator scales by det itself
+#pragma unroll
+        for (int g = 0; g < 4; ++g) G.s[g] = __dmul_rn(d[g], c_q4.w[g]);
+        return;
     }
     const double d01 = __dmul_rn(d[0], d[1]), d23 = __dmul_rn(d[2], d[3]);
     const double inv = 1.0 / __dmul_rn(d01, d23);
@@ -160,9 +172,18 @@ __device__ __forceinline__ void geom_init<FE_QUAD4>(ElemGeom<FE_QUAD4>& G, const
     }
 }
 
+template <> __device__ __forceinline__ void geom_init<FE_QUAD4, false>(ElemGeom<FE_QUAD4>& G, const double (&x)[4],
+                                                                       const double (&y)[4], bool weighted) {
+    geom_init_q4<false>(G, x, y, weighted);
+}
+template <> __device__ __forceinline__ void geom_init<FE_QUAD4, true>(ElemGeom<FE_QUAD4>& G, const double (&x)[4],
+                                                                      const double (&y)[4], bool weighted) {
+    geom_init_q4<true>(G, x, y, weighted);
+}
+
 // Adjugate gradients at Gauss point g:  ax_b = J11 dHr_b - J01 dHs_b, ay_b = J00 dHs_b - J10 dHr_b and
 // their scaled copies sx_b = ax_b / det, sy_b = ay_b / det (times the Gauss weight when weighted).
-template <int ET>
+template <int ET, bool MASS = false>
 __device__ __forceinline__ void gauss_point(int g, const ElemGeom<ET>& G, bool weighted,
                                             double (&ax)[Elem<ET>::NNPE], double (&ay)[Elem<ET>::NNPE],
                                             double (&sx)[Elem<ET>::NNPE], double (&sy)[Elem<ET>::NNPE]) {
@@ -178,6 +199,17 @@ __device__ __forceinline__ void gauss_point(int g, const ElemGeom<ET>& G, bool w
     // every product / sum below is written with explicit roundings so that all kernels that evaluate an
     // element (tiled, row-tile, multi-thread Quad9) produce the same bits regardless of FMA contraction
     const double det = fma(j00, j11, -__dmul_rn(j01, j10));
+    if constexpr (MASS) {
+        const double m = __dmul_rn(det, E::w(g));
+#pragma unroll
+        for (int b = 0; b < E::NNPE; ++b) {
+            ax[b] = E::H(g, b);
+            ay[b] = 0.0;
+            sx[b] = __dmul_rn(ax[b], m);
+            sy[b] = 0.0;
+        }
+        return;
+    }
     double s = 1.0 / det;
     if (weighted) s = __dmul_rn(s, E::w(g));
 #pragma unroll
@@ -190,9 +222,23 @@ __device__ __forceinline__ void gauss_point(int g, const ElemGeom<ET>& G, bool w
 }
 
 template <>
-__device__ __forceinline__ void gauss_point<FE_QUAD4>(int g, const ElemGeom<FE_QUAD4>& G, bool weighted,
-                                                      double (&ax)[4], double (&ay)[4], double (&sx)[4],
-                                                      double (&sy)[4]) {
+__device__ __forceinline__ void gauss_point<FE_QUAD4, true>(int g, const ElemGeom<FE_QUAD4>& G, bool weighted,
+                                                            double (&ax)[4], double (&ay)[4], double (&sx)[4],
+                                                            double (&sy)[4]) {
+    const double m = G.s[g];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        ax[b] = c_q4.H[g][b];
+        ay[b] = 0.0;
+        sx[b] = __dmul_rn(ax[b], m);
+        sy[b] = 0.0;
+    }
+}
+
+template <>
+__device__ __forceinline__ void gauss_point<FE_QUAD4, false>(int g, const ElemGeom<FE_QUAD4>& G, bool weighted,
+                                                             double (&ax)[4], double (&ay)[4], double (&sx)[4],
+                                                             double (&sy)[4]) {
     double ps, ms, pr, mr, j00, j01, j10, j11;
     q4_table(g, ps, ms, pr, mr);
     q4_jacobian(g, G, j00, j01, j10, j11);
@@ -223,7 +269,7 @@ template <int N> struct SymLayout {
     __host__ __device__ static constexpr int offdiag(int a, int b) { return 2 * N + 3 * pair_index(a, b); }
 };
 
-template <int ET>
+template <int ET, bool MASS = false>
 __device__ __forceinline__ void element_sym(const double (&x)[Elem<ET>::NNPE], const double (&y)[Elem<ET>::NNPE],
                                             bool weighted, double (&out)[SymLayout<Elem<ET>::NNPE>::kSize]) {
     using E = Elem<ET>;
@@ -231,11 +277,11 @@ __device__ __forceinline__ void element_sym(const double (&x)[Elem<ET>::NNPE], c
 #pragma unroll
     for (int i = 0; i < S::kSize; ++i) out[i] = 0.0;
     ElemGeom<ET> G;
-    geom_init<ET>(G, x, y, weighted);
+    geom_init<ET, MASS>(G, x, y, weighted);
 #pragma unroll
     for (int g = 0; g < E::NG; ++g) {
         double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
-        gauss_point<ET>(g, G, weighted, ax, ay, sx, sy);
+        gauss_point<ET, MASS>(g, G, weighted, ax, ay, sx, sy);
 #pragma unroll
         for (int a = 0; a < E::NNPE; ++a) {
             out[2 * a] = fma(sx[a], ax[a], fma(sy[a], ay[a], out[2 * a]));
@@ -274,7 +320,7 @@ __device__ __forceinline__ void sym_block(const double* __restrict__ s, int a, i
 
 // Row pair of local node a:  L[b], P[b], Q[b] for all b.  `a` is a run-time value; operands are picked
 // with selects so everything stays in registers.  Same pair arithmetic as element_sym.
-template <int ET>
+template <int ET, bool MASS = false>
 __device__ __forceinline__ void element_row_pair(const double (&x)[Elem<ET>::NNPE],
                                                  const double (&y)[Elem<ET>::NNPE], int a, bool weighted,
                                                  double (&L)[Elem<ET>::NNPE], double (&P)[Elem<ET>::NNPE],
@@ -283,11 +329,11 @@ __device__ __forceinline__ void element_row_pair(const double (&x)[Elem<ET>::NNP
 #pragma unroll
     for (int b = 0; b < E::NNPE; ++b) L[b] = P[b] = Q[b] = 0.0;
     ElemGeom<ET> G;
-    geom_init<ET>(G, x, y, weighted);
+    geom_init<ET, MASS>(G, x, y, weighted);
 #pragma unroll
     for (int g = 0; g < E::NG; ++g) {
         double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
-        gauss_point<ET>(g, G, weighted, ax, ay, sx, sy);
+        gauss_point<ET, MASS>(g, G, weighted, ax, ay, sx, sy);
         double axa = 0.0, aya = 0.0, sxa = 0.0, sya = 0.0;
 #pragma unroll
         for (int b = 0; b < E::NNPE; ++b) {

@@ -323,7 +323,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // Full upper-triangular block element matrix: block (lo,hi) = [L, P, Q] at 3*tri(lo,hi); diagonal blocks
 // store Q = P.  Same pair arithmetic as element_row_pair (fe_element.cuh).
-template <int ET>
+template <int ET, bool MASS>
 __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], const double (&y)[Elem<ET>::NNPE],
                                             bool weighted, double (&out)[3 * TileLayout<Elem<ET>::NNPE>::kBlocks]) {
     using E = Elem<ET>;
@@ -331,11 +331,11 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
 #pragma unroll
     for (int i = 0; i < 3 * T::kBlocks; ++i) out[i] = 0.0;
     ElemGeom<ET> G;
-    geom_init<ET>(G, x, y, weighted);
+    geom_init<ET, MASS>(G, x, y, weighted);
 #pragma unroll
     for (int g = 0; g < E::NG; ++g) {
         double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
-        gauss_point<ET>(g, G, weighted, ax, ay, sx, sy);
+        gauss_point<ET, MASS>(g, G, weighted, ax, ay, sx, sy);
 #pragma unroll
         for (int a = 0; a < E::NNPE; ++a) {
 #pragma unroll
@@ -354,7 +354,7 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
 // Quad9: one of five threads of an element evaluates the block rows A1 (and A2) of the upper triangle --
 // {0}, {1,8}, {2,7}, {3,6}, {4,5}: nine blocks = 27 accumulators each -- reading the element's node
 // coordinates from shared memory.  Same pair arithmetic (and therefore the same bits) as element_row_pair.
-template <int A1, int A2>
+template <int A1, int A2, bool MASS>
 __device__ __forceinline__ void q9_block_rows(const double2* __restrict__ xy, bool weighted, double* __restrict__ dst) {
     constexpr int N = 9;
     using T = TileLayout<N>;
@@ -377,14 +377,14 @@ __device__ __forceinline__ void q9_block_rows(const double2* __restrict__ xy, bo
             j11 = fma(hs, p.y, j11);
         }
         const double det = fma(j00, j11, -__dmul_rn(j01, j10));
-        double s = 1.0 / det;
-        if (weighted) s = __dmul_rn(s, c_q9.w[g]);
+        double s = MASS ? __dmul_rn(det, c_q9.w[g]) : 1.0 / det;
+        if (!MASS && weighted) s = __dmul_rn(s, c_q9.w[g]);
         double sx1 = 0.0, sy1 = 0.0, sx2 = 0.0, sy2 = 0.0;
 #pragma unroll
         for (int b = A1; b < N; ++b) {
             const double hr = c_q9.dH[g][0][b], hs = c_q9.dH[g][1][b];
-            const double ax = fma(j11, hr, -__dmul_rn(j01, hs));
-            const double ay = fma(j00, hs, -__dmul_rn(j10, hr));
+            const double ax = MASS ? c_q9.H[g][b] : fma(j11, hr, -__dmul_rn(j01, hs));
+            const double ay = MASS ? 0.0 : fma(j00, hs, -__dmul_rn(j10, hr));
             if (b == A1) {
                 sx1 = __dmul_rn(ax, s);
                 sy1 = __dmul_rn(ay, s);
@@ -430,7 +430,7 @@ __device__ __forceinline__ void q9_block_rows(const double2* __restrict__ xy, bo
 // Persistent kernel: CTA c processes tiles c, c + G, c + 2G, ...  While tile t is computed, the plan
 // records of tile t + G stream into the other shared-memory buffer (cp.async) and its connectivity row
 // and coordinates are prefetched into registers, so no global-memory latency is exposed per tile.
-template <int ET>
+template <int ET, bool MASS>
 __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayout<Elem<ET>::NNPE>::kCtas) k_assemble_tiled(
     int64_t ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords,
     const int4* __restrict__ tdesc, const int2* __restrict__ tnode, const uint16_t* __restrict__ tloc,
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
             const bool active = tg[0] >= 0;
             if (active && dbg != 2) {
                 double ke[3 * T::kBlocks];
-                element_tri<ET>(x, y, weighted != 0, ke);
+                element_tri<ET, MASS>(x, y, weighted != 0, ke);
                 double* dst = slab + tid * SS;
 #pragma unroll
                 for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
@@ -548,11 +548,11 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 const double2* xy = s_xy + row * N;
                 double* dst = slab + row * SS;
                 switch (part) {          // warp-uniform: kRowThreads is a multiple of 32
-                    case 0: q9_block_rows<0, -1>(xy, weighted != 0, dst); break;
-                    case 1: q9_block_rows<1, 8>(xy, weighted != 0, dst); break;
-                    case 2: q9_block_rows<2, 7>(xy, weighted != 0, dst); break;
-                    case 3: q9_block_rows<3, 6>(xy, weighted != 0, dst); break;
-                    default: q9_block_rows<4, 5>(xy, weighted != 0, dst); break;
+                    case 0: q9_block_rows<0, -1, MASS>(xy, weighted != 0, dst); break;
+                    case 1: q9_block_rows<1, 8, MASS>(xy, weighted != 0, dst); break;
+                    case 2: q9_block_rows<2, 7, MASS>(xy, weighted != 0, dst); break;
+                    case 3: q9_block_rows<3, 6, MASS>(xy, weighted != 0, dst); break;
+                    default: q9_block_rows<4, 5, MASS>(xy, weighted != 0, dst); break;
                 }
             }
         }
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                     xq[a] = pq.x;
                     yq[a] = pq.y;
                 }
-                element_tri<ET>(xq, yq, weighted != 0, ke);
+                element_tri<ET, MASS>(xq, yq, weighted != 0, ke);
                 double* dst = slab + row * SS;
 #pragma unroll
                 for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <int ET>
+template <int ET, bool MASS>
 static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coords, const int32_t* tdesc,
                         const int2* tnode, const uint16_t* tloc, const uint32_t* twork, const uint32_t* tchunk,
                         double* vals, int weighted, cudaStream_t st) {
@@ -658,8 +658,8 @@ static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coor
     FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int64_t grid = (int64_t)sms * T::kCtas;
     if (grid > ntiles) grid = ntiles;
-    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
-    k_assemble_tiled<ET><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
+    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
+    k_assemble_tiled<ET, MASS><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
         ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc), tnode, tloc,
         twork, tchunk, vals, weighted, dbg);
     FE_CHECK_LAUNCH("k_assemble_tiled");
@@ -805,7 +805,7 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
                       const uint32_t* tchunk, double* vals, void* stream) {
     using namespace fe;
     FE_REQUIRE(ntiles >= 0, "negative size");
-    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED) {
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
         set_error("fe_assemble_tiled: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
@@ -816,13 +816,16 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
     if (rc != FE_OK) return rc;
     const int w = op == FE_OP_WEIGHTED;
     const int2* nd = static_cast<const int2*>(tnode);
+#define FE_TILED_CASE(ET)                                                                                       \
+    case ET:                                                                                                    \
+        return op == FE_OP_MASS                                                                                 \
+                   ? launch_tiled<ET, true>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, 1, st)  \
+                   : launch_tiled<ET, false>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
     switch (elem_type) {
-        case FE_QUAD4:
-            return launch_tiled<FE_QUAD4>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
-        case FE_TRI3:
-            return launch_tiled<FE_TRI3>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
-        case FE_QUAD9:
-            return launch_tiled<FE_QUAD9>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
+        FE_TILED_CASE(FE_QUAD4)
+        FE_TILED_CASE(FE_TRI3)
+        FE_TILED_CASE(FE_QUAD9)
+#undef FE_TILED_CASE
         default:
             set_error("fe_assemble_tiled: element type %d has no tiled kernel (use fe_assemble)", elem_type);
             return FE_ERR_UNSUPPORTED;

@@ -73,7 +73,8 @@ class FemProblem:
         ndarray); coordinates: float64 (nnode, >=2), row i <-> tag i+1 (elements.py:41-58).
 
         Keyword-only extensions: ``device`` (torch device, default current CUDA device) and
-        ``operator`` ("reference" = un-weighted B^T B detJ as elements.py:162, "weighted" = times gpWei).
+        ``operator`` ("reference" = un-weighted B^T B detJ as elements.py:162, "weighted" = times gpWei,
+        "mass" = sum_g gpWei H^T H detJ from the reference's H / gpWei tables, on the same CSR pattern).
         """
         self.nnode = coordinates.shape[0]
         self.nelem = len(conectivity)
@@ -81,7 +82,7 @@ class FemProblem:
         self.conectivity = conectivity
         self.coordinates = coordinates
         self._device = device
-        self._operator = {"reference": 0, "weighted": 1}[operator]
+        self._operator = {"reference": 0, "weighted": 1, "mass": 2}[operator]
         self._dev = None        # device-side state, created on first assemble()
         self._K_host = None
         self._brhs_host = None
@@ -122,10 +123,24 @@ class FemProblem:
         return [formFunction(r, s) for r in gpoints for s in gpoints]
 
     # ------------------------------------------------------- boundary conditions (elements.py:202-229)
-    def setBoundaryConditions(self, bcNodesList, *, verbose=True):
+    def setBoundaryConditions(self, bcNodesList, *, verbose=True, mode="reference", traction=(1.0, 1.0)):
         """bcNodesList = 4 iterables of 1-based tags [bottom, right, top, left]; bottom -> Dirichlet
         x,y; left -> nodal load ("Neumann") x,y.  Prints both dof sets like the reference unless
-        ``verbose=False``."""
+        ``verbose=False``.
+
+        ``mode="reference"`` keeps the reference's semantics exactly (row-only Dirichlet, nodal load 1.0 per
+        dof written last so it overrides the Dirichlet value at the shared corner; elements.py:185-197).
+        ``mode="corrected"``: Dirichlet wins at shared nodes, the load is the consistent
+        edge integral of the constant ``traction`` over the left side (mesh-size independent), and ``K`` is
+        the symmetrically eliminated matrix."""
+        if mode not in ("reference", "corrected"):
+            raise ValueError("mode must be 'reference' or 'corrected'")
+        self._bc_mode = mode
+        self._traction = (float(traction[0]), float(traction[1]))
+        self._load_edges = None
+        if mode == "corrected":
+            from . import mesh
+            self._load_edges = mesh.boundary_edges(self.conectivity, bcNodesList[3])
         dofSetDir = [[0, 1], [], [], []]
         dofSetNeu = [[], [], [], [0, 1]]
         dirDof, neuDof = set(), set()
@@ -138,6 +153,8 @@ class FemProblem:
         if verbose:
             print(dirDof)
             print(neuDof)
+        if mode == "corrected":
+            neuDof -= dirDof
         self.dofDir = list(dirDof)
         self.dofNeu = list(neuDof)
 
@@ -165,6 +182,36 @@ class FemProblem:
 
     def assembleMatrix(self, vec):
         return 0
+
+    # ------------------------------------------------------- post-processing
+    def _field(self, U):
+        import torch
+        st = self._state()
+        u = torch.from_numpy(np.ascontiguousarray(np.asarray(U, dtype=np.float64).reshape(-1))).to(st["coords"].device)
+        if u.numel() != 2 * self.nnode:
+            raise ValueError("U must hold 2 values per node")
+        return st, u
+
+    def gaussGradients(self, U):
+        """(nelem, ngauss, 4): Elem.getHgrad(Hrs[g], J_g) * u_e = (du/dx, du/dy, dv/dx, dv/dy) at every Gauss
+        point of every element (elements.py:25-32), computed by fe_gauss_gradients."""
+        import torch
+        st, u = self._field(U)
+        return torch.ops.feprogram.gauss_gradients(st["conn"], st["coords"], u,
+                                                   _ELEM_CODES[self.elem.elemType]).cpu().numpy()
+
+    def nodalStrain(self, U):
+        """(nnode, 3): nodal means of (du/dx, dv/dy, du/dy + dv/dx) -- the "Tensiones" array of the reference's
+        writer (python_to_xml.py:19-22), computed by fe_nodal_strain."""
+        import torch
+        from . import ops
+        st, u = self._field(U)
+        et = _ELEM_CODES[self.elem.elemType]
+        if "pattern" in st:
+            eptr, einc = st["pattern"].eptr, st["pattern"].einc
+        else:
+            eptr, einc = torch.ops.feprogram.incidence(st["conn"], self.nnode, et)
+        return torch.ops.feprogram.nodal_strain(st["conn"], st["coords"], u, eptr, einc, et).cpu().numpy()
 
     # ------------------------------------------------------------------------------- device state
     def _torch_device(self):
@@ -217,7 +264,13 @@ class FemProblem:
             st["dirmask"] = torch.empty(pat.nrows, dtype=torch.uint8, device=dev)
         dir_d = torch.as_tensor(np.asarray(self.dofDir, dtype=np.int64), device=dev)
         neu_d = torch.as_tensor(np.asarray(self.dofNeu, dtype=np.int64), device=dev)
-        torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
+        if getattr(self, "_bc_mode", "reference") == "corrected":
+            torch.ops.feprogram.bc_rhs(dir_d, neu_d[:0], 0.0, st["rhs"], st["dirmask"])
+            edges = torch.from_numpy(self._load_edges).to(dev)
+            torch.ops.feprogram.edge_load(edges, st["coords"], self._traction[0], self._traction[1], st["dirmask"],
+                                          st["rhs"])
+        else:
+            torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
         self._K_host = None
         self._brhs_host = None
         self._assembled = True
@@ -239,7 +292,9 @@ class FemProblem:
             st = self._dev
             pat = st["pattern"]
             vals = st["vals"].clone()
-            torch.ops.feprogram.apply_bc(0, pat.row_ptr, pat.col_idx, vals, st["rhs"], st["dirmask"])
+            sym = getattr(self, "_bc_mode", "reference") == "corrected"      # zero Dirichlet values: rhs unchanged
+            torch.ops.feprogram.apply_bc(1 if sym else 0, pat.row_ptr, pat.col_idx, vals,
+                                         st["rhs"].clone() if sym else st["rhs"], st["dirmask"])
             K = sp.csr_matrix((vals.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
                               shape=(pat.nrows, pat.nrows))
             # Dirichlet rows keep only their unit diagonal (canonical form of the LIL deletes, elements.py:187-191)

@@ -124,3 +124,24 @@ def shuffle_numbering(conn: np.ndarray, coords: np.ndarray, bc_sets, seed: int =
     new_conn = (perm[np.asarray(conn, dtype=np.int64) - 1] + 1).astype(conn.dtype)
     new_sets = [set((perm[np.fromiter(s, dtype=np.int64, count=len(s)) - 1] + 1).tolist()) for s in bc_sets]
     return new_conn, new_coords, new_sets, perm
+
+
+def boundary_edges(conn1: np.ndarray, nodes) -> np.ndarray:
+    """0-based boundary edges -- element sides whose corner pair occurs in one element only -- all of whose
+    nodes are in ``nodes`` (1-based tags): rows (a, b) for Quad4 / Tri3, (a, b, mid) for Quad9."""
+    conn = np.asarray(conn1 if isinstance(conn1, np.ndarray) else np.stack([np.asarray(c) for c in conn1])).astype(np.int64)
+    nnpe = conn.shape[1]
+    nc = 3 if nnpe == 3 else 4
+    a = np.concatenate([conn[:, k] for k in range(nc)])
+    b = np.concatenate([conn[:, (k + 1) % nc] for k in range(nc)])
+    cols = [a, b]
+    if nnpe == 9:
+        cols.append(np.concatenate([conn[:, nc + k] for k in range(nc)]))
+    key = np.minimum(a, b) * (int(conn.max()) + 1) + np.maximum(a, b)
+    _, first, count = np.unique(key, return_index=True, return_counts=True)
+    bnd = np.sort(first[count == 1])
+    tags = np.fromiter((int(t) for t in nodes), dtype=np.int64)
+    on = np.ones(bnd.size, dtype=bool)
+    for c in cols:
+        on &= np.isin(c[bnd], tags)
+    return (np.stack([c[bnd[on]] for c in cols], axis=1) - 1).astype(np.int32)

@@ -92,6 +92,41 @@ def element_matrices(conn: Tensor, coords: Tensor, elem_type: int, op: int) -> T
     return ke
 
 
+@torch.library.custom_op("feprogram::gauss_gradients", mutates_args=())
+def gauss_gradients(conn: Tensor, coords: Tensor, U: Tensor, elem_type: int) -> Tensor:
+    """(nelem, ng2, 4) fp64: (du/dx, du/dy, dv/dx, dv/dy) at every Gauss point.  fe_gauss_gradients."""
+    _chk_dev(conn, coords, U)
+    _want(conn, torch.int32, "conn")
+    _want(coords, torch.float64, "coords")
+    _want(U, torch.float64, "U")
+    nelem, nnpe = conn.shape
+    ng2 = 1 if nnpe == 3 else nnpe
+    if U.numel() != 2 * coords.shape[0]:
+        raise ValueError("U must hold 2 values per node")
+    with torch.cuda.device(conn.device):
+        out = torch.empty((nelem, ng2, 4), dtype=torch.float64, device=conn.device)
+        _lib.check(_lib.lib().fe_gauss_gradients(elem_type, nelem, _ptr(conn), _ptr(coords), _ptr(U), _ptr(out),
+                                                 _stream(conn)))
+    return out
+
+
+@torch.library.custom_op("feprogram::nodal_strain", mutates_args=())
+def nodal_strain(conn: Tensor, coords: Tensor, U: Tensor, eptr: Tensor, einc: Tensor, elem_type: int) -> Tensor:
+    """(nnode, 3) fp64 nodal means of (du/dx, dv/dy, du/dy + dv/dx).  fe_nodal_strain."""
+    _chk_dev(conn, coords, U, eptr, einc)
+    _want(conn, torch.int32, "conn")
+    _want(coords, torch.float64, "coords")
+    _want(U, torch.float64, "U")
+    nnode = coords.shape[0]
+    if U.numel() != 2 * nnode:
+        raise ValueError("U must hold 2 values per node")
+    with torch.cuda.device(conn.device):
+        out = torch.empty((nnode, 3), dtype=torch.float64, device=conn.device)
+        _lib.check(_lib.lib().fe_nodal_strain(elem_type, nnode, _ptr(eptr), _ptr(einc), _ptr(conn), _ptr(coords),
+                                              _ptr(U), _ptr(out), _stream(conn)))
+    return out
+
+
 @torch.library.custom_op("feprogram::incidence", mutates_args=())
 def incidence(conn: Tensor, nnode: int, elem_type: int) -> Tuple[Tensor, Tensor]:
     """node -> (element*16 + local node) incidence: (eptr[nnode+1], einc[nelem*nnpe]) int32."""
@@ -176,6 +211,20 @@ def bc_rhs(dir_dofs: Tensor, neu_dofs: Tensor, neu_value: float, rhs: Tensor, di
     with torch.cuda.device(rhs.device):
         _lib.check(_lib.lib().fe_bc_rhs(rhs.numel(), _ptr(dir_dofs), dir_dofs.numel(), _ptr(neu_dofs),
                                         neu_dofs.numel(), float(neu_value), _ptr(rhs), _ptr(dirmask), _stream(rhs)))
+
+
+@torch.library.custom_op("feprogram::edge_load", mutates_args=("rhs",))
+def edge_load(edges: Tensor, coords: Tensor, tx: float, ty: float, dirmask: Tensor, rhs: Tensor) -> None:
+    """rhs += consistent load of the traction (tx, ty) on the boundary edges (skipping Dirichlet dofs)."""
+    _chk_dev(edges, coords, dirmask, rhs)
+    _want(edges, torch.int32, "edges")
+    _want(coords, torch.float64, "coords")
+    _want(dirmask, torch.uint8, "dirmask")
+    if edges.numel() == 0:
+        return
+    with torch.cuda.device(rhs.device):
+        _lib.check(_lib.lib().fe_edge_load(edges.shape[1], edges.shape[0], _ptr(edges), _ptr(coords), float(tx),
+                                           float(ty), _ptr(dirmask), _ptr(rhs), _stream(rhs)))
 
 
 @torch.library.custom_op("feprogram::apply_bc", mutates_args=("vals", "rhs"))

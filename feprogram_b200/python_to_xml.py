@@ -15,7 +15,9 @@ def _s(a):
     return np.asarray(a).astype(str)
 
 
-def writeXML_nodeData(coords, conect, nodedata, nameFile):
+def writeXML_nodeData(coords, conect, nodedata, nameFile, nodeStress=None):
+    """``nodeStress`` (optional, (nnode, 3)): also writes the "Tensiones" PointData array in the layout of the
+    block the reference keeps commented out (python_to_xml.py:19-22); None reproduces the reference's file."""
     coords = np.asarray(coords)
     nnode = coords.shape[0]
     nelem = len(conect)
@@ -30,6 +32,12 @@ def writeXML_nodeData(coords, conect, nodedata, nameFile):
         f.write(" <UnstructuredGrid>\n")
         f.write('  <Piece NumberOfPoints="{}" NumberOfCells="{}">\n'.format(nnode, nelem))
         f.write('   <PointData Vectors="Tensiones">\n')
+        if nodeStress is not None:
+            t = _s(np.asarray(nodeStress)[:, :3])
+            f.write('    <DataArray Name="Tensiones" NumberOfComponents="3" type="Float32"  format="ascii">\n    ')
+            f.write("".join(np.char.add(np.char.add(np.char.add(np.char.add(" ", t[:, 0]), np.char.add(" ", t[:, 1])),
+                                                    np.char.add(" ", t[:, 2])), "\n").tolist()))
+            f.write("\n    </DataArray>")
         f.write('    <DataArray Name="Velocidad" NumberOfComponents="2" type="Float32" format="ascii">\n    ')
         d = _s(data[:, :2])
         f.write("".join(np.char.add(np.char.add(np.char.add(" ", d[:, 0]), np.char.add(" ", d[:, 1])), "\n").tolist()))

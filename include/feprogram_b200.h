@@ -63,6 +63,9 @@ extern "C" {
 /* ---- operators -------------------------------------------------------------------------- */
 #define FE_OP_REFERENCE 0 /* Ke = sum_g B^T B detJ, 2 dof/node, no weights (elements.py:153-163) */
 #define FE_OP_WEIGHTED 1  /* same, each Gauss term times gpWei[g] (elements.py:137; extension)   */
+#define FE_OP_MASS 2      /* Me[2a+c,2b+c] = sum_g gpWei[g] H_g[a] H_g[b] detJ_g from the reference's own H and
+                             gpWei tables (elements.py:94-113, built but unused there; extension); entries
+                             across the two components are stored zeros, so K and M share one pattern */
 
 /* Copies the thread-local message of the last failing call into buf (NUL-terminated). */
 void fe_last_error(char* buf, size_t len);
@@ -206,6 +209,12 @@ int fe_bc_rhs(int64_t nrows, const int64_t* dir_dofs, int64_t n_dir, const int64
               double neu_value, double* rhs, uint8_t* dirmask, void* stream);
 int fe_apply_bc(int mode, int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, double* vals,
                 double* rhs, const uint8_t* dirmask, void* stream);
+/* "Corrected" load (extension): consistent nodal load of a constant traction (tx, ty)
+ * on boundary edges instead of the reference's mesh-independent nodal 1.0 (elements.py:195-197 FIXME):
+ * rhs[2n+c] += t_c * int N_n ds.  edges: DEVICE int32 [nedge][nodes_per_edge], 0-based, (a, b) or
+ * (a, b, mid).  Dirichlet dofs (dirmask != 0; dirmask may be NULL) are not touched.  Call after fe_bc_rhs. */
+int fe_edge_load(int nodes_per_edge, int64_t nedge, const int32_t* edges, const double* coords, double tx, double ty,
+                 const uint8_t* dirmask, double* rhs, void* stream);
 
 /* ---- S: solve -----------------------------------------------------------------------------------
  * Replaces spsolve(K, brhs) (elements.py:241-243) by Jacobi-preconditioned CG on the SPD system
@@ -236,6 +245,19 @@ size_t fe_pcg_workspace_bytes(int64_t nrows);
 int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
            const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit,
            int32_t check_every, void* work, double* info, const int32_t* nptr, const int32_t* nadj, void* stream);
+
+/* ---- post-processing of the solved field -----------------------------------------
+ * fe_gauss_gradients: grad[e][g][0..3] = H_grad_g u_e = (du/dx, du/dy, dv/dx, dv/dy) at every Gauss point,
+ *   the operator Elem.getHgrad builds (elements.py:25-32; defined there, never called).  U is the solution
+ *   as solveProblem returns it (2 * nnode doubles, node-interleaved); grad has nelem * ng2 * 4 doubles.
+ * fe_nodal_strain: strain[n][0..2] = mean over the elements incident to node n (eptr/einc from
+ *   fe_incidence_*: element * 16 + local node, ascending element id) of the element's Gauss-point mean of B u_e =
+ *   (du/dx, dv/dy, du/dy + dv/dx) (Elem.funB rows 0-2, elements.py:15-23): the 3-component nodal array the
+ *   reference's writer reserves as "Tensiones" (python_to_xml.py:19-22, commented out there). */
+int fe_gauss_gradients(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, const double* U,
+                       double* grad, void* stream);
+int fe_nodal_strain(int elem_type, int64_t nnode, const int32_t* eptr, const int32_t* einc, const int32_t* conn,
+                    const double* coords, const double* U, double* strain, void* stream);
 
 /* ---- multi-GPU (one host process per GPU, NCCL over NVLink) ------------------------------------------
  * The reference has no distributed code; this is the north_star's scale-out of the solve.  Elements are

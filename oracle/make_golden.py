@@ -67,8 +67,44 @@ def scalar_case(kind, n):
                      len(run["dofDir"]), len(run["dofNeu"]), U.min(), U.max(), np.linalg.norm(U)])
 
 
+def mass_golden():
+    """N^T N element matrices built from the reference's own H / gpWei / Hrs objects (ref_runner.mass_matrix)."""
+    X4 = np.array([[0, 0], [2, 0.1], [2.3, 1.2], [-0.1, 0.9]], dtype=np.float64)
+    fem4 = ref_runner.make_problem(np.array([[1, 2, 3, 4]]), X4)
+    rng = np.random.default_rng(7)
+    c9, x9, _ = mesh.structured_quad9(1)
+    x9 = 3.0 * x9 + rng.uniform(-0.12, 0.12, size=x9.shape)
+    fem9 = ref_runner.make_problem(c9, x9)
+    conn, coords, _ = case_mesh(4, 6, True, True)
+    fem = ref_runner.make_problem(conn, coords)
+    me = np.array([ref_runner.mass_matrix(fem, conn[e] - 1) for e in range(len(conn))])
+    np.savez_compressed(os.path.join(OUT, "mass_single.npz"), X4=X4, me4=ref_runner.mass_matrix(fem4, np.arange(4)),
+                        conn9=c9, X9=x9, me9=ref_runner.mass_matrix(fem9, c9[0] - 1), conn=conn, coords=coords, me=me,
+                        versions=np.array([np.__version__, scipy.__version__]))
+    print("mass_single.npz written")
+
+
+def post_golden():
+    """Velocity gradients through the reference's own Elem.getHgrad on small perturbed, shuffled meshes."""
+    out = {}
+    rng = np.random.default_rng(3)
+    for kind, n in ((4, 5), (9, 3)):
+        conn, coords, _ = case_mesh(kind, n, True, True)
+        U = rng.standard_normal(2 * coords.shape[0])
+        fem = ref_runner.make_problem(conn, coords)
+        out.update({"conn%d" % kind: conn, "coords%d" % kind: coords, "U%d" % kind: U,
+                    "grad%d" % kind: ref_runner.gauss_gradients(fem, conn, U)})
+    np.savez_compressed(os.path.join(OUT, "post_gradients.npz"), versions=np.array([np.__version__, scipy.__version__]),
+                        **out)
+    print("post_gradients.npz written")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["mass"]:
+        return mass_golden()
+    if sys.argv[1:] == ["post"]:
+        return post_golden()
     # tables (T1-T4)
     d4, h4, w4 = ref_runner.tables(4)
     d9, h9, w9 = ref_runner.tables(9)
@@ -107,6 +143,8 @@ def main():
         conn, coords, _ = gen(3, 2)
         U = rng.standard_normal((coords.shape[0], 2)) * 1e3
         writer.writeXML_nodeData(coords * np.array([2.0, 10.0]), conn, U, os.path.join(OUT, "writer_case%d" % k))
+    mass_golden()
+    post_golden()
     print("golden fixtures written to", OUT)
 
 

@@ -78,6 +78,35 @@ def element_matrix(fem, tags0):
         return np.asarray(fem.getKe(np.asarray(tags0)))
 
 
+def mass_matrix(fem, tags0):
+    """The N^T N product of the north_star built from the reference's OWN objects: fem.H / fem.gpWei / fem.Hrs
+    (elements.py:94-140; the reference fills them and never uses H or gpWei), Elem.getpos and np.linalg.det as
+    getKe does (elements.py:159-160): Me = sum_g gpWei_g H_g^T H_g detJ_g on each of the two components."""
+    tags0 = np.asarray(tags0)
+    X = fem.elem.getpos(tags0, fem.coordinates)
+    n = len(tags0)
+    me = np.zeros((2 * n, 2 * n))
+    for g in range(len(fem.Hrs)):
+        J = fem.Hrs[g] * X
+        h = np.asarray(fem.H[g]).ravel()
+        m = fem.gpWei[g] * np.outer(h, h) * np.linalg.det(J)
+        me[0::2, 0::2] += m
+        me[1::2, 1::2] += m
+    return me
+
+
+def gauss_gradients(fem, conn1, U):
+    """H_grad u_e at every Gauss point through the reference's own Elem.getHgrad (elements.py:25-32)."""
+    U = np.asarray(U, dtype=np.float64).reshape(-1)
+    out = []
+    for tags in np.asarray(conn1):
+        t0 = np.asarray(tags) - 1
+        X = fem.elem.getpos(t0, fem.coordinates)
+        ue = np.matrix(np.stack([U[2 * t0], U[2 * t0 + 1]], axis=1).ravel()).T
+        out.append([np.asarray(fem.elem.getHgrad(fem.Hrs[g], fem.Hrs[g] * X) * ue).ravel() for g in range(len(fem.Hrs))])
+    return np.array(out)
+
+
 def assemble_prebc(conn1, coords):
     """Pre-BC K straight from the reference: dofDir = dofNeu = [] then assemble()."""
     fem = make_problem(conn1, coords)

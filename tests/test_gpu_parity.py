@@ -476,3 +476,159 @@ def test_kernels_stay_inside_their_output_buffers(torch_cuda, kind, n):
         torch.cuda.synchronize()
         assert bool((big[:G] == sentinel).all()) and bool((big[-G:] == sentinel).all())
         assert not bool((y == sentinel).any())
+
+
+# ---------------------------------------------------------------------------------------------------
+# mass operator (FE_OP_MASS): N^T N on the reference's H / gpWei tables (extension)
+# ---------------------------------------------------------------------------------------------------
+def test_mass_element_matrices_against_reference_tables(torch_cuda):
+    """fe_element_matrices(op=mass) vs the product assembled from the reference's own fem.H / fem.gpWei /
+    fem.Hrs objects (tests/golden/mass_single.npz, oracle/make_golden.py mass_golden)."""
+    torch = torch_cuda
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mass_single.npz"))
+    for conn1, X, want in ((np.array([[1, 2, 3, 4]]), g["X4"], g["me4"][None]), (g["conn9"], g["X9"], g["me9"][None]),
+                           (g["conn"], g["coords"], g["me"])):
+        conn0, xy = dev_mesh(torch, conn1, X)
+        me = torch.ops.feprogram.element_matrices(conn0, xy, conn1.shape[1], 2).cpu().numpy()
+        assert rel_max(me, want) < 1e-13
+        assert np.all(me[:, 0::2, 1::2] == 0.0) and np.all(me[:, 1::2, 0::2] == 0.0)
+        assert rel_max(me, orc.mass_matrices(conn1 - 1, X)) < 1e-13
+
+
+@pytest.mark.parametrize("kind,n,shuffle", [(4, 37, False), (4, 29, True), (9, 17, True), (3, 31, True)])
+def test_mass_assembly_all_kernels(torch_cuda, kind, n, shuffle):
+    """Assembled M: same pattern as K, values vs the oracle, tiled == row kernel bit for bit, bit-wise
+    symmetric, and 1^T M 1 = 2 * sum_e sum_g gpWei detJ (partition of unity of the shape functions)."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
+    conn, coords, bc = gen(n, n + 2)
+    mx, my = (2 * n, 2 * (n + 2)) if kind == 9 else (n, n + 2)
+    coords = mesh.perturb_interior(coords, mx, my, 0.15, seed=5)
+    if shuffle:
+        conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=6)
+    conn0, xy = dev_mesh(torch, conn, coords)
+    pat = ops.symbolic(conn0, coords.shape[0], kind, 2)
+    v_rows = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v_rows, 2)
+    plan = ops.tile_plan(conn0, xy, pat)
+    assert plan is not None
+    v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, plan, v, 2)
+    assert torch.equal(v, v_rows)
+    M = sp.csr_matrix((v.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()), shape=(pat.nrows,) * 2)
+    Mo = orc.assemble_csr(conn - 1, coords, kind, mass=True)
+    assert np.array_equal(M.indptr, Mo.indptr) and np.array_equal(M.indices, Mo.indices)
+    assert rel_max(M.data, Mo.data) < VAL_TOL
+    assert abs(M - M.T).max() == 0.0
+    dH, H, w = orc.tables(kind)
+    X = coords[conn - 1]
+    J = np.einsum("gka,eaj->egkj", dH, X)
+    det = J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+    total = 2.0 * float((det * w[None, :] * (H.sum(axis=1) ** 2)[None, :]).sum())
+    assert abs(M.sum() - total) < 1e-11 * abs(total)
+
+
+def test_mass_facade_operator(torch_cuda, golden):
+    z = golden("q9_6x6_pert_shuf")
+    fem = run_facade(z, operator="mass")
+    Mo = orc.assemble_csr(z["conn"] - 1, z["coords"], mass=True)
+    M = fem.csr_prebc()
+    assert np.array_equal(M.indptr, Mo.indptr) and np.array_equal(M.indices, Mo.indices)
+    assert rel_max(M.data, Mo.data) < VAL_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# post-processing kernels (SURVEY.md §8f row 4): Elem.getHgrad at every Gauss point, nodal strain
+# ---------------------------------------------------------------------------------------------------
+def test_gauss_gradients_against_reference_getHgrad(torch_cuda):
+    torch = torch_cuda
+    import os
+    from feprogram_b200.elements import FemProblem
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "post_gradients.npz"))
+    for k in (4, 9):
+        fem = FemProblem(g["conn%d" % k], g["coords%d" % k])
+        got = fem.gaussGradients(g["U%d" % k])
+        want = g["grad%d" % k]
+        assert got.shape == want.shape and rel_max(got, want) < 1e-12
+        eps = fem.nodalStrain(g["U%d" % k])
+        assert rel_max(eps, orc.nodal_strain(g["conn%d" % k] - 1, g["coords%d" % k], g["U%d" % k])) < 1e-12
+
+
+@pytest.mark.parametrize("kind,n", [(4, 300), (9, 120), (3, 257)])
+def test_post_kernels_medium_and_linear_field(torch_cuda, kind, n):
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
+    conn, coords, bc = gen(n, n + 1)
+    mx, my = (2 * n, 2 * (n + 1)) if kind == 9 else (n, n + 1)
+    coords = mesh.perturb_interior(coords, mx, my, 0.2, seed=8)
+    conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=9)
+    conn0, xy = dev_mesh(torch, conn, coords)
+    rng = np.random.default_rng(10)
+    U = rng.standard_normal(2 * coords.shape[0])
+    u = torch.from_numpy(U).cuda()
+    grad = torch.ops.feprogram.gauss_gradients(conn0, xy, u, kind).cpu().numpy()
+    assert rel_max(grad, orc.gauss_gradients(conn - 1, coords, U, kind)) < 1e-11
+    eptr, einc = torch.ops.feprogram.incidence(conn0, coords.shape[0], kind)
+    eps = torch.ops.feprogram.nodal_strain(conn0, xy, u, eptr, einc, kind).cpu().numpy()
+    assert rel_max(eps, orc.nodal_strain(conn - 1, coords, U, kind)) < 1e-11
+    eps2 = torch.ops.feprogram.nodal_strain(conn0, xy, u, eptr, einc, kind).cpu().numpy()
+    assert np.array_equal(eps, eps2)                               # fixed summation order
+    A = np.array([[0.3, -1.2], [2.0, 0.7]])
+    ulin = torch.from_numpy((coords @ A.T).ravel()).cuda()
+    epl = torch.ops.feprogram.nodal_strain(conn0, xy, ulin, eptr, einc, kind).cpu().numpy()
+    assert np.abs(epl - np.array([A[0, 0], A[1, 1], A[0, 1] + A[1, 0]])[None, :]).max() < 1e-9
+    z = torch.ops.feprogram.gauss_gradients(conn0[:0], xy, u, kind)
+    assert z.shape[0] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# "corrected" boundary-condition mode (SURVEY.md §8f row 1)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n", [(4, 24), (9, 10)])
+def test_corrected_bc_mode(torch_cuda, kind, n):
+    from feprogram_b200 import mesh
+    from feprogram_b200.elements import FemProblem
+    gen = mesh.structured_quad4 if kind == 4 else mesh.structured_quad9
+    conn, coords, bc = gen(n, n + 1)
+    mx, my = (2 * n, 2 * (n + 1)) if kind == 9 else (n, n + 1)
+    coords = mesh.perturb_interior(coords, mx, my, 0.15, seed=3)
+    conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=4)
+    fem = FemProblem(conn, coords)
+    fem.setMatrix()
+    fem.setBoundaryConditions(bc, verbose=False, mode="corrected", traction=(1.0, -0.5))
+    fem.assemble()
+    fem.rtol = 1e-12
+    U = fem.solveProblem()
+    edges0 = mesh.boundary_edges(conn, bc[3])
+    assert edges0.shape == ((n + 1) if kind == 4 else (n + 1), 2 if kind == 4 else 3)
+    Ks, f, u = orc.solve_corrected(conn - 1, coords, fem.dofDir, edges0, (1.0, -0.5))
+    b = np.asarray(fem.brhs.todense()).ravel()
+    assert np.abs(b - f).max() < 1e-14 * np.abs(f).max()
+    # total load = traction * side length (left side of the unit square), minus what the Dirichlet corner took
+    full = orc.edge_loads(edges0, coords, (1.0, -0.5), 2 * coords.shape[0])
+    assert abs(full[0::2].sum() - 1.0) < 1e-13 and abs(full[1::2].sum() + 0.5) < 1e-13
+    K = fem.K.tocsr()
+    assert abs(K - K.T).max() == 0.0
+    assert rel_max(K.toarray(), Ks.toarray()) < VAL_TOL
+    assert np.linalg.norm(U - u) / np.linalg.norm(u) < SOL_TOL
+    assert np.all(U[np.asarray(fem.dofDir)] == 0.0)
+
+
+def test_corrected_mode_is_mesh_independent(torch_cuda):
+    """The reference's nodal load makes |U| grow with refinement; the consistent load
+    does not."""
+    from feprogram_b200 import mesh
+    from feprogram_b200.elements import FemProblem
+    tip = []
+    for n in (16, 32):
+        conn, coords, bc = mesh.structured_quad4(n)
+        fem = FemProblem(conn, coords)
+        fem.setMatrix()
+        fem.setBoundaryConditions(bc, verbose=False, mode="corrected")
+        fem.assemble()
+        U = fem.solveProblem().reshape(-1, 2)
+        tip.append(U[(n + 1) * n])            # top-left corner node
+    assert np.abs(tip[1] - tip[0]).max() < 0.05 * np.abs(tip[0]).max()

@@ -53,3 +53,90 @@ def test_vtu_writer_matches_live_reference(tmp_path):
         writeXML_nodeData(coords, conn, U, a)
         ref.writeXML_nodeData(coords, conn, U, b)
         assert open(a + ".vtu").read() == open(b + ".vtu").read()
+
+
+def test_vtu_writer_optional_stress_array(tmp_path):
+    """nodeStress=None is the reference's file; with it the "Tensiones" array of the block the reference keeps
+    commented out (python_to_xml.py:19-22) is added in front of "Velocidad"."""
+    import numpy as np
+    from feprogram_b200 import mesh, python_to_xml
+    conn, coords, _ = mesh.structured_quad4(2, 2)
+    U = np.arange(18, dtype=np.float64).reshape(9, 2) / 7
+    S = np.arange(27, dtype=np.float64).reshape(9, 3) / 3
+    python_to_xml.writeXML_nodeData(coords, conn, U, str(tmp_path / "a"))
+    python_to_xml.writeXML_nodeData(coords, conn, U, str(tmp_path / "b"), nodeStress=S)
+    a, b = (tmp_path / "a.vtu").read_text(), (tmp_path / "b.vtu").read_text()
+    assert 'Name="Tensiones"' not in a and 'Name="Tensiones" NumberOfComponents="3"' in b
+    head, tail = b.split('    <DataArray Name="Tensiones"')
+    rest = tail.split("</DataArray>", 1)[1]
+    assert head + rest == a
+    assert " {} {} {}\n".format(S[4, 0], S[4, 1], S[4, 2]) in b
+
+
+MSH_TINY = """$MeshFormat
+4.1 0 8
+$EndMeshFormat
+$PhysicalNames
+1
+1 2 "Bottom"
+$EndPhysicalNames
+$Entities
+0 0 0 0
+$EndEntities
+$Nodes
+3 6 1 6
+0 1 0 1
+1
+0 0 0
+1 1 0 1
+2
+1 0 0
+2 1 1 4
+3
+4
+5
+6
+2 0 0 0.5 0.5
+2 1 0 0.5 1
+1 1 0 0.25 1
+0 1 0 0 1
+$EndNodes
+$Elements
+3 5 1 5
+1 1 1 2
+1 1 2
+2 2 3
+1 2 1 1
+3 3 4
+2 1 3 2
+4 1 2 5 6
+5 2 3 4 5
+$EndElements
+"""
+
+
+def test_msh_reader_handwritten_file(tmp_path):
+    """MSH 4.1 ASCII with several node blocks (one parametric) and line + quad element blocks."""
+    import numpy as np
+    from feprogram_b200 import gmsh_api
+    p = tmp_path / "tiny.msh"
+    p.write_text(MSH_TINY)
+    conn, coords, bc = gmsh_api.readMsh(str(p))
+    assert [list(map(int, c)) for c in conn] == [[1, 2, 5, 6], [2, 3, 4, 5]] and conn[0].dtype == np.uint64
+    assert coords.shape == (6, 2) and np.array_equal(coords[[0, 2, 5]], [[0, 0], [2, 0], [0, 1]])
+    assert bc == [{1, 2, 3}, {3, 4}, set(), set()]
+
+
+def test_msh_round_trip_and_solve_contract(tmp_path):
+    import numpy as np
+    from feprogram_b200 import gmsh_api, mesh
+    for gen in (mesh.structured_quad4, mesh.structured_quad9):
+        conn, coords, bc = gen(4, 3)
+        coords = mesh.perturb_interior(coords, *((8, 6) if conn.shape[1] == 9 else (4, 3)), 0.2, seed=2)
+        conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=3)
+        path = str(tmp_path / ("m%d.msh" % conn.shape[1]))
+        gmsh_api.writeMsh(path, conn, coords, bc)
+        c2, x2, b2 = gmsh_api.readMsh(path)
+        assert np.array_equal(np.stack(c2).astype(np.int64), conn)
+        assert np.array_equal(x2, coords)                      # repr() round-trips float64
+        assert [set(int(t) for t in s) for s in bc] == b2

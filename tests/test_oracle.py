@@ -125,3 +125,55 @@ def test_live_reference(kind, n):
     d4, h4, w4 = ref_runner.tables(kind)
     t = orc.tables(kind)
     assert np.array_equal(t[0], d4) and np.array_equal(t[1], h4) and np.array_equal(t[2], w4)
+
+
+def test_mass_oracle_against_reference_built_golden():
+    """orc.mass_matrices vs N^T N assembled from the reference's own H / gpWei / Hrs objects (frozen)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mass_single.npz"))
+    assert np.abs(orc.mass_matrices(np.arange(4)[None, :], g["X4"])[0] - g["me4"]).max() < 1e-14 * np.abs(g["me4"]).max()
+    assert np.abs(orc.mass_matrices(g["conn9"] - 1, g["X9"])[0] - g["me9"]).max() < 1e-14 * np.abs(g["me9"]).max()
+    assert np.abs(orc.mass_matrices(g["conn"] - 1, g["coords"]) - g["me"]).max() < 1e-14 * np.abs(g["me"]).max()
+    M = orc.assemble_csr(g["conn"] - 1, g["coords"], mass=True)
+    K = orc.assemble_csr(g["conn"] - 1, g["coords"])
+    assert np.array_equal(M.indptr, K.indptr) and np.array_equal(M.indices, K.indices)   # one pattern for K and M
+
+
+@pytest.mark.skipif(not ref_runner.available(), reason="reference tree not present on this box")
+def test_mass_live_reference_objects():
+    from feprogram_b200 import mesh
+    conn, coords, _ = mesh.structured_quad9(3)
+    coords = mesh.perturb_interior(coords, 6, 6, 0.2, seed=11)
+    fem = ref_runner.make_problem(conn, coords)
+    want = np.array([ref_runner.mass_matrix(fem, conn[e] - 1) for e in range(len(conn))])
+    got = orc.mass_matrices(conn - 1, coords)
+    assert np.abs(got - want).max() < 1e-14 * np.abs(want).max()
+
+
+def test_gradient_oracle_against_reference_getHgrad_golden():
+    """orc.gauss_gradients vs the reference's own Elem.getHgrad applied at every Gauss point (frozen)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "post_gradients.npz"))
+    for k in (4, 9):
+        got = orc.gauss_gradients(g["conn%d" % k] - 1, g["coords%d" % k], g["U%d" % k])
+        assert np.abs(got - g["grad%d" % k]).max() < 1e-13 * np.abs(got).max()
+    # a linear field has a constant gradient; the nodal strain recovers it exactly
+    from feprogram_b200 import mesh
+    conn, coords, _ = mesh.structured_quad4(6, 5)
+    coords = mesh.perturb_interior(coords, 6, 5, 0.2, seed=1)
+    A = np.array([[0.3, -1.2], [2.0, 0.7]])
+    U = (coords @ A.T).ravel()
+    eps = orc.nodal_strain(conn - 1, coords, U)
+    assert np.abs(eps - np.array([A[0, 0], A[1, 1], A[0, 1] + A[1, 0]])[None, :]).max() < 1e-12
+
+
+@pytest.mark.skipif(not ref_runner.available(), reason="reference tree not present on this box")
+def test_gradient_live_reference():
+    from feprogram_b200 import mesh
+    conn, coords, _ = mesh.structured_quad9(2, 3)
+    coords = mesh.perturb_interior(coords, 4, 6, 0.2, seed=4)
+    U = np.random.default_rng(5).standard_normal(2 * coords.shape[0])
+    fem = ref_runner.make_problem(conn, coords)
+    want = ref_runner.gauss_gradients(fem, conn, U)
+    got = orc.gauss_gradients(conn - 1, coords, U)
+    assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
