@@ -36,7 +36,7 @@ class LocalMesh:
     elem_gid: np.ndarray        # (nelem_local,) int64
     n_own_elems: int            # elements of this rank's own block (the rest are ghost elements)
     coords: np.ndarray          # (nnode_local, 2) fp64
-    node_gid: np.ndarray        # (nnode_local,) int64: owned (ascending) then ghosts by (owner, gid)
+    node_gid: np.ndarray        # (nnode_local,) int64: owned then ghosts grouped by owner (ascending gid, or Z-curve)
     n_owned: int
     ghost_owner: np.ndarray     # (n_ghost,) int32 owner rank of each ghost node (non-decreasing)
     # filled by exchange_send_lists(): neighbours and the node-level send lists
@@ -76,9 +76,27 @@ def element_blocks(nelem: int, world: int) -> np.ndarray:
     return (np.arange(world + 1, dtype=np.int64) * nelem) // world
 
 
+def morton_keys(xy: np.ndarray, lo: np.ndarray, span: np.ndarray) -> np.ndarray:
+    """Z-curve keys (16 bits per axis) of points inside the box (lo, lo + span)."""
+    q = np.clip(((xy - lo) / np.maximum(span, 1e-300) * 65535.0).astype(np.int64), 0, 65535)
+
+    def spread(v):
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        v = (v | (v << 1)) & 0x55555555
+        return v
+
+    return spread(q[:, 0]) | (spread(q[:, 1]) << 1)
+
+
 def partition_mesh(conn0: np.ndarray, coords: np.ndarray, rank: int, world: int,
-                   bounds: Optional[np.ndarray] = None) -> LocalMesh:
-    """General (unstructured, any numbering) partition from the full mesh.  conn0 is GLOBAL 0-based."""
+                   bounds: Optional[np.ndarray] = None, locality: bool = False) -> LocalMesh:
+    """General (unstructured, any numbering) partition from the full mesh.  conn0 is GLOBAL 0-based.
+
+    ``locality``: number the rank's owned nodes (and each owner's group of ghosts) along a Z-curve instead of
+    by ascending global id -- for meshes whose global numbering has no locality (BASELINE cfg5), so that the
+    local CSR rows of an assembly tile are contiguous and the SpMV's gathers stay cached."""
     conn0 = np.asarray(conn0, dtype=np.int64)
     nelem, nnpe = conn0.shape
     nnode = coords.shape[0]
@@ -95,6 +113,11 @@ def partition_mesh(conn0: np.ndarray, coords: np.ndarray, rank: int, world: int,
     ghosts = touched[owner[touched] != rank]
     ghosts = ghosts[np.lexsort((ghosts, owner[ghosts]))]
     owned = np.nonzero(mine)[0]
+    if locality:
+        lo = coords[touched, :2].min(axis=0)
+        span = coords[touched, :2].max(axis=0) - lo
+        owned = owned[np.argsort(morton_keys(coords[owned, :2], lo, span), kind="stable")]
+        ghosts = ghosts[np.lexsort((morton_keys(coords[ghosts, :2], lo, span), owner[ghosts]))]
     node_gid = np.concatenate([owned, ghosts]).astype(np.int64)
     g2l = np.full(nnode, -1, dtype=np.int64)
     g2l[node_gid] = np.arange(node_gid.size)
@@ -161,11 +184,14 @@ def exchange_send_lists(m: LocalMesh, group=None) -> LocalMesh:
     dist.all_gather_object(gathered, {q: v[0] for q, v in need.items()}, group=group)
     sends = {q: gathered[q][m.rank] for q in range(m.world) if q != m.rank and m.rank in gathered[q]}
     owned_gid = m.node_gid[: m.n_owned]
+    sorter = np.argsort(owned_gid, kind="stable")              # owned nodes need not be in ascending gid order
+    sorted_gid = owned_gid[sorter]
     m.nbr, m.send_nodes, m.recv_range = [], [], []
     for q in sorted(set(need) | set(sends)):
         m.nbr.append(q)
         gids = np.asarray(sends.get(q, []), dtype=np.int64)
-        loc = np.searchsorted(owned_gid, gids)
+        pos = np.minimum(np.searchsorted(sorted_gid, gids), max(0, sorted_gid.size - 1))
+        loc = sorter[pos] if gids.size else np.zeros(0, dtype=np.int64)
         assert np.array_equal(owned_gid[loc], gids), "a neighbour asked for a node this rank does not own"
         m.send_nodes.append(loc)
         m.recv_range.append(need[q][1:] if q in need else (m.n_owned + n_ghost, m.n_owned + n_ghost))

@@ -68,13 +68,16 @@ _ELEM_CODES = {"Quad4": 4, "Quad9": 9}
 
 
 class FemProblem:
-    def __init__(self, conectivity, coordinates, *, device=None, operator="reference"):
+    def __init__(self, conectivity, coordinates, *, device=None, operator="reference", renumber=None):
         """conectivity: sequence of equal-length 1-D integer arrays of 1-BASED node tags (or a 2-D
         ndarray); coordinates: float64 (nnode, >=2), row i <-> tag i+1 (elements.py:41-58).
 
         Keyword-only extensions: ``device`` (torch device, default current CUDA device) and
         ``operator`` ("reference" = un-weighted B^T B detJ as elements.py:162, "weighted" = times gpWei,
-        "mass" = sum_g gpWei H^T H detJ from the reference's H / gpWei tables, on the same CSR pattern).
+        "mass" = sum_g gpWei H^T H detJ from the reference's H / gpWei tables, on the same CSR pattern);
+        ``renumber``: solve on a Morton-renumbered copy of the mesh (None = only when the input numbering has no
+        locality, e.g. BASELINE cfg5's shuffled tags).  Everything visible -- dof numbering, ``K``, ``brhs``,
+        the solution -- stays in the reference's numbering; ``K`` is then assembled on demand in that numbering.
         """
         self.nnode = coordinates.shape[0]
         self.nelem = len(conectivity)
@@ -82,6 +85,7 @@ class FemProblem:
         self.conectivity = conectivity
         self.coordinates = coordinates
         self._device = device
+        self._renumber = renumber
         self._operator = {"reference": 0, "weighted": 1, "mass": 2}[operator]
         self._dev = None        # device-side state, created on first assemble()
         self._K_host = None
@@ -207,7 +211,7 @@ class FemProblem:
         from . import ops
         st, u = self._field(U)
         et = _ELEM_CODES[self.elem.elemType]
-        if "pattern" in st:
+        if "pattern" in st and st["perm"] is None:
             eptr, einc = st["pattern"].eptr, st["pattern"].einc
         else:
             eptr, einc = torch.ops.feprogram.incidence(st["conn"], self.nnode, et)
@@ -238,11 +242,30 @@ class FemProblem:
         xy = np.asarray(self.coordinates, dtype=np.float64)
         if xy.shape[1] != 2 or not xy.flags.c_contiguous:
             xy = np.ascontiguousarray(xy[:, :2])
-        self._dev = {
+        st = {
             "conn": torch.ops.feprogram.tags_to_conn(tags),                       # elements.py:172 `elem-1`
             "coords": torch.from_numpy(xy).to(dev, non_blocking=True),
         }
+        ren = self._renumber
+        if ren is None:      # a row-major lattice spans ~sqrt(nnode) ids per element, a shuffled one ~nnode/2
+            ren = self.nnode > 100000 and ops.numbering_span(st["conn"]) > 64.0 * np.sqrt(self.nnode)
+        st["conn_s"], st["coords_s"], st["perm"] = st["conn"], st["coords"], None
+        if ren:
+            perm, order = ops.locality_order(st["coords"])
+            st["perm"] = perm                                                     # reference node -> solver node
+            st["conn_s"] = perm[st["conn"].to(torch.int64)].to(torch.int32).contiguous()
+            st["coords_s"] = st["coords"][order].contiguous()
+        self._dev = st
         return self._dev
+
+    def _solver_dofs(self, dofs):
+        """Reference dof ids -> dof ids of the (possibly renumbered) solver mesh, as a device tensor."""
+        import torch
+        st = self._dev
+        d = torch.as_tensor(np.asarray(dofs, dtype=np.int64), device=st["conn"].device)
+        if st["perm"] is None:
+            return d
+        return 2 * st["perm"][d // 2] + d % 2
 
     # ---------------------------------------------------------------------- assemble (elements.py:165-200)
     def assemble(self):
@@ -251,23 +274,26 @@ class FemProblem:
         st = self._state()
         et = _ELEM_CODES[self.elem.elemType]
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
-            st["pattern"] = ops.symbolic(st["conn"], self.nnode, et, 2)
-            st["plan"] = ops.tile_plan(st["conn"], st["coords"], st["pattern"])
+            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)
+            st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"])
         pat = st["pattern"]
         dev = st["conn"].device
         if "vals" not in st:
             st["vals"] = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
-        ops.assemble_values(st["conn"], st["coords"], pat, st["plan"], st["vals"], self._operator)
+        ops.assemble_values(st["conn_s"], st["coords_s"], pat, st["plan"], st["vals"], self._operator)
+        st.pop("vals_ref", None)
         # boundary conditions: rhs + Dirichlet mask (matrix itself stays un-modified on the device)
         if "rhs" not in st:
             st["rhs"] = torch.empty(pat.nrows, dtype=torch.float64, device=dev)
             st["dirmask"] = torch.empty(pat.nrows, dtype=torch.uint8, device=dev)
-        dir_d = torch.as_tensor(np.asarray(self.dofDir, dtype=np.int64), device=dev)
-        neu_d = torch.as_tensor(np.asarray(self.dofNeu, dtype=np.int64), device=dev)
+        dir_d = self._solver_dofs(self.dofDir)
+        neu_d = self._solver_dofs(self.dofNeu)
         if getattr(self, "_bc_mode", "reference") == "corrected":
             torch.ops.feprogram.bc_rhs(dir_d, neu_d[:0], 0.0, st["rhs"], st["dirmask"])
             edges = torch.from_numpy(self._load_edges).to(dev)
-            torch.ops.feprogram.edge_load(edges, st["coords"], self._traction[0], self._traction[1], st["dirmask"],
+            if st["perm"] is not None:
+                edges = st["perm"][edges.to(torch.int64)].to(torch.int32).contiguous()
+            torch.ops.feprogram.edge_load(edges, st["coords_s"], self._traction[0], self._traction[1], st["dirmask"],
                                           st["rhs"])
         else:
             torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
@@ -276,10 +302,30 @@ class FemProblem:
         self._assembled = True
 
     # --------------------------------------------------------------- lazily materialised scipy views
+    def _ref_system(self):
+        """(pattern, values, rhs, dirmask) in the REFERENCE numbering.  Without renumbering these are the solver's
+        own arrays; with it the matrix is assembled on demand on the un-renumbered mesh (same element order and
+        pair arithmetic => the same bits as a direct assembly) and rhs / mask are permuted back."""
+        import torch
+        from . import ops
+        st = self._dev
+        if st["perm"] is None:
+            return st["pattern"], st["vals"], st["rhs"], st["dirmask"]
+        if "pattern_ref" not in st:
+            et = _ELEM_CODES[self.elem.elemType]
+            st["pattern_ref"] = ops.symbolic(st["conn"], self.nnode, et, 2)
+            st["plan_ref"] = ops.tile_plan(st["conn"], st["coords"], st["pattern_ref"])
+        pat = st["pattern_ref"]
+        if "vals_ref" not in st:
+            st["vals_ref"] = torch.empty(pat.nnz, dtype=torch.float64, device=st["conn"].device)
+            ops.assemble_values(st["conn"], st["coords"], pat, st["plan_ref"], st["vals_ref"], self._operator)
+        back = lambda v: v.view(-1, 2)[st["perm"]].reshape(-1).contiguous()  # noqa: E731
+        return pat, st["vals_ref"], back(st["rhs"]), back(st["dirmask"])
+
     def csr_prebc(self):
         """Pre-BC K as scipy CSR (indptr/indices bit-identical to the reference's fem.K.tocsr())."""
-        pat = self._dev["pattern"]
-        return sp.csr_matrix((self._dev["vals"].cpu().numpy(), pat.col_idx.cpu().numpy(),
+        pat, vals, _, _ = self._ref_system()
+        return sp.csr_matrix((vals.cpu().numpy(), pat.col_idx.cpu().numpy(),
                               pat.row_ptr.cpu().numpy()), shape=(pat.nrows, pat.nrows))
 
     @property
@@ -289,16 +335,15 @@ class FemProblem:
             return sp.lil_matrix((n, n))
         if self._K_host is None:
             import torch
-            st = self._dev
-            pat = st["pattern"]
-            vals = st["vals"].clone()
+            pat, vals, rhs, dirmask = self._ref_system()
+            vals = vals.clone()
             sym = getattr(self, "_bc_mode", "reference") == "corrected"      # zero Dirichlet values: rhs unchanged
             torch.ops.feprogram.apply_bc(1 if sym else 0, pat.row_ptr, pat.col_idx, vals,
-                                         st["rhs"].clone() if sym else st["rhs"], st["dirmask"])
+                                         rhs.clone() if sym else rhs, dirmask)
             K = sp.csr_matrix((vals.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
                               shape=(pat.nrows, pat.nrows))
             # Dirichlet rows keep only their unit diagonal (canonical form of the LIL deletes, elements.py:187-191)
-            mask = st["dirmask"].cpu().numpy().astype(bool)
+            mask = dirmask.cpu().numpy().astype(bool)
             rows = np.repeat(np.arange(pat.nrows), np.diff(K.indptr))
             keep = ~mask[rows] | (K.indices == rows)
             counts = np.bincount(rows[keep], minlength=pat.nrows)
@@ -316,7 +361,10 @@ class FemProblem:
         if not self._assembled:
             return sp.lil_matrix((self.nnode * 2, 1))
         if self._brhs_host is None:
-            self._brhs_host = sp.csc_matrix(self._dev["rhs"].cpu().numpy()[:, None])
+            rhs = self._dev["rhs"]
+            if self._dev["perm"] is not None:
+                rhs = rhs.view(-1, 2)[self._dev["perm"]].reshape(-1)
+            self._brhs_host = sp.csc_matrix(rhs.cpu().numpy()[:, None])
         return self._brhs_host
 
     @brhs.setter
@@ -337,4 +385,6 @@ class FemProblem:
         self.solver_info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]),
                                 converged=bool(info[3]))
         st["x"] = x
+        if st["perm"] is not None:
+            x = x.view(-1, 2)[st["perm"]].reshape(-1)          # back to the reference's dof numbering
         return x.cpu().numpy()

@@ -325,6 +325,41 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern
 
 
 # --------------------------------------------------------------------------------------------
+# locality renumbering (solver-internal; the reference numbering stays the public one)
+# --------------------------------------------------------------------------------------------
+def numbering_span(conn: Tensor) -> float:
+    """Median over the elements of (largest - smallest node id): ~ the row length of the lattice for a
+    row-major numbering, ~ nnode / 2 for a random one."""
+    if conn.shape[0] == 0:
+        return 0.0
+    c = conn[:: max(1, conn.shape[0] // 65536)].to(torch.int64)
+    return float((c.max(dim=1).values - c.min(dim=1).values).to(torch.float64).median().item())
+
+
+def locality_order(coords: Tensor) -> Tuple[Tensor, Tensor]:
+    """(perm, order): Morton (Z-curve) order of the nodes; node `old` becomes node perm[old], order = perm^-1.
+    Used only inside the solver: assembly tiles then own (nearly) contiguous CSR row ranges and the SpMV
+    gathers of x stay in L1/L2, whatever the input numbering (BASELINE cfg5: shuffled node numbering)."""
+    xy = coords[:, :2]
+    lo = xy.min(dim=0).values
+    span = (xy.max(dim=0).values - lo).clamp_min(1e-300)
+    q = ((xy - lo) / span * 65535.0).to(torch.int64).clamp_(0, 65535)
+
+    def spread(v):
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        v = (v | (v << 1)) & 0x55555555
+        return v
+
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << 1)
+    order = torch.argsort(key, stable=True)
+    perm = torch.empty_like(order)
+    perm[order] = torch.arange(order.numel(), device=order.device)
+    return perm, order
+
+
+# --------------------------------------------------------------------------------------------
 # tile plan for the fast assembly kernel
 # --------------------------------------------------------------------------------------------
 import os as _os

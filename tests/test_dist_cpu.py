@@ -76,7 +76,10 @@ def _worker(rank, world, port, kind, structured, out):
             mx = n if kind == 4 else 2 * n
             coords = mesh.perturb_interior(coords, mx, mx, 0.2, seed=3)
             conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=8)
-            m = fdist.exchange_send_lists(fdist.partition_mesh(conn - 1, coords, rank, world))
+            # Quad9 case: Z-curve local numbering (owned nodes no longer in ascending global id)
+            m = fdist.exchange_send_lists(fdist.partition_mesh(conn - 1, coords, rank, world, locality=(kind == 9)))
+            if kind == 9 and m.n_owned > 2:
+                assert not np.all(np.diff(m.node_gid[: m.n_owned]) > 0)
         conn0 = conn - 1
         K = orc.assemble_csr(conn0, coords)
         d, nn = orc.boundary_dofs(bc)

@@ -36,7 +36,7 @@ def test_rank_shares_reproduce_single_domain_rows_bitwise(world, kind):
                       shape=(pat.nrows, pat.nrows))
     seen = np.zeros(coords.shape[0], dtype=int)
     for rank in range(world):
-        m = fdist.partition_mesh(conn - 1, coords, rank, world)
+        m = fdist.partition_mesh(conn - 1, coords, rank, world, locality=(world == 3 or kind == 9))
         p = fdist.DistFemProblem(m, "cuda:0", kind, comm=None)
         p.assemble()
         Kl = sp.csr_matrix((p.vals.cpu().numpy(), p.pat.col_idx.cpu().numpy(), p.pat.row_ptr.cpu().numpy()),
@@ -66,7 +66,7 @@ for case in ("general", "structured"):
         conn, coords, bc = mesh.structured_quad4(48)
         coords = mesh.perturb_interior(coords, 48, 48, 0.2, seed=2)
         conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=3)
-        m = fdist.exchange_send_lists(fdist.partition_mesh(conn - 1, coords, rank, world))
+        m = fdist.exchange_send_lists(fdist.partition_mesh(conn - 1, coords, rank, world, locality=True))
         d = np.array(sorted(bc[0]), dtype=np.int64) - 1; l = np.array(sorted(bc[3]), dtype=np.int64) - 1
         g2l = np.full(coords.shape[0], -1, dtype=np.int64); g2l[m.node_gid] = np.arange(m.nnode)
         loc = lambda nodes: np.sort(np.concatenate([2 * g2l[nodes][g2l[nodes] >= 0], 2 * g2l[nodes][g2l[nodes] >= 0] + 1]))

@@ -632,3 +632,47 @@ def test_corrected_mode_is_mesh_independent(torch_cuda):
         U = fem.solveProblem().reshape(-1, 2)
         tip.append(U[(n + 1) * n])            # top-left corner node
     assert np.abs(tip[1] - tip[0]).max() < 0.05 * np.abs(tip[0]).max()
+
+
+# ---------------------------------------------------------------------------------------------------
+# solver-internal locality renumbering (BASELINE cfg5: shuffled node numbering)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["q4_12x12_pert_shuf", "q9_6x6_pert_shuf"])
+def test_renumbered_solver_keeps_reference_numbering(torch_cuda, golden, name):
+    z = golden(name)
+    a = run_facade(z, renumber=False)
+    b = run_facade(z, renumber=True)
+    assert b._dev["perm"] is not None and a._dev["perm"] is None
+    Ka, Kb = a.csr_prebc(), b.csr_prebc()
+    assert np.array_equal(Ka.indptr, Kb.indptr) and np.array_equal(Ka.indices, Kb.indices)
+    assert np.array_equal(Ka.data, Kb.data)                      # same element order, same pair arithmetic
+    assert np.array_equal(a.brhs.toarray(), b.brhs.toarray())
+    assert abs(a.K - b.K).max() == 0.0
+    for fem in (a, b):
+        fem.rtol = 1e-12
+    Ua, Ub = a.solveProblem(), b.solveProblem()
+    assert np.linalg.norm(Ub - z["U"]) / np.linalg.norm(z["U"]) < SOL_TOL
+    assert np.linalg.norm(Ub - Ua) / np.linalg.norm(Ua) < 1e-9
+
+
+def test_renumbering_is_automatic_for_shuffled_large_meshes(torch_cuda):
+    from feprogram_b200 import mesh
+    from feprogram_b200.elements import FemProblem
+    conn, coords, bc = mesh.structured_quad4(360)
+    fem = FemProblem(conn, coords)
+    fem.setMatrix(); fem.setBoundaryConditions(bc, verbose=False); fem.assemble()
+    assert fem._dev["perm"] is None                              # row-major lattice: already local
+    coords_p = mesh.perturb_interior(coords, 360, 360, 0.2, seed=0)
+    conn2, coords2, bc2, _ = mesh.shuffle_numbering(conn, coords_p, bc, seed=1)
+    fem2 = FemProblem(conn2, coords2)
+    fem2.setMatrix(); fem2.setBoundaryConditions(bc2, verbose=False, mode="corrected"); fem2.assemble()
+    assert fem2._dev["perm"] is not None
+    U2 = fem2.solveProblem()
+    fem3 = FemProblem(conn2, coords2, renumber=False)
+    fem3.setMatrix(); fem3.setBoundaryConditions(bc2, verbose=False, mode="corrected"); fem3.assemble()
+    U3 = fem3.solveProblem()
+    assert fem2.solver_info["converged"] and np.linalg.norm(U2 - U3) / np.linalg.norm(U3) < 1e-7
+    K2 = fem2.csr_prebc()
+    Ko = orc.assemble_csr(conn2 - 1, coords2)
+    assert np.array_equal(K2.indptr, Ko.indptr) and np.array_equal(K2.indices, Ko.indices)
+    assert rel_max(K2.data, Ko.data) < VAL_TOL
