@@ -102,7 +102,9 @@ def partition_mesh(conn0: np.ndarray, coords: np.ndarray, rank: int, world: int,
     nnode = coords.shape[0]
     bounds = element_blocks(nelem, world) if bounds is None else np.asarray(bounds, dtype=np.int64)
     first = np.full(nnode, nelem, dtype=np.int64)
-    np.minimum.at(first, conn0.ravel(), np.repeat(np.arange(nelem, dtype=np.int64), nnpe))
+    # lowest incident element of every node: element-major writes in DESCENDING element order, the last
+    # (= lowest) one stays (what np.minimum.at computes, two orders of magnitude faster on 10^8 entries)
+    first[conn0[::-1].ravel()] = np.repeat(np.arange(nelem - 1, -1, -1, dtype=np.int64), nnpe)
     owner = np.searchsorted(bounds, first, side="right") - 1
     owner[first == nelem] = -1                                   # nodes without elements belong to nobody
     mine = owner == rank
