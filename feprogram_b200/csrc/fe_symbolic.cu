@@ -118,26 +118,56 @@ __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, int nnpe,
     }
 }
 
+// One CTA expands kExpandNodes consecutive nodes: their rows form one contiguous range of col_idx, written
+// flat (coalesced, 16-byte stores for ndof = 2); the owning node of an entry is found by binary search in the
+// CTA's slice of nptr held in shared memory.  A node's ndof rows are ndof copies of the same column sequence.
+constexpr int kExpandNodes = 512;
 template <typename IdxT>
 __global__ void __launch_bounds__(256) k_csr_expand(int64_t nnode, int ndof, const int32_t* __restrict__ nptr,
                                                     const int32_t* __restrict__ nadj, IdxT* __restrict__ row_ptr,
                                                     int32_t* __restrict__ col_idx) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nrows = nnode * ndof;
-    if (r > nrows) return;
-    if (r == nrows) {
-        row_ptr[r] = (IdxT)((int64_t)ndof * ndof * nptr[nnode]);
-        return;
+    __shared__ int sp[kExpandNodes + 1];
+    const int64_t n0 = (int64_t)blockIdx.x * kExpandNodes;
+    const int cnt = (int)((nnode - n0) < kExpandNodes ? (nnode - n0) : kExpandNodes);
+    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) sp[i] = nptr[n0 + i];
+    __syncthreads();
+    const int nd2 = ndof * ndof;
+    for (int i = threadIdx.x; i < cnt * ndof; i += blockDim.x) {
+        const int ln = i / ndof, c = i - ln * ndof;
+        row_ptr[n0 * ndof + i] = (IdxT)((int64_t)nd2 * sp[ln] + (int64_t)c * ndof * (sp[ln + 1] - sp[ln]));
     }
-    const int64_t n = r / ndof;
-    const int c = (int)(r - n * ndof);
-    const int p0 = nptr[n];
-    const int deg = nptr[n + 1] - p0;
-    const int64_t start = (int64_t)ndof * ndof * p0 + (int64_t)c * ndof * deg;
-    row_ptr[r] = (IdxT)start;
-    for (int p = 0; p < deg; ++p) {
-        const int m = nadj[p0 + p];
-        for (int d = 0; d < ndof; ++d) col_idx[start + (int64_t)ndof * p + d] = ndof * m + d;
+    if (n0 + cnt == nnode && threadIdx.x == 0) row_ptr[nnode * ndof] = (IdxT)((int64_t)nd2 * sp[cnt]);
+    const int q0 = sp[0], q1 = sp[cnt];
+    auto node_of = [&](int q) {   // largest i with sp[i] <= q
+        int lo = 0, hi = cnt;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sp[mid] <= q) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
+    if (ndof == 2) {
+        int4* out = reinterpret_cast<int4*>(col_idx);   // cudaMalloc'd base, segments start at multiples of 4
+        for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+            const int i = node_of(q);
+            const int p0 = sp[i], deg2 = 2 * (sp[i + 1] - p0);
+            int v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int kk = 4 * (q - p0) + j;
+                if (kk >= deg2) kk -= deg2;
+                v[j] = 2 * __ldg(nadj + p0 + (kk >> 1)) + (kk & 1);
+            }
+            out[q] = make_int4(v[0], v[1], v[2], v[3]);
+        }
+    } else {
+        const int64_t g0 = (int64_t)nd2 * q0, g1 = (int64_t)nd2 * q1;
+        for (int64_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+            const int i = node_of((int)(g / nd2));
+            const int p0 = sp[i], deg = sp[i + 1] - p0;
+            const int kk = (int)((g - (int64_t)nd2 * p0) % (ndof * deg));
+            col_idx[g] = ndof * __ldg(nadj + p0 + kk / ndof) + kk % ndof;
+        }
     }
 }
 
@@ -224,13 +254,14 @@ int fe_csr_expand(int ndof, int64_t nnode, const int32_t* nptr, const int32_t* n
     using namespace fe;
     FE_REQUIRE(ndof >= 1 && ndof <= 3 && nnode >= 0 && nptr && nadj && row_ptr && col_idx,
                "null pointer, negative size or ndof out of range");
+    FE_REQUIRE(ndof != 2 || (reinterpret_cast<uintptr_t>(col_idx) & 15) == 0, "col_idx must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
-    const int64_t nrows = nnode * ndof;
+    const unsigned grid = nnode > 0 ? grid_for(nnode, kExpandNodes) : 1u;
     if (idx64)
-        k_csr_expand<int64_t><<<grid_for(nrows + 1, 256), 256, 0, st>>>(nnode, ndof, nptr, nadj,
+        k_csr_expand<int64_t><<<grid, 256, 0, st>>>(nnode, ndof, nptr, nadj,
                                                                         static_cast<int64_t*>(row_ptr), col_idx);
     else
-        k_csr_expand<int32_t><<<grid_for(nrows + 1, 256), 256, 0, st>>>(nnode, ndof, nptr, nadj,
+        k_csr_expand<int32_t><<<grid, 256, 0, st>>>(nnode, ndof, nptr, nadj,
                                                                         static_cast<int32_t*>(row_ptr), col_idx);
     FE_CHECK_LAUNCH("k_csr_expand");
     return FE_OK;

@@ -158,64 +158,126 @@ __global__ void k_tile_bucket(int64_t nnode, const int32_t* __restrict__ owner, 
 // One thread per tile: sort the tile's node list ascending (deterministic order after the atomic bucket
 // fill); lay out items and work items (noff[2i], noff[2i+1] = item / work offset of tile-node slot i
 // inside its tile); collect the sorted, distinct halo elements.
-__global__ void __launch_bounds__(64) k_tile_layout(int64_t ntiles, const int32_t* __restrict__ tile_nptr,
-                                                    int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ eptr,
-                                                    const int32_t* __restrict__ einc, const int32_t* __restrict__ einv,
-                                                    const int32_t* __restrict__ nptr, int32_t* __restrict__ noff,
-                                                    int32_t* __restrict__ thalo, int32_t* __restrict__ tile_icount,
-                                                    int32_t* __restrict__ tile_hcount, int32_t* __restrict__ tile_wcount,
-                                                    int32_t* __restrict__ stats, int he) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per tile: (1) sort the tile's owned nodes by id (rank sort in shared memory), (2) per-node item /
+// work offsets by warp scans, (3) the halo list = sorted set of the foreign elements incident to owned nodes
+// (candidates collected in shared memory, rank-sorted, first occurrences compacted).
+constexpr int kLayoutWarps = 4, kLayoutNodes = 256, kLayoutCand = 1024;
+__global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
+    int64_t ntiles, const int32_t* __restrict__ tile_nptr, int32_t* __restrict__ tile_nodes,
+    const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc, const int32_t* __restrict__ einv,
+    const int32_t* __restrict__ nptr, int32_t* __restrict__ noff, int32_t* __restrict__ thalo,
+    int32_t* __restrict__ tile_icount, int32_t* __restrict__ tile_hcount, int32_t* __restrict__ tile_wcount,
+    int32_t* __restrict__ stats, int he) {
+    __shared__ int s_nodes[kLayoutWarps][kLayoutNodes];
+    __shared__ int s_cand[kLayoutWarps][kLayoutCand];
+    __shared__ int s_sorted[kLayoutWarps][kLayoutCand];
+    __shared__ int s_ncand[kLayoutWarps];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * kLayoutWarps + w;
     if (t > ntiles) return;
     if (t == ntiles) {
-        tile_icount[t] = tile_hcount[t] = tile_wcount[t] = 0;
+        if (lane == 0) tile_icount[t] = tile_hcount[t] = tile_wcount[t] = 0;
         return;
     }
-    const int lo = tile_nptr[t], hi = tile_nptr[t + 1];
-    for (int i = lo + 1; i < hi; ++i) {
-        const int v = tile_nodes[i];
-        int j = i;
-        while (j > lo && tile_nodes[j - 1] > v) {
-            tile_nodes[j] = tile_nodes[j - 1];
-            --j;
+    const int lo = tile_nptr[t], hi = tile_nptr[t + 1], nn = hi - lo;
+    if (nn > kLayoutNodes) {        // beyond every tile capacity: report it, the host discards this plan
+        if (lane == 0) {
+            tile_icount[t] = tile_hcount[t] = tile_wcount[t] = 0;
+            atomicMax(stats + 0, nn);
         }
-        tile_nodes[j] = v;
+        return;
     }
-    int hl[kHaloElemsMax];
-    int ni = 0, nh = 0, nw = 0, maxcnt = 0;
-    bool overflow = false;
-    for (int i = lo; i < hi; ++i) {
-        const int n = tile_nodes[i];
-        noff[2 * (int64_t)i] = ni;
-        noff[2 * (int64_t)i + 1] = nw;
-        const int k0 = eptr[n], k1 = eptr[n + 1];
-        ni += k1 - k0;
-        maxcnt = (k1 - k0) > maxcnt ? (k1 - k0) : maxcnt;
-        nw += nptr[n + 1] - nptr[n];
-        for (int k = k0; k < k1; ++k) {
-            const int e = einc[k] >> 4;
-            if (tile_of(einv, e) == (int)t) continue;
-            int j = nh;
-            while (j > 0 && hl[j - 1] > e) --j;
-            if (j > 0 && hl[j - 1] == e) continue;
-            if (nh == he) {
-                overflow = true;
-                continue;
+    int* nodes = s_nodes[w];
+    int* cand = s_cand[w];
+    int* sorted = s_sorted[w];
+    for (int i = lane; i < nn; i += 32) sorted[i] = tile_nodes[lo + i];
+    if (lane == 0) s_ncand[w] = 0;
+    __syncwarp();
+    for (int i = lane; i < nn; i += 32) {       // node ids are distinct: rank = number of smaller ids
+        const int v = sorted[i];
+        int r = 0;
+        for (int j = 0; j < nn; ++j) r += sorted[j] < v;
+        nodes[r] = v;
+    }
+    __syncwarp();
+    int ni = 0, nw = 0, maxcnt = 0;
+    for (int i0 = 0; i0 < nn; i0 += 32) {
+        const int i = i0 + lane;
+        int ci = 0, cw = 0, n = 0, k0 = 0;
+        if (i < nn) {
+            n = nodes[i];
+            tile_nodes[lo + i] = n;
+            k0 = eptr[n];
+            ci = eptr[n + 1] - k0;
+            cw = nptr[n + 1] - nptr[n];
+        }
+        int si = ci, sw = cw;               // inclusive warp scans
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int ui = __shfl_up_sync(0xffffffffu, si, d), uw = __shfl_up_sync(0xffffffffu, sw, d);
+            if (lane >= d) {
+                si += ui;
+                sw += uw;
             }
-            for (int q = nh; q > j; --q) hl[q] = hl[q - 1];
-            hl[j] = e;
-            ++nh;
         }
+        if (i < nn) {
+            noff[2 * (int64_t)(lo + i)] = ni + si - ci;
+            noff[2 * (int64_t)(lo + i) + 1] = nw + sw - cw;
+            maxcnt = ci > maxcnt ? ci : maxcnt;
+            for (int k = k0; k < k0 + ci; ++k) {
+                const int e = einc[k] >> 4;
+                if (tile_of(einv, e) == (int)t) continue;
+                const int slot = atomicAdd(&s_ncand[w], 1);
+                if (slot < kLayoutCand) cand[slot] = e;
+            }
+        }
+        ni += __shfl_sync(0xffffffffu, si, 31);
+        nw += __shfl_sync(0xffffffffu, sw, 31);
     }
-    for (int j = 0; j < nh; ++j) thalo[t * he + j] = hl[j];
-    tile_icount[t] = (ni + 1) & ~1;    // even: item locators are staged with 4-byte cp.async
-    tile_hcount[t] = nh;
-    tile_wcount[t] = (nw + 31) & ~31;  // chunks of 32 work items never straddle tiles
-    atomicMax(stats + 0, hi - lo);
-    atomicMax(stats + 1, ni);
-    atomicMax(stats + 2, overflow ? he + 1 : nh);
-    atomicMax(stats + 3, maxcnt);
-    atomicMax(stats + 5, nw);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int o = __shfl_xor_sync(0xffffffffu, maxcnt, d);
+        maxcnt = o > maxcnt ? o : maxcnt;
+    }
+    __syncwarp();
+    int nc = s_ncand[w];
+    bool overflow = nc > kLayoutCand;
+    if (overflow) nc = kLayoutCand;
+    for (int i = lane; i < nc; i += 32) {       // stable rank sort (duplicates keep their order)
+        const int v = cand[i];
+        int r = 0;
+        for (int j = 0; j < nc; ++j) {
+            const int u = cand[j];
+            r += (u < v) || (u == v && j < i);
+        }
+        sorted[r] = v;
+    }
+    __syncwarp();
+    int nh = 0;                                  // compact first occurrences, ascending
+    for (int i0 = 0; i0 < nc; i0 += 32) {
+        const int i = i0 + lane;
+        const bool first = i < nc && (i == 0 || sorted[i] != sorted[i - 1]);
+        const unsigned m = __ballot_sync(0xffffffffu, first);
+        if (first) {
+            const int pos = nh + __popc(m & ((1u << lane) - 1u));
+            if (pos < he) thalo[t * he + pos] = sorted[i];
+        }
+        nh += __popc(m);
+    }
+    if (nh > he) {
+        overflow = true;
+        nh = he;
+    }
+    if (lane == 0) {
+        tile_icount[t] = (ni + 1) & ~1;    // even: item locators are staged with 4-byte cp.async
+        tile_hcount[t] = nh;
+        tile_wcount[t] = (nw + 31) & ~31;  // chunks of 32 work items never straddle tiles
+        atomicMax(stats + 0, nn);
+        atomicMax(stats + 1, ni);
+        atomicMax(stats + 2, overflow ? he + 1 : nh);
+        atomicMax(stats + 3, maxcnt);
+        atomicMax(stats + 5, nw);
+    }
 }
 
 // Tile-ordered copy of the connectivity: row r of tile t = own element r (r < own count) or halo element
@@ -748,7 +810,7 @@ int fe_tile_layout(int elem_type, int64_t nnode, int64_t ntiles, const int32_t* 
         FE_CHECK_LAUNCH("k_tile_bucket");
     }
     const int64_t s = ntiles + 1;
-    k_tile_layout<<<grid_for(ntiles + 1, 64), 64, 0, st>>>(ntiles, tile_nptr, tile_nodes, eptr, einc, einv, nptr, noff,
+    k_tile_layout<<<grid_for(ntiles + 1, kLayoutWarps), 32 * kLayoutWarps, 0, st>>>(ntiles, tile_nptr, tile_nodes, eptr, einc, einv, nptr, noff,
                                                           thalo, tile_counts, tile_counts + s, tile_counts + 2 * s,
                                                           stats, halo_cap(nnpe_of(elem_type)));
     FE_CHECK_LAUNCH("k_tile_layout");

@@ -224,9 +224,13 @@ class FemProblem:
             raise RuntimeError("feprogram_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         return torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
 
-    def _state(self):
-        """Uploads connectivity (int32, 0-based) and coordinates once."""
+    def _state(self, defer_coords=False):
+        """Uploads connectivity (int32, 0-based) and coordinates once.  The coordinates travel on a side stream
+        behind the connectivity so that the first part of the symbolic phase (which only needs the
+        connectivity) overlaps their transfer; ``defer_coords`` leaves the wait to the caller (assemble)."""
         if self._dev is not None:
+            if not defer_coords:
+                self._coords_ready()
             return self._dev
         import torch
         from . import ops  # noqa: F401  (registers torch.ops.feprogram.*)
@@ -238,18 +242,28 @@ class FemProblem:
             conn = conn.astype(np.int64)
         if conn.dtype.kind == "u":                       # gmsh hands out uint64 tags; same bits as int64
             conn = conn.view(np.int64 if conn.dtype.itemsize == 8 else np.int32)
-        tags = torch.from_numpy(np.ascontiguousarray(conn)).to(dev, non_blocking=True)
         xy = np.asarray(self.coordinates, dtype=np.float64)
         if xy.shape[1] != 2 or not xy.flags.c_contiguous:
             xy = np.ascontiguousarray(xy[:, :2])
+        main = torch.cuda.current_stream(dev)
+        tags = torch.from_numpy(np.ascontiguousarray(conn)).to(dev, non_blocking=True)
+        side = torch.cuda.Stream(dev)
+        side.wait_event(main.record_event())          # one host->device transfer at a time: connectivity first
+        with torch.cuda.stream(side):
+            coords_d = torch.from_numpy(xy).to(dev, non_blocking=True)
+        coords_d.record_stream(main)
         st = {
             "conn": torch.ops.feprogram.tags_to_conn(tags),                       # elements.py:172 `elem-1`
-            "coords": torch.from_numpy(xy).to(dev, non_blocking=True),
+            "coords": coords_d,
+            "coords_event": side.record_event(),
         }
+        self._dev = st
         ren = self._renumber
         if ren is None:      # a row-major lattice spans ~sqrt(nnode) ids per element, a shuffled one ~nnode/2
             ren = self.nnode > 100000 and ops.numbering_span(st["conn"]) > 64.0 * np.sqrt(self.nnode)
         st["conn_s"], st["coords_s"], st["perm"] = st["conn"], st["coords"], None
+        if ren or not defer_coords:
+            self._coords_ready()
         if ren:
             perm, order = ops.locality_order(st["coords"])
             st["perm"] = perm                                                     # reference node -> solver node
@@ -257,6 +271,13 @@ class FemProblem:
             st["coords_s"] = st["coords"][order].contiguous()
         self._dev = st
         return self._dev
+
+    def _coords_ready(self):
+        """Makes the current stream wait for the coordinate upload (once)."""
+        import torch
+        ev = self._dev.pop("coords_event", None)
+        if ev is not None:
+            torch.cuda.current_stream(self._dev["conn"].device).wait_event(ev)
 
     def _solver_dofs(self, dofs):
         """Reference dof ids -> dof ids of the (possibly renumbered) solver mesh, as a device tensor."""
@@ -271,11 +292,13 @@ class FemProblem:
     def assemble(self):
         import torch
         from . import ops
-        st = self._state()
+        st = self._state(defer_coords=True)
         et = _ELEM_CODES[self.elem.elemType]
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
-            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)
+            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)     # overlaps the coordinate upload
+            self._coords_ready()
             st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"])
+        self._coords_ready()
         pat = st["pattern"]
         dev = st["conn"].device
         if "vals" not in st:
