@@ -33,6 +33,10 @@ namespace fe {
 #define FE_HALO_ELEMS 32
 #define FE_TILE_CTAS 3
 #endif
+#ifndef FE_HALF_WARP_ROWS
+#define FE_HALF_WARP_ROWS 0   // phase 2a experiment: two lanes per block, one row half each (compact store
+                              // footprints); measured SLOWER on B200 (cfg2 1.91 ms vs 1.71 ms) -- kept for reference
+#endif
 #ifndef FE_Q9_CTAS
 #define FE_Q9_CTAS 2
 #endif
@@ -76,10 +80,13 @@ template <int N> struct TileLayout {
     static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
     // shared copy of the rows' node coordinates (multi-thread-per-element types only)
     static constexpr size_t kXyBytes = kParts > 1 ? (size_t)kRows * N * 16 : 0;
+    // per row: (j00, j01, j10, j11, scale) of every Gauss point (multi-thread-per-element types only)
+    static constexpr int kJacStride = 5 * N;       // Quad9: N Gauss points; odd stride
+    static constexpr size_t kJacBytes = kParts > 1 ? (size_t)kRows * kJacStride * 8 : 0;
     // one set of staged plan records (16-byte aligned size); the kernel double-buffers it
     static constexpr size_t kRecBytes = (size_t)kMaxWork * 4 + (size_t)kMaxNodes * 8 + (size_t)(kMaxWork / 32) * 4 +
                                         (size_t)kMaxItems * 2;
-    static constexpr size_t kSmem = (size_t)kSlabDoubles * sizeof(double) + 2 * kRecBytes + kXyBytes;
+    static constexpr size_t kSmem = (size_t)kSlabDoubles * sizeof(double) + 2 * kRecBytes + kXyBytes + kJacBytes;
     // block index of the pair lo <= hi in the upper triangle (row-major)
     __host__ __device__ static constexpr int tri(int lo, int hi) { return lo * N - lo * (lo - 1) / 2 + (hi - lo); }
 };
@@ -413,11 +420,36 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
     for (int a = 0; a < E::NNPE; ++a) out[3 * T::tri(a, a) + 2] = out[3 * T::tri(a, a) + 1];
 }
 
+// Quad9: Jacobian J_g = dH_g X and the scale s_g (1/det, times the Gauss weight when weighted; det * weight for
+// the mass operator) of Gauss point g -- same expressions as gauss_point<ET> (fe_element.cuh), computed ONCE per
+// element (the five threads of an element share the nine Gauss points) instead of by every thread.
+template <bool MASS>
+__device__ __forceinline__ void q9_jacobian(const double2* __restrict__ xy, int g, bool weighted, double* __restrict__ out) {
+    double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const double2 p = xy[b];
+        const double hr = c_q9.dH[g][0][b], hs = c_q9.dH[g][1][b];
+        j00 = fma(hr, p.x, j00);
+        j01 = fma(hr, p.y, j01);
+        j10 = fma(hs, p.x, j10);
+        j11 = fma(hs, p.y, j11);
+    }
+    const double det = fma(j00, j11, -__dmul_rn(j01, j10));
+    double s = MASS ? __dmul_rn(det, c_q9.w[g]) : 1.0 / det;
+    if (!MASS && weighted) s = __dmul_rn(s, c_q9.w[g]);
+    out[0] = j00;
+    out[1] = j01;
+    out[2] = j10;
+    out[3] = j11;
+    out[4] = s;
+}
+
 // Quad9: one of five threads of an element evaluates the block rows A1 (and A2) of the upper triangle --
 // {0}, {1,8}, {2,7}, {3,6}, {4,5}: nine blocks = 27 accumulators each -- reading the element's node
 // coordinates from shared memory.  Same pair arithmetic (and therefore the same bits) as element_row_pair.
 template <int A1, int A2, bool MASS>
-__device__ __forceinline__ void q9_block_rows(const double2* __restrict__ xy, bool weighted, double* __restrict__ dst) {
+__device__ __forceinline__ void q9_block_rows(const double* __restrict__ Jrow, double* __restrict__ dst) {
     constexpr int N = 9;
     using T = TileLayout<N>;
     constexpr int N1 = N - A1, N2 = A2 >= 0 ? N - A2 : 1;
@@ -426,21 +458,11 @@ __device__ __forceinline__ void q9_block_rows(const double2* __restrict__ xy, bo
     for (int i = 0; i < 3 * N1; ++i) acc1[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 3 * N2; ++i) acc2[i] = 0.0;
-#pragma unroll 1
+#pragma unroll 3
     for (int g = 0; g < 9; ++g) {
-        double j00 = 0.0, j01 = 0.0, j10 = 0.0, j11 = 0.0;
-#pragma unroll
-        for (int b = 0; b < N; ++b) {
-            const double2 p = xy[b];
-            const double hr = c_q9.dH[g][0][b], hs = c_q9.dH[g][1][b];
-            j00 = fma(hr, p.x, j00);
-            j01 = fma(hr, p.y, j01);
-            j10 = fma(hs, p.x, j10);
-            j11 = fma(hs, p.y, j11);
-        }
-        const double det = fma(j00, j11, -__dmul_rn(j01, j10));
-        double s = MASS ? __dmul_rn(det, c_q9.w[g]) : 1.0 / det;
-        if (!MASS && weighted) s = __dmul_rn(s, c_q9.w[g]);
+        // Jacobian and scale of this Gauss point: evaluated once per element by q9_jacobians (shared memory)
+        const double j00 = Jrow[5 * g], j01 = Jrow[5 * g + 1], j10 = Jrow[5 * g + 2], j11 = Jrow[5 * g + 3];
+        const double s = Jrow[5 * g + 4];
         double sx1 = 0.0, sy1 = 0.0, sx2 = 0.0, sy2 = 0.0;
 #pragma unroll
         for (int b = A1; b < N; ++b) {
@@ -568,6 +590,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
     if constexpr (kSingle) load_xy(tg, x, y);
     int buf = 0;
     double2* s_xy = reinterpret_cast<double2*>(rec_base + 2 * T::kRecBytes);   // Quad9 only
+    double* s_jac = reinterpret_cast<double*>(rec_base + 2 * T::kRecBytes + T::kXyBytes);   // Quad9 only
 
     for (; t < ntiles; t += gridDim.x) {
         const int64_t tn = t + gridDim.x, tn2 = tn + gridDim.x;
@@ -606,15 +629,21 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
             }
             __syncthreads();
             const int part = tid / T::kRowThreads, row = tid - part * T::kRowThreads;
-            if (row < T::kRows && __ldg(rows + row * N) >= 0) {
-                const double2* xy = s_xy + row * N;
+            const bool live = row < T::kRows && __ldg(rows + row * N) >= 0;
+            if (live) {
+                for (int g = part; g < 9; g += T::kParts)
+                    q9_jacobian<MASS>(s_xy + row * N, g, weighted != 0, s_jac + row * T::kJacStride + 5 * g);
+            }
+            __syncthreads();
+            if (live) {
+                const double* jr = s_jac + row * T::kJacStride;
                 double* dst = slab + row * SS;
                 switch (part) {          // warp-uniform: kRowThreads is a multiple of 32
-                    case 0: q9_block_rows<0, -1, MASS>(xy, weighted != 0, dst); break;
-                    case 1: q9_block_rows<1, 8, MASS>(xy, weighted != 0, dst); break;
-                    case 2: q9_block_rows<2, 7, MASS>(xy, weighted != 0, dst); break;
-                    case 3: q9_block_rows<3, 6, MASS>(xy, weighted != 0, dst); break;
-                    default: q9_block_rows<4, 5, MASS>(xy, weighted != 0, dst); break;
+                    case 0: q9_block_rows<0, -1, MASS>(jr, dst); break;
+                    case 1: q9_block_rows<1, 8, MASS>(jr, dst); break;
+                    case 2: q9_block_rows<2, 7, MASS>(jr, dst); break;
+                    case 3: q9_block_rows<3, 6, MASS>(jr, dst); break;
+                    default: q9_block_rows<4, 5, MASS>(jr, dst); break;
                 }
             }
         }
@@ -663,6 +692,39 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
             const int2* node = s_node(buf);
             const uint16_t* locs = s_loc(buf);
             // ---- phase 2a: off-diagonal work items ---------------------------------------------------
+#if FE_HALF_WARP_ROWS
+            // Two lanes per work item: lane j < 16 writes the (L, P) half of block j (row 2n), lane j + 16 the
+            // (Q, L) half (row 2n + 1), so ONE store instruction covers 16 blocks x 32 B of (nearly) contiguous
+            // CSR values instead of two instructions that each touch every line of a 32-block span.
+            for (int q0 = (tid & ~31); q0 < nw; q0 += kTileThreads) {
+                const unsigned ch = chunk[q0 >> 5];
+                const int sub = lane & 15, half = lane >> 4;
+                const unsigned recA = work[q0 + sub], recB = work[q0 + 16 + sub];
+                const unsigned firstA = __ballot_sync(0xFFFFFFFFu, (recA & kWorkFirst) != 0) & 0xFFFFu;
+                const unsigned firstB = __ballot_sync(0xFFFFFFFFu, (recB & kWorkFirst) != 0) << 16;
+                const unsigned firsts = firstA | firstB;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned rec = h ? recB : recA;
+                    const int item = 16 * h + sub;
+                    const unsigned before = firsts & (0xFFFFFFFFu >> (31 - item));
+                    const int ln = (int)(ch >> 7) - 1 + __popc(before);
+                    const int p = before ? item - (31 - __clz(before)) : (int)(ch & 127u) + item;
+                    if (rec == 0u || (rec & kWorkSelf)) continue;   // padding or diagonal block
+                    const int2 nd = node[ln];
+                    const int deg = nd.y & 127;
+                    const unsigned s0 = rec & 0x1FFFu, s1 = (rec >> 13) & 0x1FFFu;
+                    const double* b0 = slab + (s0 >> (T::kTriBits + 1)) * SS + 3 * ((s0 >> 1) & T::kTriMask);
+                    const double* b1 = slab + (s1 >> (T::kTriBits + 1)) * SS + 3 * ((s1 >> 1) & T::kTriMask);
+                    const int f0 = s0 & 1, f1 = s1 & 1;            // transposed block: P and Q trade places
+                    const double L = b0[0] + b1[0];
+                    // half 0 needs P = [1 + f], half 1 needs Q = [2 - f]
+                    const double X = b0[half ? 2 - f0 : 1 + f0] + b1[half ? 2 - f1 : 1 + f1];
+                    double* out = vals + 4 * (int64_t)nd.x + 2 * p + (half ? 2 * deg : 0);
+                    __stcs(reinterpret_cast<double2*>(out), half ? make_double2(X, L) : make_double2(L, X));
+                }
+            }
+#else
             for (int q = tid; q < nw; q += kTileThreads) {
                 const unsigned rec = work[q];
                 const unsigned ch = chunk[q >> 5];
@@ -683,6 +745,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
                 __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(Q, L));
             }
+#endif
             // ---- phase 2b: diagonal blocks, one thread per owned node ---------------------------------
             for (int ln = tid; ln < nn; ln += kTileThreads) {
                 const int2 nd = node[ln];
