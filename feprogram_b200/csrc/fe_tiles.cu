@@ -33,10 +33,6 @@ namespace fe {
 #define FE_HALO_ELEMS 32
 #define FE_TILE_CTAS 3
 #endif
-#ifndef FE_HALF_WARP_ROWS
-#define FE_HALF_WARP_ROWS 0   // phase 2a experiment: two lanes per block, one row half each (compact store
-                              // footprints); measured SLOWER on B200 (cfg2 1.91 ms vs 1.71 ms) -- kept for reference
-#endif
 #ifndef FE_Q9_CTAS
 #define FE_Q9_CTAS 2
 #endif
@@ -692,39 +688,6 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
             const int2* node = s_node(buf);
             const uint16_t* locs = s_loc(buf);
             // ---- phase 2a: off-diagonal work items ---------------------------------------------------
-#if FE_HALF_WARP_ROWS
-            // Two lanes per work item: lane j < 16 writes the (L, P) half of block j (row 2n), lane j + 16 the
-            // (Q, L) half (row 2n + 1), so ONE store instruction covers 16 blocks x 32 B of (nearly) contiguous
-            // CSR values instead of two instructions that each touch every line of a 32-block span.
-            for (int q0 = (tid & ~31); q0 < nw; q0 += kTileThreads) {
-                const unsigned ch = chunk[q0 >> 5];
-                const int sub = lane & 15, half = lane >> 4;
-                const unsigned recA = work[q0 + sub], recB = work[q0 + 16 + sub];
-                const unsigned firstA = __ballot_sync(0xFFFFFFFFu, (recA & kWorkFirst) != 0) & 0xFFFFu;
-                const unsigned firstB = __ballot_sync(0xFFFFFFFFu, (recB & kWorkFirst) != 0) << 16;
-                const unsigned firsts = firstA | firstB;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const unsigned rec = h ? recB : recA;
-                    const int item = 16 * h + sub;
-                    const unsigned before = firsts & (0xFFFFFFFFu >> (31 - item));
-                    const int ln = (int)(ch >> 7) - 1 + __popc(before);
-                    const int p = before ? item - (31 - __clz(before)) : (int)(ch & 127u) + item;
-                    if (rec == 0u || (rec & kWorkSelf)) continue;   // padding or diagonal block
-                    const int2 nd = node[ln];
-                    const int deg = nd.y & 127;
-                    const unsigned s0 = rec & 0x1FFFu, s1 = (rec >> 13) & 0x1FFFu;
-                    const double* b0 = slab + (s0 >> (T::kTriBits + 1)) * SS + 3 * ((s0 >> 1) & T::kTriMask);
-                    const double* b1 = slab + (s1 >> (T::kTriBits + 1)) * SS + 3 * ((s1 >> 1) & T::kTriMask);
-                    const int f0 = s0 & 1, f1 = s1 & 1;            // transposed block: P and Q trade places
-                    const double L = b0[0] + b1[0];
-                    // half 0 needs P = [1 + f], half 1 needs Q = [2 - f]
-                    const double X = b0[half ? 2 - f0 : 1 + f0] + b1[half ? 2 - f1 : 1 + f1];
-                    double* out = vals + 4 * (int64_t)nd.x + 2 * p + (half ? 2 * deg : 0);
-                    __stcs(reinterpret_cast<double2*>(out), half ? make_double2(X, L) : make_double2(L, X));
-                }
-            }
-#else
             for (int q = tid; q < nw; q += kTileThreads) {
                 const unsigned rec = work[q];
                 const unsigned ch = chunk[q >> 5];
@@ -745,7 +708,6 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
                 __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(Q, L));
             }
-#endif
             // ---- phase 2b: diagonal blocks, one thread per owned node ---------------------------------
             for (int ln = tid; ln < nn; ln += kTileThreads) {
                 const int2 nd = node[ln];
