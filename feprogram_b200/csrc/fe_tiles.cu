@@ -510,7 +510,12 @@ __device__ __forceinline__ void q9_block_rows(const double* __restrict__ Jrow, d
 // Persistent kernel: CTA c processes tiles c, c + G, c + 2G, ...  While tile t is computed, the plan
 // records of tile t + G stream into the other shared-memory buffer (cp.async) and its connectivity row
 // and coordinates are prefetched into registers, so no global-memory latency is exposed per tile.
-template <int ET, bool MASS>
+// PF selects where the prefetches of the following tiles are issued (bit 0: connectivity row, bit 1: tile
+// descriptor): 0 = at the top of the iteration (row two tiles ahead; they land during phase 1), 1 = right
+// after barrier A of the previous tile (in flight during phase 2).  Chosen per element type / tile regularity
+// from measurements (cfg2 Quad4: 0 -> 1.70 ms, 1 -> 1.80 ms; perturbed Quad4 in pack mode: 1.90 / 1.78 ms;
+// Tri3, whose phase 1 is too short to hide a load: 3 -> 1.39 ms against 1.75 ms).
+template <int ET, bool MASS, int PF>
 __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayout<Elem<ET>::NNPE>::kCtas) k_assemble_tiled(
     int64_t ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords,
     const int4* __restrict__ tdesc, const int2* __restrict__ tnode, const uint16_t* __restrict__ tloc,
@@ -570,10 +575,19 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
 
     // ---- prologue: first tile of this CTA --------------------------------------------------------------
     constexpr bool kSingle = T::kParts == 1;          // one thread per element (Quad4 / Tri3)
+    constexpr bool kDescAhead = (PF & 2) != 0, kRowBehind = (PF & 1) != 0;
     constexpr int NR = kSingle ? N : 1;               // register prefetch buffers exist only in that case
     int64_t t = blockIdx.x;
     if (t >= ntiles) return;
-    int4 d0 = __ldg(tdesc + 2 * t), d1 = __ldg(tdesc + 2 * t + 1);
+    auto load_desc = [&](int64_t tt, int4& a, int4& b) {   // pinned like the other prefetches
+        asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(tdesc + 2 * tt));
+        asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(tdesc + 2 * tt + 1));
+    };
+    int4 d0, d1, e0, e1;
+    load_desc(t, d0, d1);
+    e0 = d0;
+    e1 = d1;
+    if (t + gridDim.x < ntiles) load_desc(t + gridDim.x, e0, e1);
     int tg[N], tgn[N];
     double x[N], y[N];
     (void)NR;
@@ -591,20 +605,21 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
     for (; t < ntiles; t += gridDim.x) {
         const int64_t tn = t + gridDim.x, tn2 = tn + gridDim.x;
         const bool more = tn < ntiles;
-        // next tile: descriptor; its connectivity row arrived during the previous iteration, so its
-        // coordinates can be pulled into L2 now; the row after that is requested two tiles ahead.
-        int4 e0 = d0, e1 = d1;
+        // Prefetch placement (per element type, measured): either at the top of the iteration (descriptor of
+        // the next tile, connectivity row two tiles ahead; they land during phase 1) or right after barrier A
+        // of the previous tile (everything in flight during phase 2, nothing issued here).
         int tgn2[N];
         tgn2[0] = -1;
-        if (more) {
-            e0 = __ldg(tdesc + 2 * tn);
-            e1 = __ldg(tdesc + 2 * tn + 1);
-            if constexpr (kSingle) {
-#ifdef FE_L2_PREFETCH
-                prefetch_xy(tgn);
-#endif
-                if (tn2 < ntiles) load_row(tn2, tgn2);
+        if constexpr (!kDescAhead) {
+            e0 = d0;
+            e1 = d1;
+            if (more) {      // plain loads: the compiler may schedule them (measurably better than pinning here)
+                e0 = __ldg(tdesc + 2 * tn);
+                e1 = __ldg(tdesc + 2 * tn + 1);
             }
+        }
+        if constexpr (kSingle && !kRowBehind) {
+            if (more && tn2 < ntiles) load_row(tn2, tgn2);
         }
         // ---- phase 1: own and halo elements -> slab --------------------------------------------------
         if constexpr (kSingle) {
@@ -670,16 +685,26 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
         else asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's records have landed
         __syncthreads();
-        // coordinates of the next tile: in flight during phase 2
+        // prefetches, in flight during phase 2: descriptor of the tile after next, connectivity row of the tile
+        // after next (straight into the register set the next tile just vacated), coordinates of the next tile
+        int4 f0 = e0, f1 = e1;
         if constexpr (kSingle) {
             if (more) {
 #pragma unroll
-                for (int a = 0; a < N; ++a) {
-                    tg[a] = tgn[a];
-                    tgn[a] = tgn2[a];
+                for (int a = 0; a < N; ++a) tg[a] = tgn[a];
+                if constexpr (kRowBehind) {
+                    load_xy(tg, x, y);                     // first: these are needed soonest
+                    tgn[0] = -1;
+                    if (tn2 < ntiles) load_row(tn2, tgn);   // straight into the set the next tile just vacated
+                } else {
+#pragma unroll
+                    for (int a = 0; a < N; ++a) tgn[a] = tgn2[a];
+                    load_xy(tg, x, y);
                 }
-                load_xy(tg, x, y);
             }
+        }
+        if constexpr (kDescAhead) {
+            if (tn2 < ntiles) load_desc(tn2, f0, f1);
         }
         if (dbg != 1) {
             const int nn = d0.y, nw = d1.y;
@@ -729,12 +754,16 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
         __syncthreads();   // slab and this record buffer are free again
         d0 = e0;
         d1 = e1;
+        if constexpr (kDescAhead) {
+            e0 = f0;
+            e1 = f1;
+        }
         buf ^= 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <int ET, bool MASS>
+template <int ET, bool MASS, int PF>
 static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coords, const int32_t* tdesc,
                         const int2* tnode, const uint16_t* tloc, const uint32_t* twork, const uint32_t* tchunk,
                         double* vals, int weighted, cudaStream_t st) {
@@ -745,8 +774,8 @@ static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coor
     FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int64_t grid = (int64_t)sms * T::kCtas;
     if (grid > ntiles) grid = ntiles;
-    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
-    k_assemble_tiled<ET, MASS><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
+    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET, MASS, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
+    k_assemble_tiled<ET, MASS, PF><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
         ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc), tnode, tloc,
         twork, tchunk, vals, weighted, dbg);
     FE_CHECK_LAUNCH("k_assemble_tiled");
@@ -892,6 +921,8 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
                       const uint32_t* tchunk, double* vals, void* stream) {
     using namespace fe;
     FE_REQUIRE(ntiles >= 0, "negative size");
+    const bool irregular = (op & FE_HINT_IRREGULAR_TILES) != 0;   // scheduling hint only: same results
+    op &= ~FE_HINT_IRREGULAR_TILES;
     if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
         set_error("fe_assemble_tiled: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
@@ -903,16 +934,19 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
     if (rc != FE_OK) return rc;
     const int w = op == FE_OP_WEIGHTED;
     const int2* nd = static_cast<const int2*>(tnode);
-#define FE_TILED_CASE(ET)                                                                                       \
-    case ET:                                                                                                    \
-        return op == FE_OP_MASS                                                                                 \
-                   ? launch_tiled<ET, true>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, 1, st)  \
-                   : launch_tiled<ET, false>(ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals, w, st);
+#define FE_TILED_ARGS ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals
     switch (elem_type) {
-        FE_TILED_CASE(FE_QUAD4)
-        FE_TILED_CASE(FE_TRI3)
-        FE_TILED_CASE(FE_QUAD9)
-#undef FE_TILED_CASE
+        case FE_QUAD4:
+            if (op == FE_OP_MASS) return launch_tiled<FE_QUAD4, true, 0>(FE_TILED_ARGS, 1, st);
+            return irregular ? launch_tiled<FE_QUAD4, false, 1>(FE_TILED_ARGS, w, st)
+                             : launch_tiled<FE_QUAD4, false, 0>(FE_TILED_ARGS, w, st);
+        case FE_TRI3:
+            return op == FE_OP_MASS ? launch_tiled<FE_TRI3, true, 3>(FE_TILED_ARGS, 1, st)
+                                    : launch_tiled<FE_TRI3, false, 3>(FE_TILED_ARGS, w, st);
+        case FE_QUAD9:
+            return op == FE_OP_MASS ? launch_tiled<FE_QUAD9, true, 0>(FE_TILED_ARGS, 1, st)
+                                    : launch_tiled<FE_QUAD9, false, 0>(FE_TILED_ARGS, w, st);
+#undef FE_TILED_ARGS
         default:
             set_error("fe_assemble_tiled: element type %d has no tiled kernel (use fe_assemble)", elem_type);
             return FE_ERR_UNSUPPORTED;

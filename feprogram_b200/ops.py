@@ -547,8 +547,9 @@ def assemble_tiled(tconn: Tensor, coords: Tensor, ntiles: int, tdesc: Tensor, tn
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):
     """Numeric assembly with whichever kernel the plan allows."""
     if plan is not None:
+        hint = 256 if plan.stats.get("mode") == "pack" else 0       # FE_HINT_IRREGULAR_TILES: schedule only
         torch.ops.feprogram.assemble_tiled(plan.tconn, coords, plan.ntiles, plan.tdesc, plan.tnode, plan.tloc,
-                                           plan.twork, plan.tchunk, vals, pat.elem_type, op)
+                                           plan.twork, plan.tchunk, vals, pat.elem_type, op | hint)
     else:
         torch.ops.feprogram.assemble(conn, coords, pat.eptr, pat.einc, pat.epos, pat.nptr, pat.max_deg, vals,
                                      pat.elem_type, op)

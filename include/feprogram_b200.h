@@ -63,6 +63,8 @@ extern "C" {
 /* ---- operators -------------------------------------------------------------------------- */
 #define FE_OP_REFERENCE 0 /* Ke = sum_g B^T B detJ, 2 dof/node, no weights (elements.py:153-163) */
 #define FE_OP_WEIGHTED 1  /* same, each Gauss term times gpWei[g] (elements.py:137; extension)   */
+#define FE_HINT_IRREGULAR_TILES 256 /* may be or-ed into `op` of fe_assemble_tiled: the plan's tiles are irregular
+                                       (packed sub-blocks); selects a kernel schedule, never changes a result */
 #define FE_OP_MASS 2      /* Me[2a+c,2b+c] = sum_g gpWei[g] H_g[a] H_g[b] detJ_g from the reference's own H and
                              gpWei tables (elements.py:94-113, built but unused there; extension); entries
                              across the two components are stored zeros, so K and M share one pattern */
