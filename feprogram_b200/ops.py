@@ -401,11 +401,11 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
     best = _tile_plan(conn, coords, pat, True, 1.0, "blocks")
     if best is not None and best.ntiles <= 1.12 * ideal + 8:
         return best
-    for scale in (1.0, 1.25, 1.6):
-        plan = _tile_plan(conn, coords, pat, True, scale, "pack")
+    for mode, scale in (("pack", 1.0), ("blocks", 0.9), ("pack", 1.25), ("pack", 1.6)):
+        plan = _tile_plan(conn, coords, pat, True, scale, mode)
         if plan is not None and (best is None or plan.ntiles < best.ntiles):
             best = plan
-        if best is not None:
+        if best is not None and best.ntiles <= 1.25 * ideal + 8:
             break
     return best
 
@@ -427,12 +427,20 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
             lo = coords.amin(dim=0)
             hi = coords.amax(dim=0)
             ext = (hi - lo).clamp_min(1e-300)
-            # cell = typical element extent per axis (sampled), so that one cell holds ~ one element
+            # cell: holds ~ one element (Tri3: the two triangles of a quad).  Its AREA comes from the sampled mean
+            # element area (distortion-proof: perturbing nodes changes extents, not the mean area), its aspect
+            # ratio from the sampled mean extents.
             sample = conn[:: max(1, nelem // 65536)][:65536].long()
             xy = coords[sample]                                               # (m, nnpe, 2)
-            size = (xy.amax(dim=1) - xy.amin(dim=1)).mean(dim=0)
-            if pat.elem_type == FE_TRI3:
-                size = size * 0.7071                                          # two triangles share a quad cell
+            ext_e = (xy.amax(dim=1) - xy.amin(dim=1)).mean(dim=0).clamp_min(1e-300)
+            nc = 3 if pat.elem_type == FE_TRI3 else 4                         # corner nodes come first
+            cx, cy = xy[:, :nc, 0], xy[:, :nc, 1]
+            area = 0.5 * (cx * torch.roll(cy, -1, dims=1) - torch.roll(cx, -1, dims=1) * cy).sum(dim=1).abs().mean()
+            cell_area = area * (2.0 if pat.elem_type == FE_TRI3 else 1.0)
+            aspect = ext_e[0] / ext_e[1]
+            size = torch.stack([torch.sqrt(cell_area * aspect), torch.sqrt(cell_area / aspect)])
+            if not bool(torch.isfinite(size).all()) or float(size.min()) <= 0.0:
+                size = ext_e * (0.7071 if pat.elem_type == FE_TRI3 else 1.0)
             size = size * cell_scale
             cell = torch.maximum(size, ext / 32767.0).clamp_min(1e-300).tolist()  # 15 bits per axis
             keys = torch.empty(nelem, dtype=torch.int32, device=dev)
