@@ -401,11 +401,14 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
     best = _tile_plan(conn, coords, pat, True, 1.0, "blocks")
     if best is not None and best.ntiles <= 1.12 * ideal + 8:
         return best
-    for mode, scale in (("pack", 1.0), ("blocks", 0.9), ("pack", 1.25), ("pack", 1.6)):
+    # irregular meshes: slightly smaller cells keep most Z-blocks at or below TE elements (a block with more is
+    # split into a full and a nearly empty tile); packing sub-blocks and coarser cells are the fall-backs
+    for mode, scale, good in (("blocks", 0.97, 1.08), ("blocks", 0.94, 1.10), ("pack", 1.0, 1.12), ("blocks", 0.9, 1.25),
+                              ("pack", 1.25, 1.25), ("pack", 1.6, 1.25)):
         plan = _tile_plan(conn, coords, pat, True, scale, mode)
         if plan is not None and (best is None or plan.ntiles < best.ntiles):
             best = plan
-        if best is not None and best.ntiles <= 1.25 * ideal + 8:
+        if best is not None and best.ntiles <= good * ideal + 8:
             break
     return best
 
