@@ -36,7 +36,6 @@ namespace fe {
 #ifndef FE_Q9_CTAS
 #define FE_Q9_CTAS 2
 #endif
-constexpr int kHaloElemsMax = 64;           // largest halo capacity of any element type (plan scratch)
 // ---- per-element-type tile configuration ------------------------------------------------------------
 // TE own elements per tile.  Quad4 / Tri3: 128 (one thread per element).  Quad9: 32 elements, FIVE threads
 // per element (its 45 node-pair blocks = 135 accumulators do not fit one thread).
@@ -565,12 +564,6 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
 #pragma unroll
         for (int a = 0; a < N; ++a)
             asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(x[a]), "=d"(y[a]) : "l"(coords + tg[a]));
-    };
-
-    auto prefetch_xy = [&](const int (&tg_)[N]) {   // pull the nodes' coordinates into L2
-        if (tg_[0] < 0) return;
-#pragma unroll
-        for (int a = 0; a < N; ++a) asm volatile("prefetch.global.L2 [%0];" ::"l"(coords + tg_[a]));
     };
 
     // ---- prologue: first tile of this CTA --------------------------------------------------------------
