@@ -1,0 +1,79 @@
+"""Host-side logic that needs no GPU: numbering locality, boundary edges, the corrected-load oracle, the facade's
+argument checking.  (The kernels behind them are covered by the -m gpu tests.)"""
+import numpy as np
+import pytest
+import torch
+
+from feprogram_b200 import mesh
+from oracle import fe_oracle as orc
+
+
+def test_locality_order_is_a_permutation_with_spatial_locality():
+    from feprogram_b200 import ops
+    conn, coords, _ = mesh.structured_quad4(64)
+    coords = mesh.perturb_interior(coords, 64, 64, 0.2, seed=1)
+    conn2, coords2, _, _ = mesh.shuffle_numbering(conn, coords, [set()] * 4, seed=2)
+    xy = torch.from_numpy(coords2)
+    perm, order = ops.locality_order(xy)
+    n = coords2.shape[0]
+    assert torch.equal(torch.sort(perm).values, torch.arange(n)) and torch.equal(perm[order], torch.arange(n))
+    c0 = torch.from_numpy((conn2 - 1).astype(np.int32))
+    span_in = ops.numbering_span(c0)
+    span_out = ops.numbering_span(perm[c0.long()].to(torch.int32))
+    assert span_in > 64.0 * np.sqrt(n) / 8 and span_out < span_in / 10          # shuffled -> local
+    # a row-major lattice is left alone by the automatic rule (span ~ row length)
+    assert ops.numbering_span(torch.from_numpy((conn - 1).astype(np.int32))) <= 66 + 1
+
+
+def test_partition_morton_keys_match_device_convention():
+    from feprogram_b200 import dist as fdist
+    xy = np.random.default_rng(0).random((500, 2))
+    k = fdist.morton_keys(xy, xy.min(axis=0), xy.max(axis=0) - xy.min(axis=0))
+    assert k.min() >= 0 and k.max() < 2 ** 32 and len(np.unique(k)) > 490
+    # points in the same quadrant share the two top key bits
+    q = ((xy[:, 0] > 0.5 * (xy[:, 0].min() + xy[:, 0].max())).astype(int)
+         + 2 * (xy[:, 1] > 0.5 * (xy[:, 1].min() + xy[:, 1].max())).astype(int))
+    assert np.array_equal(k >> 30, q)
+
+
+@pytest.mark.parametrize("kind", [4, 9, 3])
+def test_boundary_edges_of_each_side(kind):
+    gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
+    nx, ny = 5, 3
+    conn, coords, bc = gen(nx, ny)
+    conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=3)
+    want = [nx, ny, nx, ny]                       # bottom, right, top, left: one edge per element side
+    for side, cnt in zip(bc, want):
+        e = mesh.boundary_edges(conn, side)
+        assert e.shape == (cnt, 3 if kind == 9 else 2) and e.dtype == np.int32
+        tags = np.fromiter((int(t) for t in side), dtype=np.int64) - 1
+        assert np.isin(e, tags).all()
+        # consistent load of a unit traction sums to the side length (1.0 on the unit square)
+        f = orc.edge_loads(e, coords, (1.0, 2.0), 2 * coords.shape[0])
+        assert abs(f[0::2].sum() - 1.0) < 1e-13 and abs(f[1::2].sum() - 2.0) < 1e-13
+    assert mesh.boundary_edges(conn, []).shape[0] == 0
+
+
+def test_quadratic_edge_load_weights():
+    # straight 3-node edge of length 2: (1/6, 1/6, 4/6) * length
+    coords = np.array([[0.0, 0.0], [2.0, 0.0], [1.0, 0.0]])
+    f = orc.edge_loads(np.array([[0, 1, 2]]), coords, (1.0, 0.0), 6)
+    assert np.allclose(f[0::2], [2 / 6, 2 / 6, 8 / 6], atol=1e-14)
+
+
+def test_facade_rejects_bad_arguments_without_touching_the_gpu():
+    from feprogram_b200.elements import FemProblem
+    conn, coords, bc = mesh.structured_quad4(3)
+    with pytest.raises(KeyError):
+        FemProblem(conn, coords, operator="nonsense")
+    fem = FemProblem(conn, coords)
+    fem.setMatrix()
+    with pytest.raises(ValueError):
+        fem.setBoundaryConditions(bc, verbose=False, mode="symmetric")
+    fem.setBoundaryConditions(bc, verbose=False, mode="corrected")
+    assert not set(fem.dofNeu) & set(fem.dofDir)            # Dirichlet wins at the shared corner
+    fem.setBoundaryConditions(bc, verbose=False)
+    assert set(fem.dofNeu) & set(fem.dofDir)                # the reference's overlap is kept in reference mode
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fem.assemble()
