@@ -214,13 +214,23 @@ class DistFemProblem:
         self.elem_type = elem_type
         self.comm = comm
         torch.cuda.set_device(self.dev)
-        self.conn = torch.from_numpy(np.ascontiguousarray(local.conn)).to(self.dev)
-        self.coords = torch.from_numpy(local.coords).to(self.dev)
+        # connectivity first; the coordinates follow on a side stream while the CSR pattern (which only needs the
+        # connectivity) is built -- as FemProblem does (elements.py, _state)
+        main = torch.cuda.current_stream(self.dev)
+        self.conn = torch.from_numpy(np.ascontiguousarray(local.conn)).to(self.dev, non_blocking=True)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_event(main.record_event())
+        with torch.cuda.stream(side):
+            self.coords = torch.from_numpy(np.ascontiguousarray(local.coords)).to(self.dev, non_blocking=True)
+        self.coords.record_stream(main)
+        coords_ready = side.record_event()
+        main.synchronize()                               # connectivity has arrived; coordinates still in flight
         t0 = time.perf_counter()
         self.pat = ops.symbolic(self.conn, local.nnode, elem_type, 2)
+        main.wait_event(coords_ready)
         self.plan = ops.tile_plan(self.conn, self.coords, self.pat)
         torch.cuda.synchronize(self.dev)
-        self.symbolic_s = time.perf_counter() - t0
+        self.symbolic_s = time.perf_counter() - t0      # may include the tail of the coordinate upload
         self.vals = torch.empty(self.pat.nnz, dtype=torch.float64, device=self.dev)
         self.nrows_owned = 2 * local.n_owned
         self.nrows_local = 2 * local.nnode
