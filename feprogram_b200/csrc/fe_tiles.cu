@@ -33,6 +33,9 @@ namespace fe {
 #define FE_HALO_ELEMS 32
 #define FE_TILE_CTAS 3
 #endif
+#ifndef FE_Q4_PARTS
+#define FE_Q4_PARTS 1       // experiment: 2 = two threads per Quad4 element (five node-pair blocks each), 2 CTAs per SM
+#endif
 #ifndef FE_Q9_CTAS
 #define FE_Q9_CTAS 2
 #endif
@@ -47,7 +50,7 @@ __host__ __device__ constexpr int halo_threads(int nnpe) { return nnpe == 4 ? FE
 // threads (irregular tiles of perturbed / unstructured meshes); those rows are evaluated in a short second
 // pass by the halo warp, so regular tiles pay nothing.
 __host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS + 16 : nnpe == 9 ? 16 : 64; }
-__host__ __device__ constexpr int tile_parts(int nnpe) { return nnpe == 9 ? 5 : 1; }      // threads per element
+__host__ __device__ constexpr int tile_parts(int nnpe) { return nnpe == 9 ? 5 : nnpe == 4 ? FE_Q4_PARTS : 1; }   // threads per element
 __host__ __device__ constexpr int tri_bits(int nnpe) { return nnpe == 9 ? 6 : 4; }        // bits of a block index
 __host__ __device__ constexpr int max_nodes(int nnpe) { return nnpe == 9 ? 192 : 2 * tile_elems(nnpe); }
 __host__ __device__ constexpr int max_items(int nnpe) { return nnpe == 9 ? 640 : 8 * tile_elems(nnpe); }
@@ -69,15 +72,15 @@ template <int N> struct TileLayout {
     static constexpr int kRows = kTE + kHalo;                  // rows per tile of tconn / the slab
     static constexpr int kZeroRow = kTE + kHalo;               // slab row of zeros (target of absent sources)
     static constexpr int kMaxNodes = max_nodes(N), kMaxItems = max_items(N), kMaxWork = max_work(N);
-    static constexpr int kCtas = kParts > 1 ? FE_Q9_CTAS : kTileCtasPerSm;   // persistent CTAs per SM
+    static constexpr int kCtas = N == 9 ? FE_Q9_CTAS : kParts > 1 ? 2 : kTileCtasPerSm;   // persistent CTAs per SM
     static constexpr int kTriBits = tri_bits(N);
     static constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
     static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
     // shared copy of the rows' node coordinates (multi-thread-per-element types only)
-    static constexpr size_t kXyBytes = kParts > 1 ? (size_t)kRows * N * 16 : 0;
+    static constexpr size_t kXyBytes = N == 9 ? (size_t)kRows * N * 16 : 0;
     // per row: (j00, j01, j10, j11, scale) of every Gauss point (multi-thread-per-element types only)
     static constexpr int kJacStride = 5 * N;       // Quad9: N Gauss points; odd stride
-    static constexpr size_t kJacBytes = kParts > 1 ? (size_t)kRows * kJacStride * 8 : 0;
+    static constexpr size_t kJacBytes = N == 9 ? (size_t)kRows * kJacStride * 8 : 0;
     // one set of staged plan records (16-byte aligned size); the kernel double-buffers it
     static constexpr size_t kRecBytes = (size_t)kMaxWork * 4 + (size_t)kMaxNodes * 8 + (size_t)(kMaxWork / 32) * 4 +
                                         (size_t)kMaxItems * 2;
@@ -415,6 +418,50 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
     for (int a = 0; a < E::NNPE; ++a) out[3 * T::tri(a, a) + 2] = out[3 * T::tri(a, a) + 1];
 }
 
+// One of NPARTS threads of an element: the upper-triangular blocks whose row node `a` this part owns (part 0:
+// the first and the last local node, part 1: the others -- 5 + 5 blocks for Quad4), written straight to the
+// element's slab row.  Same pair arithmetic as element_tri; the geometry is evaluated by every part.
+template <int ET, bool MASS, int PART>
+__device__ __forceinline__ void element_tri_part(const double (&x)[Elem<ET>::NNPE], const double (&y)[Elem<ET>::NNPE],
+                                                 bool weighted, double* __restrict__ dst) {
+    using E = Elem<ET>;
+    using T = TileLayout<E::NNPE>;
+    constexpr int N = E::NNPE;
+    double out[3 * T::kBlocks];
+#pragma unroll
+    for (int i = 0; i < 3 * T::kBlocks; ++i) out[i] = 0.0;
+    ElemGeom<ET> G;
+    geom_init<ET, MASS>(G, x, y, weighted);
+#pragma unroll
+    for (int g = 0; g < E::NG; ++g) {
+        double ax[N], ay[N], sx[N], sy[N];
+        gauss_point<ET, MASS>(g, G, weighted, ax, ay, sx, sy);
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            if (((a == 0 || a == N - 1) ? 0 : 1) != PART) continue;
+#pragma unroll
+            for (int b = a; b < N; ++b) {
+                const int o = 3 * T::tri(a, b);
+                out[o] = fma(sx[a], ax[b], fma(sy[a], ay[b], out[o]));
+                out[o + 1] = fma(sy[a], ax[b], out[o + 1]);
+                if (b > a) out[o + 2] = fma(sx[a], ay[b], out[o + 2]);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+        if (((a == 0 || a == N - 1) ? 0 : 1) != PART) continue;
+        out[3 * T::tri(a, a) + 2] = out[3 * T::tri(a, a) + 1];
+#pragma unroll
+        for (int b = a; b < N; ++b) {
+            const int o = 3 * T::tri(a, b);
+            dst[o] = out[o];
+            dst[o + 1] = out[o + 1];
+            dst[o + 2] = out[o + 2];
+        }
+    }
+}
+
 // Quad9: Jacobian J_g = dH_g X and the scale s_g (1/det, times the Gauss weight when weighted; det * weight for
 // the mass operator) of Gauss point g -- same expressions as gauss_point<ET> (fe_element.cuh), computed ONCE per
 // element (the five threads of an element share the nine Gauss points) instead of by every thread.
@@ -549,8 +596,10 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
     };
     // Prefetching loads are volatile asm so that the compiler keeps them where they are written (well
     // ahead of their first use, on the far side of the barriers) instead of sinking them to the use.
+    // register path (Quad4 / Tri3): thread -> (slab row, part); one part per element unless FE_Q4_PARTS = 2
+    const int part = tid / T::kRowThreads, rowid = tid - part * T::kRowThreads;
     auto load_row = [&](int64_t t, int (&tg)[N]) {
-        const int32_t* row = tconn + (t * T::kRows + tid) * N;
+        const int32_t* row = tconn + (t * T::kRows + rowid) * N;
         if constexpr (N == 4) {
             asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
                          : "=r"(tg[0]), "=r"(tg[1]), "=r"(tg[2]), "=r"(tg[3]) : "l"(row));
@@ -567,7 +616,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
     };
 
     // ---- prologue: first tile of this CTA --------------------------------------------------------------
-    constexpr bool kSingle = T::kParts == 1;          // one thread per element (Quad4 / Tri3)
+    constexpr bool kSingle = N != 9;                  // register path: rows and coordinates prefetched per thread
     constexpr bool kDescAhead = (PF & 2) != 0, kRowBehind = (PF & 1) != 0;
     constexpr int NR = kSingle ? N : 1;               // register prefetch buffers exist only in that case
     int64_t t = blockIdx.x;
@@ -618,11 +667,17 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
         if constexpr (kSingle) {
             const bool active = tg[0] >= 0;
             if (active && dbg != 2) {
-                double ke[3 * T::kBlocks];
-                element_tri<ET, MASS>(x, y, weighted != 0, ke);
-                double* dst = slab + tid * SS;
+                double* dst = slab + rowid * SS;
+                if constexpr (T::kParts == 1) {
+                    double ke[3 * T::kBlocks];
+                    element_tri<ET, MASS>(x, y, weighted != 0, ke);
 #pragma unroll
-                for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+                    for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+                } else if (part == 0) {          // warp-uniform: kRowThreads is a multiple of 32
+                    element_tri_part<ET, MASS, 0>(x, y, weighted != 0, dst);
+                } else {
+                    element_tri_part<ET, MASS, 1>(x, y, weighted != 0, dst);
+                }
             }
         } else if (dbg != 2) {
             // Quad9: stage the rows' node coordinates, then five threads per row evaluate block rows
@@ -632,7 +687,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 if (node >= 0) s_xy[i] = __ldg(coords + node);
             }
             __syncthreads();
-            const int part = tid / T::kRowThreads, row = tid - part * T::kRowThreads;
+            const int row = rowid;
             const bool live = row < T::kRows && __ldg(rows + row * N) >= 0;
             if (live) {
                 for (int g = part; g < 9; g += T::kParts)
@@ -651,11 +706,11 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 }
             }
         }
-        if constexpr (T::kRows > T::kThreads) {
-            // overflow halo rows (irregular tiles only): second pass of the halo warp, not prefetched
+        if constexpr (kSingle && T::kRows > T::kRowThreads) {
+            // overflow halo rows (irregular tiles only): second pass of the halo warp(s), not prefetched
             const int nh = d1.z;
-            const int row = tid + (T::kThreads - kTileElems);          // rows kThreads.. for threads TE..
-            if (nh > T::kThreads - kTileElems && tid >= kTileElems && row < kTileElems + nh && dbg != 2) {
+            const int row = rowid + (T::kRowThreads - kTileElems);     // rows kRowThreads.. for threads TE..
+            if (nh > T::kRowThreads - kTileElems && rowid >= kTileElems && row < kTileElems + nh && dbg != 2) {
                 const int32_t* rp = tconn + (t * T::kRows + row) * N;
                 int tq[N];
                 double xq[N], yq[N], ke[3 * T::kBlocks];
@@ -667,10 +722,16 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                     xq[a] = pq.x;
                     yq[a] = pq.y;
                 }
-                element_tri<ET, MASS>(xq, yq, weighted != 0, ke);
                 double* dst = slab + row * SS;
+                if constexpr (T::kParts == 1) {
+                    element_tri<ET, MASS>(xq, yq, weighted != 0, ke);
 #pragma unroll
-                for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+                    for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+                } else if (part == 0) {
+                    element_tri_part<ET, MASS, 0>(xq, yq, weighted != 0, dst);
+                } else {
+                    element_tri_part<ET, MASS, 1>(xq, yq, weighted != 0, dst);
+                }
             }
         }
         // records of the next tile start streaming into the other buffer
