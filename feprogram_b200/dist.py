@@ -200,6 +200,25 @@ def exchange_send_lists(m: LocalMesh, group=None) -> LocalMesh:
     return m
 
 
+def peer_ghost_tables(m: LocalMesh, group=None):
+    """For every ghost node of this rank: (owner rank, node index inside the owner) -- what a peer-memory SpMV
+    needs to read the owner's copy directly.  Collective over torch.distributed (any backend): every owner
+    publishes what it sends to whom (owner-local node indices, in the requester's ghost order)."""
+    import torch.distributed as dist
+    lists = [None] * m.world
+    dist.all_gather_object(lists, {int(q): np.asarray(s_).tolist() for q, s_ in zip(m.nbr, m.send_nodes)}, group=group)
+    n_ghost = m.nnode - m.n_owned
+    grank = np.zeros(max(1, n_ghost), dtype=np.int32)
+    gridx = np.zeros(max(1, n_ghost), dtype=np.int32)
+    for q, (a, b) in zip(m.nbr, m.recv_range):
+        if b > a:
+            theirs = np.asarray(lists[q][m.rank], dtype=np.int32)
+            assert theirs.size == b - a
+            grank[a - m.n_owned: b - m.n_owned] = q
+            gridx[a - m.n_owned: b - m.n_owned] = theirs
+    return grank, gridx
+
+
 # ----------------------------------------------------------------------------------------------------
 # device side
 # ----------------------------------------------------------------------------------------------------
@@ -335,18 +354,7 @@ class DistFemProblem:
         self._seq = 0
         self._peer_p = torch.tensor(list(hp.buffer_ptrs), dtype=torch.int64, device=self.dev)
         self._peer_flags = torch.tensor(list(hf.buffer_ptrs), dtype=torch.int64, device=self.dev)
-        # what every owner sends to whom (owner-local node indices, in the requester's ghost order)
-        lists = [None] * m.world
-        dist.all_gather_object(lists, {int(q): np.asarray(s).tolist() for q, s in zip(m.nbr, m.send_nodes)}, group=group)
-        n_ghost = m.nnode - m.n_owned
-        grank = np.zeros(max(1, n_ghost), dtype=np.int32)
-        gridx = np.zeros(max(1, n_ghost), dtype=np.int32)
-        for q, (a, b) in zip(m.nbr, m.recv_range):
-            if b > a:
-                theirs = np.asarray(lists[q][m.rank], dtype=np.int32)
-                assert theirs.size == b - a
-                grank[a - m.n_owned: b - m.n_owned] = q
-                gridx[a - m.n_owned: b - m.n_owned] = theirs
+        grank, gridx = peer_ghost_tables(m, group)
         self._ghost_rank = torch.from_numpy(grank).to(self.dev)
         self._ghost_ridx = torch.from_numpy(gridx).to(self.dev)
         self._nbr_dev = torch.from_numpy(np.ascontiguousarray(self._nbr, dtype=np.int32)).to(self.dev) \

@@ -136,6 +136,14 @@ def _worker(rank, world, port, kind, structured, out):
         _halo(m, halo, x)
         err = np.linalg.norm(x - U[gdof]) / np.linalg.norm(U)
         assert err < 1e-8, err
+        # peer-memory tables (fe_dist_pcg_p2p): ghost g lives at node gridx[g] of rank grank[g]
+        grank, gridx = fdist.peer_ghost_tables(m)
+        gids = [None] * world
+        dist.all_gather_object(gids, m.node_gid[: m.n_owned].tolist())
+        ng = m.nnode - m.n_owned
+        assert np.array_equal(grank[:ng], m.ghost_owner)
+        for g in range(ng):
+            assert gids[grank[g]][gridx[g]] == m.node_gid[m.n_owned + g]
         out.put((rank, "ok", it))
     except Exception as e:  # noqa: BLE001
         import traceback
