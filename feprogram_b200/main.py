@@ -19,41 +19,42 @@ from .gmsh_api import getMeshInfo
 from .python_to_xml import writeXML_nodeData
 
 
+class _Laps:
+    """Wall-clock laps logged with the reference's labels (main.py:14-46)."""
+
+    def __init__(self):
+        self.start = self.last = datetime.now()
+
+    def lap(self, label):
+        now = datetime.now()
+        logging.info("%s: %f sec", label, (now - self.last).total_seconds())
+        self.last = now
+
+    def total(self, label):
+        logging.info("%s: %f sec", label, (datetime.now() - self.start).total_seconds())
+
+
 def run(outname, nx=None, ny=None, quad9=False):
-    t1 = datetime.now()
     logging.basicConfig(level="INFO")
+    laps = _Laps()
     if nx is None:
         conectivity, coordinates, bcNodeTags = getMeshInfo()
     else:
         gen = mesh.structured_quad9 if quad9 else mesh.structured_quad4
         conectivity, coordinates, bcNodeTags = gen(nx, ny or nx)
         coordinates = coordinates * np.array([2.0, 10.0])   # the reference's 2 x 10 rectangle (gmsh_api.py:36-40)
-    t2 = datetime.now()
-    logging.info("Crear malla: %f sec", (t2 - t1).total_seconds())
-
+    laps.lap("Crear malla")
     fem = FemProblem(conectivity, coordinates)
-    t3 = datetime.now()
-    logging.info("Crear elemento fem: %f sec", (t3 - t2).total_seconds())
-
-    fem.setMatrix()
-    t4 = datetime.now()
-    logging.info("Seteo inicial de matrices: %f sec", (t4 - t3).total_seconds())
-
-    fem.setBoundaryConditions(bcNodeTags, verbose=False)
-    t5 = datetime.now()
-    logging.info("Seteo de BC en nodos: %f sec", (t5 - t4).total_seconds())
-
-    fem.assemble()
-    t6 = datetime.now()
-    logging.info("Ensamblaje de matrices: %f sec", (t6 - t5).total_seconds())
-
+    laps.lap("Crear elemento fem")
+    for label, call in (("Seteo inicial de matrices", fem.setMatrix),
+                        ("Seteo de BC en nodos", lambda: fem.setBoundaryConditions(bcNodeTags, verbose=False)),
+                        ("Ensamblaje de matrices", fem.assemble)):
+        call()
+        laps.lap(label)
     U = fem.solveProblem()
-    t7 = datetime.now()
-    logging.info("Calculo de velocidades: %f sec", (t7 - t6).total_seconds())
-
+    laps.lap("Calculo de velocidades")
     U = U.reshape((coordinates.shape[0], 2))
-    t8 = datetime.now()
-    logging.info("Tiempo total: %f sec", (t8 - t1).total_seconds())
+    laps.total("Tiempo total")
     writeXML_nodeData(coordinates, conectivity, U, outname)
     return U
 

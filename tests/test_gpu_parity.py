@@ -676,3 +676,17 @@ def test_renumbering_is_automatic_for_shuffled_large_meshes(torch_cuda):
     Ko = orc.assemble_csr(conn2 - 1, coords2)
     assert np.array_equal(K2.indptr, Ko.indptr) and np.array_equal(K2.indices, Ko.indices)
     assert rel_max(K2.data, Ko.data) < VAL_TOL
+
+
+def test_main_driver_runs_the_reference_call_order(torch_cuda, tmp_path, caplog):
+    """feprogram_b200.main.run = the reference's main.py (mesh -> FemProblem -> setMatrix -> BCs -> assemble ->
+    solve -> .vtu) on the CUDA path, with the reference's log labels."""
+    import logging
+    from feprogram_b200 import main as drv
+    with caplog.at_level(logging.INFO):
+        U = drv.run(str(tmp_path / "out"), nx=4, ny=6)
+    assert U.shape == (35, 2) and np.isfinite(U).all() and np.all(U[:5] == [[1.0, 1.0]] + [[0.0, 0.0]] * 4)
+    text = (tmp_path / "out.vtu").read_text()
+    assert 'Name="Velocidad"' in text and 'NumberOfPoints="35" NumberOfCells="24"' in text
+    for label in ("Crear malla", "Ensamblaje de matrices", "Calculo de velocidades", "Tiempo total"):
+        assert any(label in r.getMessage() for r in caplog.records)
