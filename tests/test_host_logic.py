@@ -77,3 +77,46 @@ def test_facade_rejects_bad_arguments_without_touching_the_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             fem.assemble()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_partition_invariants_random_meshes(seed):
+    """partition_mesh on shuffled meshes of every element type, 2..5 ranks, both local numberings: every node
+    owned exactly once, every rank holds all elements touching its owned nodes, local ids map back to the
+    global mesh, ghosts are grouped by owner, element blocks tile the element range."""
+    from feprogram_b200 import dist as fdist
+    rng = np.random.default_rng(seed)
+    kind = (4, 9, 3)[seed % 3]
+    gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
+    nx, ny = int(rng.integers(3, 9)), int(rng.integers(3, 9))
+    conn, coords, bc = gen(nx, ny)
+    conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=seed + 10)
+    conn0 = conn - 1
+    world = int(rng.integers(2, 6))
+    locality = bool(seed & 1)
+    bounds = fdist.element_blocks(conn0.shape[0], world)
+    assert bounds[0] == 0 and bounds[-1] == conn0.shape[0] and np.all(np.diff(bounds) >= 0)
+    owned_count = np.zeros(coords.shape[0], dtype=int)
+    for rank in range(world):
+        m = fdist.partition_mesh(conn0, coords, rank, world, locality=locality)
+        owned = m.node_gid[: m.n_owned]
+        owned_count[owned] += 1
+        # local connectivity maps back to the global one, elements in ascending global id, own block first-class
+        assert np.array_equal(m.node_gid[m.conn], conn0[m.elem_gid])
+        assert np.all(np.diff(m.elem_gid) > 0)
+        assert m.n_own_elems == int(((m.elem_gid >= bounds[rank]) & (m.elem_gid < bounds[rank + 1])).sum())
+        assert np.array_equal(m.coords, coords[m.node_gid, :2])
+        # every element touching an owned node is present
+        touching = np.nonzero(np.isin(conn0, owned).any(axis=1))[0]
+        assert np.array_equal(touching, m.elem_gid)
+        # owner of a node = rank of the block holding its lowest incident element; ghosts grouped by owner
+        first = np.full(coords.shape[0], conn0.shape[0])
+        np.minimum.at(first, conn0.ravel(), np.repeat(np.arange(conn0.shape[0]), conn0.shape[1]))
+        own_rank = np.searchsorted(bounds, first, side="right") - 1
+        assert np.all(own_rank[owned] == rank)
+        ghosts = m.node_gid[m.n_owned:]
+        assert np.array_equal(own_rank[ghosts], m.ghost_owner) and np.all(np.diff(m.ghost_owner) >= 0)
+        assert not np.any(m.ghost_owner == rank)
+        if not locality:
+            assert np.all(np.diff(owned) > 0)
+    assert np.all(owned_count == 1)
