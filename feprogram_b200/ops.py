@@ -364,6 +364,7 @@ def locality_order(coords: Tensor) -> Tuple[Tensor, Tensor]:
 # --------------------------------------------------------------------------------------------
 import os as _os
 FE_TILE_SORT_BY_ID = _os.environ.get("FE_TILE_SORT_BY_ID", "1") == "1"   # tuning knob
+FE_PLAN_DEDUP = _os.environ.get("FE_PLAN_DEDUP", "0") == "1"             # share identical tile records (experimental)
 
 
 @dataclass
@@ -377,6 +378,72 @@ class TilePlan:
     tchunk: Tensor          # int32 (uint32 bit pattern) [work items / 32]
     ntiles: int
     stats: dict
+
+
+def dedup_tile_records(tdesc: Tensor, tloc: Tensor, twork: Tensor, tchunk: Tensor):
+    """Lets tiles with identical tile-local records (item locators, work items, chunk heads) share ONE copy.
+
+    The records only hold tile-local indices (slab rows, block ids, neighbour positions), so on regular meshes
+    almost every interior tile carries the same bytes; the kernel reaches them through the offsets in `tdesc`
+    and needs no change.  Shared records stay in L2 instead of being streamed from HBM for every tile.
+    Returns (tdesc, tloc, twork, tchunk, n_unique); equality is verified element by element, so a hash collision
+    can only cost the sharing, never correctness.  Pure torch; works on any device."""
+    ntiles = tdesc.shape[0]
+    dev = tdesc.device
+    if ntiles < 2:
+        return tdesc, tloc, twork, tchunk, ntiles
+    d = tdesc.to(torch.int64)
+    i0, ni, w0, nw = d[:, 2], d[:, 3], d[:, 4], d[:, 5]
+    tiles = torch.arange(ntiles, device=dev)
+    K1, K2, K3 = 0x9E3779B97F4A7C15 - (1 << 64), 0x2545F4914F6CDD1D, 0x632BE59BD9B4E019   # odd 64-bit constants
+
+    def seg_hash(vals: Tensor, start: Tensor, count: Tensor):
+        """(owner tile of each element, position inside its tile, per-tile hash) of the ranges [start, start + count)"""
+        owner = torch.repeat_interleave(tiles, count)
+        base = torch.repeat_interleave(start, count)
+        idx = base + (torch.arange(owner.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(count, 0) - count, count))
+        pos = idx - base
+        v = vals[idx].to(torch.int64)
+        mixed = (v * K2 + pos * K1 + 12345) * ((pos << 1) | 1)
+        mixed = mixed ^ (mixed >> 29)
+        h = torch.zeros(ntiles, dtype=torch.int64, device=dev).index_add_(0, owner, mixed * K3)
+        return owner, idx, pos, h
+
+    loc16 = tloc.view(torch.int16)
+    ow_w, idx_w, pos_w, h_w = seg_hash(twork, w0, nw)
+    ow_l, idx_l, pos_l, h_l = seg_hash(loc16, i0, ni)
+    ow_c, idx_c, pos_c, h_c = seg_hash(tchunk, w0 >> 5, nw >> 5)
+    key = torch.stack([nw, ni, h_w, h_l, h_c], dim=1)
+    _, inv = torch.unique(key, dim=0, return_inverse=True)
+    rep = torch.full((int(inv.max().item()) + 1,), ntiles, dtype=torch.int64, device=dev).scatter_reduce_(
+        0, inv, tiles, reduce="amin")[inv]                                  # representative (lowest) tile of each class
+    # exact verification against the representative's records
+    same = (bool((twork[idx_w] == twork[w0[rep][ow_w] + pos_w]).all())
+            and bool((loc16[idx_l] == loc16[i0[rep][ow_l] + pos_l]).all())
+            and bool((tchunk[idx_c] == tchunk[(w0[rep] >> 5)[ow_c] + pos_c]).all()))
+    if not same:
+        return tdesc, tloc, twork, tchunk, ntiles
+    is_rep = rep == tiles
+    n_unique = int(is_rep.sum().item())
+    if n_unique == ntiles:
+        return tdesc, tloc, twork, tchunk, ntiles
+    # compact: keep the representatives' ranges, in order; offsets of the kept ranges by prefix sums
+    new_w0 = torch.cumsum(torch.where(is_rep, nw, torch.zeros_like(nw)), 0) - torch.where(is_rep, nw, torch.zeros_like(nw))
+    new_i0 = torch.cumsum(torch.where(is_rep, ni, torch.zeros_like(ni)), 0) - torch.where(is_rep, ni, torch.zeros_like(ni))
+    keep_w, keep_l, keep_c = is_rep[ow_w], is_rep[ow_l], is_rep[ow_c]
+    twork_n = twork[idx_w[keep_w]].contiguous()
+    tloc_n = loc16[idx_l[keep_l]].contiguous().view(torch.uint16)
+    tchunk_n = tchunk[idx_c[keep_c]].contiguous()
+    if twork_n.numel() < 32:
+        twork_n = torch.cat([twork_n, torch.zeros(32 - twork_n.numel(), dtype=twork.dtype, device=dev)])
+    if tloc_n.numel() < 2:
+        tloc_n = torch.cat([tloc_n.view(torch.int16), torch.zeros(2, dtype=torch.int16, device=dev)]).view(torch.uint16)
+    if tchunk_n.numel() < 1:
+        tchunk_n = torch.zeros(1, dtype=tchunk.dtype, device=dev)
+    out = tdesc.clone()
+    out[:, 2] = new_i0[rep].to(tdesc.dtype)
+    out[:, 4] = new_w0[rep].to(tdesc.dtype)
+    return out.contiguous(), tloc_n, twork_n, tchunk_n, n_unique
 
 
 def _scan_into(src: Tensor, dst: Tensor, ws: Tensor):
@@ -538,6 +605,8 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                              tile_ptr[1, :-1], tile_ptr[1, 1:] - tile_ptr[1, :-1],
                              tile_ptr[3, :-1], tile_ptr[3, 1:] - tile_ptr[3, :-1],
                              tile_ptr[2, 1:] - tile_ptr[2, :-1], z], dim=1).contiguous()
+        if FE_PLAN_DEDUP:
+            tdesc, tloc, twork, tchunk, info["record_sets"] = dedup_tile_records(tdesc, tloc, twork, tchunk)
     return TilePlan(tconn, tdesc, tnode, tloc, twork, tchunk, ntiles, info)
 
 
