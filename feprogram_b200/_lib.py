@@ -46,12 +46,16 @@ PROTOTYPES = {
     "fe_tile_records": (_i, [_i, _i64, _p, _p, _p, _i64] + [_p] * 14),
     "fe_tile_conn": (_i, [_i, _i64] + [_p] * 7),
     "fe_assemble_tiled": (_i, [_i, _i, _i64] + [_p] * 9),
+    "fe_tile_ws_params": (None, [_i, C.POINTER(_i32)]),
+    "fe_tile_ws_sizes": (_i, [_i, _i64] + [_p] * 6),
+    "fe_tile_ws_build": (_i, [_i, _i64, _i64] + [_p] * 18),
+    "fe_assemble_ws": (_i, [_i, _i, _i64] + [_p] * 7),
     "fe_bc_rhs": (_i, [_i64, _p, _i64, _p, _i64, _f64, _p, _p, _p]),
     "fe_apply_bc": (_i, [_i, _i64, _i, _p, _p, _p, _p, _p, _p]),
-    "fe_spmv": (_i, [_i64, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "fe_spmv": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _p]),
     "fe_csr_diagonal": (_i, [_i64, _i, _p, _p, _p, _p, _p]),
     "fe_pcg_workspace_bytes": (_sz, [_i64]),
-    "fe_pcg": (_i, [_i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _p, _p]),
+    "fe_pcg": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _p, _p]),
     "fe_spmv_nodal": (_i, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_dist_available": (_i, []),
     "fe_dist_unique_id": (_i, [_p]),
@@ -62,7 +66,7 @@ PROTOTYPES = {
     "fe_gauss_gradients": (_i, [_i, _i64, _p, _p, _p, _p, _p]),
     "fe_nodal_strain": (_i, [_i, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_dist_pcg_workspace_bytes": (_sz, [_i64]),
-    "fe_dist_pcg": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _i32,
+    "fe_dist_pcg": (_i, [_i64, _i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _i32,
                          _p, _p, _p, _p, _p, _p, _p, _p]),
     "fe_dist_pcg_p2p": (_i, [_i64, _i64, _i, _p, _p, _p, _p, _p, _p, _f64, _f64, _i64, _i32, _p, _p, _p, _i32,
                              _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64, _p]),
@@ -117,6 +121,12 @@ def tile_params(elem_type: int):
     lib().fe_tile_params(elem_type, out)
     return dict(tile_elems=out[0], halo_cap=out[1], max_nodes=out[2], max_items=out[3], max_work=out[4],
                 tile_rows=out[5])
+
+
+def tile_ws_params(elem_type: int):
+    out = (_i32 * 4)()
+    lib().fe_tile_ws_params(elem_type, out)
+    return dict(blob_cap=out[0], stage_cap=out[1], max_deg=out[2], max_nodes=out[3])
 
 
 def limits():

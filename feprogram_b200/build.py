@@ -3,8 +3,7 @@
     python -m feprogram_b200.build [--force] [--verbose]
 
 Cross-compiles without a GPU.  The built .so is git-ignored but travels to the GPU box with the
-repository snapshot.  Also builds the C oracle (oracle/libfe_oracle.so) with gcc when asked to
-(``build_oracle``) -- building the checker is not using it.
+repository snapshot.
 """
 from __future__ import annotations
 
@@ -62,6 +61,7 @@ def _stamp(srcs) -> str:
             h.update(open(os.path.join(CSRC, f), "rb").read())
     h.update(open(os.path.join(ROOT, "include", "feprogram_b200.h"), "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("FE_EXTRA_DEFS", "").encode())     # developer-only extra -D flags are part of the identity
     return h.hexdigest()
 
 
@@ -75,11 +75,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     inc, nccl_lib = _nccl_paths()
     extra_inc = ["-I", inc, "-DFE_WITH_NCCL"] if inc else []
-    if os.environ.get("FE_EXTRA_DEFS"):       # tuning experiments: extra -D flags, space separated
+    if os.environ.get("FE_EXTRA_DEFS"):       # developer builds only (profiling macros); hashed into the stamp
         extra_inc += os.environ["FE_EXTRA_DEFS"].split()
-    if os.environ.get("FE_TILE_CONFIG"):      # tuning experiments: "TE,HE,CTAS"
-        te, he, ctas = os.environ["FE_TILE_CONFIG"].split(",")
-        extra_inc += ["-DFE_TILE_ELEMS=" + te, "-DFE_HALO_ELEMS=" + he, "-DFE_TILE_CTAS=" + ctas]
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
@@ -108,21 +105,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return LIB
-
-
-def build_oracle(force: bool = False) -> str | None:
-    """gcc build of the plain-C oracle (test infrastructure); returns the .so path or None if absent."""
-    src = os.path.join(ROOT, "oracle", "fe_oracle.c")
-    if not os.path.exists(src):
-        return None
-    out = os.path.join(ROOT, "oracle", "libfe_oracle.so")
-    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
-        return out
-    cmd = ["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", out, src, "-lm"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("gcc failed on the C oracle:\n%s" % r.stderr)
-    return out
 
 
 if __name__ == "__main__":

@@ -64,13 +64,10 @@ template <typename IdxT>
 static int dist_pcg_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, const int32_t* col_idx, const double* vals,
                          const double* rhs, const uint8_t* mask, double* x, double rtol, double atol, int64_t maxit,
                          int check_every, void* work, double* info, const Halo& h, const int32_t* nptr,
-                         const int32_t* nadj, cudaStream_t st) {
+                         const int32_t* nadj, int64_t nnz_owned, cudaStream_t st) {
     PcgWork w = carve(work, nloc);
     double* g = w.partB + 2 * kMaxPartials;  // 8 doubles of globally reduced scalars
-    IdxT last;
-    FE_CUDA_TRY(cudaMemcpyAsync(&last, row_ptr + nown, sizeof(IdxT), cudaMemcpyDeviceToHost, st));
-    FE_CUDA_TRY(cudaStreamSynchronize(st));
-    const int lpr = pick_lpr(nown, (int64_t)last);
+    const int lpr = pick_lpr(nown, nnz_owned);
     const Mat<IdxT> A{nown, row_ptr, col_idx, vals, nptr, nadj, lpr};
     int gv = 0, rc;
     if ((rc = persistent_grid((const void*)k_pcg_update, kVecThreads, &gv)) != FE_OK) return rc;
@@ -97,7 +94,7 @@ static int dist_pcg_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, const 
     for (;;) {
         FE_CUDA_TRY(cudaMemcpyAsync(hs, w.scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
         FE_CUDA_TRY(cudaStreamSynchronize(st));
-        if (hs[S_DONE_C] != 0.0 || launched >= maxit) break;   // identical on all ranks (same global scalars)
+        if (hs[S_DONE_C] != 0.0 || hs[S_ERR] != 0.0 || launched >= maxit) break;   // identical on all ranks (same global scalars)
         int64_t batch = check_every;
         if (launched + batch > maxit) batch = maxit - launched;
         for (int64_t k = 0; k < batch; ++k) {
@@ -117,12 +114,7 @@ static int dist_pcg_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, const 
         launched += batch;
     }
     if ((rc = halo_exchange(h, x, st)) != FE_OK) return rc;   // ghost part of the solution
-    if (info) {
-        info[0] = hs[S_ITERS];
-        info[1] = hs[S_RR0] > 0.0 ? sqrt(hs[S_RR] / hs[S_RR0]) : 0.0;
-        info[2] = sqrt(hs[S_RR0]);
-        info[3] = hs[S_DONE_C];
-    }
+    fill_info(hs, info);
     return FE_OK;
 }
 
@@ -144,6 +136,29 @@ struct PeerHalo {
     int n_nbr;
     const int32_t* nbr_dev;       // device [n_nbr]: neighbour ranks (for the signal kernel)
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Waits until *flag >= need (a peer publishes it with st.release.sys).  Exponential __nanosleep back-off, a
+// wall-clock bound (kPeerTimeoutNs) instead of a spin count, and an early exit once any waiter of this solve has
+// already recorded an error -- a dead or absent peer costs one time-out, not one per waiter.
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;   // 2 s
+__device__ __forceinline__ bool peer_wait(const long long* flag, long long need, const double* scal) {
+    if (ld_acquire_sys_s64(flag) >= need) return true;
+    const unsigned long long t0 = global_ns();
+    unsigned ns = 32;
+    for (;;) {
+        if (ld_acquire_sys_s64(flag) >= need) return true;
+        if (scal && *reinterpret_cast<const volatile double*>(scal + S_ERR) != 0.0) return false;
+        if (global_ns() - t0 > kPeerTimeoutNs) return false;
+        __nanosleep(ns);
+        if (ns < 2048) ns <<= 1;
+    }
+}
 
 __device__ __forceinline__ double2 ld_peer_f64x2(const double2* p) {
     double2 v;
@@ -180,13 +195,7 @@ __global__ void __launch_bounds__(kVecThreads) k_spmv_nodal_p2p(
                 } else {                                  // ghost column: the owner's copy over NVLink
                     const int g = m - (int)nown_nodes;
                     const int q = __ldg(h.ghost_rank + g);
-                    long long spins = 0;
-                    while (ld_acquire_sys_s64(myflags + q) < need) {   // owner has not published this version yet
-                        if (++spins > (1ll << 27)) {
-                            scal[S_ERR] = 1.0;            // reported by the host: peer wait timed out
-                            break;
-                        }
-                    }
+                    if (!peer_wait(myflags + q, need, scal)) scal[S_ERR] = (double)kErrPeerTimeout;   // host reports it
                     const double2* src = reinterpret_cast<const double2*>(h.peer_p[q] + (int64_t)parity * h.pstride);
                     xv = ld_peer_f64x2(src + __ldg(h.ghost_ridx + g));
                 }
@@ -285,11 +294,11 @@ static int dist_pcg_p2p_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, co
     for (;;) {
         FE_CUDA_TRY(cudaMemcpyAsync(hs, w.scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
         FE_CUDA_TRY(cudaStreamSynchronize(st));
-        if (hs[S_ERR] != 0.0) {
-            set_error("fe_dist_pcg_p2p: timed out waiting for a neighbour's direction vector");
+        if (hs[S_ERR] == (double)kErrPeerTimeout) {
+            set_error("fe_dist_pcg_p2p: timed out waiting for a neighbour's direction vector or reduction slot");
             return FE_ERR_NCCL;
         }
-        if (hs[S_DONE_C] != 0.0 || launched >= maxit) break;
+        if (hs[S_DONE_C] != 0.0 || hs[S_ERR] != 0.0 || launched >= maxit) break;
         int64_t batch = check_every;
         if (launched + batch > maxit) batch = maxit - launched;
         for (int64_t k = 0; k < batch; ++k) {
@@ -313,12 +322,7 @@ static int dist_pcg_p2p_impl(int64_t nown, int64_t nloc, const IdxT* row_ptr, co
         launched += batch;
     }
     if ((rc = halo_exchange(h, x, st)) != FE_OK) return rc;
-    if (info) {
-        info[0] = hs[S_ITERS];
-        info[1] = hs[S_RR0] > 0.0 ? sqrt(hs[S_RR] / hs[S_RR0]) : 0.0;
-        info[2] = sqrt(hs[S_RR0]);
-        info[3] = hs[S_DONE_C];
-    }
+    fill_info(hs, info);
     return FE_OK;
 }
 
@@ -432,13 +436,15 @@ int fe_dist_pcg_p2p(int64_t nrows_owned, int64_t nrows_local, int idx64, const v
 
 size_t fe_dist_pcg_workspace_bytes(int64_t nrows_local) { return fe_pcg_workspace_bytes(nrows_local) + 64; }
 
-int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void* row_ptr, const int32_t* col_idx,
-                const double* vals, const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol,
-                int64_t maxit, int32_t check_every, void* work, double* info, void* comm, int32_t n_nbr,
+int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int64_t nnz_owned, int idx64, const void* row_ptr,
+                const int32_t* col_idx, const double* vals, const double* rhs, const uint8_t* dirmask, double* x,
+                double rtol, double atol, int64_t maxit, int32_t check_every, void* work, double* info, void* comm,
+                int32_t n_nbr,
                 const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx, double* sendbuf,
                 const int64_t* recv_off, const int32_t* nptr, const int32_t* nadj, void* stream) {
     using namespace fe;
-    FE_REQUIRE(nrows_owned >= 0 && nrows_local >= nrows_owned && row_ptr && col_idx && vals && rhs && x && work && comm,
+    FE_REQUIRE(nrows_owned >= 0 && nrows_local >= nrows_owned && nnz_owned >= 0 && row_ptr && col_idx && vals && rhs &&
+                   x && work && comm,
                "null pointer or bad size");
     FE_REQUIRE(maxit >= 0 && check_every >= 1 && n_nbr >= 0, "maxit must be >= 0 and check_every >= 1");
     FE_REQUIRE(n_nbr == 0 || (nbr_rank && send_off && recv_off), "null halo description");
@@ -449,9 +455,10 @@ int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void*
     cudaStream_t st = as_stream(stream);
     if (idx64)
         return dist_pcg_impl<int64_t>(nrows_owned, nrows_local, static_cast<const int64_t*>(row_ptr), col_idx, vals,
-                                      rhs, dirmask, x, rtol, atol, maxit, check_every, work, info, h, nptr, nadj, st);
+                                      rhs, dirmask, x, rtol, atol, maxit, check_every, work, info, h, nptr, nadj,
+                                      nnz_owned, st);
     return dist_pcg_impl<int32_t>(nrows_owned, nrows_local, static_cast<const int32_t*>(row_ptr), col_idx, vals, rhs,
-                                  dirmask, x, rtol, atol, maxit, check_every, work, info, h, nptr, nadj, st);
+                                  dirmask, x, rtol, atol, maxit, check_every, work, info, h, nptr, nadj, nnz_owned, st);
 #else
     set_error("built without NCCL");
     return FE_ERR_NCCL;

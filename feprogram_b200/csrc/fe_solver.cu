@@ -9,8 +9,6 @@
 //   A: Ap = A p (masked), partial dots p.Ap                       [fe SpMV traffic]
 //   B: alpha = rz/pAp; x += alpha p; r -= alpha Ap; partial r.z, r.r with z = Minv r   [7 vector streams]
 //   C: beta = rz'/rz; p = Minv r + beta p; convergence flag                            [4 vector streams]
-#include <stdlib.h>
-
 #include "fe_common.cuh"
 
 namespace fe {
@@ -23,6 +21,9 @@ constexpr int kScalarDoubles = 16;
 // Flags and scalars are double-buffered between kernels so that no kernel reads a location one of its
 // own blocks writes:  DONE_C / RZ_CUR are written by kernel C and read by A and B;  DONE_B / RZ_PREV
 // are written by kernel B and read by C.
+// S_ERR: 0 = fine, kErrPeerTimeout = a peer-memory wait timed out, kErrBreakdown = CG breakdown (NaN residual or
+// p.Ap <= 0: the matrix is not SPD on the free dofs).  info[3] reports 1 only for a genuine ||r|| <= tol stop.
+constexpr int kErrPeerTimeout = 1, kErrBreakdown = 2;
 enum { S_RZ_CUR = 0, S_RZ_PREV = 1, S_RR = 2, S_RR0 = 3, S_TOL2 = 4, S_ITERS = 5, S_DONE_C = 6, S_PAP = 7, S_DONE_B = 8, S_ERR = 9 };
 
 // ---- deterministic block reduction (fixed shuffle tree, then warp 0 over the warp sums) ----------
@@ -91,11 +92,19 @@ __device__ __forceinline__ bool peer_reduced(const PeerRed& pr, long long seq, i
     __syncthreads();
     if ((int)threadIdx.x < pr.world) {
         const long long* ver = pr.versions[pr.rank] + threadIdx.x;
-        long long spins = 0;
-        while (ld_acquire_sys_s64(ver) < seq + 1) {
-            if (++spins > (1ll << 26)) {
-                timed_out = 1;
-                break;
+        if (ld_acquire_sys_s64(ver) < seq + 1) {           // exponential back-off, wall-clock bound (2 s)
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+            unsigned ns = 32;
+            while (ld_acquire_sys_s64(ver) < seq + 1) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 2000000000ull) {
+                    timed_out = 1;
+                    break;
+                }
+                __nanosleep(ns);
+                if (ns < 2048) ns <<= 1;
             }
         }
     }
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_init3(int nb, const double*
         scal[S_DONE_C] = (rr <= t) ? 1.0 : 0.0;
         scal[S_DONE_B] = 0.0;
         scal[S_PAP] = 0.0;
-        scal[S_ERR] = ok ? 0.0 : 1.0;
+        scal[S_ERR] = ok ? 0.0 : (double)kErrPeerTimeout;
     }
 }
 
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_update(int64_t n, int nbA, 
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_DONE_B] = done ? 1.0 : 0.0;
     if (done) return;
     double gv[1];
-    if (pr.world && !peer_reduced(pr, seq, 1, gv) && threadIdx.x == 0) scal[S_ERR] = 1.0;
+    if (pr.world && !peer_reduced(pr, seq, 1, gv) && threadIdx.x == 0) scal[S_ERR] = (double)kErrPeerTimeout;
     const double pAp = pr.world ? gv[0] : g ? g[0] : sum_partials(partA, nbA, 1, sm);
     const double rz_cur = scal[S_RZ_CUR];
     const double alpha = rz_cur / pAp;
@@ -315,6 +324,8 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_update(int64_t n, int nbA, 
         if (blockIdx.x == 0) {
             scal[S_RZ_PREV] = rz_cur;  // nobody reads RZ_PREV during this kernel
             scal[S_PAP] = pAp;
+            // p.Ap <= 0 with a non-zero direction: the operator is not positive definite on the free dofs
+            if (!(pAp > 0.0) && rz_cur != 0.0) scal[S_ERR] = fmax(scal[S_ERR], (double)kErrBreakdown);
         }
     }
 }
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int64_t n, int nb
     __shared__ double sm[kVecThreads / 32];
     if (scal[S_DONE_B] != 0.0) return;
     double gv[2];
-    if (pr.world && !peer_reduced(pr, seq, 2, gv) && threadIdx.x == 0) scal[S_ERR] = 1.0;
+    if (pr.world && !peer_reduced(pr, seq, 2, gv) && threadIdx.x == 0) scal[S_ERR] = (double)kErrPeerTimeout;
     const double rz_new = pr.world ? gv[0] : g ? g[0] : sum_partials(partB, nbB, 2, sm);
     const double rr = pr.world ? gv[1] : g ? g[1] : sum_partials(partB + 1, nbB, 2, sm);
     const double beta = rz_new / scal[S_RZ_PREV];
@@ -341,8 +352,22 @@ __global__ void __launch_bounds__(kVecThreads) k_pcg_direction(int64_t n, int nb
         scal[S_RZ_CUR] = rz_new;
         scal[S_RR] = rr;
         scal[S_ITERS] += 1.0;
-        if (rr <= scal[S_TOL2] || !(rr == rr)) scal[S_DONE_C] = 1.0;
+        if (rr <= scal[S_TOL2]) {
+            scal[S_DONE_C] = 1.0;
+        } else if (!(rr == rr) || !(rr < 1.0e300)) {   // breakdown (NaN / overflow): stop, and say so -- not "converged"
+            scal[S_DONE_C] = 1.0;
+            scal[S_ERR] = fmax(scal[S_ERR], (double)kErrBreakdown);
+        }
     }
+}
+
+// info[0..3] = iterations, ||r||/||r0||, ||r0||, stop reason: 1 converged, 0 iteration limit, -2 breakdown
+static void fill_info(const double* hs, double* info) {
+    if (!info) return;
+    info[0] = hs[S_ITERS];
+    info[1] = hs[S_RR0] > 0.0 ? sqrt(hs[S_RR] / hs[S_RR0]) : 0.0;
+    info[2] = sqrt(hs[S_RR0]);
+    info[3] = hs[S_ERR] != 0.0 ? -hs[S_ERR] : ((hs[S_DONE_C] != 0.0 && hs[S_RR] <= hs[S_TOL2]) ? 1.0 : 0.0);
 }
 
 static int persistent_grid(const void* func, int threads, int* out) {
@@ -358,12 +383,6 @@ static int persistent_grid(const void* func, int threads, int* out) {
 }
 
 static int pick_lpr(int64_t nrows, int64_t nnz) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("FE_SPMV_LPR");
-        forced = e ? atoi(e) : 0;
-    }
-    if (forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
     // few lanes per row keep several independent loads in flight per thread (measured on B200:
     // 18 nnz/row: 4 lanes 6.26 TB/s, 8 lanes 4.95, 2 lanes 5.16; 32 nnz/row: 4 lanes 4.64 TB/s, 8 lanes 4.14,
@@ -409,11 +428,7 @@ template <bool DOT>
 static int launch_spmv_nodal(int64_t nnode, const int32_t* nptr, const int32_t* nadj, const double* vals,
                              const double* x, double* y, const uint8_t* mask, double* partials, const double* scal,
                              int* grid_out, cudaStream_t st) {
-    static int lanes = -1;
-    if (lanes < 0) {
-        const char* e = getenv("FE_NODAL_LANES");
-        lanes = e ? atoi(e) : 4;   // measured on B200, 9 blocks per node row: 4 lanes 664 it/s, 2 lanes 638, 1 lane 564
-    }
+    constexpr int lanes = 4;   // measured on B200, 9 blocks per node row: 4 lanes 664 it/s, 2 lanes 638, 1 lane 564
 #define FE_NODAL_CASE(LN)                                                                                      \
     case LN: {                                                                                                  \
         int g = 0;                                                                                              \
@@ -426,13 +441,7 @@ static int launch_spmv_nodal(int64_t nnode, const int32_t* nptr, const int32_t* 
         break;                                                                                                  \
     }
     switch (lanes) {
-        FE_NODAL_CASE(1)
-        FE_NODAL_CASE(2)
         FE_NODAL_CASE(4)
-        FE_NODAL_CASE(8)
-        default:
-            set_error("nodal spmv: bad lanes %d", lanes);
-            return FE_ERR_INVALID;
     }
 #undef FE_NODAL_CASE
     FE_CHECK_LAUNCH("k_spmv_nodal");
@@ -480,16 +489,9 @@ static PcgWork carve(void* work, int64_t nrows) {
 template <typename IdxT>
 static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, const double* vals, const double* rhs,
                     const uint8_t* mask, double* x, double rtol, double atol, int64_t maxit, int check_every,
-                    void* work, double* info, const int32_t* nptr, const int32_t* nadj, cudaStream_t st) {
+                    void* work, double* info, const int32_t* nptr, const int32_t* nadj, int64_t nnz, cudaStream_t st) {
     PcgWork w = carve(work, nrows);
-    int64_t nnz_host = 0;
-    {
-        IdxT last;
-        FE_CUDA_TRY(cudaMemcpyAsync(&last, row_ptr + nrows, sizeof(IdxT), cudaMemcpyDeviceToHost, st));
-        FE_CUDA_TRY(cudaStreamSynchronize(st));
-        nnz_host = (int64_t)last;
-    }
-    const int lpr = pick_lpr(nrows, nnz_host);
+    const int lpr = pick_lpr(nrows, nnz);
     const Mat<IdxT> A{nrows, row_ptr, col_idx, vals, nptr, nadj, lpr};
     int gv = 0, rc;
     if ((rc = persistent_grid((const void*)k_pcg_update, kVecThreads, &gv)) != FE_OK) return rc;
@@ -512,7 +514,7 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
     for (;;) {
         FE_CUDA_TRY(cudaMemcpyAsync(hs, w.scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
         FE_CUDA_TRY(cudaStreamSynchronize(st));
-        if (hs[S_DONE_C] != 0.0 || launched >= maxit) break;
+        if (hs[S_DONE_C] != 0.0 || hs[S_ERR] != 0.0 || launched >= maxit) break;
         int64_t batch = check_every;
         if (launched + batch > maxit) batch = maxit - launched;
         for (int64_t k = 0; k < batch; ++k) {
@@ -526,12 +528,7 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
         FE_CHECK_LAUNCH("pcg iteration");
         launched += batch;
     }
-    if (info) {
-        info[0] = hs[S_ITERS];
-        info[1] = hs[S_RR0] > 0.0 ? sqrt(hs[S_RR] / hs[S_RR0]) : 0.0;
-        info[2] = sqrt(hs[S_RR0]);
-        info[3] = hs[S_DONE_C];
-    }
+    fill_info(hs, info);
     return FE_OK;
 }
 
@@ -539,26 +536,13 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
 
 extern "C" {
 
-int fe_spmv(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals, const double* x,
-            double* y, const uint8_t* rowmask, void* stream) {
+int fe_spmv(int64_t nrows, int64_t nnz, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+            const double* x, double* y, const uint8_t* rowmask, void* stream) {
     using namespace fe;
-    FE_REQUIRE(nrows >= 0 && row_ptr && col_idx && vals && x && y, "null pointer or negative size");
+    FE_REQUIRE(nrows >= 0 && nnz >= 0 && row_ptr && col_idx && vals && x && y, "null pointer or negative size");
     if (nrows == 0) return FE_OK;
     cudaStream_t st = as_stream(stream);
-    // lanes per row from the average row length; read back nnz once (tiny, stream-ordered)
-    int64_t nnz = 0;
-    if (idx64) {
-        int64_t last;
-        FE_CUDA_TRY(cudaMemcpyAsync(&last, static_cast<const int64_t*>(row_ptr) + nrows, 8, cudaMemcpyDeviceToHost, st));
-        FE_CUDA_TRY(cudaStreamSynchronize(st));
-        nnz = last;
-    } else {
-        int32_t last;
-        FE_CUDA_TRY(cudaMemcpyAsync(&last, static_cast<const int32_t*>(row_ptr) + nrows, 4, cudaMemcpyDeviceToHost, st));
-        FE_CUDA_TRY(cudaStreamSynchronize(st));
-        nnz = last;
-    }
-    const int lpr = pick_lpr(nrows, nnz);
+    const int lpr = pick_lpr(nrows, nnz);   // lanes per row from the average row length (nnz is a host argument: no read-back)
     if (idx64)
         return launch_spmv<int64_t, false>(lpr, nrows, static_cast<const int64_t*>(row_ptr), col_idx, vals, x, y,
                                            rowmask, nullptr, nullptr, nullptr, st);
@@ -597,11 +581,11 @@ size_t fe_pcg_workspace_bytes(int64_t nrows) {
     return (size_t)(4 * n + fe::kScalarDoubles + 3 * fe::kMaxPartials) * sizeof(double);
 }
 
-int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals, const double* rhs,
-           const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit, int32_t check_every, void* work,
-           double* info, const int32_t* nptr, const int32_t* nadj, void* stream) {
+int fe_pcg(int64_t nrows, int64_t nnz, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+           const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit,
+           int32_t check_every, void* work, double* info, const int32_t* nptr, const int32_t* nadj, void* stream) {
     using namespace fe;
-    FE_REQUIRE(nrows >= 0 && row_ptr && col_idx && vals && rhs && x && work, "null pointer or negative size");
+    FE_REQUIRE(nrows >= 0 && nnz >= 0 && row_ptr && col_idx && vals && rhs && x && work, "null pointer or negative size");
     FE_REQUIRE(maxit >= 0 && check_every >= 1, "maxit must be >= 0 and check_every >= 1");
     if (nrows == 0) {
         if (info) info[0] = info[1] = info[2] = 0.0, info[3] = 1.0;
@@ -610,9 +594,9 @@ int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx
     cudaStream_t st = as_stream(stream);
     if (idx64)
         return pcg_impl<int64_t>(nrows, static_cast<const int64_t*>(row_ptr), col_idx, vals, rhs, dirmask, x, rtol,
-                                 atol, maxit, check_every, work, info, nptr, nadj, st);
+                                 atol, maxit, check_every, work, info, nptr, nadj, nnz, st);
     return pcg_impl<int32_t>(nrows, static_cast<const int32_t*>(row_ptr), col_idx, vals, rhs, dirmask, x, rtol, atol,
-                             maxit, check_every, work, info, nptr, nadj, st);
+                             maxit, check_every, work, info, nptr, nadj, nnz, st);
 }
 
 }  // extern "C"

@@ -22,41 +22,9 @@
 //             src = slab row << 5 | block(lo,hi) << 1 | transposed;  absent src1 points at a zero block
 //   tchunk[]  uint32 per 32 work items  (local node of the chunk's first item, +1, -1 if that item starts a
 //             node) << 7 | p of that item: lanes rebuild (node, p) with one ballot
-#include <stdlib.h>
-
-#include "fe_element.cuh"
+#include "fe_tile_config.cuh"
 
 namespace fe {
-
-#ifndef FE_TILE_ELEMS
-#define FE_TILE_ELEMS 128
-#define FE_HALO_ELEMS 32
-#define FE_TILE_CTAS 3
-#endif
-#ifndef FE_Q4_PARTS
-#define FE_Q4_PARTS 1       // experiment: 2 = two threads per Quad4 element (five node-pair blocks each), 2 CTAs per SM
-#endif
-#ifndef FE_Q9_CTAS
-#define FE_Q9_CTAS 2
-#endif
-// ---- per-element-type tile configuration ------------------------------------------------------------
-// TE own elements per tile.  Quad4 / Tri3: 128 (one thread per element).  Quad9: 32 elements, FIVE threads
-// per element (its 45 node-pair blocks = 135 accumulators do not fit one thread).
-__host__ __device__ constexpr int tile_elems(int nnpe) { return nnpe == 9 ? 32 : FE_TILE_ELEMS; }
-// halo element threads per CTA.  Quad4 threads need ~124 registers, so its CTA is kept at 5 warps
-// (128 + 32 threads, 15 warps per SM => 128 registers available); Tri3 is register-light.
-__host__ __device__ constexpr int halo_threads(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS : nnpe == 9 ? 32 : 64; }
-// Slab rows for halo elements.  Quad4 tiles may carry up to 16 more halo elements than the CTA has halo
-// threads (irregular tiles of perturbed / unstructured meshes); those rows are evaluated in a short second
-// pass by the halo warp, so regular tiles pay nothing.
-__host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS + 16 : nnpe == 9 ? 16 : 64; }
-__host__ __device__ constexpr int tile_parts(int nnpe) { return nnpe == 9 ? 5 : nnpe == 4 ? FE_Q4_PARTS : 1; }   // threads per element
-__host__ __device__ constexpr int tri_bits(int nnpe) { return nnpe == 9 ? 6 : 4; }        // bits of a block index
-__host__ __device__ constexpr int max_nodes(int nnpe) { return nnpe == 9 ? 192 : 2 * tile_elems(nnpe); }
-__host__ __device__ constexpr int max_items(int nnpe) { return nnpe == 9 ? 640 : 8 * tile_elems(nnpe); }
-__host__ __device__ constexpr int max_work(int nnpe) { return nnpe == 9 ? 3072 : 12 * tile_elems(nnpe); }   // x32
-constexpr int kTileCtasPerSm = FE_TILE_CTAS;     // persistent grid = SMs x this
-constexpr unsigned kWorkFirst = 1u << 26, kWorkSelf = 1u << 27;
 
 template <int N> struct TileLayout {
     static constexpr int kBlocks = N * (N + 1) / 2;            // upper-triangular node pairs incl. diagonal
@@ -388,36 +356,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// Full upper-triangular block element matrix: block (lo,hi) = [L, P, Q] at 3*tri(lo,hi); diagonal blocks
-// store Q = P.  Same pair arithmetic as element_row_pair (fe_element.cuh).
-template <int ET, bool MASS>
-__device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], const double (&y)[Elem<ET>::NNPE],
-                                            bool weighted, double (&out)[3 * TileLayout<Elem<ET>::NNPE>::kBlocks]) {
-    using E = Elem<ET>;
-    using T = TileLayout<E::NNPE>;
-#pragma unroll
-    for (int i = 0; i < 3 * T::kBlocks; ++i) out[i] = 0.0;
-    ElemGeom<ET> G;
-    geom_init<ET, MASS>(G, x, y, weighted);
-#pragma unroll
-    for (int g = 0; g < E::NG; ++g) {
-        double ax[E::NNPE], ay[E::NNPE], sx[E::NNPE], sy[E::NNPE];
-        gauss_point<ET, MASS>(g, G, weighted, ax, ay, sx, sy);
-#pragma unroll
-        for (int a = 0; a < E::NNPE; ++a) {
-#pragma unroll
-            for (int b = a; b < E::NNPE; ++b) {
-                const int o = 3 * T::tri(a, b);
-                out[o] = fma(sx[a], ax[b], fma(sy[a], ay[b], out[o]));
-                out[o + 1] = fma(sy[a], ax[b], out[o + 1]);
-                if (b > a) out[o + 2] = fma(sx[a], ay[b], out[o + 2]);
-            }
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < E::NNPE; ++a) out[3 * T::tri(a, a) + 2] = out[3 * T::tri(a, a) + 1];
-}
-
 // One of NPARTS threads of an element: the upper-triangular blocks whose row node `a` this part owns (part 0:
 // the first and the last local node, part 1: the others -- 5 + 5 blocks for Quad4), written straight to the
 // element's slab row.  Same pair arithmetic as element_tri; the geometry is evaluated by every part.
@@ -565,8 +503,7 @@ template <int ET, bool MASS, int PF>
 __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayout<Elem<ET>::NNPE>::kCtas) k_assemble_tiled(
     int64_t ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords,
     const int4* __restrict__ tdesc, const int2* __restrict__ tnode, const uint16_t* __restrict__ tloc,
-    const uint32_t* __restrict__ twork, const uint32_t* __restrict__ tchunk, double* __restrict__ vals, int weighted,
-    int dbg) {
+    const uint32_t* __restrict__ twork, const uint32_t* __restrict__ tchunk, double* __restrict__ vals, int weighted) {
     using E = Elem<ET>;
     constexpr int N = E::NNPE;
     using T = TileLayout<N>;
@@ -666,7 +603,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
         // ---- phase 1: own and halo elements -> slab --------------------------------------------------
         if constexpr (kSingle) {
             const bool active = tg[0] >= 0;
-            if (active && dbg != 2) {
+            if (active) {
                 double* dst = slab + rowid * SS;
                 if constexpr (T::kParts == 1) {
                     double ke[3 * T::kBlocks];
@@ -679,7 +616,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                     element_tri_part<ET, MASS, 1>(x, y, weighted != 0, dst);
                 }
             }
-        } else if (dbg != 2) {
+        } else {
             // Quad9: stage the rows' node coordinates, then five threads per row evaluate block rows
             const int32_t* rows = tconn + t * T::kRows * N;
             for (int i = tid; i < T::kRows * N; i += kTileThreads) {
@@ -710,7 +647,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
             // overflow halo rows (irregular tiles only): second pass of the halo warp(s), not prefetched
             const int nh = d1.z;
             const int row = rowid + (T::kRowThreads - kTileElems);     // rows kRowThreads.. for threads TE..
-            if (nh > T::kRowThreads - kTileElems && rowid >= kTileElems && row < kTileElems + nh && dbg != 2) {
+            if (nh > T::kRowThreads - kTileElems && rowid >= kTileElems && row < kTileElems + nh) {
                 const int32_t* rp = tconn + (t * T::kRows + row) * N;
                 int tq[N];
                 double xq[N], yq[N], ke[3 * T::kBlocks];
@@ -760,7 +697,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
         if constexpr (kDescAhead) {
             if (tn2 < ntiles) load_desc(tn2, f0, f1);
         }
-        if (dbg != 1) {
+        {
             const int nn = d0.y, nw = d1.y;
             const uint32_t* work = s_work(buf);
             const uint32_t* chunk = s_chunk(buf);
@@ -822,7 +759,6 @@ static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coor
                         const int2* tnode, const uint16_t* tloc, const uint32_t* twork, const uint32_t* tchunk,
                         double* vals, int weighted, cudaStream_t st) {
     using T = TileLayout<Elem<ET>::NNPE>;
-    const int dbg = getenv("FE_TILED_DBG") ? atoi(getenv("FE_TILED_DBG")) : 0;  // phase isolation for profiling
     int dev = 0, sms = 0;
     FE_CUDA_TRY(cudaGetDevice(&dev));
     FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -831,7 +767,7 @@ static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coor
     FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET, MASS, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
     k_assemble_tiled<ET, MASS, PF><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
         ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc), tnode, tloc,
-        twork, tchunk, vals, weighted, dbg);
+        twork, tchunk, vals, weighted);
     FE_CHECK_LAUNCH("k_assemble_tiled");
     return FE_OK;
 }

@@ -1,0 +1,585 @@
+// K3, warp-specialised form: the numeric assembly kernel for Quad4 / Tri3 meshes, and the two plan kernels that
+// lay out its per-tile records.
+//
+// Same tiling, ownership and arithmetic as fe_tiles.cu (a tile = <= TE elements of one Morton block; every node,
+// hence every CSR row block, is owned by exactly one tile; element matrices are evaluated once per tile into a
+// shared-memory slab; every CSR value is the sum of the contributing slab blocks in ascending element id and is
+// written exactly once) -- so the bits are those of fe_assemble / fe_assemble_tiled.  What differs is how a tile
+// moves through the SM.  One persistent CTA per SM, three roles that never meet at a CTA-wide barrier:
+//
+//   producer warps   tasks = (tile, chunk of 32 slab rows), dealt round-robin over the producer warps ACROSS tiles:
+//                    load the connectivity row (prefetched one task ahead) and the node coordinates, evaluate the
+//                    upper-triangular block element matrix in fp64 registers, wait until the slab slot is free,
+//                    store the row, arrive on slab_full[slot].
+//   consumer warps   one thread per (owned node, half of its neighbour list): wait for the tile's records
+//                    (rec_full) and slab (slab_full); for every neighbour position p sum the <= 2 contributing
+//                    slab blocks (lanes = consecutive nodes: same block, consecutive odd-strided rows => no bank
+//                    conflicts on regular meshes), the diagonal block over all incident elements, and write the
+//                    2x2 block into the staging buffer AT ITS FINAL CSR OFFSET inside the tile's row range;
+//                    release slab and records, fence.proxy.async, arrive on staged_full[slot].
+//   DMA warp         cp.async.bulk (TMA, 1-D) of the next tiles' record blobs into the record ring
+//                    (mbarrier complete_tx), and -- once a staging buffer is full -- one cp.async.bulk
+//                    shared -> global per contiguous run of owned CSR rows (a tile of a row-major lattice: 8 runs
+//                    of 4.6 KB instead of 2300 16-byte stores), then wait_group.read and stage_free[slot].
+//
+// Rings: 2 slab slots, 2 record slots, 2 staging slots; six mbarrier pairs; phases advance with the tile index.
+//
+// Per-tile plan (built once per mesh by fe_tile_ws_sizes / fe_tile_ws_build from the same owner / layout /
+// halo arrays as the fe_tiles.cu plan):
+//   tconn      int32 [ntiles][TE + HC][nnpe]   connectivity in tile order (own rows, then halo rows; -1 = unused)
+//   tdesc      int32 x 4 per tile              {blob offset / 16, blob bytes, first run, run count}
+//   blob       16-byte aligned, tile-local indices only (identical for all interior tiles of a regular mesh):
+//                header   uint32 x 4           {owned nodes nn, nn rounded up to 32 (nnp), max degree, byte offset of locs}
+//                node     uint32 x 2 [nnp]     {staging offset / 16 | deg << 16 | self << 23,  cnt | item offset << 4}
+//                rec      uint32 [maxdeg][nnp] neighbour position p of node ln at [p * nnp + ln]:
+//                                              src0 | src1 << 13, src = slab row << (TB+1) | block << 1 | transposed;
+//                                              an absent source points at the slab's zero row
+//                locs     uint16 [items]       incidence items of the diagonal blocks: slab row << 4 | local node
+//   truns      16 bytes per run                {CSR value offset / 2 (int64), staging offset / 16, length / 16}
+#include "fe_tile_config.cuh"
+
+namespace fe {
+
+template <int N> struct WsLayout {
+    static constexpr int kBlocks = N * (N + 1) / 2;
+    static constexpr int kSS = (3 * kBlocks) | 1;                 // slab row stride in doubles (odd: conflict-free rows)
+    static constexpr int kTE = tile_elems(N);
+    static constexpr int kRows = kTE + halo_cap(N);               // slab rows = rows per tile of tconn
+    static constexpr int kChunks = (kRows + 31) / 32;             // producer tasks per tile
+    static constexpr int kZeroRow = kRows;
+    static constexpr int kSlabDoubles = (((kRows + 1) * kSS) + 1) & ~1;
+    static constexpr int kTriBits = tri_bits(N);
+    static constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
+    static constexpr int kSrcBits = 13;
+    static constexpr int kPW = 7, kCW = 8;                        // producer / consumer warps (+ one DMA warp)
+    static constexpr int kThreads = 32 * (kPW + kCW + 1);
+    static constexpr int kBarBytes = 128;
+    static constexpr int kBlobCap = 12 * 1024;                    // bytes of one record slot
+    static constexpr int kStageCap = 48 * 1024;                   // bytes of one staging slot (CSR values of a tile)
+    static constexpr size_t kSlabBytes = (size_t)kSlabDoubles * sizeof(double);
+    static constexpr size_t kSmem = kBarBytes + 2 * kSlabBytes + 2 * (size_t)kBlobCap + 2 * (size_t)kStageCap;
+    static_assert(kRows + 1 < (1 << (kSrcBits - kTriBits - 1)), "slab row does not fit a source field");
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+                 : "memory");
+}
+
+// =================================================================================================
+// numeric kernel
+// =================================================================================================
+template <int ET, bool MASS>
+__global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assemble_ws(
+    int ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords, const int4* __restrict__ tdesc,
+    const unsigned char* __restrict__ blobs, const int4* __restrict__ truns, double* __restrict__ vals, int weighted) {
+    using E = Elem<ET>;
+    constexpr int N = E::NNPE;
+    using T = WsLayout<N>;
+    constexpr int SS = T::kSS;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* slab0 = reinterpret_cast<double*>(smem + T::kBarBytes);
+    unsigned char* rec0 = smem + T::kBarBytes + 2 * T::kSlabBytes;
+    unsigned char* stage0 = rec0 + 2 * T::kBlobCap;
+    // barrier ids (x2 slots each)
+    enum { B_SLAB_FULL = 0, B_SLAB_EMPTY = 2, B_REC_FULL = 4, B_REC_EMPTY = 6, B_STAGED = 8, B_STAGE_FREE = 10 };
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int id, int slot) { return bar0 + 8u * (uint32_t)(id + slot); };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x;
+    const int K = (ntiles - (int)blockIdx.x + G - 1) / G;       // tiles of this CTA: blockIdx.x + k * G
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(B_SLAB_FULL, s), T::kChunks);
+            mbar_init(bar(B_SLAB_EMPTY, s), T::kCW);
+            mbar_init(bar(B_REC_FULL, s), 1);
+            mbar_init(bar(B_REC_EMPTY, s), T::kCW);
+            mbar_init(bar(B_STAGED, s), T::kCW);
+            mbar_init(bar(B_STAGE_FREE, s), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 6) slab0[(tid / 3) * T::kSlabDoubles + T::kZeroRow * SS + (tid % 3)] = 0.0;   // zero block of both slots
+    __syncthreads();
+
+    if (warp < T::kPW) {
+        // ================================ producers ================================
+        const long long total = (long long)K * T::kChunks;
+        auto row_addr = [&](long long j) -> const int32_t* {
+            const int k = (int)(j / T::kChunks), c = (int)(j - (long long)k * T::kChunks);
+            const int row = c * 32 + lane;
+            if (row >= T::kRows) return nullptr;
+            const long long t = (long long)blockIdx.x + (long long)k * G;
+            return tconn + (t * T::kRows + row) * N;
+        };
+        auto load_row = [&](const int32_t* p, int (&tg)[N]) {
+            tg[0] = -1;
+            if (!p) return;
+            if constexpr (N == 4) {
+                asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(tg[0]), "=r"(tg[1]), "=r"(tg[2]), "=r"(tg[3]) : "l"(p));
+            } else {
+#pragma unroll
+                for (int a = 0; a < N; ++a) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(tg[a]) : "l"(p + a));
+            }
+        };
+        int tg[N], tgn[N];
+        long long j = warp;
+        if (j < total) load_row(row_addr(j), tg);
+        for (; j < total; j += T::kPW) {
+            const int k = (int)(j / T::kChunks), c = (int)(j - (long long)k * T::kChunks);
+            const int row = c * 32 + lane;
+            const int slot = k & 1;
+            tgn[0] = -1;
+            if (j + T::kPW < total) load_row(row_addr(j + T::kPW), tgn);
+            const bool active = row < T::kRows && tg[0] >= 0;
+            double ke[3 * T::kBlocks];
+            if (active) {
+                double x[N], y[N];
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    const double2 p = __ldg(coords + tg[a]);
+                    x[a] = p.x;
+                    y[a] = p.y;
+                }
+                element_tri<ET, MASS>(x, y, weighted != 0, ke);
+            }
+            mbar_wait(bar(B_SLAB_EMPTY, slot), ((k >> 1) & 1) ^ 1);     // consumers are done with tile k - 2
+            if (active) {
+                double* dst = slab0 + slot * T::kSlabDoubles + row * SS;
+#pragma unroll
+                for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_SLAB_FULL, slot));
+#pragma unroll
+            for (int a = 0; a < N; ++a) tg[a] = tgn[a];
+        }
+    } else if (warp < T::kPW + T::kCW) {
+        // ================================ consumers ================================
+        const int cw = warp - T::kPW;
+        for (int k = 0; k < K; ++k) {
+            const int slot = k & 1;
+            const uint32_t par = (k >> 1) & 1;
+            const unsigned char* rec = rec0 + slot * T::kBlobCap;
+            const double* slab = slab0 + slot * T::kSlabDoubles;
+            double* stage = reinterpret_cast<double*>(stage0 + slot * T::kStageCap);
+            mbar_wait(bar(B_REC_FULL, slot), par);
+            const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
+            const int nn = (int)hdr.x, nnp = (int)hdr.y;
+            const uint2* node = reinterpret_cast<const uint2*>(rec + 16);
+            const uint32_t* recs = reinterpret_cast<const uint32_t*>(rec + 16 + 8 * nnp);
+            const uint16_t* locs = reinterpret_cast<const uint16_t*>(rec + hdr.w);
+            mbar_wait(bar(B_STAGE_FREE, slot), par ^ 1);                // bulk stores of tile k - 2 have read the buffer
+            mbar_wait(bar(B_SLAB_FULL, slot), par);
+            const int wph = nnp >> 5;                                   // warps per half
+            for (int wt = cw; wt < 2 * wph; wt += T::kCW) {
+                const int half = wt >= wph ? 1 : 0;
+                const int ln = (wt - half * wph) * 32 + lane;
+                if (ln >= nn) continue;
+                const uint2 nd = node[ln];
+                const int deg = (nd.x >> 16) & 127, self = (nd.x >> 23) & 127;
+                const int pm = (deg + 1) >> 1;
+                const int p0 = half ? pm : 0, p1 = half ? deg : pm;
+                double* row0 = stage + 2 * (nd.x & 0xFFFFu);
+                double* row1 = row0 + 2 * deg;
+#pragma unroll 2
+                for (int p = p0; p < p1; ++p) {
+                    if (p == self) continue;
+                    const uint32_t r = recs[p * nnp + ln];
+                    const uint32_t s0 = r & 0x1FFFu, s1 = (r >> T::kSrcBits) & 0x1FFFu;
+                    const double* b0 = slab + (s0 >> (T::kTriBits + 1)) * SS + 3 * ((s0 >> 1) & T::kTriMask);
+                    const double* b1 = slab + (s1 >> (T::kTriBits + 1)) * SS + 3 * ((s1 >> 1) & T::kTriMask);
+                    const int f0 = s0 & 1, f1 = s1 & 1;                 // transposed block: P and Q trade places
+                    const double L = b0[0] + b1[0];
+                    const double P = b0[1 + f0] + b1[1 + f1];
+                    const double Q = b0[2 - f0] + b1[2 - f1];
+                    *reinterpret_cast<double2*>(row0 + 2 * p) = make_double2(L, P);
+                    *reinterpret_cast<double2*>(row1 + 2 * p) = make_double2(Q, L);
+                }
+                if (self >= p0 && self < p1) {                          // diagonal block: all incident elements
+                    const int cnt = nd.y & 15, ioff = nd.y >> 4;
+                    double L = 0.0, P = 0.0;
+                    for (int q = 0; q < cnt; ++q) {
+                        const unsigned loc = locs[ioff + q];
+                        const int a = loc & 15;
+                        const double* b = slab + (loc >> 4) * SS + 3 * (a * N - ((a * (a - 1)) >> 1));
+                        L += b[0];
+                        P += b[1];
+                    }
+                    *reinterpret_cast<double2*>(row0 + 2 * self) = make_double2(L, P);
+                    *reinterpret_cast<double2*>(row1 + 2 * self) = make_double2(P, L);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk store
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar(B_SLAB_EMPTY, slot));
+                mbar_arrive(bar(B_REC_EMPTY, slot));
+                mbar_arrive(bar(B_STAGED, slot));
+            }
+        }
+    } else {
+        // ================================ DMA warp ================================
+        auto tile_of = [&](int k) { return (long long)blockIdx.x + (long long)k * G; };
+        auto issue_rec = [&](int k, const int4 d) {     // lane 0 only
+            const int slot = k & 1;
+            mbar_arrive_expect_tx(bar(B_REC_FULL, slot), (uint32_t)d.y);
+            bulk_load(smem_u32(rec0 + slot * T::kBlobCap), blobs + 16ll * (long long)(unsigned)d.x, (uint32_t)d.y,
+                      bar(B_REC_FULL, slot));
+        };
+        int4 d_cur = make_int4(0, 0, 0, 0), d_nxt = d_cur, d_nxt2 = d_cur;
+        if (K > 0) d_cur = __ldg(tdesc + tile_of(0));
+        if (K > 1) d_nxt = __ldg(tdesc + tile_of(1));
+        if (lane == 0) {
+            if (K > 0) issue_rec(0, d_cur);
+            if (K > 1) issue_rec(1, d_nxt);
+        }
+        for (int k = 0; k < K; ++k) {
+            const int slot = k & 1;
+            const uint32_t par = (k >> 1) & 1;
+            if (k + 2 < K) d_nxt2 = __ldg(tdesc + tile_of(k + 2));
+            const int r0 = d_cur.z, nr = d_cur.w;
+            int4 run = make_int4(0, 0, 0, 0);
+            if (lane < nr) run = __ldg(truns + r0 + lane);               // in flight while the consumers finish the tile
+            mbar_wait(bar(B_STAGED, slot), par);
+            if (lane == 0 && k + 2 < K) {
+                mbar_wait(bar(B_REC_EMPTY, slot), par);                   // (already complete: consumers arrive on it first)
+                issue_rec(k + 2, d_nxt2);
+            }
+            const uint32_t sbase = smem_u32(stage0 + slot * T::kStageCap);
+            for (int i = lane; i < nr; i += 32) {
+                if (i >= 32) run = __ldg(truns + r0 + i);
+                const long long off2 = (long long)(((unsigned long long)(unsigned)run.y << 32) | (unsigned)run.x);
+                bulk_store(vals + 2 * off2, sbase + 16u * (uint32_t)run.z, 16u * (uint32_t)run.w);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_STAGE_FREE, slot));
+            d_cur = d_nxt;
+            d_nxt = d_nxt2;
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+template <int ET, bool MASS>
+static int launch_ws(int64_t ntiles, const int32_t* tconn, const double* coords, const int32_t* tdesc, const void* blobs,
+                     const void* truns, double* vals, int weighted, cudaStream_t st) {
+    using T = WsLayout<Elem<ET>::NNPE>;
+    int dev = 0, sms = 0;
+    FE_CUDA_TRY(cudaGetDevice(&dev));
+    FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t grid = sms;
+    if (grid > ntiles) grid = ntiles;
+    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_ws<ET, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
+    k_assemble_ws<ET, MASS><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
+        (int)ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc),
+        static_cast<const unsigned char*>(blobs), static_cast<const int4*>(truns), vals, weighted);
+    FE_CHECK_LAUNCH("k_assemble_ws");
+    return FE_OK;
+}
+
+// =================================================================================================
+// plan kernels
+// =================================================================================================
+// One warp per tile: maximum degree, number of runs of consecutive node ids (= contiguous CSR row ranges), blob size.
+// tile_nodes is sorted ascending inside each tile (fe_tile_layout).  tsz[t] = blob bytes / 16, tsz[s + t] = runs.
+// stats: [0] max blob bytes, [1] max staging bytes, [2] max degree, [3] max owned nodes.
+__global__ void __launch_bounds__(128) k_tile_ws_sizes(int64_t ntiles, const int32_t* __restrict__ tile_nptr,
+                                                       const int32_t* __restrict__ tile_iptr,
+                                                       const int32_t* __restrict__ tile_nodes,
+                                                       const int32_t* __restrict__ nptr, int32_t* __restrict__ tsz,
+                                                       int32_t* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t s = ntiles + 1;
+    if (t > ntiles) return;
+    if (t == ntiles) {
+        if (lane == 0) tsz[t] = tsz[s + t] = 0;
+        return;
+    }
+    const int lo = tile_nptr[t], nn = tile_nptr[t + 1] - lo;
+    const int ni = tile_iptr[t + 1] - tile_iptr[t];
+    int maxdeg = 0, sumdeg = 0, runs = 0;
+    for (int i = lane; i < nn; i += 32) {
+        const int n = tile_nodes[lo + i];
+        const int deg = nptr[n + 1] - nptr[n];
+        maxdeg = deg > maxdeg ? deg : maxdeg;
+        sumdeg += deg;
+        runs += (i == 0 || tile_nodes[lo + i - 1] != n - 1) ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int m = __shfl_xor_sync(0xffffffffu, maxdeg, d);
+        maxdeg = m > maxdeg ? m : maxdeg;
+        sumdeg += __shfl_xor_sync(0xffffffffu, sumdeg, d);
+        runs += __shfl_xor_sync(0xffffffffu, runs, d);
+    }
+    if (lane == 0) {
+        const int nnp = (nn + 31) & ~31;
+        const int bytes = (16 + 8 * nnp + 4 * maxdeg * nnp + 2 * ni + 15) & ~15;
+        tsz[t] = bytes >> 4;
+        tsz[s + t] = runs;
+        atomicMax(stats + 0, bytes);
+        atomicMax(stats + 1, 32 * sumdeg);
+        atomicMax(stats + 2, maxdeg);
+        atomicMax(stats + 3, nn);
+    }
+}
+
+// One warp per tile: blob header, the padding entries [nn, nnp) of the node / record arrays, the run list, tdesc.
+__global__ void __launch_bounds__(128) k_tile_ws_runs(int64_t ntiles, const int32_t* __restrict__ tile_nptr,
+                                                      const int32_t* __restrict__ tile_iptr,
+                                                      const int32_t* __restrict__ tile_nodes,
+                                                      const int32_t* __restrict__ nptr, const int32_t* __restrict__ noff,
+                                                      const int32_t* __restrict__ blob_off,
+                                                      const int32_t* __restrict__ run_off,
+                                                      unsigned char* __restrict__ blobs, int4* __restrict__ truns,
+                                                      int4* __restrict__ tdesc, int zero_src) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    const int lo = tile_nptr[t], nn = tile_nptr[t + 1] - lo;
+    const int ni = tile_iptr[t + 1] - tile_iptr[t];
+    const int nnp = (nn + 31) & ~31;
+    int maxdeg = 0;
+    for (int i = lane; i < nn; i += 32) {
+        const int n = tile_nodes[lo + i];
+        const int deg = nptr[n + 1] - nptr[n];
+        maxdeg = deg > maxdeg ? deg : maxdeg;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int m = __shfl_xor_sync(0xffffffffu, maxdeg, d);
+        maxdeg = m > maxdeg ? m : maxdeg;
+    }
+    unsigned char* blob = blobs + 16ll * blob_off[t];
+    const int bytes = 16 * (blob_off[t + 1] - blob_off[t]);
+    const int loc_byte = 16 + 8 * nnp + 4 * maxdeg * nnp;
+    if (lane == 0) {
+        *reinterpret_cast<uint4*>(blob) = make_uint4((unsigned)nn, (unsigned)nnp, (unsigned)maxdeg, (unsigned)loc_byte);
+        tdesc[t] = make_int4(blob_off[t], bytes, run_off[t], run_off[t + 1] - run_off[t]);
+    }
+    uint2* node = reinterpret_cast<uint2*>(blob + 16);
+    uint32_t* recs = reinterpret_cast<uint32_t*>(blob + 16 + 8 * nnp);
+    const uint32_t zrec = (uint32_t)zero_src | ((uint32_t)zero_src << 13);
+    for (int ln = nn + lane; ln < nnp; ln += 32) {
+        node[ln] = make_uint2(0u, 0u);
+        for (int p = 0; p < maxdeg; ++p) recs[p * nnp + ln] = zrec;
+    }
+    for (int b = loc_byte + 2 * ni + lane; b < bytes; b += 32) blob[b] = 0;      // tail padding
+    if (lane == 0 && ni > 0) reinterpret_cast<uint16_t*>(blob + loc_byte)[ni - 1] = 0;   // item counts are padded to even
+    // runs: a run starts at slot i when the previous owned node is not n - 1
+    int base = run_off[t];
+    for (int i0 = 0; i0 < nn; i0 += 32) {
+        const int i = i0 + lane;
+        int n = -2, start = 0;
+        if (i < nn) {
+            n = tile_nodes[lo + i];
+            start = (i == 0 || tile_nodes[lo + i - 1] != n - 1) ? 1 : 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, start != 0);
+        if (start) {
+            // length: up to the next run start (or the end of the tile)
+            int j = i + 1;
+            while (j < nn && tile_nodes[lo + j] == tile_nodes[lo + j - 1] + 1) ++j;
+            const int last = tile_nodes[lo + j - 1];
+            const long long v2 = 2ll * nptr[n];                                   // value offset / 2 (4 values per node-level nz)
+            const int len16 = 2 * (nptr[last + 1] - nptr[n]);                     // 32 bytes per node-level non-zero
+            const int st16 = 2 * noff[2 * (int64_t)(lo + i) + 1];                 // staging offset / 16 = 2 * work offset
+            truns[base + __popc(m & ((1u << lane) - 1u))] =
+                make_int4((int)(v2 & 0xffffffffll), (int)(v2 >> 32), st16, len16);
+        }
+        base += __popc(m);
+    }
+}
+
+// One thread per tile-node slot: node descriptor, records (one per neighbour position), item locators.
+__global__ void __launch_bounds__(128) k_tile_ws_records(
+    int64_t nslots, int nnpe, const int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ owner,
+    const int32_t* __restrict__ tile_nptr, const int32_t* __restrict__ tile_hptr, const int32_t* __restrict__ noff,
+    const int32_t* __restrict__ thalo, const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc,
+    const uint8_t* __restrict__ epos, const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr,
+    const int32_t* __restrict__ nadj, const int32_t* __restrict__ blob_off, unsigned char* __restrict__ blobs,
+    int32_t* __restrict__ stats, int te, int he, int tribits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots) return;
+    const int n = tile_nodes[i];
+    const int t = owner[n];
+    const int lo = tile_nptr[t], nn = tile_nptr[t + 1] - lo;
+    const int nnp = (nn + 31) & ~31;
+    const int ln = (int)(i - lo);
+    const int ioff = noff[2 * i], woff = noff[2 * i + 1];
+    const int k0 = eptr[n], cnt = eptr[n + 1] - k0;
+    const int p0 = nptr[n], deg = nptr[n + 1] - p0;
+    const int nh = tile_hptr[t + 1] - tile_hptr[t];
+    const int32_t* hl = thalo + (int64_t)t * he;
+    unsigned char* blob = blobs + 16ll * blob_off[t];
+    const uint4 hdr = *reinterpret_cast<const uint4*>(blob);        // written by k_tile_ws_runs (earlier launch)
+    const int maxdeg = (int)hdr.z;
+    int self = 0;
+    for (int p = 0; p < deg; ++p) self = (nadj[p0 + p] == n) ? p : self;
+    if (cnt > 15 || deg > 127 || deg > kMaxAdj || 2 * woff > 0xFFFF || ioff >= (1 << 28)) {   // not representable
+        atomicMax(stats + 4, 1);
+        return;
+    }
+    uint2* node = reinterpret_cast<uint2*>(blob + 16);
+    uint32_t* recs = reinterpret_cast<uint32_t*>(blob + 16 + 8 * nnp);
+    uint16_t* locs = reinterpret_cast<uint16_t*>(blob + hdr.w);
+    node[ln] = make_uint2((unsigned)(2 * woff) | ((unsigned)deg << 16) | ((unsigned)self << 23),
+                          (unsigned)cnt | ((unsigned)ioff << 4));
+    const unsigned kZeroSrc = (unsigned)(te + he) << (tribits + 1);
+    unsigned short src[kMaxAdj][2];
+    for (int p = 0; p < deg; ++p) src[p][0] = src[p][1] = (unsigned short)kZeroSrc;
+    for (int j = 0; j < cnt; ++j) {
+        const int item = einc[k0 + j];
+        const int e = item >> 4, a = item & 15;
+        const int pos = einv[e];
+        int row;
+        if ((pos >> 8) == t) {
+            row = pos & 255;
+        } else {  // position inside the tile's sorted halo list
+            int l = 0, h = nh - 1;
+            while (l < h) {
+                const int mid = (l + h) >> 1;
+                if (hl[mid] < e) l = mid + 1;
+                else h = mid;
+            }
+            row = te + l;
+        }
+        locs[ioff + j] = (uint16_t)((row << 4) | a);
+        for (int b = 0; b < nnpe; ++b) {
+            const int p = epos[(int64_t)(k0 + j) * nnpe + b];
+            if (p == self) continue;
+            const int blo = a < b ? a : b, bhi = a < b ? b : a;
+            const int tri = blo * nnpe - blo * (blo - 1) / 2 + (bhi - blo);
+            const unsigned short s = (unsigned short)((row << (tribits + 1)) | (tri << 1) | (a > b ? 1 : 0));
+            if (src[p][0] == kZeroSrc) src[p][0] = s;
+            else if (src[p][1] == kZeroSrc) src[p][1] = s;
+            else atomicMax(stats + 4, 1);  // a node pair shared by more than two elements
+        }
+    }
+    for (int p = 0; p < maxdeg; ++p) {
+        const unsigned a = p < deg ? src[p][0] : kZeroSrc, b = p < deg ? src[p][1] : kZeroSrc;
+        recs[p * nnp + ln] = a | (b << 13);
+    }
+}
+
+}  // namespace fe
+
+extern "C" {
+
+void fe_tile_ws_params(int elem_type, int32_t out[4]) {
+    using namespace fe;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (elem_type == FE_QUAD4) {
+        out[0] = WsLayout<4>::kBlobCap, out[1] = WsLayout<4>::kStageCap, out[2] = 127, out[3] = 256;
+    } else if (elem_type == FE_TRI3) {
+        out[0] = WsLayout<3>::kBlobCap, out[1] = WsLayout<3>::kStageCap, out[2] = 127, out[3] = 256;
+    }
+}
+
+int fe_tile_ws_sizes(int elem_type, int64_t ntiles, const int32_t* tile_ptr, const int32_t* tile_nodes, const int32_t* nptr,
+                     int32_t* tsz, int32_t* stats, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(elem_type == FE_QUAD4 || elem_type == FE_TRI3, "the warp-specialised kernel handles Quad4 / Tri3");
+    FE_REQUIRE(ntiles >= 0 && tile_ptr && tsz && stats, "null pointer or negative size");
+    cudaStream_t st = as_stream(stream);
+    FE_CUDA_TRY(cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
+    FE_REQUIRE(ntiles == 0 || (tile_nodes && nptr), "null pointer");
+    const int64_t s = ntiles + 1;
+    k_tile_ws_sizes<<<grid_for(ntiles + 1, 4), 128, 0, st>>>(ntiles, tile_ptr, tile_ptr + s, tile_nodes, nptr, tsz, stats);
+    FE_CHECK_LAUNCH("k_tile_ws_sizes");
+    return FE_OK;
+}
+
+int fe_tile_ws_build(int elem_type, int64_t nslots, int64_t ntiles, const int32_t* tile_nodes, const int32_t* owner,
+                     const int32_t* tile_ptr, const int32_t* noff, const int32_t* thalo, const int32_t* eptr,
+                     const int32_t* einc, const uint8_t* epos, const int32_t* eloc, const int32_t* nptr,
+                     const int32_t* nadj, const int32_t* blob_off, const int32_t* run_off, void* blobs, void* truns,
+                     int32_t* tdesc, int32_t* stats, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(elem_type == FE_QUAD4 || elem_type == FE_TRI3, "the warp-specialised kernel handles Quad4 / Tri3");
+    FE_REQUIRE(nslots >= 0 && ntiles >= 0, "negative size");
+    if (ntiles == 0) return FE_OK;
+    FE_REQUIRE(tile_nodes && owner && tile_ptr && noff && thalo && eptr && einc && epos && eloc && nptr && nadj &&
+                   blob_off && run_off && blobs && truns && tdesc && stats,
+               "null pointer");
+    const int nnpe = nnpe_of(elem_type);
+    cudaStream_t st = as_stream(stream);
+    const int64_t s = ntiles + 1;
+    const int te = tile_elems(nnpe), he = halo_cap(nnpe), tb = tri_bits(nnpe);
+    k_tile_ws_runs<<<grid_for(ntiles, 4), 128, 0, st>>>(ntiles, tile_ptr, tile_ptr + s, tile_nodes, nptr, noff, blob_off,
+                                                        run_off, static_cast<unsigned char*>(blobs),
+                                                        static_cast<int4*>(truns), reinterpret_cast<int4*>(tdesc),
+                                                        (te + he) << (tb + 1));
+    FE_CHECK_LAUNCH("k_tile_ws_runs");
+    if (nslots > 0) {
+        k_tile_ws_records<<<grid_for(nslots, 128), 128, 0, st>>>(
+            nslots, nnpe, tile_nodes, owner, tile_ptr, tile_ptr + 2 * s, noff, thalo, eptr, einc, epos, eloc, nptr, nadj,
+            blob_off, static_cast<unsigned char*>(blobs), stats, te, he, tb);
+        FE_CHECK_LAUNCH("k_tile_ws_records");
+    }
+    return FE_OK;
+}
+
+int fe_assemble_ws(int elem_type, int op, int64_t ntiles, const int32_t* tconn, const double* coords, const int32_t* tdesc,
+                   const void* blobs, const void* truns, double* vals, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(ntiles >= 0 && ntiles < ((int64_t)1 << 31), "bad tile count");
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
+        set_error("fe_assemble_ws: unsupported operator %d", op);
+        return FE_ERR_UNSUPPORTED;
+    }
+    if (ntiles == 0) return FE_OK;
+    FE_REQUIRE(tconn && coords && tdesc && blobs && truns && vals, "null pointer");
+    FE_REQUIRE((reinterpret_cast<uintptr_t>(vals) & 15) == 0 && (reinterpret_cast<uintptr_t>(blobs) & 15) == 0,
+               "vals and blobs must be 16-byte aligned (bulk copies)");
+    cudaStream_t st = as_stream(stream);
+    int rc = ensure_tables_tu(st);
+    if (rc != FE_OK) return rc;
+    const int w = op == FE_OP_WEIGHTED;
+    switch (elem_type) {
+        case FE_QUAD4:
+            return op == FE_OP_MASS ? launch_ws<FE_QUAD4, true>(ntiles, tconn, coords, tdesc, blobs, truns, vals, 1, st)
+                                    : launch_ws<FE_QUAD4, false>(ntiles, tconn, coords, tdesc, blobs, truns, vals, w, st);
+        case FE_TRI3:
+            return op == FE_OP_MASS ? launch_ws<FE_TRI3, true>(ntiles, tconn, coords, tdesc, blobs, truns, vals, 1, st)
+                                    : launch_ws<FE_TRI3, false>(ntiles, tconn, coords, tdesc, blobs, truns, vals, w, st);
+        default:
+            set_error("fe_assemble_ws: element type %d is not handled by this kernel (use fe_assemble_tiled)", elem_type);
+            return FE_ERR_UNSUPPORTED;
+    }
+}
+
+}  // extern "C"

@@ -253,6 +253,7 @@ class DistFemProblem:
         self.vals = torch.empty(self.pat.nnz, dtype=torch.float64, device=self.dev)
         self.nrows_owned = 2 * local.n_owned
         self.nrows_local = 2 * local.nnode
+        self.nnz_owned = 4 * int(self.pat.nptr[local.n_owned].item())   # host copy: the SpMV / PCG calls take it as an argument
         nbr, send_off, send_idx, recv_off = local.halo_arrays(2)
         self._nbr, self._send_off, self._recv_off = nbr, send_off, recv_off       # host arrays (kept alive)
         self.send_idx = torch.from_numpy(send_idx).to(self.dev)
@@ -321,7 +322,7 @@ class DistFemProblem:
         with torch.cuda.device(self.dev):
             st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
             pat = self.pat
-            _lib.check(_lib.lib().fe_spmv(self.nrows_owned, int(pat.row_ptr.dtype == torch.int64),
+            _lib.check(_lib.lib().fe_spmv(self.nrows_owned, self.nnz_owned, int(pat.row_ptr.dtype == torch.int64),
                                           C.c_void_p(pat.row_ptr.data_ptr()), C.c_void_p(pat.col_idx.data_ptr()),
                                           C.c_void_p(self.vals.data_ptr()), C.c_void_p(x.data_ptr()),
                                           C.c_void_p(y.data_ptr()), None, st))
@@ -335,6 +336,21 @@ class DistFemProblem:
         import torch.distributed._symmetric_memory as symm_mem
         m = self.m
         group = group or dist.group.WORLD
+        # The peer-memory kernels wait inside a kernel for flags other ranks write: that is only live when every
+        # rank runs on its OWN GPU and all of them can map each other's memory.  Check both collectively and
+        # stay on the NCCL path otherwise (returns False; solve() then uses fe_dist_pcg).
+        props = torch.cuda.get_device_properties(self.dev)
+        mine = (str(getattr(props, "uuid", "")) or "%s/%d" % (os.uname().nodename, self.dev.index), self.dev.index)
+        devs = [None] * m.world
+        dist.all_gather_object(devs, mine, group=group)
+        distinct = len({d[0] for d in devs}) == m.world
+        peer_ok = all(q == self.dev.index or torch.cuda.can_device_access_peer(self.dev.index, q)
+                      for _, q in devs) if distinct else False
+        oks = [None] * m.world
+        dist.all_gather_object(oks, bool(distinct and peer_ok), group=group)
+        if not all(oks):
+            self.p2p = False
+            return False
         sizes = [None] * m.world
         dist.all_gather_object(sizes, self.nrows_local, group=group)
         self._pstride = (max(sizes) + 15) // 16 * 16
@@ -363,6 +379,7 @@ class DistFemProblem:
         torch.cuda.synchronize(self.dev)
         dist.barrier(group=group)
         self.p2p = True
+        return True
 
     def solve(self, rtol: float = 1e-10, maxit: int = 100000, check_every: int = 50, p2p=None):
         import torch
@@ -379,14 +396,15 @@ class DistFemProblem:
         n, nbr, soff, sidx, sbuf, roff = self._halo_args()
         with torch.cuda.device(self.dev):
             st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
-            _lib.check(L.fe_dist_pcg(self.nrows_owned, self.nrows_local, int(pat.row_ptr.dtype == torch.int64),
+            _lib.check(L.fe_dist_pcg(self.nrows_owned, self.nrows_local, self.nnz_owned, int(pat.row_ptr.dtype == torch.int64),
                                      C.c_void_p(pat.row_ptr.data_ptr()), C.c_void_p(pat.col_idx.data_ptr()),
                                      C.c_void_p(self.vals.data_ptr()), C.c_void_p(self.rhs.data_ptr()),
                                      C.c_void_p(self.dirmask.data_ptr()), C.c_void_p(x.data_ptr()), float(rtol), 0.0,
                                      int(maxit), int(check_every), C.c_void_p(work.data_ptr()),
                                      info.ctypes.data_as(C.c_void_p), self.comm, n, nbr, soff, sidx, sbuf, roff,
                                      C.c_void_p(pat.nptr.data_ptr()), C.c_void_p(pat.nadj.data_ptr()), st))
-        self.info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]), converged=bool(info[3]))
+        self.info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]), converged=info[3] == 1.0,
+                         breakdown=info[3] < 0.0)
         return x
 
 
@@ -413,7 +431,8 @@ class DistFemProblem:
                                          dp(self._peer_flags), dp(self._ghost_rank), dp(self._ghost_ridx),
                                          dp(self._nbr_dev), self._pstride, dp(self._pbuf), epoch,
                                          dp(self._peer_red), dp(self._peer_rver), seq, st))
-        self.info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]), converged=bool(info[3]))
+        self.info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]), converged=info[3] == 1.0,
+                         breakdown=info[3] < 0.0)
         return x
 
 
@@ -421,18 +440,18 @@ class DistFemProblem:
 # bench.py support: weak-scaling workload, rank r = one n x n element block of the n x (world*n) mesh
 # ----------------------------------------------------------------------------------------------------
 class _BenchPart:
-    def __init__(self, n: int, rank: int, world: int, dev, ny_per_rank: int):
+    def __init__(self, n: int, rank: int, world: int, dev, ny_per_rank: int, halo: str = "p2p", comm=None):
         import torch
         self.torch = torch
         self.m, self.bc = structured_quad4_block(n, ny_per_rank, rank, world)
-        self.comm = DistFemProblem.make_comm(rank, world, dev)
+        self.comm = comm if comm is not None else DistFemProblem.make_comm(rank, world, dev)
+        warm, _ = structured_quad4_block(64, 64, rank, world)     # tiny problem first: CUDA module load, first mallocs
+        DistFemProblem(warm, dev, 4, self.comm).assemble()
         self.p = DistFemProblem(self.m, dev, 4, self.comm)
-        self.p = DistFemProblem(self.m, dev, 4, self.comm)        # second build: excludes context / module load
         self.p.set_bc(self.bc["dir"], self.bc["neu"])
         self.symbolic_s = self.p.symbolic_s
         self.halo = "nccl"
-        if world > 1 and os.environ.get("FE_P2P", "1") != "0":
-            self.p.enable_p2p()
+        if world > 1 and halo == "p2p" and self.p.enable_p2p():
             self.halo = "peer-memory (NVLink loads + flag-gated scalar exchange)"
         self.nelem_owned = self.m.n_own_elems
         self.tiled = self.p.plan is not None
@@ -516,5 +535,5 @@ class _BenchPart:
                 "includes": "per rank: H2D, symbolic phase, numeric assembly, BCs, D2H rhs + checksum", "checksum": chk}
 
 
-def build_structured_block(n: int, rank: int, world: int, dev, ny_per_rank: int = 0):
-    return _BenchPart(n, rank, world, dev, ny_per_rank or n)
+def build_structured_block(n: int, rank: int, world: int, dev, ny_per_rank: int = 0, halo: str = "p2p", comm=None):
+    return _BenchPart(n, rank, world, dev, ny_per_rank or n, halo, comm)

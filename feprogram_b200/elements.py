@@ -405,8 +405,20 @@ class FemProblem:
         maxit = self.maxit if self.maxit is not None else 20 * pat.nrows + 100
         info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, st["vals"], st["rhs"], st["dirmask"], x,
                                        self.rtol, 0.0, maxit, 50, pat.nptr, pat.nadj)
+        stop = float(info[3])
         self.solver_info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]),
-                                converged=bool(info[3]))
+                                converged=stop == 1.0, breakdown=stop < 0.0)
+        if stop < 0.0 or not np.isfinite(self.solver_info["relres"]):
+            # the reference's spsolve also handles indefinite systems (and warns on singular ones); CG cannot:
+            # say so loudly instead of handing back a NaN / meaningless iterate as if it were the solution
+            raise RuntimeError(
+                "solveProblem: conjugate-gradient breakdown after %d iterations (relres %r): the assembled matrix is "
+                "not positive definite on the free dofs (mixed element orientation, a degenerate element, or no "
+                "Dirichlet support?)" % (self.solver_info["iterations"], self.solver_info["relres"]))
+        if stop != 1.0:
+            import warnings
+            warnings.warn("solveProblem: PCG stopped at the iteration limit (%d) with relative residual %.3e > rtol %.1e"
+                          % (self.solver_info["iterations"], self.solver_info["relres"], self.rtol), RuntimeWarning)
         st["x"] = x
         if st["perm"] is not None:
             x = x.view(-1, 2)[st["perm"]].reshape(-1)          # back to the reference's dof numbering

@@ -1,12 +1,15 @@
 """``getMeshInfo()`` with the reference's contract (/root/reference/gmsh_api.py:13-113; next-row f-2 of
 SURVEY.md §8, not on the hot path): returns ``(conectivity, coordinates, bcNodesList)`` of the 2 x 10
-rectangle meshed with quads of size lc = 0.25 -- 1-based tags, coordinates (nnode, 3), four boundary tag
-sets ordered [bottom, right, top, left].
+rectangle meshed with quads of size lc = 0.25 -- 1-based tags, coordinates (nnode, 2) (gmsh_api.py:104-106),
+four boundary tag sets ordered [bottom, right, top, left].
 
 The reference drives the gmsh SDK (an external C++ mesher).  When ``gmsh`` is importable the same model is
-built with it; otherwise (this image has no gmsh) the transfinite-equivalent structured 8 x 40 quad mesh
-of the same rectangle is generated, which is what gmsh's recombined mesh of this geometry amounts to.
+built with it (same calls, including the ``tp-EFAF.msh`` side-effect file); otherwise (this image has no gmsh)
+a WARNING is logged and the transfinite-equivalent structured 8 x 40 quad mesh of the same rectangle is
+generated, which is what gmsh's recombined mesh of this geometry amounts to.
 """
+import logging
+
 import numpy as np
 
 from . import mesh
@@ -23,7 +26,7 @@ LX, LY, LC = 2.0, 10.0, 0.25
 def _structured():
     nx, ny = int(round(LX / LC)), int(round(LY / LC))
     conn, xy, bc = mesh.structured_quad4(nx, ny, dtype=np.uint64)
-    coords = np.zeros((xy.shape[0], 3))
+    coords = np.zeros((xy.shape[0], 2))
     coords[:, 0] = xy[:, 0] * LX
     coords[:, 1] = xy[:, 1] * LY
     return list(conn), coords, bc
@@ -33,6 +36,9 @@ def getMeshInfo():
     try:
         import gmsh  # noqa: F401
     except Exception:
+        logging.getLogger(__name__).warning(
+            "gmsh is not importable: getMeshInfo() returns the structured 8 x 40 Quad4 mesh of the 2 x 10 rectangle "
+            "instead of gmsh's recombined mesh (same contract, not the same node numbering)")
         return _structured()
     gmsh.initialize()
     try:
@@ -46,18 +52,27 @@ def getMeshInfo():
         gmsh.model.geo.addLine(4, 1, 4)
         gmsh.model.geo.addCurveLoop([4, 1, -2, 3], 1)
         gmsh.model.geo.addPlaneSurface([1], 1)
+        gmsh.model.addPhysicalGroup(0, [1, 2], 1)
+        for line, (group, name) in enumerate(((2, "Bottom"), (3, "Right"), (4, "Top"), (5, "Left")), start=1):
+            gmsh.model.addPhysicalGroup(1, [line], group)
+            gmsh.model.setPhysicalName(1, group, name)
+        gmsh.model.addPhysicalGroup(2, [1], 6)
+        gmsh.model.setPhysicalName(2, 6, "Interior")
+        gmsh.model.geo.mesh.setRecombine(2, 1)          # as the reference (gmsh_api.py:84): recombine surface 1
         gmsh.model.geo.synchronize()
-        gmsh.option.setNumber("Mesh.RecombineAll", 1)
         gmsh.model.mesh.generate(2)
-        tags, xyz, _ = gmsh.model.mesh.getNodes()
-        coords = np.zeros((int(tags.max()), 3))
-        coords[np.asarray(tags, dtype=np.int64) - 1] = np.asarray(xyz).reshape(-1, 3)
-        _, _, enodes = gmsh.model.mesh.getElements(2)
-        conn = [np.asarray(r) for r in np.asarray(enodes[0], dtype=np.uint64).reshape(-1, 4)]
+        gmsh.write("tp-EFAF.msh")                       # the reference's side-effect file (gmsh_api.py:90)
         sides = []
-        for line in (1, 2, 3, 4):          # bottom, right, top, left
-            ntags, _, _ = gmsh.model.mesh.getNodes(1, line, includeBoundary=True)
-            sides.append(set(int(t) for t in ntags))
+        for line in (1, 2, 3, 4):                       # bottom, right, top, left: nodes of the 1-D elements
+            _, _, enodes1 = gmsh.model.mesh.getElements(1, line)
+            sides.append(set(enodes1[0]))
+        etypes, _, enodes = gmsh.model.mesh.getElements(2, 1)
+        nnpe = _MSH_TYPES[int(etypes[0])][1]
+        conn = [np.asarray(r) for r in np.asarray(enodes[0], dtype=np.uint64).reshape(-1, nnpe)]
+        tags, xyz, _ = gmsh.model.mesh.getNodes()
+        coords = np.zeros((len(tags), 2))               # row order = gmsh's node order, as gmsh_api.py:104-106
+        coords[:, 0] = xyz[0::3]
+        coords[:, 1] = xyz[1::3]
         return conn, coords, sides
     finally:
         gmsh.finalize()

@@ -16,7 +16,7 @@ import numpy as np
 from . import mesh
 from .elements import FemProblem
 from .gmsh_api import getMeshInfo
-from .python_to_xml import writeXML_nodeData
+from .python_to_xml import writeXML, writeXML_nodeData  # noqa: F401  (the reference's import line, main.py:7)
 
 
 class _Laps:
@@ -47,7 +47,7 @@ def run(outname, nx=None, ny=None, quad9=False):
     fem = FemProblem(conectivity, coordinates)
     laps.lap("Crear elemento fem")
     for label, call in (("Seteo inicial de matrices", fem.setMatrix),
-                        ("Seteo de BC en nodos", lambda: fem.setBoundaryConditions(bcNodeTags, verbose=False)),
+                        ("Seteo de BC en nodos", lambda: fem.setBoundaryConditions(bcNodeTags)),   # prints both dof sets, as the reference
                         ("Ensamblaje de matrices", fem.assemble)):
         call()
         laps.lap(label)

@@ -243,7 +243,7 @@ def spmv(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, x: Tensor, y: Tensor, r
     _want(vals, torch.float64, "vals")
     _want(x, torch.float64, "x")
     with torch.cuda.device(vals.device):
-        _lib.check(_lib.lib().fe_spmv(row_ptr.numel() - 1, int(row_ptr.dtype == torch.int64), _ptr(row_ptr),
+        _lib.check(_lib.lib().fe_spmv(row_ptr.numel() - 1, col_idx.numel(), int(row_ptr.dtype == torch.int64), _ptr(row_ptr),
                                       _ptr(col_idx), _ptr(vals), _ptr(x), _ptr(y), _ptr(rowmask), _stream(vals)))
 
 
@@ -271,7 +271,8 @@ def csr_diagonal(row_ptr: Tensor, col_idx: Tensor, vals: Tensor) -> Tensor:
 def pcg(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, rhs: Tensor, dirmask: Optional[Tensor], x: Tensor,
         rtol: float, atol: float, maxit: int, check_every: int, nptr: Optional[Tensor] = None,
         nadj: Optional[Tensor] = None) -> Tensor:
-    """Jacobi-PCG with Dirichlet dofs held at rhs[D]; returns CPU tensor [iters, relres, ||r0||, converged].
+    """Jacobi-PCG with Dirichlet dofs held at rhs[D]; returns CPU tensor [iters, relres, ||r0||, stop] with
+    stop = 1 converged, 0 iteration limit, -2 CG breakdown (matrix not SPD on the free dofs / NaN).
     nptr/nadj: node-level pattern of a 2-dof matrix (node-block SpMV inside the iteration)."""
     _chk_dev(row_ptr, col_idx, vals, rhs, dirmask, x, nptr, nadj)
     n = row_ptr.numel() - 1
@@ -279,7 +280,7 @@ def pcg(row_ptr: Tensor, col_idx: Tensor, vals: Tensor, rhs: Tensor, dirmask: Op
     with torch.cuda.device(vals.device):
         L = _lib.lib()
         work = torch.empty(L.fe_pcg_workspace_bytes(n), dtype=torch.uint8, device=vals.device)
-        _lib.check(L.fe_pcg(n, int(row_ptr.dtype == torch.int64), _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(rhs),
+        _lib.check(L.fe_pcg(n, col_idx.numel(), int(row_ptr.dtype == torch.int64), _ptr(row_ptr), _ptr(col_idx), _ptr(vals), _ptr(rhs),
                             _ptr(dirmask), _ptr(x), float(rtol), float(atol), int(maxit), int(check_every), _ptr(work),
                             info.ctypes.data_as(C.c_void_p), _ptr(nptr), _ptr(nadj), _stream(vals)))
     return torch.from_numpy(info)
@@ -362,22 +363,25 @@ def locality_order(coords: Tensor) -> Tuple[Tensor, Tensor]:
 # --------------------------------------------------------------------------------------------
 # tile plan for the fast assembly kernel
 # --------------------------------------------------------------------------------------------
-import os as _os
-FE_TILE_SORT_BY_ID = _os.environ.get("FE_TILE_SORT_BY_ID", "1") == "1"   # tuning knob
-FE_PLAN_DEDUP = _os.environ.get("FE_PLAN_DEDUP", "0") == "1"             # share identical tile records (experimental)
 
 
 @dataclass
 class TilePlan:
     """One-time plan of fe_assemble_tiled (device tensors, tile-major; formats in csrc/fe_tiles.cu)."""
     tconn: Tensor           # int32 [ntiles, tile_rows, nnpe]: connectivity in tile order (own + halo rows)
-    tdesc: Tensor           # int32 [ntiles, 8]: node offset/count, item offset/count, work offset/count, 0, 0
-    tnode: Tensor           # int32 [nslots, 2]
-    tloc: Tensor            # uint16 [items]
-    twork: Tensor           # int32 (uint32 bit pattern) [work items, padded to 32 per tile]
-    tchunk: Tensor          # int32 (uint32 bit pattern) [work items / 32]
+    tdesc: Tensor           # int32 [ntiles, 8] (barrier-phased kernel) or [ntiles, 4] (warp-specialised kernel)
+    tnode: Optional[Tensor]   # int32 [nslots, 2]                                              } barrier-phased
+    tloc: Optional[Tensor]    # uint16 [items]                                                 } kernel only
+    twork: Optional[Tensor]   # int32 (uint32 bit pattern) [work items, padded to 32 per tile] } (fe_assemble_tiled)
+    tchunk: Optional[Tensor]  # int32 (uint32 bit pattern) [work items / 32]                   }
     ntiles: int
     stats: dict
+    blobs: Optional[Tensor] = None    # uint8: per-tile record blobs  } warp-specialised kernel (fe_assemble_ws)
+    truns: Optional[Tensor] = None    # int32 [runs, 4]               }
+
+    @property
+    def warp_specialised(self) -> bool:
+        return self.blobs is not None
 
 
 def dedup_tile_records(tdesc: Tensor, tloc: Tensor, twork: Tensor, tchunk: Tensor):
@@ -450,29 +454,33 @@ def _scan_into(src: Tensor, dst: Tensor, ws: Tensor):
     _lib.check(_lib.lib().fe_exclusive_scan_i32(_ptr(src), _ptr(dst), src.numel(), _ptr(ws), _stream(src)))
 
 
-def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -> Optional[TilePlan]:
+def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, kernel: str = "auto") -> Optional[TilePlan]:
     """Builds the tile plan; returns None when the mesh does not fit the tiled kernel's capacities
-    (the caller then uses the row-tile kernel fe_assemble, which has none).
+    (the caller then uses the row-tile kernel fe_assemble, which has none).  ``kernel``: "auto" = the
+    warp-specialised kernel where it exists (Quad4 / Tri3) and its capacities hold, else the barrier-phased one;
+    "ws" / "phased" force one of them (tests compare the two bit for bit).
 
     Elements are ordered along the Morton curve of a grid of one-element cells.  Strategy 1 ("blocks"): a
     tile = one aligned Z-block of 128 cells (exact 8x16 patches on structured meshes).  If that needs many
     more tiles than nelem/TE (irregular meshes: blocks with > TE elements get split, others are underfull)
     or overflows a capacity, strategy 2 ("pack") fills tiles with consecutive 16-cell sub-blocks up to TE
     elements; coarser cells are the last resort."""
+    if kernel not in ("auto", "ws", "phased"):
+        raise ValueError("kernel must be 'auto', 'ws' or 'phased'")
     if not morton:
-        return _tile_plan(conn, coords, pat, False, 1.0, "blocks")
+        return _tile_plan(conn, coords, pat, False, 1.0, "blocks", kernel)
     te = _lib.tile_params(pat.elem_type)["tile_elems"]
     if te == 0 or pat.nelem == 0:
         return None
     ideal = (pat.nelem + te - 1) // te
-    best = _tile_plan(conn, coords, pat, True, 1.0, "blocks")
+    best = _tile_plan(conn, coords, pat, True, 1.0, "blocks", kernel)
     if best is not None and best.ntiles <= 1.12 * ideal + 8:
         return best
     # irregular meshes: slightly smaller cells keep most Z-blocks at or below TE elements (a block with more is
     # split into a full and a nearly empty tile); packing sub-blocks and coarser cells are the fall-backs
     for mode, scale, good in (("blocks", 0.97, 1.08), ("blocks", 0.94, 1.10), ("pack", 1.0, 1.12), ("blocks", 0.9, 1.25),
                               ("pack", 1.25, 1.25), ("pack", 1.6, 1.25)):
-        plan = _tile_plan(conn, coords, pat, True, scale, mode)
+        plan = _tile_plan(conn, coords, pat, True, scale, mode, kernel)
         if plan is not None and (best is None or plan.ntiles < best.ntiles):
             best = plan
         if best is not None and best.ntiles <= good * ideal + 8:
@@ -481,7 +489,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True) -
 
 
 def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_scale: float,
-               mode: str) -> Optional[TilePlan]:
+               mode: str, kernel: str = "auto") -> Optional[TilePlan]:
     L = _lib.lib()
     params = _lib.tile_params(pat.elem_type)
     if params["halo_cap"] == 0 or pat.nelem == 0 or pat.nnode == 0:
@@ -546,12 +554,11 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         starts = torch.nonzero(flag).flatten()
         row = (idx - starts[tid.long()]).to(torch.int32)
         tile_estart = torch.cat([starts, torch.tensor([nelem], device=dev)]).to(torch.int32)
-        if FE_TILE_SORT_BY_ID:
-            # inside a tile order the elements by element id
-            etile = torch.empty(nelem, dtype=torch.int32, device=dev)
-            etile[eperm.long()] = tid
-            eperm = torch.sort(etile, stable=True).indices.to(torch.int32)
-            del etile
+        # inside a tile order the elements by element id
+        etile = torch.empty(nelem, dtype=torch.int32, device=dev)
+        etile[eperm.long()] = tid
+        eperm = torch.sort(etile, stable=True).indices.to(torch.int32)
+        del etile
         eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
         eloc[eperm.long()] = (tid << 8) | row          # tid / row are per sorted position
         del block, flag, seg_start, tid, starts, row, idx
@@ -587,6 +594,41 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         if (max_nodes > params["max_nodes"] or max_items >= params["max_items"] - 1 or max_halo > hcap
                 or max_work > params["max_work"]):
             return None
+        tconn = torch.empty((ntiles, params["tile_rows"], conn.shape[1]), dtype=torch.int32, device=dev)
+        _lib.check(L.fe_tile_conn(pat.elem_type, ntiles, _ptr(conn), _ptr(eperm), _ptr(tile_estart), _ptr(thalo),
+                                  _ptr(tile_ptr), _ptr(tconn), st))
+        wsp = _lib.tile_ws_params(pat.elem_type)
+        if kernel != "phased" and wsp["blob_cap"] > 0:
+            # ---- warp-specialised kernel: per-tile record blobs + runs of contiguous CSR rows ----
+            tsz = torch.empty((2, s), dtype=torch.int32, device=dev)
+            wstats = torch.empty(8, dtype=torch.int32, device=dev)
+            _lib.check(L.fe_tile_ws_sizes(pat.elem_type, ntiles, _ptr(tile_ptr), _ptr(tile_nodes), _ptr(pat.nptr),
+                                          _ptr(tsz), _ptr(wstats), st))
+            offs = torch.empty((2, s), dtype=torch.int32, device=dev)
+            _scan_into(tsz[0], offs[0], ws)
+            _scan_into(tsz[1], offs[1], ws)
+            wt = torch.cat([offs[:, ntiles], wstats]).cpu().tolist()              # host sync: sizes + capacities
+            blob16, nruns = int(wt[0]), int(wt[1])
+            info.update(max_blob=int(wt[2]), max_stage=int(wt[3]), max_deg=int(wt[4]), runs=nruns, blob_bytes=16 * blob16)
+            fits = (wt[2] <= wsp["blob_cap"] and wt[3] <= wsp["stage_cap"] and wt[4] <= wsp["max_deg"]
+                    and wt[5] <= wsp["max_nodes"] and blob16 < 2 ** 31)
+            if fits:
+                blobs = torch.empty(max(16, 16 * blob16), dtype=torch.uint8, device=dev)
+                truns = torch.empty((max(1, nruns), 4), dtype=torch.int32, device=dev)
+                tdesc = torch.empty((ntiles, 4), dtype=torch.int32, device=dev)
+                _lib.check(L.fe_tile_ws_build(pat.elem_type, nslots, ntiles, _ptr(tile_nodes), _ptr(owner), _ptr(tile_ptr),
+                                              _ptr(noff), _ptr(thalo), _ptr(pat.eptr), _ptr(pat.einc), _ptr(pat.epos),
+                                              _ptr(einv), _ptr(pat.nptr), _ptr(pat.nadj), _ptr(offs[0]), _ptr(offs[1]),
+                                              _ptr(blobs), _ptr(truns), _ptr(tdesc), _ptr(wstats), st))
+                if int(wstats[4].item()) != 0:
+                    return None
+                info["kernel"] = "ws"
+                return TilePlan(tconn, tdesc, None, None, None, None, ntiles, info, blobs, truns)
+            if kernel == "ws":
+                return None
+        elif kernel == "ws":
+            return None
+        info["kernel"] = "phased"
         tnode = torch.empty((max(1, nslots), 2), dtype=torch.int32, device=dev)
         tloc = torch.zeros(max(2, n_items), dtype=torch.uint16, device=dev)
         twork = torch.zeros(max(32, n_work), dtype=torch.int32, device=dev)
@@ -597,16 +639,11 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                                      _ptr(twork), _ptr(tchunk), _ptr(stats), st))
         if int(stats[4].item()) != 0:
             return None
-        tconn = torch.empty((ntiles, params["tile_rows"], conn.shape[1]), dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_conn(pat.elem_type, ntiles, _ptr(conn), _ptr(eperm), _ptr(tile_estart), _ptr(thalo),
-                                  _ptr(tile_ptr), _ptr(tconn), st))
         z = torch.zeros(ntiles, dtype=torch.int32, device=dev)
         tdesc = torch.stack([tile_ptr[0, :-1], tile_ptr[0, 1:] - tile_ptr[0, :-1],
                              tile_ptr[1, :-1], tile_ptr[1, 1:] - tile_ptr[1, :-1],
                              tile_ptr[3, :-1], tile_ptr[3, 1:] - tile_ptr[3, :-1],
                              tile_ptr[2, 1:] - tile_ptr[2, :-1], z], dim=1).contiguous()
-        if FE_PLAN_DEDUP:
-            tdesc, tloc, twork, tchunk, info["record_sets"] = dedup_tile_records(tdesc, tloc, twork, tchunk)
     return TilePlan(tconn, tdesc, tnode, tloc, twork, tchunk, ntiles, info)
 
 
@@ -624,9 +661,25 @@ def assemble_tiled(tconn: Tensor, coords: Tensor, ntiles: int, tdesc: Tensor, tn
                                                 _stream(vals)))
 
 
+@torch.library.custom_op("feprogram::assemble_ws", mutates_args=("vals",))
+def assemble_ws(tconn: Tensor, coords: Tensor, ntiles: int, tdesc: Tensor, blobs: Tensor, truns: Tensor, vals: Tensor,
+                elem_type: int, op: int) -> None:
+    """Numeric assembly, warp-specialised tiled kernel (same results as feprogram::assemble, bit for bit)."""
+    _chk_dev(tconn, coords, tdesc, blobs, truns, vals)
+    _want(tconn, torch.int32, "tconn")
+    _want(coords, torch.float64, "coords")
+    _want(vals, torch.float64, "vals")
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.lib().fe_assemble_ws(elem_type, op, ntiles, _ptr(tconn), _ptr(coords), _ptr(tdesc), _ptr(blobs),
+                                             _ptr(truns), _ptr(vals), _stream(vals)))
+
+
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):
     """Numeric assembly with whichever kernel the plan allows."""
-    if plan is not None:
+    if plan is not None and plan.warp_specialised:
+        torch.ops.feprogram.assemble_ws(plan.tconn, coords, plan.ntiles, plan.tdesc, plan.blobs, plan.truns, vals,
+                                        pat.elem_type, op)
+    elif plan is not None:
         hint = 256 if plan.stats.get("mode") == "pack" else 0       # FE_HINT_IRREGULAR_TILES: schedule only
         torch.ops.feprogram.assemble_tiled(plan.tconn, coords, plan.ntiles, plan.tdesc, plan.tnode, plan.tloc,
                                            plan.twork, plan.tchunk, vals, pat.elem_type, op | hint)

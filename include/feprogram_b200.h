@@ -195,6 +195,32 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
                       const int32_t* tdesc, const void* tnode, const uint16_t* tloc, const uint32_t* twork,
                       const uint32_t* tchunk, double* vals, void* stream);
 
+/* ---- A2/A3 numeric assembly, warp-specialised tiled form (Quad4 / Tri3; the benchmarked kernel) ----------
+ * Same contract, tiling and bit-identical results as fe_assemble_tiled; one persistent CTA per SM whose producer
+ * warps (element matrices -> shared-memory slab), consumer warps (slab -> CSR blocks staged in their final layout)
+ * and DMA warp (1-D TMA bulk copies: record blobs in, contiguous CSR row ranges out) hand tiles to each other
+ * through mbarriers.  Its plan reuses steps 1-5 and 7 of the fe_assemble_tiled plan (owner, layout, halo lists,
+ * tile_ptr rows, tconn) and replaces step 6 by:
+ *  6a. fe_tile_ws_sizes : tsz[0..s) = record-blob size / 16 of every tile, tsz[s..2s) = number of runs of
+ *                         consecutive owned node ids (= contiguous CSR row ranges); stats[0] max blob bytes,
+ *                         stats[1] max bytes of CSR values of a tile, stats[2] max degree, stats[3] max owned nodes.
+ *  6b. fe_exclusive_scan_i32 x2 : blob_off[s], run_off[s] <- scans of the two rows of tsz.
+ *  6c. fe_tile_ws_build : blobs (16 * blob_off[ntiles] bytes), truns (16 bytes per run), tdesc (4 int32 per tile);
+ *                         stats[4] != 0 afterwards means the mesh is not representable (use fe_assemble).
+ * The plan is usable iff stats[0] <= out[0], stats[1] <= out[1], stats[2] <= out[2], stats[3] <= out[3] of
+ * fe_tile_ws_params (all 0 for element types this kernel does not handle) and stats[4] == 0.  Blob / run formats
+ * are documented in feprogram_b200/csrc/fe_tiles_ws.cu.  vals and blobs must be 16-byte aligned. */
+void fe_tile_ws_params(int elem_type, int32_t out[4]);
+int fe_tile_ws_sizes(int elem_type, int64_t ntiles, const int32_t* tile_ptr, const int32_t* tile_nodes,
+                     const int32_t* nptr, int32_t* tsz, int32_t* stats, void* stream);
+int fe_tile_ws_build(int elem_type, int64_t nslots, int64_t ntiles, const int32_t* tile_nodes, const int32_t* owner,
+                     const int32_t* tile_ptr, const int32_t* noff, const int32_t* thalo, const int32_t* eptr,
+                     const int32_t* einc, const uint8_t* epos, const int32_t* eloc, const int32_t* nptr,
+                     const int32_t* nadj, const int32_t* blob_off, const int32_t* run_off, void* blobs, void* truns,
+                     int32_t* tdesc, int32_t* stats, void* stream);
+int fe_assemble_ws(int elem_type, int op, int64_t ntiles, const int32_t* tconn, const double* coords,
+                   const int32_t* tdesc, const void* blobs, const void* truns, double* vals, void* stream);
+
 /* ---- B1-B3: boundary conditions ---------------------------------------------------------------
  * fe_bc_rhs replaces the brhs writes of elements.py:185-197: rhs <- 0; rhs[dir] <- 0;
  * rhs[neu] <- neu_value (Neumann written last, so it wins on shared dofs); dirmask[d] <- 1 on
@@ -223,6 +249,8 @@ int fe_edge_load(int nodes_per_edge, int64_t nedge, const int32_t* edges, const 
  * the reference's Dirichlet treatment is equivalent to.
  *
  * fe_spmv: y <- A x with A in CSR.  If rowmask != NULL rows with rowmask[r] != 0 give y[r] = 0.
+ *   nnz (= row_ptr[nrows], a HOST value the caller knows from the symbolic phase) only selects the
+ *   lanes-per-row schedule; passing it keeps the call free of any device read-back or synchronisation.
  *
  * fe_csr_diagonal: diag[r] <- A[r,r] (0 if not stored).
  *
@@ -232,10 +260,13 @@ int fe_edge_load(int nodes_per_edge, int64_t nedge, const int32_t* edges, const 
  *   ignored: starts from 0 / the Dirichlet lift).  Converged when ||r||_2 <= rtol*||r0||_2 or
  *   ||r||_2 <= atol.  work: 4*nrows doubles + FE_PCG_SCALAR_DOUBLES doubles + 2*fe_pcg_blocks(nrows)
  *   doubles of scratch, see fe_pcg_workspace_bytes.  info (HOST, 4 doubles): iterations, final
- *   ||r||/||r0||, ||r0||, converged flag.  check_every: iterations between host polls (>=1).
+ *   ||r||/||r0||, ||r0||, stop reason: 1 = converged (||r|| <= tolerance), 0 = iteration limit reached,
+ *   -2 = CG breakdown (NaN residual or p.Ap <= 0: the matrix is not SPD on the free dofs; x is not a
+ *   solution), -1 = a peer-memory wait timed out (fe_dist_pcg_p2p only; that call also returns an error).
+ *   check_every: iterations between host polls (>=1): the one documented synchronisation of this header.
  *   nptr/nadj (optional, may be NULL): node-level pattern of a 2-dof matrix -> node-block SpMV.
  */
-int fe_spmv(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+int fe_spmv(int64_t nrows, int64_t nnz, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
             const double* x, double* y, const uint8_t* rowmask, void* stream);
 /* Same product read through the node-level pattern of a 2-dof matrix in this library's value layout (one
  * column index per 2x2 block): 24 % fewer bytes.  fe_pcg / fe_dist_pcg use it when nptr/nadj are given. */
@@ -244,7 +275,7 @@ int fe_spmv_nodal(int64_t nnode, const int32_t* nptr, const int32_t* nadj, const
 int fe_csr_diagonal(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
                     double* diag, void* stream);
 size_t fe_pcg_workspace_bytes(int64_t nrows);
-int fe_pcg(int64_t nrows, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
+int fe_pcg(int64_t nrows, int64_t nnz, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,
            const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol, int64_t maxit,
            int32_t check_every, void* work, double* info, const int32_t* nptr, const int32_t* nadj, void* stream);
 
@@ -279,7 +310,8 @@ int fe_nodal_strain(int elem_type, int64_t nnode, const int32_t* eptr, const int
  *                          are local dof ids < nrows_local), one halo exchange + two scalar all-reduces
  *                          per iteration; every rank returns the same iteration count and residual.
  *                          x, rhs, dirmask have nrows_local entries; on return x is valid on owned AND
- *                          ghost dofs.  work: fe_dist_pcg_workspace_bytes(nrows_local). */
+ *                          ghost dofs.  work: fe_dist_pcg_workspace_bytes(nrows_local).  nnz_owned =
+ *                          row_ptr[nrows_owned] as a HOST value (schedule selection only, no read-back). */
 int fe_dist_available(void);
 int fe_dist_unique_id(uint8_t* out128);
 int fe_dist_comm_init(const uint8_t* id128, int rank, int nranks, void** comm_out);
@@ -288,11 +320,11 @@ int fe_dist_halo_exchange(void* comm, int32_t n_nbr, const int32_t* nbr_rank, co
                           const int32_t* send_idx, double* sendbuf, const int64_t* recv_off, double* vec,
                           void* stream);
 size_t fe_dist_pcg_workspace_bytes(int64_t nrows_local);
-int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int idx64, const void* row_ptr, const int32_t* col_idx,
-                const double* vals, const double* rhs, const uint8_t* dirmask, double* x, double rtol, double atol,
-                int64_t maxit, int32_t check_every, void* work, double* info, void* comm, int32_t n_nbr,
-                const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx, double* sendbuf,
-                const int64_t* recv_off, const int32_t* nptr, const int32_t* nadj, void* stream);
+int fe_dist_pcg(int64_t nrows_owned, int64_t nrows_local, int64_t nnz_owned, int idx64, const void* row_ptr,
+                const int32_t* col_idx, const double* vals, const double* rhs, const uint8_t* dirmask, double* x,
+                double rtol, double atol, int64_t maxit, int32_t check_every, void* work, double* info, void* comm,
+                int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_off, const int32_t* send_idx,
+                double* sendbuf, const int64_t* recv_off, const int32_t* nptr, const int32_t* nadj, void* stream);
 /* fe_dist_pcg with the per-iteration halo taken out of NCCL: the SpMV loads the ghost entries of the search
  * direction directly from the owning GPU's memory over NVLink (peer pointers from CUDA IPC / torch symmetric
  * memory), gated by per-neighbour version flags.  Same arithmetic, same iterates as fe_dist_pcg (bitwise).

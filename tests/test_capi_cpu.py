@@ -58,7 +58,7 @@ def test_unknown_element_type_reports_error(lib):
 
 def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
     from feprogram_b200 import _lib
-    rc = lib.fe_spmv(10, 0, None, None, None, None, None, None, None)
+    rc = lib.fe_spmv(10, 180, 0, None, None, None, None, None, None, None)
     assert rc == -1 and "null" in _lib.last_error()
     rc = lib.fe_assemble(4, 7, 1, 1, None, None, None, None, None, None, 9, None, None)
     assert rc == -1

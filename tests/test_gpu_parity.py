@@ -352,13 +352,16 @@ def test_tiled_and_row_kernels_agree_bitwise(torch_cuda, kind, n, shuffle):
     ops.assemble_values(conn0, xy, pat, None, v_rows)
     checked = 0
     for morton in (True, False):
-        plan = ops.tile_plan(conn0, xy, pat, morton=morton)
-        if plan is None:       # tile capacities exceeded (e.g. input-order strips): the facade falls back to rows
-            continue
-        checked += 1
-        v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
-        ops.assemble_values(conn0, xy, pat, plan, v)
-        assert torch.equal(v, v_rows)
+        for kernel in ("ws", "phased"):    # warp-specialised (mbarrier / TMA) kernel and barrier-phased kernel
+            plan = ops.tile_plan(conn0, xy, pat, morton=morton, kernel=kernel)
+            if plan is None:   # tile capacities exceeded (e.g. input-order strips): the facade falls back to rows
+                continue
+            assert plan.warp_specialised == (kernel == "ws")
+            checked += 1
+            v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+            ops.assemble_values(conn0, xy, pat, plan, v)
+            assert torch.equal(v, v_rows), (kernel, morton)
+    assert checked >= 2
     K = sp.csr_matrix((v_rows.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
                       shape=(pat.nrows, pat.nrows))
     assert abs(K - K.T).max() == 0.0
@@ -435,8 +438,9 @@ def test_maxit_and_nonconvergence_are_reported(torch_cuda, golden):
     z = golden("q9_4x4")
     fem = run_facade(z)
     fem.maxit = 3
-    U = fem.solveProblem()
-    assert fem.solver_info["iterations"] == 3 and not fem.solver_info["converged"]
+    with pytest.warns(RuntimeWarning, match="iteration limit"):
+        U = fem.solveProblem()
+    assert fem.solver_info["iterations"] == 3 and not fem.solver_info["converged"] and not fem.solver_info["breakdown"]
     assert np.all(np.isfinite(U))
 
 
@@ -690,3 +694,121 @@ def test_main_driver_runs_the_reference_call_order(torch_cuda, tmp_path, caplog)
     assert 'Name="Velocidad"' in text and 'NumberOfPoints="35" NumberOfCells="24"' in text
     for label in ("Crear malla", "Ensamblaje de matrices", "Calculo de velocidades", "Tiempo total"):
         assert any(label in r.getMessage() for r in caplog.records)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-size parity of the BENCHMARKED kernel: the tiled kernel at the measured configurations, where every
+# persistent CTA runs hundreds of tiles (steady-state double buffering), against the independent row kernel
+# ---------------------------------------------------------------------------------------------------------
+def _strip_oracle_check(torch, pat, vals, gen, kind, n, j0, coords_full, mx, my):
+    """Rows of the nodes in lattice rows j0+1 .. j0+2 depend only on element rows j0 .. j0+2: compare them with the
+    oracle run on that strip (same coordinates), structure bit-exact and values to VAL_TOL."""
+    w = mx + 1
+    per = 2 if kind == 9 else 1                              # lattice rows per element row
+    sub_conn, sub_coords, _ = gen(n, 3)
+    nsub = sub_coords.shape[0]
+    base = j0 * per * w                                      # first lattice node of the strip inside the full mesh
+    sub_coords = coords_full[base:base + nsub].copy()
+    Ko = orc.assemble_csr(sub_conn - 1, sub_coords, kind)
+    g0, g1 = 2 * ((j0 * per + per) * w), 2 * ((j0 * per + 2 * per) * w)   # global rows: lattice rows of element row j0+1
+    rp = pat.row_ptr[g0:g1 + 1].cpu().numpy().astype(np.int64)
+    got = vals[rp[0]:rp[-1]].cpu().numpy()
+    s0, s1 = g0 - 2 * base, g1 - 2 * base
+    want = Ko.data[Ko.indptr[s0]:Ko.indptr[s1]]
+    assert got.shape == want.shape and rel_max(got, want) < VAL_TOL
+    cols = pat.col_idx[rp[0]:rp[-1]].cpu().numpy().astype(np.int64)
+    assert np.array_equal(cols - 2 * base, Ko.indices[Ko.indptr[s0]:Ko.indptr[s1]])
+
+
+@pytest.mark.parametrize("kind,n,perturb", [(4, 4096, False), (4, 4096, True), (9, 1024, False), (3, 3500, True)])
+def test_full_size_tiled_equals_rows_bitwise(torch_cuda, kind, n, perturb):
+    """cfg2 (Quad4 4096^2, structured and perturbed), Quad9 1024^2 and Tri3 3500^2 x 2: the tiled kernel that
+    bench.py times, on a NaN-prefilled output, equals the row kernel bit for bit; a strip of its rows equals
+    the oracle on the sub-mesh that determines them."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
+    conn, coords, _ = gen(n, dtype=np.int32)
+    mx = my = 2 * n if kind == 9 else n
+    if perturb:
+        coords = mesh.perturb_interior(coords, mx, my, 0.2, seed=7)
+    conn0 = torch.from_numpy(conn - 1).cuda()
+    xy = torch.from_numpy(coords).cuda()
+    del conn
+    pat = ops.symbolic(conn0, coords.shape[0], kind, 2)
+    plan = ops.tile_plan(conn0, xy, pat)
+    assert plan is not None, "the benchmark mesh must get the tiled kernel"
+    assert plan.warp_specialised == (kind != 9), "Quad4 / Tri3 benchmark meshes must get the warp-specialised kernel"
+    v_tiled = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, plan, v_tiled)
+    assert not bool(torch.isnan(v_tiled).any()), "an entry of K was never written"
+    v_rows = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v_rows)
+    assert torch.equal(v_tiled, v_rows)
+    del v_rows
+    v2 = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, plan, v2)
+    assert torch.equal(v_tiled, v2), "reruns must be bit-identical"
+    del v2
+    _strip_oracle_check(torch, pat, v_tiled, gen, kind, n, n // 3, coords, mx, my)
+
+
+def test_pcg_breakdown_is_reported_not_returned_as_converged(torch_cuda):
+    """An indefinite system (elements of mixed orientation: half of them have negative Jacobians, so their
+    element matrices are negative semi-definite) must not come back as a converged solution."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh
+    from feprogram_b200.elements import FemProblem
+    conn, coords, bc = mesh.structured_quad4(12)
+    conn = conn.copy()
+    conn[::2] = conn[::2, ::-1]                      # clockwise: negative determinant
+    fem = FemProblem(conn, coords)
+    fem.setMatrix()
+    fem.setBoundaryConditions(bc, verbose=False)
+    fem.assemble()
+    fem.maxit = 2000
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            U = fem.solveProblem()
+    except RuntimeError as e:
+        assert "breakdown" in str(e)
+        assert fem.solver_info["breakdown"] and not fem.solver_info["converged"]
+    else:       # CG may also simply fail to converge on an indefinite matrix: then it must say so
+        assert not fem.solver_info["converged"] or \
+            np.linalg.norm(fem.K.tocsr() @ U - np.asarray(fem.brhs.todense()).ravel()) < 1e-6
+
+
+@pytest.mark.slow
+def test_cfg2_pcg_runs_to_convergence(torch_cuda):
+    """BASELINE config 2 solved to convergence once (about 7 n iterations): the true residual of the returned
+    iterate, recomputed with fe_spmv on the unmodified matrix, meets the tolerance."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh
+    from feprogram_b200.elements import FemProblem
+    n = 4096
+    conn, coords, bc = mesh.structured_quad4(n, dtype=np.int32)
+    fem = FemProblem(conn, coords)
+    fem.setMatrix()
+    fem.setBoundaryConditions(bc, verbose=False)
+    fem.assemble()
+    fem.rtol = 1e-9
+    fem.maxit = 60000
+    U = fem.solveProblem()
+    info = fem.solver_info
+    assert info["converged"] and 5 * n < info["iterations"] < 12 * n, info
+    st = fem._dev
+    pat = st["pattern"]
+    x = torch.from_numpy(U).cuda()
+    y = torch.empty_like(x)
+    torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, st["vals"], x, y, None)
+    free = st["dirmask"] == 0
+    r = (st["rhs"] - y)[free]
+    b = st["rhs"].clone()
+    # right-hand side of the free block: b_I - K_ID g_D
+    g = torch.where(free, torch.zeros_like(x), x)
+    torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, st["vals"], g, y, None)
+    b0 = (b - y)[free]
+    assert float(r.norm() / b0.norm()) <= 1e-8
+    assert torch.equal(x[~free], st["rhs"][~free])           # Dirichlet dofs hold their values exactly

@@ -12,7 +12,7 @@ from conftest import GOLDEN
 def test_getmeshinfo_contract():
     from feprogram_b200.gmsh_api import getMeshInfo
     conn, coords, bc = getMeshInfo()
-    assert len(conn) == 8 * 40 and len(conn[0]) == 4 and coords.shape == (9 * 41, 3)
+    assert len(conn) == 8 * 40 and len(conn[0]) == 4 and coords.shape == (9 * 41, 2)
     assert np.asarray(conn).min() == 1 and np.asarray(conn).max() == coords.shape[0]
     assert len(bc) == 4 and all(isinstance(s, set) for s in bc)
     assert coords[:, 0].max() == 2.0 and coords[:, 1].max() == 10.0
@@ -140,3 +140,23 @@ def test_msh_round_trip_and_solve_contract(tmp_path):
         assert np.array_equal(np.stack(c2).astype(np.int64), conn)
         assert np.array_equal(x2, coords)                      # repr() round-trips float64
         assert [set(int(t) for t in s) for s in bc] == b2
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/python_to_xml.py"), reason="reference tree not present")
+def test_other_writers_match_live_reference(tmp_path):
+    """writeXML (main.py:7 imports it) and the legacy writeVTK produce the reference's files byte for byte."""
+    spec = importlib.util.spec_from_file_location("_ref_writer2", "/root/reference/python_to_xml.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from feprogram_b200 import python_to_xml as ours
+    for k, (conn, coords, U) in enumerate(_case()):
+        a, b = str(tmp_path / ("o%d" % k)), str(tmp_path / ("r%d" % k))
+        ours.writeXML(coords, conn, U, a, None)
+        ref.writeXML(coords, conn, U, b, None)
+        assert open(a + ".vtu").read() == open(b + ".vtu").read()
+    conn, coords, U = _case()[0]
+    xyz = np.concatenate([coords, np.zeros((coords.shape[0], 1))], axis=1)
+    a, b = str(tmp_path / "ov"), str(tmp_path / "rv")
+    ours.writeVTK(xyz, conn, U, a, None)
+    ref.writeVTK(xyz, conn, U, b, None)
+    assert open(a + ".vtk").read() == open(b + ".vtk").read()
