@@ -37,6 +37,8 @@ PROTOTYPES = {
     "fe_adjacency_fill": (_i, [_i, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_csr_expand": (_i, [_i, _i64, _p, _p, _i, _p, _p, _p]),
     "fe_assemble": (_i, [_i, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+    "fe_tile_form_count": (_i, [_i, _i64, _i64] + [_p] * 10),
+    "fe_tile_form_sort": (_i, [_i, _i64] + [_p] * 8),
     "fe_tile_params": (None, [_i, C.POINTER(_i32)]),
     "fe_exclusive_scan_i32": (_i, [_p, _p, _i64, _p, _p]),
     "fe_morton_keys": (_i, [_i, _i64, _p, _p, _f64, _f64, _f64, _f64, _p, _p]),

@@ -1,0 +1,161 @@
+// Tile formation on the device (one-time plan step 1 of fe_assemble_tiled / fe_assemble_ws): groups the elements
+// into tiles of <= TE elements of one aligned Morton block WITHOUT a global sort -- a counting sort by block
+// (histogram, scan, scatter) followed by a per-block sort in shared memory.  Result (identical to sorting the
+// elements by (Morton key, id), cutting every block into runs of TE, and ordering each tile by element id):
+//   eperm[nelem]        elements in tile order
+//   eloc[nelem]         tile << 8 | row of every element
+//   tile_estart[nt+1]   offsets of the tiles in eperm
+// Integer atomics only bucket; every bucket is sorted afterwards, so the outputs are deterministic.
+#include "fe_tile_config.cuh"
+
+namespace fe {
+
+constexpr int kFormCap = 1024;     // elements of one Morton block the per-block sort handles
+
+__global__ void k_block_hist(int64_t nelem, const int32_t* __restrict__ keys, int shift, int32_t* __restrict__ hist) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nelem) atomicAdd(hist + (keys[e] >> shift), 1);
+}
+
+// tpb[b] = tiles of block b (and tpb[nb] = 0: slot of the grand total after the scan); status |= 1 on oversize blocks
+__global__ void k_block_tiles(int64_t nb, int32_t* __restrict__ hist, int te, int32_t* __restrict__ tpb,
+                              int32_t* __restrict__ status) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
+    if (b == nb) {
+        hist[b] = 0;
+        tpb[b] = 0;
+        return;
+    }
+    const int c = hist[b];
+    tpb[b] = (c + te - 1) / te;
+    if (c > kFormCap) atomicMax(status, 1);
+}
+
+__global__ void k_block_scatter(int64_t nelem, const int32_t* __restrict__ keys, int shift,
+                                const int32_t* __restrict__ ebase, int32_t* __restrict__ cursor,
+                                int32_t* __restrict__ tmp) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    const int b = keys[e] >> shift;
+    tmp[ebase[b] + atomicAdd(cursor + b, 1)] = (int32_t)e;
+}
+
+// One warp per non-empty block.  <= TE elements: rank-sort by element id.  More: rank-sort by (key, id), cut into
+// runs of TE, then order every run by element id.
+constexpr int kFormWarps = 4;
+__global__ void __launch_bounds__(32 * kFormWarps) k_block_sort(int64_t nb, const int32_t* __restrict__ ebase,
+                                                               const int32_t* __restrict__ tbase,
+                                                               const int32_t* __restrict__ tmp,
+                                                               const int32_t* __restrict__ keys, int te,
+                                                               int32_t* __restrict__ eperm, int32_t* __restrict__ eloc,
+                                                               int32_t* __restrict__ tile_estart) {
+    __shared__ int s_a[kFormWarps][kFormCap];
+    __shared__ int s_b[kFormWarps][kFormCap];
+    __shared__ int s_k[kFormWarps][kFormCap];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * kFormWarps + w;
+    if (b > nb) return;
+    if (b == nb) {
+        if (lane == 0) tile_estart[tbase[nb]] = ebase[nb];
+        return;
+    }
+    const int lo = ebase[b], cnt = ebase[b + 1] - lo;
+    if (cnt == 0 || cnt > kFormCap) return;
+    const int t0 = tbase[b];
+    int* a = s_a[w];
+    int* o = s_b[w];
+    for (int i = lane; i < cnt; i += 32) a[i] = tmp[lo + i];
+    __syncwarp();
+    if (cnt <= te) {
+        for (int i = lane; i < cnt; i += 32) {        // ids are distinct: rank = number of smaller ids
+            const int v = a[i];
+            int r = 0;
+            for (int j = 0; j < cnt; ++j) r += a[j] < v;
+            eperm[lo + r] = v;
+            eloc[v] = (t0 << 8) | r;
+        }
+        if (lane == 0) tile_estart[t0] = lo;
+        return;
+    }
+    int* kk = s_k[w];
+    for (int i = lane; i < cnt; i += 32) kk[i] = keys[a[i]];
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {            // order by (key, id)
+        const int v = a[i], kv = kk[i];
+        int r = 0;
+        for (int j = 0; j < cnt; ++j) r += (kk[j] < kv) || (kk[j] == kv && a[j] < v);
+        o[r] = v;
+    }
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {            // inside each run of TE: order by id
+        const int v = o[i];
+        const int r0 = (i / te) * te, r1 = r0 + te < cnt ? r0 + te : cnt;
+        int r = 0;
+        for (int j = r0; j < r1; ++j) r += o[j] < v;
+        eperm[lo + r0 + r] = v;
+        eloc[v] = ((t0 + i / te) << 8) | r;
+    }
+    for (int q = lane; q * te < cnt; q += 32) tile_estart[t0 + q] = lo + q * te;
+}
+
+}  // namespace fe
+
+extern "C" {
+
+// Step A (before the host reads ntiles): histogram, tiles per block, both scans, scatter.
+//   keys[nelem]; nb = number of Morton blocks (keys >> log2(TE) < nb); hist[nb+1], tpb[nb+1], ebase[nb+1], tbase[nb+1],
+//   cursor[nb], tmp[nelem], status[1] int32 scratch / outputs; scan_ws: fe_scan_workspace_bytes(nb + 1).
+// Afterwards tbase[nb] = ntiles, status[0] != 0 = a block holds more than 1024 elements (use another tiling).
+int fe_tile_form_count(int elem_type, int64_t nelem, int64_t nb, const int32_t* keys, int32_t* hist, int32_t* tpb,
+                       int32_t* ebase, int32_t* tbase, int32_t* cursor, int32_t* tmp, int32_t* status, void* scan_ws,
+                       void* stream) {
+    using namespace fe;
+    const int nnpe = nnpe_of(elem_type);
+    if (!nnpe) {
+        set_error("fe_tile_form_count: Invalid elemType %d", elem_type);
+        return FE_ERR_UNSUPPORTED;
+    }
+    FE_REQUIRE(nelem >= 0 && nb >= 1 && nb < ((int64_t)1 << 30), "bad size");
+    FE_REQUIRE(keys && hist && tpb && ebase && tbase && cursor && tmp && status && scan_ws, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    const int te = tile_elems(nnpe);
+    int shift = 0;
+    while ((1 << shift) < te) ++shift;
+    FE_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)(nb + 1) * sizeof(int32_t), st));
+    FE_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)nb * sizeof(int32_t), st));
+    FE_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    if (nelem > 0) {
+        k_block_hist<<<grid_for(nelem, 256), 256, 0, st>>>(nelem, keys, shift, hist);
+        FE_CHECK_LAUNCH("k_block_hist");
+    }
+    k_block_tiles<<<grid_for(nb + 1, 256), 256, 0, st>>>(nb, hist, te, tpb, status);
+    FE_CHECK_LAUNCH("k_block_tiles");
+    int rc = exclusive_scan_i32(hist, ebase, nb + 1, scan_ws, st);
+    if (rc != FE_OK) return rc;
+    rc = exclusive_scan_i32(tpb, tbase, nb + 1, scan_ws, st);
+    if (rc != FE_OK) return rc;
+    if (nelem > 0) {
+        k_block_scatter<<<grid_for(nelem, 256), 256, 0, st>>>(nelem, keys, shift, ebase, cursor, tmp);
+        FE_CHECK_LAUNCH("k_block_scatter");
+    }
+    return FE_OK;
+}
+
+// Step B: per-block sort -> eperm, eloc, tile_estart[ntiles + 1].
+int fe_tile_form_sort(int elem_type, int64_t nb, const int32_t* ebase, const int32_t* tbase, const int32_t* tmp,
+                      const int32_t* keys, int32_t* eperm, int32_t* eloc, int32_t* tile_estart, void* stream) {
+    using namespace fe;
+    const int nnpe = nnpe_of(elem_type);
+    if (!nnpe) {
+        set_error("fe_tile_form_sort: Invalid elemType %d", elem_type);
+        return FE_ERR_UNSUPPORTED;
+    }
+    FE_REQUIRE(nb >= 1 && ebase && tbase && tmp && keys && eperm && eloc && tile_estart, "null pointer or bad size");
+    k_block_sort<<<grid_for(nb + 1, kFormWarps), 32 * kFormWarps, 0, as_stream(stream)>>>(
+        nb, ebase, tbase, tmp, keys, tile_elems(nnpe), eperm, eloc, tile_estart);
+    FE_CHECK_LAUNCH("k_block_sort");
+    return FE_OK;
+}
+
+}  // extern "C"

@@ -51,7 +51,11 @@ template <int N> struct WsLayout {
     static constexpr int kTriBits = tri_bits(N);
     static constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
     static constexpr int kSrcBits = 13;
-    static constexpr int kPW = 7, kCW = 8;                        // producer / consumer warps (+ one DMA warp)
+#ifndef FE_WS_PW
+#define FE_WS_PW 7
+#define FE_WS_CW 8
+#endif
+    static constexpr int kPW = FE_WS_PW, kCW = FE_WS_CW;          // producer / consumer warps (+ one DMA warp)
     static constexpr int kThreads = 32 * (kPW + kCW + 1);
     static constexpr int kBarBytes = 128;
     static constexpr int kBlobCap = 12 * 1024;                    // bytes of one record slot
@@ -170,7 +174,12 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                     x[a] = p.x;
                     y[a] = p.y;
                 }
+#if defined(FE_WS_WHATIF) && FE_WS_WHATIF == 1      // developer timing build: no element arithmetic (wrong results)
+#pragma unroll
+                for (int i = 0; i < 3 * T::kBlocks; ++i) ke[i] = x[i & (N - 1)];
+#else
                 element_tri<ET, MASS>(x, y, weighted != 0, ke);
+#endif
             }
             mbar_wait(bar(B_SLAB_EMPTY, slot), ((k >> 1) & 1) ^ 1);     // consumers are done with tile k - 2
             if (active) {
@@ -201,7 +210,11 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             mbar_wait(bar(B_STAGE_FREE, slot), par ^ 1);                // bulk stores of tile k - 2 have read the buffer
             mbar_wait(bar(B_SLAB_FULL, slot), par);
             const int wph = nnp >> 5;                                   // warps per half
+#if defined(FE_WS_WHATIF) && FE_WS_WHATIF == 2      // developer timing build: consumers only hand the buffers on
+            for (int wt = cw; wt < 0; wt += T::kCW) {
+#else
             for (int wt = cw; wt < 2 * wph; wt += T::kCW) {
+#endif
                 const int half = wt >= wph ? 1 : 0;
                 const int ln = (wt - half * wph) * 32 + lane;
                 if (ln >= nn) continue;
@@ -279,7 +292,12 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             for (int i = lane; i < nr; i += 32) {
                 if (i >= 32) run = __ldg(truns + r0 + i);
                 const long long off2 = (long long)(((unsigned long long)(unsigned)run.y << 32) | (unsigned)run.x);
+#if !(defined(FE_WS_WHATIF) && FE_WS_WHATIF == 3)   // developer timing build 3: no output stores
                 bulk_store(vals + 2 * off2, sbase + 16u * (uint32_t)run.z, 16u * (uint32_t)run.w);
+#else
+                (void)off2;
+                (void)sbase;
+#endif
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -168,6 +168,17 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
  *                             (use fe_assemble).
  * The plan is usable iff stats[0] <= out[2], stats[1] < out[3], stats[2] <= out[1], stats[5] <= out[4]
  * of fe_tile_params and stats[4] == 0.  Record formats are documented in feprogram_b200/csrc/fe_tiles.cu. */
+/* Step 1 without a global sort (the default path of the Python facade): fe_tile_form_count buckets the elements
+ * by Morton block (keys >> log2(TE); nb blocks) -- histogram, tiles per block, scans, scatter -- after which
+ * tbase[nb] = ntiles and status[0] != 0 flags a block of more than 1024 elements (use another tiling);
+ * fe_tile_form_sort orders every block in shared memory and writes eperm, eloc and tile_estart[ntiles + 1].
+ * Same result as sorting by (key, element id), cutting blocks into runs of TE and ordering each tile by id.
+ * Scratch: hist, tpb, ebase, tbase [nb + 1], cursor [nb], tmp [nelem], status [1] int32; scan_ws for nb + 1. */
+int fe_tile_form_count(int elem_type, int64_t nelem, int64_t nb, const int32_t* keys, int32_t* hist, int32_t* tpb,
+                       int32_t* ebase, int32_t* tbase, int32_t* cursor, int32_t* tmp, int32_t* status, void* scan_ws,
+                       void* stream);
+int fe_tile_form_sort(int elem_type, int64_t nb, const int32_t* ebase, const int32_t* tbase, const int32_t* tmp,
+                      const int32_t* keys, int32_t* eperm, int32_t* eloc, int32_t* tile_estart, void* stream);
 void fe_tile_params(int elem_type, int32_t out[6]);
 int fe_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scan_ws, void* stream);
 int fe_morton_keys(int elem_type, int64_t nelem, const int32_t* conn, const double* coords, double xmin,

@@ -17,8 +17,12 @@ sys.path.insert(0, ROOT)
 
 def main():
     import torch
-    from feprogram_b200 import build
-    build.build()
+    from feprogram_b200 import _lib
+    if os.environ.get("FE_LIB"):                 # developer builds with extra -D flags (tools/experiments/variants)
+        _lib.LIB_PATH = os.path.join(ROOT, os.environ["FE_LIB"])
+    else:
+        from feprogram_b200 import build
+        build.build()
     from feprogram_b200 import mesh, ops
     kind, n = int(sys.argv[1]), int(sys.argv[2])
     perturb = len(sys.argv) > 3 and sys.argv[3] == "1"
@@ -37,7 +41,9 @@ def main():
     v_rows = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
     ops.assemble_values(conn0, xy, pat, None, v_rows)
     torch.cuda.synchronize()
-    for kernel in ("ws", "phased"):
+    kernels = os.environ.get("FE_KERNELS", "ws,phased").split(",")
+    out["lib"] = os.environ.get("FE_LIB", "release")
+    for kernel in kernels:
         t0 = time.perf_counter()
         plan = ops.tile_plan(conn0, xy, pat, kernel=kernel)
         torch.cuda.synchronize()
