@@ -289,11 +289,57 @@ class FemProblem:
         return 2 * st["perm"][d // 2] + d % 2
 
     # ---------------------------------------------------------------------- assemble (elements.py:165-200)
+    def _bc_early(self, st):
+        """Right-hand side and Dirichlet mask do not depend on K (elements.py:185-197 only writes brhs from the dof
+        sets): in the reference's BC mode they are built on a side stream at the START of assemble() and the rhs
+        travels to a pinned host buffer while the connectivity / coordinates are still uploading (PCIe is full
+        duplex), so that brhs is on the host when assemble() returns, as in the reference."""
+        import torch
+        dev = st["conn"].device
+        main = torch.cuda.current_stream(dev)
+        side = st.get("bc_stream")
+        if side is None:
+            side = st["bc_stream"] = torch.cuda.Stream(dev)
+        nrows = 2 * self.nnode
+        with torch.cuda.stream(side):
+            if "rhs" not in st:
+                st["rhs"] = torch.empty(nrows, dtype=torch.float64, device=dev)
+                st["dirmask"] = torch.empty(nrows, dtype=torch.uint8, device=dev)
+                st["rhs"].record_stream(main)
+                st["dirmask"].record_stream(main)
+            dir_d = self._solver_dofs(self.dofDir)
+            neu_d = self._solver_dofs(self.dofNeu)
+            torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
+            st["bc_event"] = side.record_event()                 # the solver (main stream) waits for this one
+            host = st.get("rhs_host")
+            if host is None:
+                host = st["rhs_host"] = torch.empty(nrows, dtype=torch.float64, pin_memory=True)
+            host.copy_(st["rhs"], non_blocking=True)
+            st["rhs_host_event"] = side.record_event()           # host readers (brhs, rhs_host) wait for this one
+
+    def rhs_host(self):
+        """The assembled right-hand side as a host array (2 * nnode,), reference dof numbering."""
+        st = self._dev
+        if st is None or not self._assembled:
+            raise RuntimeError("assemble() must be called first")
+        ev = st.get("rhs_host_event")
+        if ev is not None and st["perm"] is None:
+            ev.synchronize()
+            return st["rhs_host"].numpy()
+        rhs = st["rhs"]
+        if st["perm"] is not None:
+            rhs = rhs.view(-1, 2)[st["perm"]].reshape(-1)
+        return rhs.cpu().numpy()
+
     def assemble(self):
         import torch
         from . import ops
         st = self._state(defer_coords=True)
         et = _ELEM_CODES[self.elem.elemType]
+        early_bc = getattr(self, "_bc_mode", "reference") == "reference" and st["perm"] is None
+        st.pop("rhs_host_event", None)
+        if early_bc:
+            self._bc_early(st)
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
             st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)     # overlaps the coordinate upload
             self._coords_ready()
@@ -306,20 +352,23 @@ class FemProblem:
         ops.assemble_values(st["conn_s"], st["coords_s"], pat, st["plan"], st["vals"], self._operator)
         st.pop("vals_ref", None)
         # boundary conditions: rhs + Dirichlet mask (matrix itself stays un-modified on the device)
-        if "rhs" not in st:
-            st["rhs"] = torch.empty(pat.nrows, dtype=torch.float64, device=dev)
-            st["dirmask"] = torch.empty(pat.nrows, dtype=torch.uint8, device=dev)
-        dir_d = self._solver_dofs(self.dofDir)
-        neu_d = self._solver_dofs(self.dofNeu)
-        if getattr(self, "_bc_mode", "reference") == "corrected":
-            torch.ops.feprogram.bc_rhs(dir_d, neu_d[:0], 0.0, st["rhs"], st["dirmask"])
-            edges = torch.from_numpy(self._load_edges).to(dev)
-            if st["perm"] is not None:
-                edges = st["perm"][edges.to(torch.int64)].to(torch.int32).contiguous()
-            torch.ops.feprogram.edge_load(edges, st["coords_s"], self._traction[0], self._traction[1], st["dirmask"],
-                                          st["rhs"])
+        if early_bc:
+            torch.cuda.current_stream(dev).wait_event(st["bc_event"])
         else:
-            torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
+            if "rhs" not in st:
+                st["rhs"] = torch.empty(pat.nrows, dtype=torch.float64, device=dev)
+                st["dirmask"] = torch.empty(pat.nrows, dtype=torch.uint8, device=dev)
+            dir_d = self._solver_dofs(self.dofDir)
+            neu_d = self._solver_dofs(self.dofNeu)
+            if getattr(self, "_bc_mode", "reference") == "corrected":
+                torch.ops.feprogram.bc_rhs(dir_d, neu_d[:0], 0.0, st["rhs"], st["dirmask"])
+                edges = torch.from_numpy(self._load_edges).to(dev)
+                if st["perm"] is not None:
+                    edges = st["perm"][edges.to(torch.int64)].to(torch.int32).contiguous()
+                torch.ops.feprogram.edge_load(edges, st["coords_s"], self._traction[0], self._traction[1], st["dirmask"],
+                                              st["rhs"])
+            else:
+                torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
         self._K_host = None
         self._brhs_host = None
         self._assembled = True
@@ -384,10 +433,7 @@ class FemProblem:
         if not self._assembled:
             return sp.lil_matrix((self.nnode * 2, 1))
         if self._brhs_host is None:
-            rhs = self._dev["rhs"]
-            if self._dev["perm"] is not None:
-                rhs = rhs.view(-1, 2)[self._dev["perm"]].reshape(-1)
-            self._brhs_host = sp.csc_matrix(rhs.cpu().numpy()[:, None])
+            self._brhs_host = sp.csc_matrix(np.array(self.rhs_host())[:, None])
         return self._brhs_host
 
     @brhs.setter

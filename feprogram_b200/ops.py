@@ -303,7 +303,14 @@ class Pattern:
     epos: Tensor
     row_ptr: Tensor
     col_idx: Tensor
-    max_deg: int
+    _max_deg: Optional[int] = None
+
+    @property
+    def max_deg(self) -> int:
+        """Largest number of distinct neighbours of a node (sizes the row kernel's tile); read back on first use."""
+        if self._max_deg is None:
+            self._max_deg = int((self.nptr[1:] - self.nptr[:-1]).max().item()) if self.nnode > 0 else 0
+        return self._max_deg
 
     @property
     def nnz(self) -> int:
@@ -321,8 +328,7 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern
     nptr, nadj, epos = torch.ops.feprogram.adjacency(conn, eptr, einc, elem_type)
     nnz = ndof * ndof * nadj.numel()
     row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
-    max_deg = int((nptr[1:] - nptr[:-1]).max().item()) if nnode > 0 else 0
-    return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx, max_deg)
+    return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx)
 
 
 # --------------------------------------------------------------------------------------------
@@ -499,32 +505,60 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
     nelem, nnode = pat.nelem, pat.nnode
     with torch.cuda.device(dev):
         st = _stream(conn)
-        # ---- element order and tile boundaries (input preparation of the one-time plan; torch sort/scan) ----
-        idx = torch.arange(nelem, dtype=torch.int64, device=dev)
+        # ---- element order and tile boundaries ----
+        idx = None
+        formed = False
         if morton:
-            lo = coords.amin(dim=0)
-            hi = coords.amax(dim=0)
-            ext = (hi - lo).clamp_min(1e-300)
             # cell: holds ~ one element (Tri3: the two triangles of a quad).  Its AREA comes from the sampled mean
             # element area (distortion-proof: perturbing nodes changes extents, not the mean area), its aspect
-            # ratio from the sampled mean extents.
+            # ratio from the sampled mean extents.  All scalars come back in ONE device -> host transfer.
             sample = conn[:: max(1, nelem // 65536)][:65536].long()
             xy = coords[sample]                                               # (m, nnpe, 2)
-            ext_e = (xy.amax(dim=1) - xy.amin(dim=1)).mean(dim=0).clamp_min(1e-300)
+            ext_e = (xy.amax(dim=1) - xy.amin(dim=1)).mean(dim=0)
             nc = 3 if pat.elem_type == FE_TRI3 else 4                         # corner nodes come first
             cx, cy = xy[:, :nc, 0], xy[:, :nc, 1]
             area = 0.5 * (cx * torch.roll(cy, -1, dims=1) - torch.roll(cx, -1, dims=1) * cy).sum(dim=1).abs().mean()
-            cell_area = area * (2.0 if pat.elem_type == FE_TRI3 else 1.0)
+            sc = torch.cat([coords.amin(dim=0), coords.amax(dim=0), ext_e, area.reshape(1)]).cpu().tolist()
+            lo_h = sc[0:2]
+            ext = [max(sc[2] - sc[0], 1e-300), max(sc[3] - sc[1], 1e-300)]
+            ext_e = [max(sc[4], 1e-300), max(sc[5], 1e-300)]
+            cell_area = sc[6] * (2.0 if pat.elem_type == FE_TRI3 else 1.0)
             aspect = ext_e[0] / ext_e[1]
-            size = torch.stack([torch.sqrt(cell_area * aspect), torch.sqrt(cell_area / aspect)])
-            if not bool(torch.isfinite(size).all()) or float(size.min()) <= 0.0:
-                size = ext_e * (0.7071 if pat.elem_type == FE_TRI3 else 1.0)
-            size = size * cell_scale
-            cell = torch.maximum(size, ext / 32767.0).clamp_min(1e-300).tolist()  # 15 bits per axis
+            size = [float(np.sqrt(cell_area * aspect)), float(np.sqrt(cell_area / aspect))]
+            if not (np.isfinite(size[0]) and np.isfinite(size[1]) and min(size) > 0.0):
+                size = [e * (0.7071 if pat.elem_type == FE_TRI3 else 1.0) for e in ext_e]
+            cell = [max(size[k] * cell_scale, ext[k] / 32767.0, 1e-300) for k in range(2)]   # 15 bits per axis
             keys = torch.empty(nelem, dtype=torch.int32, device=dev)
-            lo_h = lo.tolist()
             _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo_h[0], lo_h[1], cell[0],
                                         cell[1], _ptr(keys), st))
+            if mode == "blocks":
+                # device-side formation: counting sort by Morton block + per-block sort (csrc/fe_tile_form.cu)
+                shift = te.bit_length() - 1
+                imax = max(min(32767, int(ext[0] / cell[0]) + 1), min(32767, int(ext[1] / cell[1]) + 1))
+                nb = max(1, (1 << (2 * max(1, imax.bit_length()))) >> shift)
+                sb = nb + 1
+                wsf = torch.empty(max(1, L.fe_scan_workspace_bytes(sb)), dtype=torch.uint8, device=dev)
+                tabs = torch.empty((4, sb), dtype=torch.int32, device=dev)          # hist, tpb, ebase, tbase
+                cursor_b = torch.empty(nb, dtype=torch.int32, device=dev)
+                tmp = torch.empty(nelem, dtype=torch.int32, device=dev)
+                fstat = torch.empty(1, dtype=torch.int32, device=dev)
+                _lib.check(L.fe_tile_form_count(pat.elem_type, nelem, nb, _ptr(keys), _ptr(tabs[0]), _ptr(tabs[1]),
+                                                _ptr(tabs[2]), _ptr(tabs[3]), _ptr(cursor_b), _ptr(tmp), _ptr(fstat),
+                                                _ptr(wsf), st))
+                ft = torch.cat([tabs[3, nb:nb + 1], fstat]).cpu().tolist()       # host sync: tile count
+                if int(ft[1]) == 0:
+                    ntiles = int(ft[0])
+                    eperm = torch.empty(nelem, dtype=torch.int32, device=dev)
+                    eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
+                    tile_estart = torch.empty(ntiles + 1, dtype=torch.int32, device=dev)
+                    _lib.check(L.fe_tile_form_sort(pat.elem_type, nb, _ptr(tabs[2]), _ptr(tabs[3]), _ptr(tmp), _ptr(keys),
+                                                   _ptr(eperm), _ptr(eloc), _ptr(tile_estart), st))
+                    formed = True
+                del tabs, cursor_b, tmp
+        if formed:
+            pass
+        elif morton:
+            idx = torch.arange(nelem, dtype=torch.int64, device=dev)
             skeys, order = torch.sort(keys, stable=True)
             eperm = order.to(torch.int32)
             if mode == "pack":
@@ -543,25 +577,27 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                 block = skeys >> (te.bit_length() - 1)                        # aligned Z-blocks of TE cells
             del keys, skeys, order
         else:
+            idx = torch.arange(nelem, dtype=torch.int64, device=dev)
             eperm = idx.to(torch.int32)
             block = idx // te
-        flag = torch.ones(nelem, dtype=torch.bool, device=dev)
-        flag[1:] = block[1:] != block[:-1]
-        seg_start = torch.nonzero(flag).flatten()[torch.cumsum(flag, dim=0) - 1]   # start of each element's block
-        flag |= ((idx - seg_start) % te) == 0                                 # at most TE elements per tile
-        tid = torch.cumsum(flag.to(torch.int32), dim=0, dtype=torch.int32) - 1
-        ntiles = int(tid[-1].item()) + 1
-        starts = torch.nonzero(flag).flatten()
-        row = (idx - starts[tid.long()]).to(torch.int32)
-        tile_estart = torch.cat([starts, torch.tensor([nelem], device=dev)]).to(torch.int32)
-        # inside a tile order the elements by element id
-        etile = torch.empty(nelem, dtype=torch.int32, device=dev)
-        etile[eperm.long()] = tid
-        eperm = torch.sort(etile, stable=True).indices.to(torch.int32)
-        del etile
-        eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
-        eloc[eperm.long()] = (tid << 8) | row          # tid / row are per sorted position
-        del block, flag, seg_start, tid, starts, row, idx
+        if not formed:
+            flag = torch.ones(nelem, dtype=torch.bool, device=dev)
+            flag[1:] = block[1:] != block[:-1]
+            seg_start = torch.nonzero(flag).flatten()[torch.cumsum(flag, dim=0) - 1]   # start of each element's block
+            flag |= ((idx - seg_start) % te) == 0                                 # at most TE elements per tile
+            tid = torch.cumsum(flag.to(torch.int32), dim=0, dtype=torch.int32) - 1
+            ntiles = int(tid[-1].item()) + 1
+            starts = torch.nonzero(flag).flatten()
+            row = (idx - starts[tid.long()]).to(torch.int32)
+            tile_estart = torch.cat([starts, torch.tensor([nelem], device=dev)]).to(torch.int32)
+            # inside a tile order the elements by element id
+            etile = torch.empty(nelem, dtype=torch.int32, device=dev)
+            etile[eperm.long()] = tid
+            eperm = torch.sort(etile, stable=True).indices.to(torch.int32)
+            del etile
+            eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
+            eloc[eperm.long()] = (tid << 8) | row          # tid / row are per sorted position
+            del block, flag, seg_start, tid, starts, row, idx
         if ntiles >= (1 << 23):
             return None
         s = ntiles + 1
