@@ -52,16 +52,18 @@ template <int N> struct WsLayout {
     static constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
     static constexpr int kSrcBits = 13;
 #ifndef FE_WS_PW
-#define FE_WS_PW 7
-#define FE_WS_CW 8
+#define FE_WS_PW 11
+#define FE_WS_CW 4
 #endif
     static constexpr int kPW = FE_WS_PW, kCW = FE_WS_CW;          // producer / consumer warps (+ one DMA warp)
     static constexpr int kThreads = 32 * (kPW + kCW + 1);
     static constexpr int kBarBytes = 128;
-    static constexpr int kBlobCap = 12 * 1024;                    // bytes of one record slot
-    static constexpr int kStageCap = 48 * 1024;                   // bytes of one staging slot (CSR values of a tile)
+    static constexpr int kBlobCap = 10 * 1024;                    // bytes of one record slot
+    static constexpr int kStageCap = 42 * 1024;                   // bytes of one staging slot (CSR values of a tile)
+    static constexpr int kCoordBytes = N * 32 * 16;               // per producer warp: next task's node coordinates
     static constexpr size_t kSlabBytes = (size_t)kSlabDoubles * sizeof(double);
-    static constexpr size_t kSmem = kBarBytes + 2 * kSlabBytes + 2 * (size_t)kBlobCap + 2 * (size_t)kStageCap;
+    static constexpr size_t kSmem = kBarBytes + 2 * kSlabBytes + 2 * (size_t)kBlobCap + 2 * (size_t)kStageCap +
+                                    (size_t)kPW * kCoordBytes;
     static_assert(kRows + 1 < (1 << (kSrcBits - kTriBits - 1)), "slab row does not fit a source field");
 };
 
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
     double* slab0 = reinterpret_cast<double*>(smem + T::kBarBytes);
     unsigned char* rec0 = smem + T::kBarBytes + 2 * T::kSlabBytes;
     unsigned char* stage0 = rec0 + 2 * T::kBlobCap;
+    unsigned char* coord0 = stage0 + 2 * T::kStageCap;
     // barrier ids (x2 slots each)
     enum { B_SLAB_FULL = 0, B_SLAB_EMPTY = 2, B_REC_FULL = 4, B_REC_EMPTY = 6, B_STAGED = 8, B_STAGE_FREE = 10 };
     const uint32_t bar0 = smem_u32(bars);
@@ -155,25 +158,46 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                 for (int a = 0; a < N; ++a) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(tg[a]) : "l"(p + a));
             }
         };
-        int tg[N], tgn[N];
+        // Software pipeline per warp: connectivity rows are loaded two tasks ahead (registers), the node coordinates
+        // of the NEXT task are gathered with cp.async into this warp's staging block while the current element
+        // matrices are evaluated -- no global-memory latency sits on a task's critical path.
+        double2* cbuf = reinterpret_cast<double2*>(coord0 + warp * T::kCoordBytes);    // [a][lane]
+        auto request_xy = [&](const int (&t)[N]) {
+            if (t[0] >= 0) {
+#pragma unroll
+                for (int a = 0; a < N; ++a)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(cbuf + a * 32 + lane)),
+                                 "l"(coords + t[a])
+                                 : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int tg[N], tgn[N], tgn2[N];
         long long j = warp;
+        tgn[0] = -1;
         if (j < total) load_row(row_addr(j), tg);
+        if (j + T::kPW < total) load_row(row_addr(j + T::kPW), tgn);
+        if (j < total) request_xy(tg);
         for (; j < total; j += T::kPW) {
             const int k = (int)(j / T::kChunks), c = (int)(j - (long long)k * T::kChunks);
             const int row = c * 32 + lane;
             const int slot = k & 1;
-            tgn[0] = -1;
-            if (j + T::kPW < total) load_row(row_addr(j + T::kPW), tgn);
+            tgn2[0] = -1;
+            if (j + 2 * T::kPW < total) load_row(row_addr(j + 2 * T::kPW), tgn2);
             const bool active = row < T::kRows && tg[0] >= 0;
-            double ke[3 * T::kBlocks];
+            asm volatile("cp.async.wait_group 0;" ::: "memory");       // this task's coordinates have landed
+            double x[N], y[N];
             if (active) {
-                double x[N], y[N];
 #pragma unroll
                 for (int a = 0; a < N; ++a) {
-                    const double2 p = __ldg(coords + tg[a]);
+                    const double2 p = cbuf[a * 32 + lane];
                     x[a] = p.x;
                     y[a] = p.y;
                 }
+            }
+            request_xy(tgn);                                            // in flight during this task's arithmetic
+            double ke[3 * T::kBlocks];
+            if (active) {
 #if defined(FE_WS_WHATIF) && FE_WS_WHATIF == 1      // developer timing build: no element arithmetic (wrong results)
 #pragma unroll
                 for (int i = 0; i < 3 * T::kBlocks; ++i) ke[i] = x[i & (N - 1)];
@@ -190,8 +214,12 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_SLAB_FULL, slot));
 #pragma unroll
-            for (int a = 0; a < N; ++a) tg[a] = tgn[a];
+            for (int a = 0; a < N; ++a) {
+                tg[a] = tgn[a];
+                tgn[a] = tgn2[a];
+            }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp < T::kPW + T::kCW) {
         // ================================ consumers ================================
         const int cw = warp - T::kPW;
@@ -222,8 +250,14 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                 const int deg = (nd.x >> 16) & 127, self = (nd.x >> 23) & 127;
                 const int pm = (deg + 1) >> 1;
                 const int p0 = half ? pm : 0, p1 = half ? deg : pm;
+                // A node's row 2n+1 lies 16 * deg bytes behind its row 2n: for odd degrees (9 on a Quad4 lattice, 7 on a
+                // Tri3 lattice) the two rows fall into different 16-byte bank groups, so letting every other group of
+                // four lanes write row 2n+1 first makes each quarter-warp store hit eight distinct groups.
+                const bool flip = ((lane >> 2) & 1) != 0;
                 double* row0 = stage + 2 * (nd.x & 0xFFFFu);
                 double* row1 = row0 + 2 * deg;
+                double* rowA = flip ? row1 : row0;
+                double* rowB = flip ? row0 : row1;
 #pragma unroll 2
                 for (int p = p0; p < p1; ++p) {
                     if (p == self) continue;
@@ -235,8 +269,8 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                     const double L = b0[0] + b1[0];
                     const double P = b0[1 + f0] + b1[1 + f1];
                     const double Q = b0[2 - f0] + b1[2 - f1];
-                    *reinterpret_cast<double2*>(row0 + 2 * p) = make_double2(L, P);
-                    *reinterpret_cast<double2*>(row1 + 2 * p) = make_double2(Q, L);
+                    *reinterpret_cast<double2*>(rowA + 2 * p) = flip ? make_double2(Q, L) : make_double2(L, P);
+                    *reinterpret_cast<double2*>(rowB + 2 * p) = flip ? make_double2(L, P) : make_double2(Q, L);
                 }
                 if (self >= p0 && self < p1) {                          // diagonal block: all incident elements
                     const int cnt = nd.y & 15, ioff = nd.y >> 4;
@@ -248,8 +282,8 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                         L += b[0];
                         P += b[1];
                     }
-                    *reinterpret_cast<double2*>(row0 + 2 * self) = make_double2(L, P);
-                    *reinterpret_cast<double2*>(row1 + 2 * self) = make_double2(P, L);
+                    *reinterpret_cast<double2*>(rowA + 2 * self) = flip ? make_double2(P, L) : make_double2(L, P);
+                    *reinterpret_cast<double2*>(rowB + 2 * self) = flip ? make_double2(L, P) : make_double2(P, L);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk store
