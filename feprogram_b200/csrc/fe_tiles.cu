@@ -293,8 +293,9 @@ __global__ void __launch_bounds__(128) k_tile_records(
     const int p0 = nptr[n], deg = nptr[n + 1] - p0;
     const int nh = tile_hptr[t + 1] - tile_hptr[t];
     const int32_t* hl = thalo + (int64_t)t * he;
-    int self = 0;
-    for (int p = 0; p < deg; ++p) self = (nadj[p0 + p] == n) ? p : self;
+    // position of n in its own neighbour list = its slot as seen from any incident element (owned nodes have one)
+    const int self = cnt > 0 ? (int)epos[(int64_t)k0 * nnpe + (einc[k0] & 15)] : 0;
+    (void)nadj;
     if (cnt > 15 || deg > 127 || deg > kMaxAdj || ioff > 0x3FFF) {  // not representable: caller uses fe_assemble
         atomicMax(stats + 4, 1);
         return;

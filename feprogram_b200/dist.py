@@ -237,7 +237,8 @@ class DistFemProblem:
         # connectivity) is built -- as FemProblem does (elements.py, _state)
         main = torch.cuda.current_stream(self.dev)
         self.conn = torch.from_numpy(np.ascontiguousarray(local.conn)).to(self.dev, non_blocking=True)
-        side = torch.cuda.Stream(self.dev)
+        from .elements import side_streams
+        side = side_streams(self.dev)[0]
         side.wait_event(main.record_event())
         with torch.cuda.stream(side):
             self.coords = torch.from_numpy(np.ascontiguousarray(local.coords)).to(self.dev, non_blocking=True)
@@ -285,6 +286,9 @@ class DistFemProblem:
     # -- assembly -----------------------------------------------------------------------------------
     def assemble(self):
         from . import ops
+        if getattr(self, "_assembled_once", False):
+            ops.share_tile_records(self.plan)          # plan re-used: identical tile records share one copy (L2-resident)
+        self._assembled_once = True
         ops.assemble_values(self.conn, self.coords, self.pat, self.plan, self.vals, 0)
 
     def set_bc(self, dir_dofs_local: np.ndarray, neu_dofs_local: np.ndarray, value: float = 1.0):

@@ -66,6 +66,19 @@ class Elem:
 
 _ELEM_CODES = {"Quad4": 4, "Quad9": 9}
 
+_SIDE_STREAMS = {}
+
+
+def side_streams(dev):
+    """(upload stream, boundary-data stream) of a device, shared by every problem on it.  PyTorch's caching
+    allocator keeps one pool per stream: a problem that made its own streams would strand the blocks it allocated
+    there (coordinates, rhs) when it dies, and every new problem would pay fresh cudaMallocs."""
+    import torch
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _SIDE_STREAMS[key]
+
 
 class FemProblem:
     def __init__(self, conectivity, coordinates, *, device=None, operator="reference", renumber=None):
@@ -247,7 +260,7 @@ class FemProblem:
             xy = np.ascontiguousarray(xy[:, :2])
         main = torch.cuda.current_stream(dev)
         tags = torch.from_numpy(np.ascontiguousarray(conn)).to(dev, non_blocking=True)
-        side = torch.cuda.Stream(dev)
+        side = side_streams(dev)[0]
         side.wait_event(main.record_event())          # one host->device transfer at a time: connectivity first
         with torch.cuda.stream(side):
             coords_d = torch.from_numpy(xy).to(dev, non_blocking=True)
@@ -297,10 +310,10 @@ class FemProblem:
         import torch
         dev = st["conn"].device
         main = torch.cuda.current_stream(dev)
-        side = st.get("bc_stream")
-        if side is None:
-            side = st["bc_stream"] = torch.cuda.Stream(dev)
+        side = side_streams(dev)[1]
         nrows = 2 * self.nnode
+        if "rhs" in st:
+            side.wait_stream(main)           # re-assembly: a solve on the main stream may still be reading rhs / dirmask
         with torch.cuda.stream(side):
             if "rhs" not in st:
                 st["rhs"] = torch.empty(nrows, dtype=torch.float64, device=dev)
@@ -344,6 +357,8 @@ class FemProblem:
             st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)     # overlaps the coordinate upload
             self._coords_ready()
             st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"])
+        else:                     # the plan is being re-used: let identical tile records share one copy (stays in L2)
+            ops.share_tile_records(st["plan"])
         self._coords_ready()
         pat = st["pattern"]
         dev = st["conn"].device

@@ -384,6 +384,8 @@ class TilePlan:
     stats: dict
     blobs: Optional[Tensor] = None    # uint8: per-tile record blobs  } warp-specialised kernel (fe_assemble_ws)
     truns: Optional[Tensor] = None    # int32 [runs, 4]               }
+    blob_off: Optional[Tensor] = None  # int32 [ntiles + 1]: original blob offsets / 16 (kept for share_tile_records)
+    shared: bool = False
 
     @property
     def warp_specialised(self) -> bool:
@@ -659,7 +661,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                 if int(wstats[4].item()) != 0:
                     return None
                 info["kernel"] = "ws"
-                return TilePlan(tconn, tdesc, None, None, None, None, ntiles, info, blobs, truns)
+                return TilePlan(tconn, tdesc, None, None, None, None, ntiles, info, blobs, truns, offs[0].clone())
             if kernel == "ws":
                 return None
         elif kernel == "ws":
@@ -708,6 +710,29 @@ def assemble_ws(tconn: Tensor, coords: Tensor, ntiles: int, tdesc: Tensor, blobs
     with torch.cuda.device(vals.device):
         _lib.check(_lib.lib().fe_assemble_ws(elem_type, op, ntiles, _ptr(tconn), _ptr(coords), _ptr(tdesc), _ptr(blobs),
                                              _ptr(truns), _ptr(vals), _stream(vals)))
+
+
+def share_tile_records(plan: Optional[TilePlan]) -> int:
+    """Lets the tiles of a warp-specialised plan whose record blobs are byte-identical share one copy (fe_tile_ws_share:
+    hash + byte-for-byte verification on the device; rewrites tdesc only, results unchanged).  Worth it when a plan
+    is used for more than one assembly: the records then stay in L2 instead of streaming from HBM for every tile.
+    Returns the number of tiles redirected (0 for other plans); idempotent."""
+    if plan is None or not plan.warp_specialised or plan.shared or plan.ntiles == 0:
+        return 0
+    dev = plan.blobs.device
+    with torch.cuda.device(dev):
+        tsize = 1 << max(4, (2 * plan.ntiles - 1).bit_length())
+        keys = torch.empty(tsize, dtype=torch.int64, device=dev)
+        reps = torch.empty(tsize, dtype=torch.int32, device=dev)
+        hashes = torch.empty(plan.ntiles, dtype=torch.int64, device=dev)
+        nshared = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().fe_tile_ws_share(plan.ntiles, _ptr(plan.tdesc), _ptr(plan.blob_off), _ptr(plan.blobs),
+                                               _ptr(keys), _ptr(reps), _ptr(hashes), tsize, _ptr(nshared),
+                                               _stream(plan.blobs)))
+        plan.shared = True
+        n = int(nshared.item())
+    plan.stats["shared_blobs"] = n
+    return n
 
 
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):

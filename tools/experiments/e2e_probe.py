@@ -51,8 +51,8 @@ def main():
         st["pattern"], st["plan"] = pat, plan
         fem.assemble()
         t = lap(t, "assemble(numeric+bc)", rec)
-        out_rhs.copy_(st["rhs"], non_blocking=True)
         chk = st["vals"].sum().item()
+        b = fem.rhs_host()
         t = lap(t, "d2h+checksum", rec)
         rec["total"] = round(1e3 * (t - t00), 3)
         del fem, st, pat, plan
@@ -66,8 +66,8 @@ def main():
         fem.setMatrix()
         fem.dofDir, fem.dofNeu = d_dofs, n_dofs
         fem.assemble()
-        out_rhs.copy_(fem._dev["rhs"], non_blocking=True)
         chk = fem._dev["vals"].sum().item()
+        b = fem.rhs_host()
         sync()
         rows.append({"pipelined_ms": round(1e3 * (time.perf_counter() - t0), 3), "alloc": torch.cuda.memory_stats()["num_device_alloc"]})
         del fem
