@@ -231,7 +231,6 @@ def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=
     plan = ops.tile_plan(conn, coords, pat)
     torch.cuda.synchronize()
     sym_s = time.perf_counter() - t0
-    ops.share_tile_records(plan)            # what FemProblem does when a plan is used again
     vals = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
     asm_bytes = conn.shape[0] * kind * 4 + nnode * 16 + pat.nnz * 8
     out = {"elements": int(conn.shape[0]), "nnz": int(pat.nnz), "symbolic_phase_s": sym_s, "renumbered": renumbered,
@@ -382,7 +381,6 @@ def run_ours(args):
             torch.cuda.synchronize()
             sym_times.append(time.perf_counter() - t0)
         symbolic_s = sorted(sym_times)[1]
-        shared_tiles = ops.share_tile_records(plan)   # what FemProblem does when a plan is used again (one-time)
         nelem_local = conn.shape[0]
         d_dofs, n_dofs = bc_dofs(bc)
         dir_d = torch.from_numpy(d_dofs).to(dev)

@@ -51,7 +51,6 @@ PROTOTYPES = {
     "fe_tile_ws_params": (None, [_i, C.POINTER(_i32)]),
     "fe_tile_ws_sizes": (_i, [_i, _i64] + [_p] * 6),
     "fe_tile_ws_build": (_i, [_i, _i64, _i64] + [_p] * 18),
-    "fe_tile_ws_share": (_i, [_i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "fe_assemble_ws": (_i, [_i, _i, _i64] + [_p] * 7),
     "fe_bc_rhs": (_i, [_i64, _p, _i64, _p, _i64, _f64, _p, _p, _p]),
     "fe_apply_bc": (_i, [_i, _i64, _i, _p, _p, _p, _p, _p, _p]),

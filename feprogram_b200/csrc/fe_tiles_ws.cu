@@ -106,16 +106,8 @@ __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, u
                  : "memory");
 }
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
-#ifdef FE_WS_EVICT_FIRST    // developer experiment: streaming L2 policy for the output
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_src),
-                 "r"(bytes), "l"(pol)
-                 : "memory");
-#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
                  : "memory");
-#endif
 }
 
 // =================================================================================================
@@ -593,115 +585,9 @@ __global__ void __launch_bounds__(128) k_tile_ws_records(
     }
 }
 
-// ---- sharing of identical record blobs -------------------------------------------------------------------
-// A blob holds tile-local indices only, so on a regular mesh (and on any mesh with repeating tile topology) almost
-// all tiles carry the same bytes.  Pointing their tdesc at ONE copy keeps the records in L2 instead of streaming
-// them from HBM for every tile (cfg2: 0.88 GB of 6.3 GB DRAM traffic per assembly).  Hash every blob, enter it in
-// an open-addressing table keyed by the hash (representative = lowest tile id), then compare byte for byte with
-// the representative before redirecting -- a hash collision can only cost the sharing, never correctness.
-__device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v) {
-    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-    h *= 0xD6E8FEB86659FD93ull;
-    return h ^ (h >> 32);
-}
-
-__global__ void __launch_bounds__(128) k_blob_hash(int64_t ntiles, const int4* __restrict__ tdesc,
-                                                   const unsigned char* __restrict__ blobs,
-                                                   unsigned long long* __restrict__ keys, int32_t* __restrict__ reps,
-                                                   unsigned long long* __restrict__ hashes, unsigned mask) {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= ntiles) return;
-    const int4 d = tdesc[t];
-    const ulonglong2* b = reinterpret_cast<const ulonglong2*>(blobs + 16ll * (unsigned)d.x);
-    const int n16 = d.y >> 4;
-    unsigned long long h = 0x243F6A8885A308D3ull + (unsigned long long)lane;
-    for (int i = lane; i < n16; i += 32) {
-        const ulonglong2 v = b[i];
-        h = mix64(mix64(h, v.x), v.y);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) h = mix64(h, __shfl_xor_sync(0xffffffffu, h, o) + (unsigned long long)o);
-    h = mix64(h, (unsigned long long)n16);
-    if (h == 0ull) h = 1ull;
-    if (lane == 0) {
-        hashes[t] = h;
-        unsigned slot = (unsigned)h & mask;
-        for (;;) {
-            const unsigned long long prev = atomicCAS(keys + slot, 0ull, h);
-            if (prev == 0ull || prev == h) {
-                atomicMin(reps + slot, (int)t);
-                break;
-            }
-            slot = (slot + 1) & mask;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128) k_blob_share(int64_t ntiles, int4* __restrict__ tdesc,
-                                                    const int32_t* __restrict__ blob_off,
-                                                    const unsigned char* __restrict__ blobs,
-                                                    const unsigned long long* __restrict__ keys,
-                                                    const int32_t* __restrict__ reps,
-                                                    const unsigned long long* __restrict__ hashes, unsigned mask,
-                                                    int32_t* __restrict__ nshared) {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= ntiles) return;
-    const unsigned long long h = hashes[t];
-    unsigned slot = (unsigned)h & mask;
-    while (keys[slot] != h) slot = (slot + 1) & mask;
-    const int rep = reps[slot];
-    if (rep == (int)t) return;
-    // blob_off is the ORIGINAL layout (tdesc of the representative may not be rewritten, but reading it would race)
-    const int n16 = blob_off[t + 1] - blob_off[t];
-    if (blob_off[rep + 1] - blob_off[rep] != n16) return;
-    const ulonglong2* a = reinterpret_cast<const ulonglong2*>(blobs + 16ll * blob_off[t]);
-    const ulonglong2* b = reinterpret_cast<const ulonglong2*>(blobs + 16ll * blob_off[rep]);
-    bool same = true;
-    for (int i = lane; i < n16; i += 32) {
-        const ulonglong2 x = a[i], y = b[i];
-        same = same && x.x == y.x && x.y == y.y;
-    }
-    same = __all_sync(0xffffffffu, same);
-    if (same && lane == 0) {
-        tdesc[t].x = blob_off[rep];
-        atomicAdd(nshared, 1);
-    }
-}
-
 }  // namespace fe
 
 extern "C" {
-
-// Lets tiles with identical record blobs share one copy (rewrites tdesc[t].x only; results are unchanged).
-// table_keys: uint64 [table_size], table_reps: int32 [table_size], hashes: uint64 [ntiles]; table_size a power of
-// two >= 2 * ntiles.  nshared[0] <- number of tiles redirected.  blob_off: the scan fe_tile_ws_build was given.
-int fe_tile_ws_share(int64_t ntiles, int32_t* tdesc, const int32_t* blob_off, const void* blobs, void* table_keys,
-                     int32_t* table_reps, void* hashes, int64_t table_size, int32_t* nshared, void* stream) {
-    using namespace fe;
-    FE_REQUIRE(ntiles >= 0 && table_size >= 2 * ntiles && (table_size & (table_size - 1)) == 0 && table_size < ((int64_t)1 << 31),
-               "table_size must be a power of two >= 2 * ntiles");
-    FE_REQUIRE(nshared, "null pointer");
-    cudaStream_t st = as_stream(stream);
-    FE_CUDA_TRY(cudaMemsetAsync(nshared, 0, sizeof(int32_t), st));
-    if (ntiles == 0) return FE_OK;
-    FE_REQUIRE(tdesc && blob_off && blobs && table_keys && table_reps && hashes, "null pointer");
-    FE_CUDA_TRY(cudaMemsetAsync(table_keys, 0, (size_t)table_size * 8, st));
-    FE_CUDA_TRY(cudaMemsetAsync(table_reps, 0x7f, (size_t)table_size * 4, st));
-    const unsigned mask = (unsigned)(table_size - 1);
-    k_blob_hash<<<grid_for(ntiles, 4), 128, 0, st>>>(ntiles, reinterpret_cast<const int4*>(tdesc),
-                                                     static_cast<const unsigned char*>(blobs),
-                                                     static_cast<unsigned long long*>(table_keys), table_reps,
-                                                     static_cast<unsigned long long*>(hashes), mask);
-    FE_CHECK_LAUNCH("k_blob_hash");
-    k_blob_share<<<grid_for(ntiles, 4), 128, 0, st>>>(ntiles, reinterpret_cast<int4*>(tdesc), blob_off,
-                                                      static_cast<const unsigned char*>(blobs),
-                                                      static_cast<const unsigned long long*>(table_keys), table_reps,
-                                                      static_cast<const unsigned long long*>(hashes), mask, nshared);
-    FE_CHECK_LAUNCH("k_blob_share");
-    return FE_OK;
-}
 
 void fe_tile_ws_params(int elem_type, int32_t out[4]) {
     using namespace fe;

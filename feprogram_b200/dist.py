@@ -286,9 +286,6 @@ class DistFemProblem:
     # -- assembly -----------------------------------------------------------------------------------
     def assemble(self):
         from . import ops
-        if getattr(self, "_assembled_once", False):
-            ops.share_tile_records(self.plan)          # plan re-used: identical tile records share one copy (L2-resident)
-        self._assembled_once = True
         ops.assemble_values(self.conn, self.coords, self.pat, self.plan, self.vals, 0)
 
     def set_bc(self, dir_dofs_local: np.ndarray, neu_dofs_local: np.ndarray, value: float = 1.0):

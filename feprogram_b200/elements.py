@@ -81,7 +81,7 @@ def side_streams(dev):
 
 
 class FemProblem:
-    def __init__(self, conectivity, coordinates, *, device=None, operator="reference", renumber=None):
+    def __init__(self, conectivity, coordinates, *, device=None, operator="reference", renumber=None, trace=False):
         """conectivity: sequence of equal-length 1-D integer arrays of 1-BASED node tags (or a 2-D
         ndarray); coordinates: float64 (nnode, >=2), row i <-> tag i+1 (elements.py:41-58).
 
@@ -91,6 +91,9 @@ class FemProblem:
         ``renumber``: solve on a Morton-renumbered copy of the mesh (None = only when the input numbering has no
         locality, e.g. BASELINE cfg5's shuffled tags).  Everything visible -- dof numbering, ``K``, ``brhs``,
         the solution -- stays in the reference's numbering; ``K`` is then assembled on demand in that numbering.
+        ``trace``: record a CUDA event + host time stamp at every stage boundary of assemble() (no synchronisation is
+        added); ``stage_times()`` returns them -- the device-side counterpart of the reference's timing log lines
+        (main.py:14-46).
         """
         self.nnode = coordinates.shape[0]
         self.nelem = len(conectivity)
@@ -98,6 +101,7 @@ class FemProblem:
         self.conectivity = conectivity
         self.coordinates = coordinates
         self._device = device
+        self._trace = [] if trace else None
         self._renumber = renumber
         self._operator = {"reference": 0, "weighted": 1, "mass": 2}[operator]
         self._dev = None        # device-side state, created on first assemble()
@@ -107,6 +111,25 @@ class FemProblem:
         self.solver_info = None
         self.rtol = 1e-10
         self.maxit = None
+
+    # ------------------------------------------------------------------ tracing
+    def _mark(self, name, stream=None):
+        if self._trace is None:
+            return
+        import time
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream(self._torch_device()))
+        self._trace.append((name, ev, time.perf_counter()))
+
+    def stage_times(self):
+        """{stage: (ms on the device, ms on the host)} since the first mark; synchronises the device."""
+        import torch
+        if not self._trace:
+            return {}
+        torch.cuda.synchronize(self._torch_device())
+        _, ev0, t0 = self._trace[0]
+        return {name: (round(ev0.elapsed_time(ev), 3), round(1e3 * (t - t0), 3)) for name, ev, t in self._trace}
 
     # ------------------------------------------------------------------ setMatrix (elements.py:60-92)
     def setMatrix(self):
@@ -259,11 +282,14 @@ class FemProblem:
         if xy.shape[1] != 2 or not xy.flags.c_contiguous:
             xy = np.ascontiguousarray(xy[:, :2])
         main = torch.cuda.current_stream(dev)
+        self._mark("start", main)
         tags = torch.from_numpy(np.ascontiguousarray(conn)).to(dev, non_blocking=True)
+        self._mark("conn uploaded", main)
         side = side_streams(dev)[0]
         side.wait_event(main.record_event())          # one host->device transfer at a time: connectivity first
         with torch.cuda.stream(side):
             coords_d = torch.from_numpy(xy).to(dev, non_blocking=True)
+            self._mark("coords uploaded", side)
         coords_d.record_stream(main)
         st = {
             "conn": torch.ops.feprogram.tags_to_conn(tags),                       # elements.py:172 `elem-1`
@@ -324,11 +350,13 @@ class FemProblem:
             neu_d = self._solver_dofs(self.dofNeu)
             torch.ops.feprogram.bc_rhs(dir_d, neu_d, 1.0, st["rhs"], st["dirmask"])   # elements.py:197 hardcoded 1
             st["bc_event"] = side.record_event()                 # the solver (main stream) waits for this one
+            self._mark("rhs built", side)
             host = st.get("rhs_host")
             if host is None:
                 host = st["rhs_host"] = torch.empty(nrows, dtype=torch.float64, pin_memory=True)
             host.copy_(st["rhs"], non_blocking=True)
             st["rhs_host_event"] = side.record_event()           # host readers (brhs, rhs_host) wait for this one
+            self._mark("rhs on host", side)
 
     def rhs_host(self):
         """The assembled right-hand side as a host array (2 * nnode,), reference dof numbering."""
@@ -351,20 +379,22 @@ class FemProblem:
         et = _ELEM_CODES[self.elem.elemType]
         early_bc = getattr(self, "_bc_mode", "reference") == "reference" and st["perm"] is None
         st.pop("rhs_host_event", None)
+        self._mark("state ready")
         if early_bc:
             self._bc_early(st)
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
             st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)     # overlaps the coordinate upload
+            self._mark("symbolic done")
             self._coords_ready()
             st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"])
-        else:                     # the plan is being re-used: let identical tile records share one copy (stays in L2)
-            ops.share_tile_records(st["plan"])
+            self._mark("plan done")
         self._coords_ready()
         pat = st["pattern"]
         dev = st["conn"].device
         if "vals" not in st:
             st["vals"] = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
         ops.assemble_values(st["conn_s"], st["coords_s"], pat, st["plan"], st["vals"], self._operator)
+        self._mark("numeric done")
         st.pop("vals_ref", None)
         # boundary conditions: rhs + Dirichlet mask (matrix itself stays un-modified on the device)
         if early_bc:

@@ -384,78 +384,10 @@ class TilePlan:
     stats: dict
     blobs: Optional[Tensor] = None    # uint8: per-tile record blobs  } warp-specialised kernel (fe_assemble_ws)
     truns: Optional[Tensor] = None    # int32 [runs, 4]               }
-    blob_off: Optional[Tensor] = None  # int32 [ntiles + 1]: original blob offsets / 16 (kept for share_tile_records)
-    shared: bool = False
 
     @property
     def warp_specialised(self) -> bool:
         return self.blobs is not None
-
-
-def dedup_tile_records(tdesc: Tensor, tloc: Tensor, twork: Tensor, tchunk: Tensor):
-    """Lets tiles with identical tile-local records (item locators, work items, chunk heads) share ONE copy.
-
-    The records only hold tile-local indices (slab rows, block ids, neighbour positions), so on regular meshes
-    almost every interior tile carries the same bytes; the kernel reaches them through the offsets in `tdesc`
-    and needs no change.  Shared records stay in L2 instead of being streamed from HBM for every tile.
-    Returns (tdesc, tloc, twork, tchunk, n_unique); equality is verified element by element, so a hash collision
-    can only cost the sharing, never correctness.  Pure torch; works on any device."""
-    ntiles = tdesc.shape[0]
-    dev = tdesc.device
-    if ntiles < 2:
-        return tdesc, tloc, twork, tchunk, ntiles
-    d = tdesc.to(torch.int64)
-    i0, ni, w0, nw = d[:, 2], d[:, 3], d[:, 4], d[:, 5]
-    tiles = torch.arange(ntiles, device=dev)
-    K1, K2, K3 = 0x9E3779B97F4A7C15 - (1 << 64), 0x2545F4914F6CDD1D, 0x632BE59BD9B4E019   # odd 64-bit constants
-
-    def seg_hash(vals: Tensor, start: Tensor, count: Tensor):
-        """(owner tile of each element, position inside its tile, per-tile hash) of the ranges [start, start + count)"""
-        owner = torch.repeat_interleave(tiles, count)
-        base = torch.repeat_interleave(start, count)
-        idx = base + (torch.arange(owner.numel(), device=dev) - torch.repeat_interleave(torch.cumsum(count, 0) - count, count))
-        pos = idx - base
-        v = vals[idx].to(torch.int64)
-        mixed = (v * K2 + pos * K1 + 12345) * ((pos << 1) | 1)
-        mixed = mixed ^ (mixed >> 29)
-        h = torch.zeros(ntiles, dtype=torch.int64, device=dev).index_add_(0, owner, mixed * K3)
-        return owner, idx, pos, h
-
-    loc16 = tloc.view(torch.int16)
-    ow_w, idx_w, pos_w, h_w = seg_hash(twork, w0, nw)
-    ow_l, idx_l, pos_l, h_l = seg_hash(loc16, i0, ni)
-    ow_c, idx_c, pos_c, h_c = seg_hash(tchunk, w0 >> 5, nw >> 5)
-    key = torch.stack([nw, ni, h_w, h_l, h_c], dim=1)
-    _, inv = torch.unique(key, dim=0, return_inverse=True)
-    rep = torch.full((int(inv.max().item()) + 1,), ntiles, dtype=torch.int64, device=dev).scatter_reduce_(
-        0, inv, tiles, reduce="amin")[inv]                                  # representative (lowest) tile of each class
-    # exact verification against the representative's records
-    same = (bool((twork[idx_w] == twork[w0[rep][ow_w] + pos_w]).all())
-            and bool((loc16[idx_l] == loc16[i0[rep][ow_l] + pos_l]).all())
-            and bool((tchunk[idx_c] == tchunk[(w0[rep] >> 5)[ow_c] + pos_c]).all()))
-    if not same:
-        return tdesc, tloc, twork, tchunk, ntiles
-    is_rep = rep == tiles
-    n_unique = int(is_rep.sum().item())
-    if n_unique == ntiles:
-        return tdesc, tloc, twork, tchunk, ntiles
-    # compact: keep the representatives' ranges, in order; offsets of the kept ranges by prefix sums
-    new_w0 = torch.cumsum(torch.where(is_rep, nw, torch.zeros_like(nw)), 0) - torch.where(is_rep, nw, torch.zeros_like(nw))
-    new_i0 = torch.cumsum(torch.where(is_rep, ni, torch.zeros_like(ni)), 0) - torch.where(is_rep, ni, torch.zeros_like(ni))
-    keep_w, keep_l, keep_c = is_rep[ow_w], is_rep[ow_l], is_rep[ow_c]
-    twork_n = twork[idx_w[keep_w]].contiguous()
-    tloc_n = loc16[idx_l[keep_l]].contiguous().view(torch.uint16)
-    tchunk_n = tchunk[idx_c[keep_c]].contiguous()
-    if twork_n.numel() < 32:
-        twork_n = torch.cat([twork_n, torch.zeros(32 - twork_n.numel(), dtype=twork.dtype, device=dev)])
-    if tloc_n.numel() < 2:
-        tloc_n = torch.cat([tloc_n.view(torch.int16), torch.zeros(2, dtype=torch.int16, device=dev)]).view(torch.uint16)
-    if tchunk_n.numel() < 1:
-        tchunk_n = torch.zeros(1, dtype=tchunk.dtype, device=dev)
-    out = tdesc.clone()
-    out[:, 2] = new_i0[rep].to(tdesc.dtype)
-    out[:, 4] = new_w0[rep].to(tdesc.dtype)
-    return out.contiguous(), tloc_n, twork_n, tchunk_n, n_unique
 
 
 def _scan_into(src: Tensor, dst: Tensor, ws: Tensor):
@@ -636,7 +568,10 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         _lib.check(L.fe_tile_conn(pat.elem_type, ntiles, _ptr(conn), _ptr(eperm), _ptr(tile_estart), _ptr(thalo),
                                   _ptr(tile_ptr), _ptr(tconn), st))
         wsp = _lib.tile_ws_params(pat.elem_type)
-        if kernel != "phased" and wsp["blob_cap"] > 0:
+        # "auto": the warp-specialised kernel where it is the faster one (measured: Quad4 1.39 ms against 1.90 ms on cfg2;
+        # Tri3's tiles are too small for its per-tile hand-offs: 1.51 ms against 1.25 ms), else the barrier-phased kernel
+        want_ws = kernel == "ws" or (kernel == "auto" and pat.elem_type == FE_QUAD4)
+        if want_ws and wsp["blob_cap"] > 0:
             # ---- warp-specialised kernel: per-tile record blobs + runs of contiguous CSR rows ----
             tsz = torch.empty((2, s), dtype=torch.int32, device=dev)
             wstats = torch.empty(8, dtype=torch.int32, device=dev)
@@ -661,7 +596,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                 if int(wstats[4].item()) != 0:
                     return None
                 info["kernel"] = "ws"
-                return TilePlan(tconn, tdesc, None, None, None, None, ntiles, info, blobs, truns, offs[0].clone())
+                return TilePlan(tconn, tdesc, None, None, None, None, ntiles, info, blobs, truns)
             if kernel == "ws":
                 return None
         elif kernel == "ws":
@@ -710,29 +645,6 @@ def assemble_ws(tconn: Tensor, coords: Tensor, ntiles: int, tdesc: Tensor, blobs
     with torch.cuda.device(vals.device):
         _lib.check(_lib.lib().fe_assemble_ws(elem_type, op, ntiles, _ptr(tconn), _ptr(coords), _ptr(tdesc), _ptr(blobs),
                                              _ptr(truns), _ptr(vals), _stream(vals)))
-
-
-def share_tile_records(plan: Optional[TilePlan]) -> int:
-    """Lets the tiles of a warp-specialised plan whose record blobs are byte-identical share one copy (fe_tile_ws_share:
-    hash + byte-for-byte verification on the device; rewrites tdesc only, results unchanged).  Worth it when a plan
-    is used for more than one assembly: the records then stay in L2 instead of streaming from HBM for every tile.
-    Returns the number of tiles redirected (0 for other plans); idempotent."""
-    if plan is None or not plan.warp_specialised or plan.shared or plan.ntiles == 0:
-        return 0
-    dev = plan.blobs.device
-    with torch.cuda.device(dev):
-        tsize = 1 << max(4, (2 * plan.ntiles - 1).bit_length())
-        keys = torch.empty(tsize, dtype=torch.int64, device=dev)
-        reps = torch.empty(tsize, dtype=torch.int32, device=dev)
-        hashes = torch.empty(plan.ntiles, dtype=torch.int64, device=dev)
-        nshared = torch.empty(1, dtype=torch.int32, device=dev)
-        _lib.check(_lib.lib().fe_tile_ws_share(plan.ntiles, _ptr(plan.tdesc), _ptr(plan.blob_off), _ptr(plan.blobs),
-                                               _ptr(keys), _ptr(reps), _ptr(hashes), tsize, _ptr(nshared),
-                                               _stream(plan.blobs)))
-        plan.shared = True
-        n = int(nshared.item())
-    plan.stats["shared_blobs"] = n
-    return n
 
 
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):

@@ -229,12 +229,6 @@ int fe_tile_ws_build(int elem_type, int64_t nslots, int64_t ntiles, const int32_
                      const int32_t* einc, const uint8_t* epos, const int32_t* eloc, const int32_t* nptr,
                      const int32_t* nadj, const int32_t* blob_off, const int32_t* run_off, void* blobs, void* truns,
                      int32_t* tdesc, int32_t* stats, void* stream);
-/* Optional: lets tiles whose record blobs are byte-identical (all interior tiles of a regular mesh) share ONE copy, so
- * the records stay in L2 instead of being streamed from HBM for every tile.  Rewrites tdesc[4 * t] only; results
- * do not change.  table_keys uint64 [table_size], table_reps int32 [table_size], hashes uint64 [ntiles] are scratch;
- * table_size = a power of two >= 2 * ntiles; nshared[0] <- tiles redirected; blob_off as given to fe_tile_ws_build. */
-int fe_tile_ws_share(int64_t ntiles, int32_t* tdesc, const int32_t* blob_off, const void* blobs, void* table_keys,
-                     int32_t* table_reps, void* hashes, int64_t table_size, int32_t* nshared, void* stream);
 int fe_assemble_ws(int elem_type, int op, int64_t ntiles, const int32_t* tconn, const double* coords,
                    const int32_t* tdesc, const void* blobs, const void* truns, double* vals, void* stream);
 

@@ -120,41 +120,3 @@ def test_partition_invariants_random_meshes(seed):
         if not locality:
             assert np.all(np.diff(owned) > 0)
     assert np.all(owned_count == 1)
-
-
-def test_tile_record_dedup_on_synthetic_plan():
-    """ops.dedup_tile_records: tiles with identical tile-local records share one copy; every tile still reads
-    exactly its original records through the rewritten offsets; alignment (32 work items, 2 locators) is kept."""
-    from feprogram_b200 import ops
-    rng = np.random.default_rng(0)
-    templ = []
-    for _ in range(3):
-        nw, ni = 32 * int(rng.integers(1, 5)), 2 * int(rng.integers(1, 20))
-        templ.append((rng.integers(0, 2 ** 31 - 1, nw).astype(np.int32), rng.integers(0, 65535, ni).astype(np.uint16),
-                      rng.integers(0, 2 ** 20, nw // 32).astype(np.int32)))
-    which = rng.integers(0, 3, 40)
-    tw, tl, tc, desc, w0, i0 = [], [], [], [], 0, 0
-    for t, k in enumerate(which):
-        a, b, c = templ[k]
-        desc.append([t * 7, 5, i0, len(b), w0, len(a), 3, 0])
-        tw.append(a); tl.append(b); tc.append(c)
-        w0 += len(a); i0 += len(b)
-    tdesc = torch.tensor(desc, dtype=torch.int32)
-    twork = torch.from_numpy(np.concatenate(tw))
-    tloc = torch.from_numpy(np.concatenate(tl).view(np.int16)).view(torch.uint16)
-    tchunk = torch.from_numpy(np.concatenate(tc))
-    nd, nl, nwk, nc, nu = ops.dedup_tile_records(tdesc, tloc, twork, tchunk)
-    assert nu == 3 and nwk.numel() == sum(len(t[0]) for t in templ) and nl.numel() == sum(len(t[1]) for t in templ)
-    for t in range(40):
-        o, n = tdesc[t].tolist(), nd[t].tolist()
-        assert torch.equal(twork[o[4]:o[4] + o[5]], nwk[n[4]:n[4] + n[5]])
-        assert torch.equal(tloc.view(torch.int16)[o[2]:o[2] + o[3]], nl.view(torch.int16)[n[2]:n[2] + n[3]])
-        assert torch.equal(tchunk[o[4] // 32:(o[4] + o[5]) // 32], nc[n[4] // 32:(n[4] + n[5]) // 32])
-        assert (o[0], o[1], o[3], o[5], o[6]) == (n[0], n[1], n[3], n[5], n[6]) and n[4] % 32 == 0 and n[2] % 2 == 0
-    # all tiles distinct: nothing changes
-    tw2 = torch.from_numpy(rng.integers(0, 2 ** 31 - 1, 64).astype(np.int32))
-    td2 = torch.tensor([[0, 1, 0, 2, 0, 32, 0, 0], [1, 1, 2, 2, 32, 32, 0, 0]], dtype=torch.int32)
-    tl2 = torch.from_numpy(np.array([1, 2, 3, 4], dtype=np.int16)).view(torch.uint16)
-    tc2 = torch.tensor([5, 6], dtype=torch.int32)
-    r = ops.dedup_tile_records(td2, tl2, tw2, tc2)
-    assert r[4] == 2 and r[0] is td2

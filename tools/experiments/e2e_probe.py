@@ -62,14 +62,15 @@ def main():
     for rep in range(3):
         sync()
         t0 = time.perf_counter()
-        fem = FemProblem(conn1.numpy(), xy_p.numpy(), device=dev)
+        fem = FemProblem(conn1.numpy(), xy_p.numpy(), device=dev, trace=(rep == 2))
         fem.setMatrix()
         fem.dofDir, fem.dofNeu = d_dofs, n_dofs
         fem.assemble()
         chk = fem._dev["vals"].sum().item()
         b = fem.rhs_host()
         sync()
-        rows.append({"pipelined_ms": round(1e3 * (time.perf_counter() - t0), 3), "alloc": torch.cuda.memory_stats()["num_device_alloc"]})
+        rows.append({"pipelined_ms": round(1e3 * (time.perf_counter() - t0), 3), "alloc": torch.cuda.memory_stats()["num_device_alloc"],
+                     "stages": fem.stage_times()})
         del fem
     print(json.dumps(rows, indent=1))
 

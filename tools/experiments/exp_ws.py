@@ -72,24 +72,6 @@ def main():
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
         out[kernel] = {"ms": ms, "equal_rows": eq, "gbs": bytes_alg / ms / 1e6, "frac": bytes_alg / ms / 1e6 / 6454.6}
-        if kernel == "ws" and os.environ.get("FE_SHARE", "1") == "1":
-            t0 = time.perf_counter()
-            nsh = ops.share_tile_records(plan)
-            torch.cuda.synchronize()
-            sh_s = time.perf_counter() - t0
-            v.fill_(float("nan"))
-            ops.assemble_values(conn0, xy, pat, plan, v)
-            eq2 = bool(torch.equal(v, v_rows))
-            for _ in range(3):
-                ops.assemble_values(conn0, xy, pat, plan, v)
-            a.record()
-            for _ in range(reps):
-                ops.assemble_values(conn0, xy, pat, plan, v)
-            b.record()
-            torch.cuda.synchronize()
-            ms2 = a.elapsed_time(b) / reps
-            out["ws_shared"] = {"ms": ms2, "equal_rows": eq2, "tiles_redirected": nsh, "of": plan.ntiles, "share_s": round(sh_s, 5),
-                                "frac": bytes_alg / ms2 / 1e6 / 6454.6}
         del v, plan
     print(json.dumps(out), flush=True)
 
