@@ -37,6 +37,7 @@ PROTOTYPES = {
     "fe_adjacency_fill": (_i, [_i, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_csr_expand": (_i, [_i, _i64, _p, _p, _i, _p, _p, _p]),
     "fe_assemble": (_i, [_i, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+    "fe_bbox": (_i, [_i64, _p, _p, _p, _p]),
     "fe_tile_form_count": (_i, [_i, _i64, _i64] + [_p] * 10),
     "fe_tile_form_sort": (_i, [_i, _i64] + [_p] * 8),
     "fe_tile_params": (None, [_i, C.POINTER(_i32)]),
@@ -49,7 +50,6 @@ PROTOTYPES = {
     "fe_tile_conn": (_i, [_i, _i64] + [_p] * 7),
     "fe_assemble_tiled": (_i, [_i, _i, _i64] + [_p] * 9),
     "fe_tile_ws_params": (None, [_i, C.POINTER(_i32)]),
-    "fe_tile_ws_sizes": (_i, [_i, _i64] + [_p] * 6),
     "fe_tile_ws_build": (_i, [_i, _i64, _i64] + [_p] * 18),
     "fe_assemble_ws": (_i, [_i, _i, _i64] + [_p] * 7),
     "fe_bc_rhs": (_i, [_i64, _p, _i64, _p, _i64, _f64, _p, _p, _p]),

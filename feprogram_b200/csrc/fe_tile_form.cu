@@ -12,6 +12,40 @@ namespace fe {
 
 constexpr int kFormCap = 1024;     // elements of one Morton block the per-block sort handles
 
+// Bounding box of the node coordinates: block partials, then one block over the partials.  out = {xmin, ymin, xmax, ymax}.
+constexpr int kBoxBlocks = 592;
+__global__ void __launch_bounds__(256) k_bbox(int64_t n, const double2* __restrict__ xy, int nparts,
+                                              const double4* __restrict__ parts_in, double4* __restrict__ out) {
+    __shared__ double4 sm[8];
+    double4 b = make_double4(1.0e300, 1.0e300, -1.0e300, -1.0e300);
+    if (parts_in) {
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+            const double4 p = parts_in[i];
+            b.x = fmin(b.x, p.x); b.y = fmin(b.y, p.y); b.z = fmax(b.z, p.z); b.w = fmax(b.w, p.w);
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            const double2 p = __ldg(xy + i);
+            b.x = fmin(b.x, p.x); b.y = fmin(b.y, p.y); b.z = fmax(b.z, p.x); b.w = fmax(b.w, p.y);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        b.x = fmin(b.x, __shfl_xor_sync(0xffffffffu, b.x, d));
+        b.y = fmin(b.y, __shfl_xor_sync(0xffffffffu, b.y, d));
+        b.z = fmax(b.z, __shfl_xor_sync(0xffffffffu, b.z, d));
+        b.w = fmax(b.w, __shfl_xor_sync(0xffffffffu, b.w, d));
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            b.x = fmin(b.x, sm[w].x); b.y = fmin(b.y, sm[w].y); b.z = fmax(b.z, sm[w].z); b.w = fmax(b.w, sm[w].w);
+        }
+        out[blockIdx.x] = b;
+    }
+}
+
 __global__ void k_block_hist(int64_t nelem, const int32_t* __restrict__ keys, int shift, int32_t* __restrict__ hist) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nelem) atomicAdd(hist + (keys[e] >> shift), 1);
@@ -102,6 +136,20 @@ __global__ void __launch_bounds__(32 * kFormWarps) k_block_sort(int64_t nb, cons
 }  // namespace fe
 
 extern "C" {
+
+// out[0..3] <- {xmin, ymin, xmax, ymax} of coords[nnode][2] (DEVICE doubles, 32-byte aligned); scratch: 592 * 4 doubles.
+int fe_bbox(int64_t nnode, const double* coords, double* scratch, double* out, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(nnode >= 1 && coords && scratch && out, "null pointer or empty mesh");
+    cudaStream_t st = as_stream(stream);
+    int g = (int)((nnode + 255) / 256);
+    if (g > kBoxBlocks) g = kBoxBlocks;
+    k_bbox<<<g, 256, 0, st>>>(nnode, reinterpret_cast<const double2*>(coords), 0, nullptr, reinterpret_cast<double4*>(scratch));
+    FE_CHECK_LAUNCH("k_bbox");
+    k_bbox<<<1, 256, 0, st>>>(0, nullptr, g, reinterpret_cast<const double4*>(scratch), reinterpret_cast<double4*>(out));
+    FE_CHECK_LAUNCH("k_bbox");
+    return FE_OK;
+}
 
 // Step A (before the host reads ntiles): histogram, tiles per block, both scans, scatter.
 //   keys[nelem]; nb = number of Morton blocks (keys >> log2(TE) < nb); hist[nb+1], tpb[nb+1], ebase[nb+1], tbase[nb+1],

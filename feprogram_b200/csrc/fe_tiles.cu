@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
     const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc, const int32_t* __restrict__ einv,
     const int32_t* __restrict__ nptr, int32_t* __restrict__ noff, int32_t* __restrict__ thalo,
     int32_t* __restrict__ tile_icount, int32_t* __restrict__ tile_hcount, int32_t* __restrict__ tile_wcount,
-    int32_t* __restrict__ stats, int he) {
+    int32_t* __restrict__ tile_blob16, int32_t* __restrict__ tile_runs, int32_t* __restrict__ stats, int he) {
     __shared__ int s_nodes[kLayoutWarps][kLayoutNodes];
     __shared__ int s_cand[kLayoutWarps][kLayoutCand];
     __shared__ int s_sorted[kLayoutWarps][kLayoutCand];
@@ -149,13 +149,13 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
     const int64_t t = (int64_t)blockIdx.x * kLayoutWarps + w;
     if (t > ntiles) return;
     if (t == ntiles) {
-        if (lane == 0) tile_icount[t] = tile_hcount[t] = tile_wcount[t] = 0;
+        if (lane == 0) tile_icount[t] = tile_hcount[t] = tile_wcount[t] = tile_blob16[t] = tile_runs[t] = 0;
         return;
     }
     const int lo = tile_nptr[t], hi = tile_nptr[t + 1], nn = hi - lo;
     if (nn > kLayoutNodes) {        // beyond every tile capacity: report it, the host discards this plan
         if (lane == 0) {
-            tile_icount[t] = tile_hcount[t] = tile_wcount[t] = 0;
+            tile_icount[t] = tile_hcount[t] = tile_wcount[t] = tile_blob16[t] = tile_runs[t] = 0;
             atomicMax(stats + 0, nn);
         }
         return;
@@ -173,17 +173,21 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
         nodes[r] = v;
     }
     __syncwarp();
-    int ni = 0, nw = 0, maxcnt = 0;
+    int ni = 0, nw = 0, maxcnt = 0, maxdeg = 0, nruns = 0;
     for (int i0 = 0; i0 < nn; i0 += 32) {
         const int i = i0 + lane;
         int ci = 0, cw = 0, n = 0, k0 = 0;
+        bool run_start = false;
         if (i < nn) {
             n = nodes[i];
             tile_nodes[lo + i] = n;
             k0 = eptr[n];
             ci = eptr[n + 1] - k0;
             cw = nptr[n + 1] - nptr[n];
+            run_start = i == 0 || nodes[i - 1] != n - 1;     // consecutive ids = one contiguous range of CSR rows
         }
+        nruns += __popc(__ballot_sync(0xffffffffu, run_start));
+        maxdeg = cw > maxdeg ? cw : maxdeg;
         int si = ci, sw = cw;               // inclusive warp scans
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -211,6 +215,8 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
     for (int d = 16; d > 0; d >>= 1) {
         const int o = __shfl_xor_sync(0xffffffffu, maxcnt, d);
         maxcnt = o > maxcnt ? o : maxcnt;
+        const int g = __shfl_xor_sync(0xffffffffu, maxdeg, d);
+        maxdeg = g > maxdeg ? g : maxdeg;
     }
     __syncwarp();
     int nc = s_ncand[w];
@@ -245,6 +251,13 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
         tile_icount[t] = (ni + 1) & ~1;    // even: item locators are staged with 4-byte cp.async
         tile_hcount[t] = nh;
         tile_wcount[t] = (nw + 31) & ~31;  // chunks of 32 work items never straddle tiles
+        // warp-specialised kernel (fe_tiles_ws.cu): record-blob size and runs of contiguous CSR rows of this tile
+        const int nnp = (nn + 31) & ~31;
+        const int blob = (16 + 8 * nnp + 4 * maxdeg * nnp + 2 * ((ni + 1) & ~1) + 15) & ~15;
+        tile_blob16[t] = blob >> 4;
+        tile_runs[t] = nruns;
+        atomicMax(stats + 6, blob);
+        atomicMax(stats + 7, 32 * nw);
         atomicMax(stats + 0, nn);
         atomicMax(stats + 1, ni);
         atomicMax(stats + 2, overflow ? he + 1 : nh);
@@ -857,7 +870,8 @@ int fe_tile_layout(int elem_type, int64_t nnode, int64_t ntiles, const int32_t* 
     const int64_t s = ntiles + 1;
     k_tile_layout<<<grid_for(ntiles + 1, kLayoutWarps), 32 * kLayoutWarps, 0, st>>>(ntiles, tile_nptr, tile_nodes, eptr, einc, einv, nptr, noff,
                                                           thalo, tile_counts, tile_counts + s, tile_counts + 2 * s,
-                                                          stats, halo_cap(nnpe_of(elem_type)));
+                                                          tile_counts + 3 * s, tile_counts + 4 * s, stats,
+                                                          halo_cap(nnpe_of(elem_type)));
     FE_CHECK_LAUNCH("k_tile_layout");
     return FE_OK;
 }

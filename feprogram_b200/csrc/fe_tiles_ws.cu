@@ -24,7 +24,7 @@
 //
 // Rings: 2 slab slots, 2 record slots, 2 staging slots; six mbarrier pairs; phases advance with the tile index.
 //
-// Per-tile plan (built once per mesh by fe_tile_ws_sizes / fe_tile_ws_build from the same owner / layout /
+// Per-tile plan (built once per mesh by fe_tile_layout + fe_tile_ws_build from the same owner / layout /
 // halo arrays as the fe_tiles.cu plan):
 //   tconn      int32 [ntiles][TE + HC][nnpe]   connectivity in tile order (own rows, then halo rows; -1 = unused)
 //   tdesc      int32 x 4 per tile              {blob offset / 16, blob bytes, first run, run count}
@@ -400,51 +400,6 @@ static int launch_ws(int64_t ntiles, const int32_t* tconn, const double* coords,
 // =================================================================================================
 // plan kernels
 // =================================================================================================
-// One warp per tile: maximum degree, number of runs of consecutive node ids (= contiguous CSR row ranges), blob size.
-// tile_nodes is sorted ascending inside each tile (fe_tile_layout).  tsz[t] = blob bytes / 16, tsz[s + t] = runs.
-// stats: [0] max blob bytes, [1] max staging bytes, [2] max degree, [3] max owned nodes.
-__global__ void __launch_bounds__(128) k_tile_ws_sizes(int64_t ntiles, const int32_t* __restrict__ tile_nptr,
-                                                       const int32_t* __restrict__ tile_iptr,
-                                                       const int32_t* __restrict__ tile_nodes,
-                                                       const int32_t* __restrict__ nptr, int32_t* __restrict__ tsz,
-                                                       int32_t* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t s = ntiles + 1;
-    if (t > ntiles) return;
-    if (t == ntiles) {
-        if (lane == 0) tsz[t] = tsz[s + t] = 0;
-        return;
-    }
-    const int lo = tile_nptr[t], nn = tile_nptr[t + 1] - lo;
-    const int ni = tile_iptr[t + 1] - tile_iptr[t];
-    int maxdeg = 0, sumdeg = 0, runs = 0;
-    for (int i = lane; i < nn; i += 32) {
-        const int n = tile_nodes[lo + i];
-        const int deg = nptr[n + 1] - nptr[n];
-        maxdeg = deg > maxdeg ? deg : maxdeg;
-        sumdeg += deg;
-        runs += (i == 0 || tile_nodes[lo + i - 1] != n - 1) ? 1 : 0;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const int m = __shfl_xor_sync(0xffffffffu, maxdeg, d);
-        maxdeg = m > maxdeg ? m : maxdeg;
-        sumdeg += __shfl_xor_sync(0xffffffffu, sumdeg, d);
-        runs += __shfl_xor_sync(0xffffffffu, runs, d);
-    }
-    if (lane == 0) {
-        const int nnp = (nn + 31) & ~31;
-        const int bytes = (16 + 8 * nnp + 4 * maxdeg * nnp + 2 * ni + 15) & ~15;
-        tsz[t] = bytes >> 4;
-        tsz[s + t] = runs;
-        atomicMax(stats + 0, bytes);
-        atomicMax(stats + 1, 32 * sumdeg);
-        atomicMax(stats + 2, maxdeg);
-        atomicMax(stats + 3, nn);
-    }
-}
-
 // One warp per tile: blob header, the padding entries [nn, nnp) of the node / record arrays, the run list, tdesc.
 __global__ void __launch_bounds__(128) k_tile_ws_runs(int64_t ntiles, const int32_t* __restrict__ tile_nptr,
                                                       const int32_t* __restrict__ tile_iptr,
@@ -597,20 +552,6 @@ void fe_tile_ws_params(int elem_type, int32_t out[4]) {
     } else if (elem_type == FE_TRI3) {
         out[0] = WsLayout<3>::kBlobCap, out[1] = WsLayout<3>::kStageCap, out[2] = 127, out[3] = 256;
     }
-}
-
-int fe_tile_ws_sizes(int elem_type, int64_t ntiles, const int32_t* tile_ptr, const int32_t* tile_nodes, const int32_t* nptr,
-                     int32_t* tsz, int32_t* stats, void* stream) {
-    using namespace fe;
-    FE_REQUIRE(elem_type == FE_QUAD4 || elem_type == FE_TRI3, "the warp-specialised kernel handles Quad4 / Tri3");
-    FE_REQUIRE(ntiles >= 0 && tile_ptr && tsz && stats, "null pointer or negative size");
-    cudaStream_t st = as_stream(stream);
-    FE_CUDA_TRY(cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
-    FE_REQUIRE(ntiles == 0 || (tile_nodes && nptr), "null pointer");
-    const int64_t s = ntiles + 1;
-    k_tile_ws_sizes<<<grid_for(ntiles + 1, 4), 128, 0, st>>>(ntiles, tile_ptr, tile_ptr + s, tile_nodes, nptr, tsz, stats);
-    FE_CHECK_LAUNCH("k_tile_ws_sizes");
-    return FE_OK;
 }
 
 int fe_tile_ws_build(int elem_type, int64_t nslots, int64_t ntiles, const int32_t* tile_nodes, const int32_t* owner,

@@ -283,6 +283,14 @@ class FemProblem:
             xy = np.ascontiguousarray(xy[:, :2])
         main = torch.cuda.current_stream(dev)
         self._mark("start", main)
+        # boundary dof sets first (tiny): a small copy issued later would queue behind the 268 MB coordinate upload on the
+        # host->device copy engine and hold back everything that depends on the right-hand side
+        pre = {}
+        if getattr(self, "dofDir", None) is not None and getattr(self, "dofNeu", None) is not None:
+            pre["dof_sets"] = (self.dofDir, self.dofNeu,
+                               torch.as_tensor(np.asarray(self.dofDir, dtype=np.int64), device=dev),
+                               torch.as_tensor(np.asarray(self.dofNeu, dtype=np.int64), device=dev))
+            pre["dof_event"] = main.record_event()
         tags = torch.from_numpy(np.ascontiguousarray(conn)).to(dev, non_blocking=True)
         self._mark("conn uploaded", main)
         side = side_streams(dev)[0]
@@ -296,6 +304,7 @@ class FemProblem:
             "coords": coords_d,
             "coords_event": side.record_event(),
         }
+        st.update(pre)
         self._dev = st
         ren = self._renumber
         if ren is None:      # a row-major lattice spans ~sqrt(nnode) ids per element, a shuffled one ~nnode/2
@@ -322,7 +331,13 @@ class FemProblem:
         """Reference dof ids -> dof ids of the (possibly renumbered) solver mesh, as a device tensor."""
         import torch
         st = self._dev
-        d = torch.as_tensor(np.asarray(dofs, dtype=np.int64), device=st["conn"].device)
+        pre = st.get("dof_sets")
+        if pre is not None and dofs is pre[0]:            # uploaded ahead of the mesh by _state()
+            d = pre[2]
+        elif pre is not None and dofs is pre[1]:
+            d = pre[3]
+        else:
+            d = torch.as_tensor(np.asarray(dofs, dtype=np.int64), device=st["conn"].device)
         if st["perm"] is None:
             return d
         return 2 * st["perm"][d // 2] + d % 2
@@ -340,6 +355,10 @@ class FemProblem:
         nrows = 2 * self.nnode
         if "rhs" in st:
             side.wait_stream(main)           # re-assembly: a solve on the main stream may still be reading rhs / dirmask
+        if "dof_event" in st:
+            side.wait_event(st["dof_event"])                     # dof sets were uploaded on the main stream
+            for t in st["dof_sets"][2:]:
+                t.record_stream(side)
         with torch.cuda.stream(side):
             if "rhs" not in st:
                 st["rhs"] = torch.empty(nrows, dtype=torch.float64, device=dev)

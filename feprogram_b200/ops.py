@@ -452,7 +452,9 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
             nc = 3 if pat.elem_type == FE_TRI3 else 4                         # corner nodes come first
             cx, cy = xy[:, :nc, 0], xy[:, :nc, 1]
             area = 0.5 * (cx * torch.roll(cy, -1, dims=1) - torch.roll(cx, -1, dims=1) * cy).sum(dim=1).abs().mean()
-            sc = torch.cat([coords.amin(dim=0), coords.amax(dim=0), ext_e, area.reshape(1)]).cpu().tolist()
+            box = torch.empty(4 * 593, dtype=torch.float64, device=dev)           # [0:4] result, rest scratch
+            _lib.check(L.fe_bbox(nnode, _ptr(coords), _ptr(box[4:]), _ptr(box), st))
+            sc = torch.cat([box[:4], ext_e, area.reshape(1)]).cpu().tolist()
             lo_h = sc[0:2]
             ext = [max(sc[2] - sc[0], 1e-300), max(sc[3] - sc[1], 1e-300)]
             ext_e = [max(sc[4], 1e-300), max(sc[5], 1e-300)]
@@ -541,23 +543,23 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         tile_ncount = torch.empty(s, dtype=torch.int32, device=dev)
         _lib.check(L.fe_tile_owner(nnode, ntiles, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner),
                                    _ptr(tile_ncount), st))
-        tile_ptr = torch.empty((4, s), dtype=torch.int32, device=dev)
+        tile_ptr = torch.empty((6, s), dtype=torch.int32, device=dev)     # nodes, items, halo, work, blob / 16, runs
         _scan_into(tile_ncount, tile_ptr[0], ws)
         cursor = torch.empty(ntiles, dtype=torch.int32, device=dev)
         tile_nodes = torch.empty(nnode, dtype=torch.int32, device=dev)
         noff = torch.empty(2 * nnode, dtype=torch.int32, device=dev)
         thalo = torch.empty((ntiles, hcap), dtype=torch.int32, device=dev)
-        counts = torch.empty((3, s), dtype=torch.int32, device=dev)
+        counts = torch.empty((5, s), dtype=torch.int32, device=dev)
         stats = torch.empty(8, dtype=torch.int32, device=dev)
         _lib.check(L.fe_tile_layout(pat.elem_type, nnode, ntiles, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
                                     _ptr(einv), _ptr(pat.nptr), _ptr(cursor), _ptr(tile_nodes), _ptr(noff),
                                     _ptr(thalo), _ptr(counts), _ptr(stats), st))
-        for r in range(3):
+        for r in range(5):
             _scan_into(counts[r], tile_ptr[r + 1], ws)
-        tail = torch.cat([tile_ptr[:, ntiles], stats]).cpu().tolist()       # one host sync
-        nslots, n_items, n_halo, n_work = (int(v) for v in tail[:4])
-        max_nodes, max_items, max_halo, max_cnt = (int(v) for v in tail[4:8])
-        max_work = int(tail[9])
+        tail = torch.cat([tile_ptr[:, ntiles], stats]).cpu().tolist()       # one host sync: every size and capacity
+        nslots, n_items, n_halo, n_work, blob16, nruns = (int(v) for v in tail[:6])
+        max_nodes, max_items, max_halo, max_cnt = (int(v) for v in tail[6:10])
+        max_work, max_blob, max_stage = int(tail[11]), int(tail[12]), int(tail[13])
         info = dict(max_nodes=max_nodes, max_items=max_items, max_halo=max_halo, max_cnt=max_cnt, max_work=max_work,
                     items=n_items, halo_elems=n_halo, work_items=n_work, morton=morton, cell_scale=cell_scale,
                     mode=mode, ntiles=ntiles)
@@ -573,25 +575,17 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         want_ws = kernel == "ws" or (kernel == "auto" and pat.elem_type == FE_QUAD4)
         if want_ws and wsp["blob_cap"] > 0:
             # ---- warp-specialised kernel: per-tile record blobs + runs of contiguous CSR rows ----
-            tsz = torch.empty((2, s), dtype=torch.int32, device=dev)
-            wstats = torch.empty(8, dtype=torch.int32, device=dev)
-            _lib.check(L.fe_tile_ws_sizes(pat.elem_type, ntiles, _ptr(tile_ptr), _ptr(tile_nodes), _ptr(pat.nptr),
-                                          _ptr(tsz), _ptr(wstats), st))
-            offs = torch.empty((2, s), dtype=torch.int32, device=dev)
-            _scan_into(tsz[0], offs[0], ws)
-            _scan_into(tsz[1], offs[1], ws)
-            wt = torch.cat([offs[:, ntiles], wstats]).cpu().tolist()              # host sync: sizes + capacities
-            blob16, nruns = int(wt[0]), int(wt[1])
-            info.update(max_blob=int(wt[2]), max_stage=int(wt[3]), max_deg=int(wt[4]), runs=nruns, blob_bytes=16 * blob16)
-            fits = (wt[2] <= wsp["blob_cap"] and wt[3] <= wsp["stage_cap"] and wt[4] <= wsp["max_deg"]
-                    and wt[5] <= wsp["max_nodes"] and blob16 < 2 ** 31)
+            wstats = torch.zeros(8, dtype=torch.int32, device=dev)
+            info.update(max_blob=max_blob, max_stage=max_stage, runs=nruns, blob_bytes=16 * blob16)
+            fits = (max_blob <= wsp["blob_cap"] and max_stage <= wsp["stage_cap"] and max_nodes <= wsp["max_nodes"]
+                    and blob16 < 2 ** 31)
             if fits:
                 blobs = torch.empty(max(16, 16 * blob16), dtype=torch.uint8, device=dev)
                 truns = torch.empty((max(1, nruns), 4), dtype=torch.int32, device=dev)
                 tdesc = torch.empty((ntiles, 4), dtype=torch.int32, device=dev)
                 _lib.check(L.fe_tile_ws_build(pat.elem_type, nslots, ntiles, _ptr(tile_nodes), _ptr(owner), _ptr(tile_ptr),
                                               _ptr(noff), _ptr(thalo), _ptr(pat.eptr), _ptr(pat.einc), _ptr(pat.epos),
-                                              _ptr(einv), _ptr(pat.nptr), _ptr(pat.nadj), _ptr(offs[0]), _ptr(offs[1]),
+                                              _ptr(einv), _ptr(pat.nptr), _ptr(pat.nadj), _ptr(tile_ptr[4]), _ptr(tile_ptr[5]),
                                               _ptr(blobs), _ptr(truns), _ptr(tdesc), _ptr(wstats), st))
                 if int(wstats[4].item()) != 0:
                     return None

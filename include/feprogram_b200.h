@@ -157,17 +157,23 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
  *  4. fe_tile_layout        : tile_nodes (ascending node id inside each tile), noff[2*nslots]
  *                             (item / work offset of each tile-node slot inside its tile),
  *                             thalo[ntiles*out[1]] (sorted distinct halo elements of each tile),
- *                             tile_counts[3*s] (items (even), halo elements, work items (x32) per
- *                             tile), stats[8]: [0] max owned nodes, [1] max items, [2] max halo
- *                             elements of a tile, [3] max incident elements of a node.
- *                             scratch: cursor[ntiles].
- *  5. fe_exclusive_scan_i32 x3 : tile_ptr[s..2s), [2s..3s), [3s..4s) <- scans of tile_counts rows
+ *                             tile_counts[5*s] (per tile: items (even), halo elements, work items
+ *                             (x32), record-blob size / 16 and runs of consecutive owned node ids --
+ *                             the last two for fe_assemble_ws), stats[8]: [0] max owned nodes, [1] max
+ *                             items, [2] max halo elements of a tile, [3] max incident elements of a
+ *                             node, [5] max work items, [6] max blob bytes, [7] max bytes of CSR values
+ *                             of a tile.  scratch: cursor[ntiles].
+ *  5. fe_exclusive_scan_i32 x3 (x5) : tile_ptr[s..2s), [2s..3s), [3s..4s) (and blob_off, run_off) <- scans
+ *                             of the rows of tile_counts
  *  6. fe_tile_records       : tnode (int2 per slot), tloc (uint16 per item), twork (uint32 per work
  *                             item, ZERO-INITIALISED by the caller), tchunk (uint32 per 32 work
  *                             items); stats[4] != 0 afterwards means the mesh is not representable
  *                             (use fe_assemble).
  * The plan is usable iff stats[0] <= out[2], stats[1] < out[3], stats[2] <= out[1], stats[5] <= out[4]
  * of fe_tile_params and stats[4] == 0.  Record formats are documented in feprogram_b200/csrc/fe_tiles.cu. */
+/* Bounding box of the mesh (anchors the Morton grid): out[0..3] <- {xmin, ymin, xmax, ymax} (DEVICE, 32-byte aligned);
+ * scratch: 592 * 4 doubles (32-byte aligned). */
+int fe_bbox(int64_t nnode, const double* coords, double* scratch, double* out, void* stream);
 /* Step 1 without a global sort (the default path of the Python facade): fe_tile_form_count buckets the elements
  * by Morton block (keys >> log2(TE); nb blocks) -- histogram, tiles per block, scans, scatter -- after which
  * tbase[nb] = ntiles and status[0] != 0 flags a block of more than 1024 elements (use another tiling);
@@ -211,19 +217,14 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
  * warps (element matrices -> shared-memory slab), consumer warps (slab -> CSR blocks staged in their final layout)
  * and DMA warp (1-D TMA bulk copies: record blobs in, contiguous CSR row ranges out) hand tiles to each other
  * through mbarriers.  Its plan reuses steps 1-5 and 7 of the fe_assemble_tiled plan (owner, layout, halo lists,
- * tile_ptr rows, tconn) and replaces step 6 by:
- *  6a. fe_tile_ws_sizes : tsz[0..s) = record-blob size / 16 of every tile, tsz[s..2s) = number of runs of
- *                         consecutive owned node ids (= contiguous CSR row ranges); stats[0] max blob bytes,
- *                         stats[1] max bytes of CSR values of a tile, stats[2] max degree, stats[3] max owned nodes.
- *  6b. fe_exclusive_scan_i32 x2 : blob_off[s], run_off[s] <- scans of the two rows of tsz.
- *  6c. fe_tile_ws_build : blobs (16 * blob_off[ntiles] bytes), truns (16 bytes per run), tdesc (4 int32 per tile);
+ * tile_ptr rows, tconn; blob_off / run_off = the scans of rows 3 and 4 of fe_tile_layout's tile_counts) and
+ * replaces step 6 by
+ *  6'. fe_tile_ws_build : blobs (16 * blob_off[ntiles] bytes), truns (16 bytes per run), tdesc (4 int32 per tile);
  *                         stats[4] != 0 afterwards means the mesh is not representable (use fe_assemble).
- * The plan is usable iff stats[0] <= out[0], stats[1] <= out[1], stats[2] <= out[2], stats[3] <= out[3] of
- * fe_tile_ws_params (all 0 for element types this kernel does not handle) and stats[4] == 0.  Blob / run formats
- * are documented in feprogram_b200/csrc/fe_tiles_ws.cu.  vals and blobs must be 16-byte aligned. */
+ * The plan is usable iff fe_tile_layout's stats[6] <= out[0], stats[7] <= out[1], stats[0] <= out[3] of
+ * fe_tile_ws_params (all 0 for element types this kernel does not handle) and stats[4] == 0 after the build.
+ * Blob / run formats are documented in feprogram_b200/csrc/fe_tiles_ws.cu.  vals and blobs must be 16-byte aligned. */
 void fe_tile_ws_params(int elem_type, int32_t out[4]);
-int fe_tile_ws_sizes(int elem_type, int64_t ntiles, const int32_t* tile_ptr, const int32_t* tile_nodes,
-                     const int32_t* nptr, int32_t* tsz, int32_t* stats, void* stream);
 int fe_tile_ws_build(int elem_type, int64_t nslots, int64_t ntiles, const int32_t* tile_nodes, const int32_t* owner,
                      const int32_t* tile_ptr, const int32_t* noff, const int32_t* thalo, const int32_t* eptr,
                      const int32_t* einc, const uint8_t* epos, const int32_t* eloc, const int32_t* nptr,
