@@ -27,6 +27,7 @@ PROTOTYPES = {
     "fe_last_error": (None, [C.c_char_p, _sz]),
     "fe_version": (C.c_char_p, []),
     "fe_limits": (None, [C.POINTER(_i32)]),
+    "fe_peek": (_i, [_p, _p, _i64, _p]),
     "fe_tables": (_i, [_i, _p, _p, _p, C.POINTER(_i32), C.POINTER(_i32)]),
     "fe_tags_to_conn": (_i, [_i, _i64, _p, _p, _p]),
     "fe_element_matrices": (_i, [_i, _i, _i64, _p, _p, _p, _p]),

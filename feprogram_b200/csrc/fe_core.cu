@@ -20,6 +20,16 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small device -> host read-back by a KERNEL writing into pinned (device-mapped) host memory.  A cudaMemcpy of a
+// few bytes queues on the device->host copy engine behind whatever large download is in flight (the 268 MB
+// right-hand side of cfg2 holds it for 5 ms); a store from a kernel does not.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_peek(const uint32_t* __restrict__ src, volatile uint32_t* dst, int nwords) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Exclusive scan, int32.  Three phases per level: tile sums -> scan of tile sums (recursive) ->
 // tile-local scan + offset.  Deterministic; one-time symbolic-phase utility, not a hot kernel.
 // ------------------------------------------------------------------------------------------------
@@ -123,6 +133,17 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, cud
 // C ABI
 // ================================================================================================
 extern "C" {
+
+int fe_peek(const void* dev_src, void* pinned_host_dst, int64_t nbytes, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(dev_src && pinned_host_dst && nbytes >= 0 && (nbytes & 3) == 0 && nbytes <= (1 << 20),
+               "null pointer, or size not a multiple of 4 / above 1 MiB");
+    if (nbytes == 0) return FE_OK;
+    k_peek<<<1, 256, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(dev_src),
+                                             static_cast<volatile uint32_t*>(pinned_host_dst), (int)(nbytes >> 2));
+    FE_CHECK_LAUNCH("k_peek");
+    return FE_OK;
+}
 
 void fe_last_error(char* buf, size_t len) {
     if (!buf || len == 0) return;

@@ -250,67 +250,76 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             const uint2* node = reinterpret_cast<const uint2*>(rec + 16);
             const uint32_t* recs = reinterpret_cast<const uint32_t*>(rec + 16 + 8 * nnp);
             const uint16_t* locs = reinterpret_cast<const uint16_t*>(rec + hdr.w);
-            mbar_wait(bar(B_STAGE_FREE, slot), par ^ 1);                // bulk stores of tile k - 2 have read the buffer
             mbar_wait(bar(B_SLAB_FULL, slot), par);
+            // The staging slot is still being read by the bulk stores of tile k - 2 for most of this tile's time.  So a
+            // thread first sums everything it owns into registers (slab reads + adds: the long part) and only then waits
+            // for the slot: the slot is busy for the few store instructions, not for the whole consumer pass.
+            bool slot_free = false;
             const int wph = nnp >> 5;                                   // warps per half of the neighbour lists
             for (int wt = cw; wt < 2 * wph; wt += T::kCW) {
                 const int half = wt >= wph ? 1 : 0;
                 const int ln = (wt - half * wph) * 32 + lane;
 #if defined(FE_WS_WHATIF) && (FE_WS_WHATIF & 2)     // developer timing build: consumers only hand the buffers on
-                if (false) {
+                const bool live = false;
 #else
-                if (ln < nn) {
+                const bool live = ln < nn;
 #endif
-                    const uint2 nd = node[ln];
-                    const int deg = (nd.x >> 16) & 127, self = (nd.x >> 23) & 127;
-                    const int pm = (deg + 1) >> 1;
-                    const int p0 = half ? pm : 0, p1 = half ? deg : pm;
-                    // A node's row 2n+1 lies 16 * deg bytes behind its row 2n: for odd degrees (9 on a Quad4 lattice, 7
-                    // on a Tri3 lattice) the two rows fall into different 16-byte bank groups, so letting every other
-                    // group of four lanes write row 2n+1 first makes each quarter-warp store hit eight distinct groups.
-                    const bool flip = ((lane >> 2) & 1) != 0;
-                    double* row0 = stage + 2 * (nd.x & 0xFFFFu);
-                    double* row1 = row0 + 2 * deg;
-                    double* rowA = flip ? row1 : row0;
-                    double* rowB = flip ? row0 : row1;
-                    // kBatch neighbour positions in flight per thread: all records, then all slab loads, then the stores
-                    for (int pb = p0; pb < p1; pb += T::kBatch) {
-                        uint32_t r[T::kBatch];
+                const uint2 nd = live ? node[ln] : make_uint2(0u, 0u);
+                const int deg = (nd.x >> 16) & 127, self = (nd.x >> 23) & 127;
+                const int pm = (deg + 1) >> 1;
+                const int p0 = half ? pm : 0, p1 = half ? deg : pm;
+                // A node's row 2n+1 lies 16 * deg bytes behind its row 2n: for odd degrees (9 on a Quad4 lattice, 7 on a
+                // Tri3 lattice) the two rows fall into different 16-byte bank groups, so letting every other group of
+                // four lanes write row 2n+1 first makes each quarter-warp store hit eight distinct groups.
+                const bool flip = ((lane >> 2) & 1) != 0;
+                double* row0 = stage + 2 * (nd.x & 0xFFFFu);
+                double* row1 = row0 + 2 * deg;
+                double* rowA = flip ? row1 : row0;
+                double* rowB = flip ? row0 : row1;
+                const bool diag = live && self >= p0 && self < p1;
+                double Ld = 0.0, Pd = 0.0;
+                if (diag) {                                             // diagonal block: all incident elements
+                    const int cnt = nd.y & 15, ioff = nd.y >> 4;
+                    for (int q = 0; q < cnt; ++q) {
+                        const unsigned loc = locs[ioff + q];
+                        const int a = loc & 15;
+                        const double* b = slab + (loc >> 4) * SS + 3 * (a * N - ((a * (a - 1)) >> 1));
+                        Ld += b[0];
+                        Pd += b[1];
+                    }
+                }
+                // kBatch neighbour positions in flight per thread: all records, then all slab loads, then the stores
+                for (int pb = p0; pb < p1 || !slot_free; pb += T::kBatch) {
+                    uint32_t r[T::kBatch];
 #pragma unroll
-                        for (int q = 0; q < T::kBatch; ++q) r[q] = pb + q < p1 ? recs[(pb + q) * nnp + ln] : T::kZeroRec;
-                        double L[T::kBatch], P[T::kBatch], Q[T::kBatch];
+                    for (int q = 0; q < T::kBatch; ++q) r[q] = pb + q < p1 ? recs[(pb + q) * nnp + ln] : T::kZeroRec;
+                    double L[T::kBatch], P[T::kBatch], Q[T::kBatch];
 #pragma unroll
-                        for (int q = 0; q < T::kBatch; ++q) {
-                            const uint32_t s0 = r[q] & T::kSrcMask, s1 = r[q] >> T::kSrcBits;
-                            const double* b0 = slab + (s0 >> 1);
-                            const double* b1 = slab + (s1 >> 1);            // the zero block if absent
-                            const int f0 = s0 & 1, f1 = s1 & 1;             // transposed block: P and Q trade places
-                            L[q] = b0[0] + b1[0];
-                            P[q] = b0[1 + f0] + b1[1 + f1];
-                            Q[q] = b0[2 - f0] + b1[2 - f1];
-                        }
+                    for (int q = 0; q < T::kBatch; ++q) {
+                        const uint32_t s0 = r[q] & T::kSrcMask, s1 = r[q] >> T::kSrcBits;
+                        const double* b0 = slab + (s0 >> 1);
+                        const double* b1 = slab + (s1 >> 1);                // the zero block if absent
+                        const int f0 = s0 & 1, f1 = s1 & 1;                 // transposed block: P and Q trade places
+                        L[q] = b0[0] + b1[0];
+                        P[q] = b0[1 + f0] + b1[1 + f1];
+                        Q[q] = b0[2 - f0] + b1[2 - f1];
+                    }
+                    if (!slot_free) {                                   // warp-uniform: first store of this warp into the slot
+                        mbar_wait(bar(B_STAGE_FREE, slot), par ^ 1);    // bulk stores of tile k - 2 have read the buffer
+                        slot_free = true;
+                    }
 #pragma unroll
-                        for (int q = 0; q < T::kBatch; ++q) {
-                            const int p = pb + q;
-                            if (p < p1 && p != self) {
-                                *reinterpret_cast<double2*>(rowA + 2 * p) = flip ? make_double2(Q[q], L[q]) : make_double2(L[q], P[q]);
-                                *reinterpret_cast<double2*>(rowB + 2 * p) = flip ? make_double2(L[q], P[q]) : make_double2(Q[q], L[q]);
-                            }
+                    for (int q = 0; q < T::kBatch; ++q) {
+                        const int p = pb + q;
+                        if (p < p1 && p != self) {
+                            *reinterpret_cast<double2*>(rowA + 2 * p) = flip ? make_double2(Q[q], L[q]) : make_double2(L[q], P[q]);
+                            *reinterpret_cast<double2*>(rowB + 2 * p) = flip ? make_double2(L[q], P[q]) : make_double2(Q[q], L[q]);
                         }
                     }
-                    if (self >= p0 && self < p1) {                      // diagonal block: all incident elements
-                        const int cnt = nd.y & 15, ioff = nd.y >> 4;
-                        double L = 0.0, P = 0.0;
-                        for (int q = 0; q < cnt; ++q) {
-                            const unsigned loc = locs[ioff + q];
-                            const int a = loc & 15;
-                            const double* b = slab + (loc >> 4) * SS + 3 * (a * N - ((a * (a - 1)) >> 1));
-                            L += b[0];
-                            P += b[1];
-                        }
-                        *reinterpret_cast<double2*>(rowA + 2 * self) = flip ? make_double2(P, L) : make_double2(L, P);
-                        *reinterpret_cast<double2*>(rowB + 2 * self) = flip ? make_double2(L, P) : make_double2(P, L);
-                    }
+                }
+                if (diag) {
+                    *reinterpret_cast<double2*>(rowA + 2 * self) = flip ? make_double2(Pd, Ld) : make_double2(Ld, Pd);
+                    *reinterpret_cast<double2*>(rowB + 2 * self) = flip ? make_double2(Ld, Pd) : make_double2(Pd, Ld);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk store

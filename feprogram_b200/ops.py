@@ -42,6 +42,29 @@ def _chk_dev(*ts: Tensor):
             raise RuntimeError("feprogram_b200 ops need contiguous tensors")
 
 
+def _read_small(parts, dtype) -> list:
+    t = parts[0] if len(parts) == 1 else torch.cat([p.reshape(-1) for p in parts])
+    t = t.contiguous()
+    if t.dtype != dtype:
+        raise TypeError("expected %s, got %s" % (dtype, t.dtype))
+    host = torch.empty(t.numel(), dtype=dtype, pin_memory=True)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().fe_peek(_ptr(t), C.c_void_p(host.data_ptr()), t.element_size() * t.numel(), _stream(t)))
+        torch.cuda.current_stream(t.device).synchronize()
+    return host.tolist()
+
+
+def read_i32(*parts: Tensor) -> list:
+    """Host copy of a few int32 device values (sizes, status words): ONE synchronisation, no copy engine (fe_peek stores
+    into pinned host memory from a kernel, so the read does not wait behind a large download on another stream)."""
+    return _read_small(parts, torch.int32)
+
+
+def read_f64(*parts: Tensor) -> list:
+    """Same for a few fp64 device values."""
+    return _read_small(parts, torch.float64)
+
+
 def _want(t: Tensor, dtype, name: str):
     if t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
@@ -160,7 +183,7 @@ def adjacency(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int) -> Tuple
         ws = torch.empty(max(1, L.fe_scan_workspace_bytes(nnode + 1)), dtype=torch.uint8, device=dev)
         _lib.check(L.fe_adjacency_count(elem_type, nnode, _ptr(conn), _ptr(eptr), _ptr(einc), _ptr(nptr),
                                         _ptr(status), _ptr(ws), _stream(conn)))
-        tail = torch.stack([nptr[nnode], status[0]]).cpu()  # the one host sync of the symbolic phase
+        tail = read_i32(nptr[nnode:nnode + 1], status)      # the one host sync of the symbolic phase
         if int(tail[1]) != 0:
             raise _lib.FeError(-4, "a node has more than %d distinct neighbours" % _lib.limits()["max_adj"])
         nnz_n = int(tail[0])
@@ -454,7 +477,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
             area = 0.5 * (cx * torch.roll(cy, -1, dims=1) - torch.roll(cx, -1, dims=1) * cy).sum(dim=1).abs().mean()
             box = torch.empty(4 * 593, dtype=torch.float64, device=dev)           # [0:4] result, rest scratch
             _lib.check(L.fe_bbox(nnode, _ptr(coords), _ptr(box[4:]), _ptr(box), st))
-            sc = torch.cat([box[:4], ext_e, area.reshape(1)]).cpu().tolist()
+            sc = read_f64(box[:4], ext_e, area.reshape(1))
             lo_h = sc[0:2]
             ext = [max(sc[2] - sc[0], 1e-300), max(sc[3] - sc[1], 1e-300)]
             ext_e = [max(sc[4], 1e-300), max(sc[5], 1e-300)]
@@ -481,7 +504,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                 _lib.check(L.fe_tile_form_count(pat.elem_type, nelem, nb, _ptr(keys), _ptr(tabs[0]), _ptr(tabs[1]),
                                                 _ptr(tabs[2]), _ptr(tabs[3]), _ptr(cursor_b), _ptr(tmp), _ptr(fstat),
                                                 _ptr(wsf), st))
-                ft = torch.cat([tabs[3, nb:nb + 1], fstat]).cpu().tolist()       # host sync: tile count
+                ft = read_i32(tabs[3, nb:nb + 1], fstat)                       # host sync: tile count
                 if int(ft[1]) == 0:
                     ntiles = int(ft[0])
                     eperm = torch.empty(nelem, dtype=torch.int32, device=dev)
@@ -556,7 +579,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                                     _ptr(thalo), _ptr(counts), _ptr(stats), st))
         for r in range(5):
             _scan_into(counts[r], tile_ptr[r + 1], ws)
-        tail = torch.cat([tile_ptr[:, ntiles], stats]).cpu().tolist()       # one host sync: every size and capacity
+        tail = read_i32(tile_ptr[:, ntiles], stats)                         # one host sync: every size and capacity
         nslots, n_items, n_halo, n_work, blob16, nruns = (int(v) for v in tail[:6])
         max_nodes, max_items, max_halo, max_cnt = (int(v) for v in tail[6:10])
         max_work, max_blob, max_stage = int(tail[11]), int(tail[12]), int(tail[13])
@@ -587,7 +610,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                                               _ptr(noff), _ptr(thalo), _ptr(pat.eptr), _ptr(pat.einc), _ptr(pat.epos),
                                               _ptr(einv), _ptr(pat.nptr), _ptr(pat.nadj), _ptr(tile_ptr[4]), _ptr(tile_ptr[5]),
                                               _ptr(blobs), _ptr(truns), _ptr(tdesc), _ptr(wstats), st))
-                if int(wstats[4].item()) != 0:
+                if read_i32(wstats[4:5])[0] != 0:
                     return None
                 info["kernel"] = "ws"
                 return TilePlan(tconn, tdesc, None, None, None, None, ntiles, info, blobs, truns)
@@ -604,7 +627,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
                                      _ptr(noff), _ptr(thalo), _ptr(pat.eptr), _ptr(pat.einc), _ptr(pat.epos),
                                      _ptr(einv), _ptr(pat.nptr), _ptr(pat.nadj), _ptr(tnode), _ptr(tloc),
                                      _ptr(twork), _ptr(tchunk), _ptr(stats), st))
-        if int(stats[4].item()) != 0:
+        if read_i32(stats[4:5])[0] != 0:
             return None
         z = torch.zeros(ntiles, dtype=torch.int32, device=dev)
         tdesc = torch.stack([tile_ptr[0, :-1], tile_ptr[0, 1:] - tile_ptr[0, :-1],

@@ -79,6 +79,12 @@ const char* fe_version(void);
  * elements per node, out[2] = max nnpe, out[3] = max Gauss points. */
 void fe_limits(int32_t out[4]);
 
+/* Small read-back (sizes, status words) without the copy engine: a kernel stores nbytes (multiple of 4, <= 1 MiB)
+ * from device memory into PINNED host memory (cudaHostAlloc / cudaMallocHost: device-accessible under unified
+ * addressing).  Stream-ordered; the caller synchronises the stream (or an event) before reading the host copy.
+ * Unlike a cudaMemcpy it does not queue behind a large download that is in flight on another stream. */
+int fe_peek(const void* dev_src, void* pinned_host_dst, int64_t nbytes, void* stream);
+
 /* ---- T1-T4: tables (host) ------------------------------------------------------------------
  * Replaces funH4/funH9/funHrs4/funHrs9 (tools/interpFunctions.py:3-84) evaluated on the tensor
  * Gauss grid by quadH/quadHrs (elements.py:94-140), same expression order => bit-identical.
