@@ -38,6 +38,7 @@ PROTOTYPES = {
     "fe_adjacency_fill": (_i, [_i, _i64, _p, _p, _p, _p, _p, _p, _p]),
     "fe_csr_expand": (_i, [_i, _i64, _p, _p, _i, _p, _p, _p]),
     "fe_assemble": (_i, [_i, _i, _i64, _i64, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+    "fe_lattice_keys": (_i, [_i, _i64, _p, _p, _p, _p]),
     "fe_bbox": (_i, [_i64, _p, _p, _p, _p]),
     "fe_tile_form_count": (_i, [_i, _i64, _i64] + [_p] * 10),
     "fe_tile_form_sort": (_i, [_i, _i64] + [_p] * 8),

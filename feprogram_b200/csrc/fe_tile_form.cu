@@ -46,6 +46,40 @@ __global__ void __launch_bounds__(256) k_bbox(int64_t n, const double2* __restri
     }
 }
 
+// Lattice numbering: every Quad4 element is {b, b+1, b+W+1, b+W} for one W (what a row-major structured generator --
+// and gmsh's transfinite meshes -- produce).  Then (b mod W, b div W) are the element's lattice coordinates and the
+// Morton keys need no node coordinates: the whole tile plan can be built while the coordinates are still uploading.
+// status[0] |= 1 when some element does not fit the pattern (the caller then uses fe_morton_keys); status[1] = W.
+__device__ __forceinline__ unsigned spread15f(unsigned v) {
+    v &= 0x7fffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+__global__ void k_lattice_keys(int64_t nelem, const int4* __restrict__ conn, int32_t* __restrict__ keys,
+                               int32_t* __restrict__ status) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int4 c0 = __ldg(conn);
+    const int W = c0.w - c0.x;
+    if (e == 0) status[1] = W;
+    if (e >= nelem) return;
+    const int4 c = __ldg(conn + e);
+    bool ok = W >= 2 && c.y == c.x + 1 && c.z == c.x + W + 1 && c.w == c.x + W;
+    int ix = 0, iy = 0;
+    if (ok) {
+        iy = c.x / W;
+        ix = c.x - iy * W;
+        ok = ix < W - 1 && ix < 32768 && iy < 32768;
+    }
+    if (!ok) {
+        atomicOr(status, 1);
+        return;
+    }
+    keys[e] = (int32_t)(spread15f((unsigned)ix) | (spread15f((unsigned)iy) << 1));
+}
+
 __global__ void k_block_hist(int64_t nelem, const int32_t* __restrict__ keys, int shift, int32_t* __restrict__ hist) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nelem) atomicAdd(hist + (keys[e] >> shift), 1);
@@ -148,6 +182,22 @@ int fe_bbox(int64_t nnode, const double* coords, double* scratch, double* out, v
     FE_CHECK_LAUNCH("k_bbox");
     k_bbox<<<1, 256, 0, st>>>(0, nullptr, g, reinterpret_cast<const double4*>(scratch), reinterpret_cast<double4*>(out));
     FE_CHECK_LAUNCH("k_bbox");
+    return FE_OK;
+}
+
+// Morton keys from a lattice numbering (Quad4 only); see k_lattice_keys.  status: 2 int32 (zeroed here).
+int fe_lattice_keys(int elem_type, int64_t nelem, const int32_t* conn, int32_t* keys, int32_t* status, void* stream) {
+    using namespace fe;
+    FE_REQUIRE(status, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    FE_CUDA_TRY(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
+    if (elem_type != FE_QUAD4 || nelem <= 0) {      // no lattice form for this element type: say "does not fit"
+        FE_CUDA_TRY(cudaMemsetAsync(status, 1, 1, st));
+        return FE_OK;
+    }
+    FE_REQUIRE(conn && keys, "null pointer");
+    k_lattice_keys<<<grid_for(nelem, 256), 256, 0, st>>>(nelem, reinterpret_cast<const int4*>(conn), keys, status);
+    FE_CHECK_LAUNCH("k_lattice_keys");
     return FE_OK;
 }
 

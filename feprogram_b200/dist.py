@@ -247,8 +247,8 @@ class DistFemProblem:
         main.synchronize()                               # connectivity has arrived; coordinates still in flight
         t0 = time.perf_counter()
         self.pat = ops.symbolic(self.conn, local.nnode, elem_type, 2)
+        self.plan = ops.tile_plan(self.conn, self.coords, self.pat, coords_ready=lambda: main.wait_event(coords_ready))
         main.wait_event(coords_ready)
-        self.plan = ops.tile_plan(self.conn, self.coords, self.pat)
         torch.cuda.synchronize(self.dev)
         self.symbolic_s = time.perf_counter() - t0      # may include the tail of the coordinate upload
         self.vals = torch.empty(self.pat.nnz, dtype=torch.float64, device=self.dev)

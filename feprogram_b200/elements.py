@@ -404,8 +404,8 @@ class FemProblem:
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
             st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)     # overlaps the coordinate upload
             self._mark("symbolic done")
-            self._coords_ready()
-            st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"])
+            # the plan waits for the coordinate upload only if it needs coordinates (a lattice numbering does not)
+            st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"], coords_ready=self._coords_ready)
             self._mark("plan done")
         self._coords_ready()
         pat = st["pattern"]

@@ -327,6 +327,7 @@ class Pattern:
     row_ptr: Tensor
     col_idx: Tensor
     _max_deg: Optional[int] = None
+    lattice: Optional[Tuple[Tensor, Tensor]] = None    # (Morton keys from a lattice numbering, status) -- fe_lattice_keys
 
     @property
     def max_deg(self) -> int:
@@ -347,11 +348,20 @@ class Pattern:
 def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern:
     """CSR pattern + element->slot map for a mesh (conn int32 0-based on the device)."""
     nelem = conn.shape[0]
+    lattice = None
+    if elem_type == FE_QUAD4 and nelem > 0:
+        # is the numbering a row-major lattice?  Then the tile plan needs no coordinates (fe_lattice_keys); the answer
+        # is read back by tile_plan, after the symbolic kernels -- no extra synchronisation here
+        with torch.cuda.device(conn.device):
+            keys = torch.empty(nelem, dtype=torch.int32, device=conn.device)
+            lstat = torch.empty(2, dtype=torch.int32, device=conn.device)
+            _lib.check(_lib.lib().fe_lattice_keys(elem_type, nelem, _ptr(conn), _ptr(keys), _ptr(lstat), _stream(conn)))
+        lattice = (keys, lstat)
     eptr, einc = torch.ops.feprogram.incidence(conn, nnode, elem_type)
     nptr, nadj, epos = torch.ops.feprogram.adjacency(conn, eptr, einc, elem_type)
     nnz = ndof * ndof * nadj.numel()
     row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
-    return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx)
+    return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx, lattice=lattice)
 
 
 # --------------------------------------------------------------------------------------------
@@ -417,11 +427,14 @@ def _scan_into(src: Tensor, dst: Tensor, ws: Tensor):
     _lib.check(_lib.lib().fe_exclusive_scan_i32(_ptr(src), _ptr(dst), src.numel(), _ptr(ws), _stream(src)))
 
 
-def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, kernel: str = "auto") -> Optional[TilePlan]:
+def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, kernel: str = "auto",
+              coords_ready=None) -> Optional[TilePlan]:
     """Builds the tile plan; returns None when the mesh does not fit the tiled kernel's capacities
     (the caller then uses the row-tile kernel fe_assemble, which has none).  ``kernel``: "auto" = the
     warp-specialised kernel where it exists (Quad4 / Tri3) and its capacities hold, else the barrier-phased one;
-    "ws" / "phased" force one of them (tests compare the two bit for bit).
+    "ws" / "phased" force one of them (tests compare the two bit for bit).  ``coords_ready``: called before the
+    coordinates are first read (the facade passes the wait for their upload); a mesh whose numbering is a row-major
+    lattice (Pattern.lattice) gets its tiles from the numbering and never calls it.
 
     Elements are ordered along the Morton curve of a grid of one-element cells.  Strategy 1 ("blocks"): a
     tile = one aligned Z-block of 128 cells (exact 8x16 patches on structured meshes).  If that needs many
@@ -436,6 +449,14 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, k
     if te == 0 or pat.nelem == 0:
         return None
     ideal = (pat.nelem + te - 1) // te
+    if pat.lattice is not None:
+        flag, w = read_i32(pat.lattice[1])
+        if flag == 0 and w >= 2:
+            plan = _tile_plan(conn, coords, pat, True, 1.0, "blocks", kernel, lattice=(pat.lattice[0], w))
+            if plan is not None:
+                return plan
+    if coords_ready is not None:
+        coords_ready()
     best = _tile_plan(conn, coords, pat, True, 1.0, "blocks", kernel)
     if best is not None and best.ntiles <= 1.12 * ideal + 8:
         return best
@@ -452,7 +473,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, k
 
 
 def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_scale: float,
-               mode: str, kernel: str = "auto") -> Optional[TilePlan]:
+               mode: str, kernel: str = "auto", lattice=None) -> Optional[TilePlan]:
     L = _lib.lib()
     params = _lib.tile_params(pat.elem_type)
     if params["halo_cap"] == 0 or pat.nelem == 0 or pat.nnode == 0:
@@ -460,12 +481,18 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
     dev = conn.device
     te, hcap = params["tile_elems"], params["halo_cap"]
     nelem, nnode = pat.nelem, pat.nnode
+    mode_name = mode
     with torch.cuda.device(dev):
         st = _stream(conn)
         # ---- element order and tile boundaries ----
         idx = None
         formed = False
-        if morton:
+        keys = None
+        if lattice is not None:
+            keys, w_lat = lattice                        # keys from the numbering: one cell per element, no coordinates
+            imax_lat = max(w_lat - 1, (nnode + w_lat - 1) // w_lat)
+            mode_name = "lattice"
+        elif morton:
             # cell: holds ~ one element (Tri3: the two triangles of a quad).  Its AREA comes from the sampled mean
             # element area (distortion-proof: perturbing nodes changes extents, not the mean area), its aspect
             # ratio from the sampled mean extents.  All scalars come back in ONE device -> host transfer.
@@ -490,10 +517,13 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
             keys = torch.empty(nelem, dtype=torch.int32, device=dev)
             _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo_h[0], lo_h[1], cell[0],
                                         cell[1], _ptr(keys), st))
+            imax_lat = None
+        if keys is not None:
             if mode == "blocks":
                 # device-side formation: counting sort by Morton block + per-block sort (csrc/fe_tile_form.cu)
                 shift = te.bit_length() - 1
-                imax = max(min(32767, int(ext[0] / cell[0]) + 1), min(32767, int(ext[1] / cell[1]) + 1))
+                imax = (min(32767, imax_lat) if imax_lat is not None else
+                        max(min(32767, int(ext[0] / cell[0]) + 1), min(32767, int(ext[1] / cell[1]) + 1)))
                 nb = max(1, (1 << (2 * max(1, imax.bit_length()))) >> shift)
                 sb = nb + 1
                 wsf = torch.empty(max(1, L.fe_scan_workspace_bytes(sb)), dtype=torch.uint8, device=dev)
@@ -585,7 +615,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         max_work, max_blob, max_stage = int(tail[11]), int(tail[12]), int(tail[13])
         info = dict(max_nodes=max_nodes, max_items=max_items, max_halo=max_halo, max_cnt=max_cnt, max_work=max_work,
                     items=n_items, halo_elems=n_halo, work_items=n_work, morton=morton, cell_scale=cell_scale,
-                    mode=mode, ntiles=ntiles)
+                    mode=mode_name, ntiles=ntiles)
         if (max_nodes > params["max_nodes"] or max_items >= params["max_items"] - 1 or max_halo > hcap
                 or max_work > params["max_work"]):
             return None

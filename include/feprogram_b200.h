@@ -180,6 +180,11 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
 /* Bounding box of the mesh (anchors the Morton grid): out[0..3] <- {xmin, ymin, xmax, ymax} (DEVICE, 32-byte aligned);
  * scratch: 592 * 4 doubles (32-byte aligned). */
 int fe_bbox(int64_t nnode, const double* coords, double* scratch, double* out, void* stream);
+/* Morton keys WITHOUT coordinates, for lattice numberings: when every Quad4 element is {b, b+1, b+W+1, b+W} for one W
+ * (row-major structured meshes, whatever their geometry), (b mod W, b div W) are the element's lattice coordinates.
+ * status[0] != 0 afterwards: the mesh does not fit (use fe_morton_keys); status[1] = W.  The tile plan built from
+ * these keys needs no coordinates, so the facade builds it while the coordinates are still uploading. */
+int fe_lattice_keys(int elem_type, int64_t nelem, const int32_t* conn, int32_t* keys, int32_t* status, void* stream);
 /* Step 1 without a global sort (the default path of the Python facade): fe_tile_form_count buckets the elements
  * by Morton block (keys >> log2(TE); nb blocks) -- histogram, tiles per block, scans, scatter -- after which
  * tbase[nb] = ntiles and status[0] != 0 flags a block of more than 1024 elements (use another tiling);

@@ -812,3 +812,31 @@ def test_cfg2_pcg_runs_to_convergence(torch_cuda):
     b0 = (b - y)[free]
     assert float(r.norm() / b0.norm()) <= 1e-8
     assert torch.equal(x[~free], st["rhs"][~free])           # Dirichlet dofs hold their values exactly
+
+
+def test_lattice_numbering_plans_without_coordinates(torch_cuda):
+    """A row-major lattice numbering (structured meshes, whatever their geometry) gets its tiles from the numbering:
+    tile_plan never asks for the coordinates (the facade overlaps their upload with the plan), the values are those
+    of the row kernel bit for bit; any other numbering falls back to centroid keys and does ask."""
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    conn, coords, bc = mesh.structured_quad4(200, 150)
+    coords = mesh.perturb_interior(coords, 200, 150, 0.25, seed=5)
+    for shuffle in (False, True):
+        c, x = conn, coords
+        if shuffle:
+            c, x, _, _ = mesh.shuffle_numbering(conn, coords, bc, seed=9)
+        conn0, xy = dev_mesh(torch, c, x)
+        pat = ops.symbolic(conn0, x.shape[0], 4, 2)
+        asked = []
+        plan = ops.tile_plan(conn0, xy, pat, coords_ready=lambda: asked.append(1))
+        assert plan is not None
+        assert (plan.stats["mode"] == "lattice") == (not shuffle)
+        assert bool(asked) == shuffle
+        v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        ops.assemble_values(conn0, xy, pat, plan, v)
+        v_rows = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+        ops.assemble_values(conn0, xy, pat, None, v_rows)
+        assert torch.equal(v, v_rows)
+        if not shuffle:                      # exact 8 x 16 tiles: 200 x 150 elements -> 13 x 19 tiles
+            assert plan.ntiles == 13 * 19
