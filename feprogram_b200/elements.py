@@ -70,13 +70,13 @@ _SIDE_STREAMS = {}
 
 
 def side_streams(dev):
-    """(upload stream, boundary-data stream) of a device, shared by every problem on it.  PyTorch's caching
-    allocator keeps one pool per stream: a problem that made its own streams would strand the blocks it allocated
-    there (coordinates, rhs) when it dies, and every new problem would pay fresh cudaMallocs."""
+    """(upload stream, boundary-data stream, CSR-expansion stream) of a device, shared by every problem on it.
+    PyTorch's caching allocator keeps one pool per stream: a problem that made its own streams would strand the
+    blocks it allocated there (coordinates, rhs) when it dies, and every new problem would pay fresh cudaMallocs."""
     import torch
     key = (dev.type, dev.index)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
     return _SIDE_STREAMS[key]
 
 
@@ -402,7 +402,9 @@ class FemProblem:
         if early_bc:
             self._bc_early(st)
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
-            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2)     # overlaps the coordinate upload
+            # overlaps the coordinate upload; the scipy-compatible row_ptr / col_idx (which neither the tile plan nor the
+            # numeric kernel reads) are expanded on a side stream, off the critical path
+            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2, csr_stream=side_streams(st["conn"].device)[2])
             self._mark("symbolic done")
             # the plan waits for the coordinate upload only if it needs coordinates (a lattice numbering does not)
             st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"], coords_ready=self._coords_ready)
@@ -414,6 +416,7 @@ class FemProblem:
             st["vals"] = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
         ops.assemble_values(st["conn_s"], st["coords_s"], pat, st["plan"], st["vals"], self._operator)
         self._mark("numeric done")
+        pat.csr_ready()                   # everything after assemble() may use row_ptr / col_idx on this stream
         st.pop("vals_ref", None)
         # boundary conditions: rhs + Dirichlet mask (matrix itself stays un-modified on the device)
         if early_bc:

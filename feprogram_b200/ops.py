@@ -328,6 +328,13 @@ class Pattern:
     col_idx: Tensor
     _max_deg: Optional[int] = None
     lattice: Optional[Tuple[Tensor, Tensor]] = None    # (Morton keys from a lattice numbering, status) -- fe_lattice_keys
+    csr_event: Optional[object] = None                 # set when row_ptr / col_idx were expanded on a side stream
+
+    def csr_ready(self) -> None:
+        """Orders the current stream after the expansion of row_ptr / col_idx (no-op unless they came from a side stream)."""
+        ev, self.csr_event = self.csr_event, None
+        if ev is not None:
+            torch.cuda.current_stream(self.row_ptr.device).wait_event(ev)
 
     @property
     def max_deg(self) -> int:
@@ -345,8 +352,10 @@ class Pattern:
         return self.ndof * self.nnode
 
 
-def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern:
-    """CSR pattern + element->slot map for a mesh (conn int32 0-based on the device)."""
+def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2, csr_stream=None) -> Pattern:
+    """CSR pattern + element->slot map for a mesh (conn int32 0-based on the device).  ``csr_stream``: expand the
+    scipy-compatible row_ptr / col_idx on that stream (concurrently with whatever follows on the current one); the
+    caller orders later users with ``Pattern.csr_ready()``."""
     nelem = conn.shape[0]
     lattice = None
     if elem_type == FE_QUAD4 and nelem > 0:
@@ -360,8 +369,21 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2) -> Pattern
     eptr, einc = torch.ops.feprogram.incidence(conn, nnode, elem_type)
     nptr, nadj, epos = torch.ops.feprogram.adjacency(conn, eptr, einc, elem_type)
     nnz = ndof * ndof * nadj.numel()
-    row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
-    return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx, lattice=lattice)
+    ev = None
+    if csr_stream is None:
+        row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
+    else:
+        main = torch.cuda.current_stream(conn.device)
+        csr_stream.wait_event(main.record_event())
+        with torch.cuda.stream(csr_stream):
+            row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
+            ev = csr_stream.record_event()
+        for t in (row_ptr, col_idx):
+            t.record_stream(main)
+        for t in (nptr, nadj):
+            t.record_stream(csr_stream)
+    return Pattern(elem_type, ndof, nnode, nelem, eptr, einc, nptr, nadj, epos, row_ptr, col_idx, lattice=lattice,
+                   csr_event=ev)
 
 
 # --------------------------------------------------------------------------------------------
