@@ -56,8 +56,30 @@ template <int N> struct WsLayout {
 #define FE_WS_DW 2
 #endif
     static constexpr int kPW = FE_WS_PW, kCW = FE_WS_CW, kDW = FE_WS_DW;   // producer / consumer / DMA warps
-    static constexpr int kThreads = 32 * (kPW + kCW + kDW);
-    static constexpr int kBatch = 5;                              // neighbour positions a consumer thread keeps in flight
+    // Register budget.  The element arithmetic needs ~125 registers, the consumers ~96, the DMA warps ~40: with one
+    // allocation for all, 16 warps of 128 registers fill the file.  FE_WS_REGSPLIT launches warp GROUPS of four
+    // (producers, consumers, DMA) with kRegLaunch registers each and lets every group set its own count
+    // (setmaxnreg), which fits 8 + 8 + 4 warps.
+#ifndef FE_WS_REGSPLIT
+#define FE_WS_REGSPLIT 0
+#endif
+    static constexpr bool kRegSplit = FE_WS_REGSPLIT != 0;
+    static constexpr int kDWPad = kRegSplit ? ((kDW + 3) & ~3) : kDW;             // DMA warps incl. idle ones of their group
+    static constexpr int kThreads = 32 * (kPW + kCW + kDWPad);
+    static constexpr int kRegP = 128, kRegC = 88, kRegD = 40;
+#ifndef FE_WS_BATCH
+#define FE_WS_BATCH 5
+#endif
+#ifndef FE_WS_PARTS
+#define FE_WS_PARTS 2
+#endif
+#ifndef FE_WS_REC_SLOTS
+#define FE_WS_REC_SLOTS 2
+#endif
+    static constexpr int kBatch = FE_WS_BATCH;                    // neighbour positions a consumer thread keeps in flight
+    static constexpr int kParts = FE_WS_PARTS;                    // slices of a node's neighbour list (one consumer thread each)
+    static constexpr int kRecSlots = FE_WS_REC_SLOTS;             // record ring: blobs are requested this many tiles ahead
+    static constexpr int kXYDepth = 2;                            // coordinate gathers in flight per producer warp (tasks)
     // record source field: (slab offset in doubles) << 1 | transposed; two of them per record
     static constexpr int kSrcBits = 14;
     static constexpr unsigned kSrcMask = (1u << kSrcBits) - 1u;
@@ -66,16 +88,20 @@ template <int N> struct WsLayout {
     static constexpr int kBarBytes = 128;
     static constexpr int kBlobCap = 10 * 1024;                    // bytes of one record slot
     static constexpr int kStageCap = 42 * 1024;                   // bytes of one staging slot (CSR values of a tile)
-    static constexpr int kCoordBytes = N * 32 * 16;               // per producer warp: next task's node coordinates
+    static constexpr int kCoordBytes = N * 32 * 16;               // per producer warp and task in flight: node coordinates
     static constexpr size_t kSlabBytes = (size_t)kSlabDoubles * sizeof(double);
-    static constexpr size_t kSmem = kBarBytes + 2 * kSlabBytes + 2 * (size_t)kBlobCap + 2 * (size_t)kStageCap +
-                                    (size_t)kPW * kCoordBytes;
+    static constexpr int kProdBytes = kXYDepth * kCoordBytes + 4 * 32 * 16;      // + ring of four connectivity rows per lane
+    static constexpr size_t kSmem = kBarBytes + 2 * kSlabBytes + (size_t)kRecSlots * kBlobCap + 2 * (size_t)kStageCap +
+                                    (size_t)kPW * kProdBytes;
     static_assert((kRows + 1) * kSS < (1 << (kSrcBits - 1)), "slab offset does not fit a source field");
     static_assert(kDW == 1 || kDW == 2, "one DMA warp, or two that take alternate tiles (= one staging slot each)");
+    static_assert(kRecSlots >= 2 && kRecSlots <= 4, "record ring: 2..4 slots");
     // A producer warp's consecutive tasks must lie at most two tiles apart: the parity waits on the 2-slot rings can
     // tell "one phase behind" from "current" but not "two phases behind".
     static_assert(kPW <= 2 * kChunks, "too many producer warps for the 2-slot slab ring");
-    static_assert(kPW + kCW + kDW <= 16, "512 threads x 128 registers fill the register file");
+    static_assert(kRegSplit ? (kPW % 4 == 0 && kCW % 4 == 0 && 32 * (kPW * kRegP + kCW * kRegC + kDWPad * kRegD) <= 65536)
+                            : (kPW + kCW + kDW <= 16),
+                  "register file: 512 threads x 128 registers, or warp groups with their own counts");
     static_assert(kSmem <= 232448, "shared memory of one CTA");
 };
 
@@ -125,10 +151,12 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     double* slab0 = reinterpret_cast<double*>(smem + T::kBarBytes);
     unsigned char* rec0 = smem + T::kBarBytes + 2 * T::kSlabBytes;
-    unsigned char* stage0 = rec0 + 2 * T::kBlobCap;
+    unsigned char* stage0 = rec0 + T::kRecSlots * T::kBlobCap;
     unsigned char* coord0 = stage0 + 2 * T::kStageCap;
-    // barrier ids (x2 slots each)
-    enum { B_SLAB_FULL = 0, B_SLAB_EMPTY = 2, B_REC_FULL = 4, B_REC_EMPTY = 6, B_STAGED = 8, B_STAGE_FREE = 10 };
+    // barrier ids (x2 slots each; the record ring has kRecSlots <= 4)
+    enum { B_SLAB_FULL = 0, B_SLAB_EMPTY = 2, B_STAGED = 4, B_STAGE_FREE = 6, B_REC_FULL = 8, B_REC_EMPTY = 12 };
+    static_assert(8 * (B_REC_EMPTY + 4) <= T::kBarBytes, "barrier block");
+    constexpr int R = T::kRecSlots;
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int id, int slot) { return bar0 + 8u * (uint32_t)(id + slot); };
 
@@ -139,78 +167,116 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(B_SLAB_FULL, s), T::kChunks);
             mbar_init(bar(B_SLAB_EMPTY, s), T::kCW);
-            mbar_init(bar(B_REC_FULL, s), 1);
-            mbar_init(bar(B_REC_EMPTY, s), T::kCW);
             mbar_init(bar(B_STAGED, s), T::kCW);
             mbar_init(bar(B_STAGE_FREE, s), 1);
+        }
+        for (int s = 0; s < R; ++s) {
+            mbar_init(bar(B_REC_FULL, s), 1);
+            mbar_init(bar(B_REC_EMPTY, s), T::kCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 6) slab0[(tid / 3) * T::kSlabDoubles + T::kZeroRow * SS + (tid % 3)] = 0.0;   // zero block of both slots
     __syncthreads();
 
+    if constexpr (T::kRegSplit) {           // warp-group-uniform: every warp of a group of four runs the same branch
+        if (warp < T::kPW) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T::kRegP));
+        else if (warp < T::kPW + T::kCW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T::kRegC));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T::kRegD));
+        if (warp >= T::kPW + T::kCW + T::kDW) return;      // padding warps of the DMA group
+    }
     if (warp < T::kPW) {
         // ================================ producers ================================
-        const long long total = (long long)K * T::kChunks;
-        auto row_addr = [&](long long j) -> const int32_t* {
-            const int k = (int)(j / T::kChunks), c = (int)(j - (long long)k * T::kChunks);
+        // Task j of this CTA = (tile j / kChunks, chunk j % kChunks); K * kChunks < 2^31 (K <= ntiles / gridDim.x).
+        const int total = K * T::kChunks;
+        auto row_addr = [&](int j) -> const int32_t* {
+            if (j >= total) return nullptr;
+            const int k = j / T::kChunks, c = j - k * T::kChunks;
             const int row = c * 32 + lane;
             if (row >= T::kRows) return nullptr;
             const long long t = (long long)blockIdx.x + (long long)k * G;
             return tconn + (t * T::kRows + row) * N;
         };
-        auto load_row = [&](const int32_t* p, int (&tg)[N]) {
-            tg[0] = -1;
-            if (!p) return;
+        // Software pipeline per warp.  DRAM latency under the output stream is about two task times, and nothing an
+        // iteration loads may be read by the same iteration (that would make every task one DRAM latency long -- also
+        // through a register-to-register rotation of prefetched rows).  So everything travels with cp.async through
+        // this warp's staging blocks, one commit group per task: while task i is evaluated, the connectivity rows of
+        // tasks i+3, i+4 and the node coordinates of tasks i+1, i+2 are in flight; wait_group 1 at the top of task i
+        // guarantees the group of task i-2 (= coordinates of task i, row of task i+2).
+        unsigned char* wbuf = coord0 + warp * T::kProdBytes;
+        double2* cbuf = reinterpret_cast<double2*>(wbuf);                          // [2][a][lane]
+        int4* rbuf = reinterpret_cast<int4*>(wbuf + 2 * T::kCoordBytes);           // [4][lane]
+        auto request_row = [&](int j, int ring) {
+            const int32_t* p = row_addr(j);
+            int4* dst = rbuf + (ring & 3) * 32 + lane;
 #if defined(FE_WS_WHATIF) && (FE_WS_WHATIF & 8)     // developer timing build: producers load nothing
-            return;
+            p = nullptr;
 #endif
-            if constexpr (N == 4) {
-                asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(tg[0]), "=r"(tg[1]), "=r"(tg[2]), "=r"(tg[3]) : "l"(p));
+            if (!p) {
+                *dst = make_int4(-1, -1, -1, -1);
+            } else if constexpr (N == 4) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(p) : "memory");
             } else {
 #pragma unroll
-                for (int a = 0; a < N; ++a) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(tg[a]) : "l"(p + a));
+                for (int a = 0; a < N; ++a)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst) + 4u * a), "l"(p + a) : "memory");
             }
         };
-        // Software pipeline per warp: connectivity rows are loaded two tasks ahead (registers), the node coordinates
-        // of the NEXT task are gathered with cp.async into this warp's staging block while the current element
-        // matrices are evaluated -- no global-memory latency sits on a task's critical path.
-        double2* cbuf = reinterpret_cast<double2*>(coord0 + warp * T::kCoordBytes);    // [a][lane]
-        auto request_xy = [&](const int (&t)[N]) {
-            if (t[0] >= 0) {
+        auto request_xy = [&](const int4 t, int buf) {
+            const int tg[4] = {t.x, t.y, t.z, t.w};
+            if (t.x >= 0) {
 #pragma unroll
                 for (int a = 0; a < N; ++a)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(cbuf + a * 32 + lane)),
-                                 "l"(coords + t[a])
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(cbuf + (buf * N + a) * 32 + lane)),
+                                 "l"(coords + tg[a])
                                  : "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        int tg[N], tgn[N], tgn2[N];
-        long long j = warp;
-        tgn[0] = -1;
-        if (j < total) load_row(row_addr(j), tg);
-        if (j + T::kPW < total) load_row(row_addr(j + T::kPW), tgn);
-        if (j < total) request_xy(tg);
-        for (; j < total; j += T::kPW) {
-            const int k = (int)(j / T::kChunks), c = (int)(j - (long long)k * T::kChunks);
+        auto direct_row = [&](int j) {          // prologue only: the first two rows are needed at once
+            int4 t = make_int4(-1, -1, -1, -1);
+            const int32_t* p = row_addr(j);
+#if defined(FE_WS_WHATIF) && (FE_WS_WHATIF & 8)
+            p = nullptr;
+#endif
+            if (p) {
+                t.x = __ldg(p), t.y = __ldg(p + 1), t.z = __ldg(p + 2);
+                if constexpr (N == 4) t.w = __ldg(p + 3);
+            }
+            return t;
+        };
+        bool act0, act1;                    // tasks i, i+1 have an element in this lane
+        int j = warp;
+        {
+            const int4 r0 = direct_row(j), r1 = direct_row(j + T::kPW);
+            request_row(j + 2 * T::kPW, 2);
+            request_row(j + 3 * T::kPW, 3);
+            request_xy(r0, 0);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            request_xy(r1, 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            act0 = r0.x >= 0;
+            act1 = r1.x >= 0;
+        }
+        int k = 0, c = warp;                // tile / chunk of task j (kPW <= 2 * kChunks)
+        while (c >= T::kChunks) c -= T::kChunks, ++k;
+        for (int it = 0; j < total; j += T::kPW, ++it) {
             const int row = c * 32 + lane;
-            const int slot = k & 1;
-            tgn2[0] = -1;
-            if (j + 2 * T::kPW < total) load_row(row_addr(j + 2 * T::kPW), tgn2);
-            const bool active = row < T::kRows && tg[0] >= 0;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");       // this task's coordinates have landed
+            const int slot = k & 1, buf = it & 1;
+            request_row(j + 4 * T::kPW, it);                            // ring slot (it + 4) & 3
+            const bool active = act0;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");        // coordinates of this task, row of task i+2
             double x[N], y[N];
             if (active) {
 #pragma unroll
                 for (int a = 0; a < N; ++a) {
-                    const double2 p = cbuf[a * 32 + lane];
+                    const double2 p = cbuf[(buf * N + a) * 32 + lane];
                     x[a] = p.x;
                     y[a] = p.y;
                 }
             }
-            request_xy(tgn);                                            // in flight during this task's arithmetic
+            const int4 ahead = rbuf[((it + 2) & 3) * 32 + lane];
+            request_xy(ahead, buf);                                     // task i+2: in flight for two task times
+            asm volatile("cp.async.commit_group;" ::: "memory");
             double ke[3 * T::kBlocks];
             if (active) {
 #if defined(FE_WS_WHATIF) && (FE_WS_WHATIF & 1)     // developer timing build: no element arithmetic (wrong results)
@@ -228,37 +294,43 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_SLAB_FULL, slot));
-#pragma unroll
-            for (int a = 0; a < N; ++a) {
-                tg[a] = tgn[a];
-                tgn[a] = tgn2[a];
-            }
+            act0 = act1;
+            act1 = ahead.x >= 0;
+            c += T::kPW;
+            while (c >= T::kChunks) c -= T::kChunks, ++k;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp < T::kPW + T::kCW) {
         // ================================ consumers ================================
         const int cw = warp - T::kPW;
+        int rslot = 0;
+        uint32_t rpar = 0;
         for (int k = 0; k < K; ++k) {
             const int slot = k & 1;
             const uint32_t par = (k >> 1) & 1;
-            const unsigned char* rec = rec0 + slot * T::kBlobCap;
+            const unsigned char* rec = rec0 + rslot * T::kBlobCap;
             const double* slab = slab0 + slot * T::kSlabDoubles;
             double* stage = reinterpret_cast<double*>(stage0 + slot * T::kStageCap);
-            mbar_wait(bar(B_REC_FULL, slot), par);
+            mbar_wait(bar(B_REC_FULL, rslot), rpar);
             const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
             const int nn = (int)hdr.x, nnp = (int)hdr.y;
             const uint2* node = reinterpret_cast<const uint2*>(rec + 16);
             const uint32_t* recs = reinterpret_cast<const uint32_t*>(rec + 16 + 8 * nnp);
             const uint16_t* locs = reinterpret_cast<const uint16_t*>(rec + hdr.w);
+            // Work units = (group of 32 owned nodes, one of kParts slices of the neighbour lists), dealt round-robin over
+            // the consumer warps.  Halves: a Quad4 lattice tile has 5 groups = 10 units on 8 warps.  Thirds would fill
+            // both rounds (15 units) but were measured slower (1.39 against 1.30 ms): every unit re-reads the node
+            // descriptors and the kernel is bound by the instructions all warps issue, not by its longest warp.
+            constexpr int parts = T::kParts;
+            const int groups = nnp >> 5;
             mbar_wait(bar(B_SLAB_FULL, slot), par);
             // The staging slot is still being read by the bulk stores of tile k - 2 for most of this tile's time.  So a
             // thread first sums everything it owns into registers (slab reads + adds: the long part) and only then waits
             // for the slot: the slot is busy for the few store instructions, not for the whole consumer pass.
             bool slot_free = false;
-            const int wph = nnp >> 5;                                   // warps per half of the neighbour lists
-            for (int wt = cw; wt < 2 * wph; wt += T::kCW) {
-                const int half = wt >= wph ? 1 : 0;
-                const int ln = (wt - half * wph) * 32 + lane;
+            for (int u = cw; u < groups * parts; u += T::kCW) {
+                const int g = u / parts, part = u - g * parts;
+                const int ln = g * 32 + lane;
 #if defined(FE_WS_WHATIF) && (FE_WS_WHATIF & 2)     // developer timing build: consumers only hand the buffers on
                 const bool live = false;
 #else
@@ -266,8 +338,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
 #endif
                 const uint2 nd = live ? node[ln] : make_uint2(0u, 0u);
                 const int deg = (nd.x >> 16) & 127, self = (nd.x >> 23) & 127;
-                const int pm = (deg + 1) >> 1;
-                const int p0 = half ? pm : 0, p1 = half ? deg : pm;
+                const int p0 = (deg * part) / parts, p1 = (deg * (part + 1)) / parts;
                 // A node's row 2n+1 lies 16 * deg bytes behind its row 2n: for odd degrees (9 on a Quad4 lattice, 7 on a
                 // Tri3 lattice) the two rows fall into different 16-byte bank groups, so letting every other group of
                 // four lanes write row 2n+1 first makes each quarter-warp store hit eight distinct groups.
@@ -326,41 +397,43 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(bar(B_SLAB_EMPTY, slot));
-                mbar_arrive(bar(B_REC_EMPTY, slot));
+                mbar_arrive(bar(B_REC_EMPTY, rslot));
                 mbar_arrive(bar(B_STAGED, slot));
             }
+            if (++rslot == R) rslot = 0, rpar ^= 1u;
         }
     } else {
-        // ================================ DMA warp ================================
+        // ================================ DMA warps ================================
         auto tile_of = [&](int k) { return (long long)blockIdx.x + (long long)k * G; };
+        auto desc_of = [&](int k) { return k < K ? __ldg(tdesc + tile_of(k)) : make_int4(0, 0, 0, 0); };
         auto issue_rec = [&](int k, const int4 d) {     // lane 0 only
-            const int slot = k & 1;
-            mbar_arrive_expect_tx(bar(B_REC_FULL, slot), (uint32_t)d.y);
-            bulk_load(smem_u32(rec0 + slot * T::kBlobCap), blobs + 16ll * (long long)(unsigned)d.x, (uint32_t)d.y,
-                      bar(B_REC_FULL, slot));
+            const int rs = k % R;
+            mbar_arrive_expect_tx(bar(B_REC_FULL, rs), (uint32_t)d.y);
+            bulk_load(smem_u32(rec0 + rs * T::kBlobCap), blobs + 16ll * (long long)(unsigned)d.x, (uint32_t)d.y,
+                      bar(B_REC_FULL, rs));
         };
         // One DMA warp walks all tiles; two DMA warps take the even / odd tiles (= one staging slot each), so the
         // bulk stores of tile k + 1 are issued while those of tile k are still draining.  What limits the output stream
         // is how many staged bytes are in flight (measured, stores alone: 1.39 ms with one tile, 1.02 ms with two).
+        // Record blobs are requested kRecSlots tiles ahead: the slot of tile k is refilled with tile k + kRecSlots as
+        // soon as the consumers have released it.
         const int dw = warp - (T::kPW + T::kCW);
-        int4 d_cur = make_int4(0, 0, 0, 0), d_one = d_cur, d_two = d_cur;
-        if (dw < K) d_cur = __ldg(tdesc + tile_of(dw));
-        if (T::kDW == 1 && K > 1) d_one = __ldg(tdesc + tile_of(1));
-        if (lane == 0) {
-            if (dw < K) issue_rec(dw, d_cur);
-            if (T::kDW == 1 && K > 1) issue_rec(1, d_one);
+        for (int k = dw; k < R && k < K; k += T::kDW) {
+            const int4 d = desc_of(k);
+            if (lane == 0) issue_rec(k, d);
         }
+        int4 d_cur = desc_of(dw), d_ahead = desc_of(dw + R);
         for (int k = dw; k < K; k += T::kDW) {
             const int slot = k & 1;
             const uint32_t par = (k >> 1) & 1;
-            if (k + 2 < K) d_two = __ldg(tdesc + tile_of(k + 2));
+            const int4 dn_cur = desc_of(k + T::kDW), dn_ahead = desc_of(k + T::kDW + R);   // next iteration's descriptors
             const int r0 = d_cur.z, nr = d_cur.w;
             int4 run = make_int4(0, 0, 0, 0);
             if (lane < nr) run = __ldg(truns + r0 + lane);               // in flight while the consumers finish the tile
             mbar_wait(bar(B_STAGED, slot), par);
-            if (lane == 0 && k + 2 < K) {
-                mbar_wait(bar(B_REC_EMPTY, slot), par);                   // (already complete: consumers arrive on it first)
-                issue_rec(k + 2, d_two);
+            if (lane == 0 && k + R < K) {
+                mbar_wait(bar(B_REC_EMPTY, k % R), (uint32_t)((k / R) & 1));   // (already complete: consumers arrive on it first)
+                issue_rec(k + R, d_ahead);
             }
             const uint32_t sbase = smem_u32(stage0 + slot * T::kStageCap);
             // one bulk store per run: fewer, larger copies drain faster (~35 ns per copy + 34 ps per byte measured)
@@ -378,12 +451,8 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_STAGE_FREE, slot));
-            if (T::kDW == 2) {
-                d_cur = d_two;
-            } else {
-                d_cur = d_one;
-                d_one = d_two;
-            }
+            d_cur = dn_cur;
+            d_ahead = dn_ahead;
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
