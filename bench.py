@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the FEM hot path on B200 (contract: one JSON line on stdout from rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg5] [--n NX]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg5|poisson] [--n NX]
 
 Workload of the main line (BASELINE.json configs[1], "cfg2"): Quad4 structured mesh NX x NX (default 4096 ->
 16.8 M elements), 2-dof reference operator, fp64.  For N > 1 every rank owns one NX x NX element block of an
@@ -24,7 +24,8 @@ over peer memory against SciPy's direct solve of the assembled system), `e2e_ful
 assemble -> solve -> U on the host at 512 x 512, beside the CPU port's assemble + spsolve).
 
 `--config cfg3` (Quad9 2048^2, stiffness + mass) and `--config cfg5` (Tri3 5000^2 x 2, perturbed, shuffled
-numbering) emit the same line for BASELINE configs[2] / configs[4] on one GPU.
+numbering) emit the same line for BASELINE configs[2] / configs[4] on one GPU; `--config poisson` (= `--operator
+poisson`) for the scalar one-dof-per-node variant of cfg2 (FE_OP_POISSON = K[0::2, 0::2] of the reference operator).
 """
 from __future__ import annotations
 
@@ -205,7 +206,7 @@ def bc_dofs(bc):
                                       2 * (np.array(sorted(s), dtype=np.int64) - 1) + 1])) for s in (bc[0], bc[3])]
 
 
-def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=False, ops_list=(0,)):
+def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=False, ops_list=(0,), ndof=2):
     """Resident-input timing of one mesh on one GPU: symbolic phase, numeric assembly per operator, SpMV, PCG.
     Returns a dict; used for cfg3 / cfg4 / cfg5 and the strong-scaling single-GPU reference."""
     from feprogram_b200 import mesh, ops
@@ -227,7 +228,7 @@ def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=
         renumbered = True
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    pat = ops.symbolic(conn, nnode, kind, 2)
+    pat = ops.symbolic(conn, nnode, kind, ndof)
     plan = ops.tile_plan(conn, coords, pat)
     torch.cuda.synchronize()
     sym_s = time.perf_counter() - t0
@@ -241,12 +242,23 @@ def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=
         for _ in range(3):
             ops.assemble_values(conn, coords, pat, plan, vals, op)
         ms = _timed(torch, lambda: ops.assemble_values(conn, coords, pat, plan, vals, op), reps)
-        out["assembly"][{0: "stiffness", 1: "weighted", 2: "mass"}[op]] = {
+        out["assembly"][{0: "stiffness", 1: "weighted", 2: "mass", 3: "stiffness"}[op]] = {
             "ms_per_launch": ms, "elements_per_s": conn.shape[0] / ms * 1e3, "gbs": asm_bytes / ms / 1e6}
-    ops.assemble_values(conn, coords, pat, plan, vals, 0)
+    ops.assemble_values(conn, coords, pat, plan, vals, ops_list[0] if ndof == 1 else 0)
+    if plan is not None and ndof == 1:      # the timed kernel against the independent row kernel, bit for bit, at this size
+        v_r = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device=dev)
+        ops.assemble_values(conn, coords, pat, None, v_r, ops_list[0])
+        out["parity_checked"] = {"kernel": out["kernel"], "against": "k_assemble_rows (independent kernel), NaN-prefilled output",
+                                 "tiled_eq_rows": bool(torch.equal(vals, v_r)), "entries": int(pat.nnz)}
+        del v_r
     if cg_iters > 0:
         d_dofs, n_dofs = bc_dofs(bc)
-        if renumbered:
+        if ndof == 1:
+            d_dofs, n_dofs = np.unique(d_dofs // 2), np.unique(n_dofs // 2)
+        if renumbered and ndof == 1:
+            d_dofs = perm[torch.from_numpy(d_dofs).to(dev)].cpu().numpy()
+            n_dofs = perm[torch.from_numpy(n_dofs).to(dev)].cpu().numpy()
+        elif renumbered:
             d_dofs = (2 * perm[torch.from_numpy(d_dofs // 2).to(dev)] + torch.from_numpy(d_dofs % 2).to(dev)).cpu().numpy()
             n_dofs = (2 * perm[torch.from_numpy(n_dofs // 2).to(dev)] + torch.from_numpy(n_dofs % 2).to(dev)).cpu().numpy()
         rhs = torch.empty(pat.nrows, dtype=torch.float64, device=dev)
@@ -258,12 +270,13 @@ def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=
             torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, vals, x, y, None)
         ms_spmv = _timed(torch, lambda: torch.ops.feprogram.spmv(pat.row_ptr, pat.col_idx, vals, x, y, None), max(reps, 5))
         sol = torch.empty(pat.nrows, dtype=torch.float64, device=dev)
-        torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, dirmask, sol, 0.0, 0.0, 10, 10, pat.nptr, pat.nadj)
+        nodal = (pat.nptr, pat.nadj) if ndof == 2 else (None, None)
+        torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, dirmask, sol, 0.0, 0.0, 10, 10, *nodal)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, vals, rhs, dirmask, sol, 0.0, 0.0, cg_iters, cg_iters,
-                                       pat.nptr, pat.nadj)
+                                       *nodal)
         b.record()
         torch.cuda.synchronize()
         spmv_bytes = 12 * pat.nnz + 20 * pat.nrows
@@ -634,7 +647,8 @@ def strong_cfg4(args, torch, dist, rank, world, dev, part):
 
 
 def run_other_config(args, torch, dev, hbm_peak, peak_src, real_stdout):
-    """--config cfg3 (Quad9 2048^2, stiffness + mass) / cfg5 (Tri3 5000^2 x 2, perturbed, shuffled tags): one GPU."""
+    """--config cfg3 (Quad9 2048^2, stiffness + mass) / cfg5 (Tri3 5000^2 x 2, perturbed, shuffled tags) / poisson (the
+    scalar one-dof-per-node variant of cfg2, SURVEY §8d: 104 algorithmic bytes per element): one GPU."""
     K, W = args.steps, max(3, args.warmup)
     clk = ClockSampler(dev.index or 0)
     clk.__enter__()
@@ -642,6 +656,10 @@ def run_other_config(args, torch, dev, hbm_peak, peak_src, real_stdout):
         n = args.n if args.n != 4096 else 2048
         r = single_gpu_case(torch, dev, 9, n, K, args.cg_iters, ops_list=(0, 2))
         workload = "quad9_%dx%d_2dof_stiffness_and_mass" % (n, n)
+    elif args.config == "poisson":
+        n = args.n
+        r = single_gpu_case(torch, dev, 4, n, K, args.cg_iters, ops_list=(3,), ndof=1)
+        workload = "quad4_%dx%d_1dof_scalar_poisson_operator" % (n, n)
     else:
         n = args.n if args.n != 4096 else 5000
         r = single_gpu_case(torch, dev, 3, n, K, args.cg_iters, perturb=True, shuffle=True)
@@ -658,6 +676,7 @@ def run_other_config(args, torch, dev, hbm_peak, peak_src, real_stdout):
                          "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"], "ms_per_launch": a["ms_per_launch"]},
             "assembly": {k: dict(v, frac=v["gbs"] / hbm_peak) for k, v in r["assembly"].items()},
             "cg": dict(r.get("cg", {}), spmv_frac=r["cg"]["spmv_gbs"] / hbm_peak) if "cg" in r else None,
+            "parity_checked": r.get("parity_checked"),
             "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": clk.summary()}
     real_stdout.write(json.dumps(line) + "\n")
     real_stdout.flush()
@@ -669,8 +688,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5"],
-                    help="cfg2 = the main line (Quad4 4096^2); cfg3 = Quad9 2048^2 stiffness + mass; cfg5 = Tri3 shuffled (1 GPU)")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "poisson"],
+                    help="cfg2 = the main line (Quad4 4096^2); cfg3 = Quad9 2048^2 stiffness + mass; cfg5 = Tri3 shuffled; "
+                         "poisson = cfg2's scalar one-dof variant (all three on 1 GPU)")
+    ap.add_argument("--operator", default=None, choices=["reference", "poisson"], help="alias: --operator poisson = --config poisson")
     ap.add_argument("--n", "--nx", dest="n", type=int, default=4096, help="elements per side of each rank's block")
     ap.add_argument("--cg-iters", type=int, default=200)
     ap.add_argument("--cpu-sample", type=int, default=1024, help="side of the CPU-baseline sample block")
@@ -685,6 +706,8 @@ def main():
     args = ap.parse_args()
     if args.kernel == "tiled":
         args.kernel = "auto"
+    if args.operator == "poisson":
+        args.config = "poisson"
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libfeprogram_b200.so")
 
 FE_OK = 0
 FE_QUAD4, FE_QUAD9, FE_TRI3 = 4, 9, 3
-FE_OP_REFERENCE, FE_OP_WEIGHTED = 0, 1
+FE_OP_REFERENCE, FE_OP_WEIGHTED, FE_OP_MASS, FE_OP_POISSON = 0, 1, 2, 3
 FE_BC_ROWS, FE_BC_SYMMETRIC = 0, 1
 
 _p = C.c_void_p

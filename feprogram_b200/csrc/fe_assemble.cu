@@ -7,12 +7,12 @@ namespace fe {
 // K1: dense Ke per element, one thread per (element, local node a) writing rows 2a and 2a+1.
 // Parity/debug entry (FemProblem.getKe); the assembly path below never stores Ke.
 // ------------------------------------------------------------------------------------------------
-template <int ET, bool MASS>
+template <int ET, bool MASS, bool SCALAR = false>
 __global__ void __launch_bounds__(128) k_element_matrices(int64_t nelem, const int32_t* __restrict__ conn,
                                                           const double2* __restrict__ coords,
                                                           double* __restrict__ Ke, int weighted) {
     using E = Elem<ET>;
-    constexpr int N = E::NNPE, M = 2 * N;
+    constexpr int N = E::NNPE, M = SCALAR ? N : 2 * N;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nelem * N) return;
     const int64_t e = idx / N;
@@ -21,6 +21,12 @@ __global__ void __launch_bounds__(128) k_element_matrices(int64_t nelem, const i
     double x[N], y[N], L[N], P[N], Q[N];
     load_element<ET>(conn, coords, e, t, x, y);
     element_row_pair<ET, MASS>(x, y, a, weighted != 0, L, P, Q);
+    if constexpr (SCALAR) {         // FE_OP_POISSON: Ke[a][b] = L = Ke2[2a][2b]
+        double* r = Ke + e * (M * M) + a * M;
+#pragma unroll
+        for (int b = 0; b < N; ++b) r[b] = L[b];
+        return;
+    }
     double* r0 = Ke + e * (M * M) + (2 * a) * M;
     double* r1 = r0 + M;
 #pragma unroll
@@ -38,9 +44,10 @@ __global__ void __launch_bounds__(128) k_element_matrices(int64_t nelem, const i
 // evaluates the node's row pair of each element matrix in registers and accumulates into the
 // node's private row block in shared memory -- a fixed summation order without atomics, so the
 // result is bit-identical from run to run.  The tile is then written once, fully coalesced.
-// Shared layout mirrors the global layout: value (row 2n+c, p, d) at 4*(nptr[n]-base) + 2*c*deg + 2p + d.
+// Shared layout mirrors the global layout: value (row 2n+c, p, d) at 4*(nptr[n]-base) + 2*c*deg + 2p + d
+// (SCALAR = FE_OP_POISSON, one dof per node: value (row n, p) at nptr[n]-base + p, the L entries only).
 // ------------------------------------------------------------------------------------------------
-template <int ET, bool MASS>
+template <int ET, bool MASS, bool SCALAR = false>
 __global__ void __launch_bounds__(128) k_assemble_rows(int64_t nnode, int R, const int32_t* __restrict__ eptr,
                                                        const int32_t* __restrict__ einc,
                                                        const uint8_t* __restrict__ epos,
@@ -53,8 +60,9 @@ __global__ void __launch_bounds__(128) k_assemble_rows(int64_t nnode, int R, con
     extern __shared__ double acc[];
     const int64_t n0 = (int64_t)blockIdx.x * R;
     const int64_t n1 = (n0 + R < nnode) ? n0 + R : nnode;
+    constexpr int kPerNz = SCALAR ? 1 : 4;
     const int base = nptr[n0];
-    const int len = 4 * (nptr[n1] - base);
+    const int len = kPerNz * (nptr[n1] - base);
     for (int i = threadIdx.x; i < len; i += blockDim.x) acc[i] = 0.0;
     __syncthreads();
 
@@ -62,7 +70,7 @@ __global__ void __launch_bounds__(128) k_assemble_rows(int64_t nnode, int R, con
     if ((int)threadIdx.x < R && n < n1) {
         const int p0 = nptr[n];
         const int deg = nptr[n + 1] - p0;
-        double* row0 = acc + 4 * (p0 - base);
+        double* row0 = acc + kPerNz * (p0 - base);
         double* row1 = row0 + 2 * deg;
         const int k1 = eptr[n + 1];
         for (int k = eptr[n]; k < k1; ++k) {
@@ -76,16 +84,20 @@ __global__ void __launch_bounds__(128) k_assemble_rows(int64_t nnode, int R, con
             const uint8_t* ps = epos + (int64_t)k * N;
 #pragma unroll
             for (int b = 0; b < N; ++b) {
-                const int pp = 2 * (int)__ldg(ps + b);
-                row0[pp] += L[b];
-                row0[pp + 1] += P[b];
-                row1[pp] += Q[b];
-                row1[pp + 1] += L[b];
+                if constexpr (SCALAR) {
+                    row0[(int)__ldg(ps + b)] += L[b];
+                } else {
+                    const int pp = 2 * (int)__ldg(ps + b);
+                    row0[pp] += L[b];
+                    row0[pp + 1] += P[b];
+                    row1[pp] += Q[b];
+                    row1[pp + 1] += L[b];
+                }
             }
         }
     }
     __syncthreads();
-    double* out = vals + 4 * (int64_t)base;
+    double* out = vals + kPerNz * (int64_t)base;
     for (int i = threadIdx.x; i < len; i += blockDim.x) out[i] = acc[i];
 }
 
@@ -96,12 +108,12 @@ __global__ void k_tags_to_conn(int64_t n, const T* __restrict__ tags, int32_t* _
     if (i < n) conn[i] = (int32_t)(tags[i] - 1);
 }
 
-template <int ET, bool MASS>
+template <int ET, bool MASS, bool SCALAR = false>
 static int launch_assemble_rows(int64_t nnode, const int32_t* conn, const double* coords, const int32_t* eptr,
                                 const int32_t* einc, const uint8_t* epos, const int32_t* nptr, int32_t max_deg,
                                 double* vals, int weighted, cudaStream_t stream) {
     // rows per CTA: as many as fit a 48 KB tile at the worst-case row-block size, warp multiple
-    const size_t per_node = (size_t)max_deg * 4 * sizeof(double);
+    const size_t per_node = (size_t)max_deg * (SCALAR ? 1 : 4) * sizeof(double);
     int R = (int)((48 * 1024) / per_node);
     R = R >= 128 ? 128 : (R / 32) * 32;
     if (R < 32) {
@@ -109,8 +121,8 @@ static int launch_assemble_rows(int64_t nnode, const int32_t* conn, const double
         return FE_ERR_CAPACITY;
     }
     const size_t smem = (size_t)R * per_node;
-    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_rows<ET, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_assemble_rows<ET, MASS><<<grid_for(nnode, R), R, smem, stream>>>(nnode, R, eptr, einc, epos, nptr, conn,
+    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_rows<ET, MASS, SCALAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_assemble_rows<ET, MASS, SCALAR><<<grid_for(nnode, R), R, smem, stream>>>(nnode, R, eptr, einc, epos, nptr, conn,
                                                                  reinterpret_cast<const double2*>(coords), vals,
                                                                  weighted);
     FE_CHECK_LAUNCH("k_assemble_rows");
@@ -140,7 +152,7 @@ int fe_element_matrices(int elem_type, int op, int64_t nelem, const int32_t* con
                         void* stream) {
     using namespace fe;
     FE_REQUIRE(nelem >= 0, "negative size");
-    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS && op != FE_OP_POISSON) {
         set_error("fe_element_matrices: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
@@ -155,6 +167,8 @@ int fe_element_matrices(int elem_type, int op, int64_t nelem, const int32_t* con
     case ET:                                                                                                    \
         if (op == FE_OP_MASS)                                                                                   \
             k_element_matrices<ET, true><<<grid_for(nelem * N, 128), 128, 0, st>>>(nelem, conn, xy, Ke, 1);     \
+        else if (op == FE_OP_POISSON)                                                                           \
+            k_element_matrices<ET, false, true><<<grid_for(nelem * N, 128), 128, 0, st>>>(nelem, conn, xy, Ke, 0); \
         else                                                                                                    \
             k_element_matrices<ET, false><<<grid_for(nelem * N, 128), 128, 0, st>>>(nelem, conn, xy, Ke, w);    \
         break;
@@ -178,7 +192,7 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
     FE_REQUIRE(nelem >= 0 && nnode >= 0 && conn && coords && eptr && einc && epos && nptr && vals,
                "null pointer or negative size");
     FE_REQUIRE(max_deg > 0, "max_deg must be positive");
-    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS && op != FE_OP_POISSON) {
         set_error("fe_assemble: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
@@ -189,6 +203,8 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
     const int w = op == FE_OP_WEIGHTED;
 #define FE_ROWS_CASE(ET)                                                                                          \
     case ET:                                                                                                      \
+        if (op == FE_OP_POISSON)                                                                                  \
+            return launch_assemble_rows<ET, false, true>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, 0, st); \
         return op == FE_OP_MASS                                                                                   \
                    ? launch_assemble_rows<ET, true>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, 1, st) \
                    : launch_assemble_rows<ET, false>(nnode, conn, coords, eptr, einc, epos, nptr, max_deg, vals, w, st);

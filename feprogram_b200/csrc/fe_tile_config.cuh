@@ -41,7 +41,9 @@ template <int N> __host__ __device__ constexpr int tri_index(int lo, int hi) { r
 
 // Full upper-triangular block element matrix: block (lo,hi) = [L, P, Q] at 3*tri_index(lo,hi); diagonal blocks
 // store Q = P.  Same pair arithmetic as element_row_pair (fe_element.cuh), so every kernel produces the same bits.
-template <int ET, bool MASS>
+// SCALAR (FE_OP_POISSON): only the L entries are evaluated (same expressions, hence the same bits as the L
+// entries of the full blocks); P and Q stay zero.
+template <int ET, bool MASS, bool SCALAR = false>
 __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], const double (&y)[Elem<ET>::NNPE],
                                             bool weighted,
                                             double (&out)[3 * (Elem<ET>::NNPE * (Elem<ET>::NNPE + 1) / 2)]) {
@@ -62,13 +64,17 @@ __device__ __forceinline__ void element_tri(const double (&x)[Elem<ET>::NNPE], c
             for (int b = a; b < N; ++b) {
                 const int o = 3 * tri_index<N>(a, b);
                 out[o] = fma(sx[a], ax[b], fma(sy[a], ay[b], out[o]));
-                out[o + 1] = fma(sy[a], ax[b], out[o + 1]);
-                if (b > a) out[o + 2] = fma(sx[a], ay[b], out[o + 2]);
+                if constexpr (!SCALAR) {
+                    out[o + 1] = fma(sy[a], ax[b], out[o + 1]);
+                    if (b > a) out[o + 2] = fma(sx[a], ay[b], out[o + 2]);
+                }
             }
         }
     }
+    if constexpr (!SCALAR) {
 #pragma unroll
-    for (int a = 0; a < N; ++a) out[3 * tri_index<N>(a, a) + 2] = out[3 * tri_index<N>(a, a) + 1];
+        for (int a = 0; a < N; ++a) out[3 * tri_index<N>(a, a) + 2] = out[3 * tri_index<N>(a, a) + 1];
+    }
 }
 
 }  // namespace fe

@@ -513,7 +513,10 @@ __device__ __forceinline__ void q9_block_rows(const double* __restrict__ Jrow, d
 // after barrier A of the previous tile (in flight during phase 2).  Chosen per element type / tile regularity
 // from measurements (cfg2 Quad4: 0 -> 1.70 ms, 1 -> 1.80 ms; perturbed Quad4 in pack mode: 1.90 / 1.78 ms;
 // Tri3, whose phase 1 is too short to hide a load: 3 -> 1.39 ms against 1.75 ms).
-template <int ET, bool MASS, int PF>
+// SCALAR = FE_OP_POISSON: one dof per node, value (row n, neighbour position p) at nptr[n] + p = the L entry of the
+// node pair's 2 x 2 block (K[0::2, 0::2] of the reference operator).  Same plan, same slab layout; phase 1 evaluates
+// and stores only the L entries (Quad4 / Tri3), phase 2 reads only those.
+template <int ET, bool MASS, int PF, bool SCALAR = false>
 __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayout<Elem<ET>::NNPE>::kCtas) k_assemble_tiled(
     int64_t ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords,
     const int4* __restrict__ tdesc, const int2* __restrict__ tnode, const uint16_t* __restrict__ tloc,
@@ -621,9 +624,10 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 double* dst = slab + rowid * SS;
                 if constexpr (T::kParts == 1) {
                     double ke[3 * T::kBlocks];
-                    element_tri<ET, MASS>(x, y, weighted != 0, ke);
+                    element_tri<ET, MASS, SCALAR>(x, y, weighted != 0, ke);
 #pragma unroll
-                    for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+                    for (int i = 0; i < 3 * T::kBlocks; ++i)
+                        if (!SCALAR || i % 3 == 0) dst[i] = ke[i];
                 } else if (part == 0) {          // warp-uniform: kRowThreads is a multiple of 32
                     element_tri_part<ET, MASS, 0>(x, y, weighted != 0, dst);
                 } else {
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 }
                 double* dst = slab + row * SS;
                 if constexpr (T::kParts == 1) {
-                    element_tri<ET, MASS>(xq, yq, weighted != 0, ke);
+                    element_tri<ET, MASS, SCALAR>(xq, yq, weighted != 0, ke);
 #pragma unroll
                     for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
                 } else if (part == 0) {
@@ -730,13 +734,18 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 const unsigned s0 = rec & 0x1FFFu, s1 = (rec >> 13) & 0x1FFFu;
                 const double* b0 = slab + (s0 >> (T::kTriBits + 1)) * SS + 3 * ((s0 >> 1) & T::kTriMask);
                 const double* b1 = slab + (s1 >> (T::kTriBits + 1)) * SS + 3 * ((s1 >> 1) & T::kTriMask);   // zeros if absent
-                const int f0 = s0 & 1, f1 = s1 & 1;            // transposed block: P and Q trade places
                 const double L = b0[0] + b1[0];
-                const double P = b0[1 + f0] + b1[1 + f1];
-                const double Q = b0[2 - f0] + b1[2 - f1];
-                double* out = vals + 4 * (int64_t)nd.x + 2 * p;
-                __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
-                __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(Q, L));
+                if constexpr (SCALAR) {
+                    (void)deg;
+                    __stcs(vals + (int64_t)nd.x + p, L);
+                } else {
+                    const int f0 = s0 & 1, f1 = s1 & 1;            // transposed block: P and Q trade places
+                    const double P = b0[1 + f0] + b1[1 + f1];
+                    const double Q = b0[2 - f0] + b1[2 - f1];
+                    double* out = vals + 4 * (int64_t)nd.x + 2 * p;
+                    __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
+                    __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(Q, L));
+                }
             }
             // ---- phase 2b: diagonal blocks, one thread per owned node ---------------------------------
             for (int ln = tid; ln < nn; ln += kTileThreads) {
@@ -749,11 +758,16 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                     const int a = loc & 15;
                     const double* b = slab + (loc >> 4) * SS + 3 * (a * N - ((a * (a - 1)) >> 1));
                     L += b[0];
-                    P += b[1];
+                    if constexpr (!SCALAR) P += b[1];
                 }
-                double* out = vals + 4 * (int64_t)nd.x + 2 * self;
-                __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
-                __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(P, L));
+                if constexpr (SCALAR) {
+                    (void)deg;
+                    __stcs(vals + (int64_t)nd.x + self, L);
+                } else {
+                    double* out = vals + 4 * (int64_t)nd.x + 2 * self;
+                    __stcs(reinterpret_cast<double2*>(out), make_double2(L, P));
+                    __stcs(reinterpret_cast<double2*>(out + 2 * deg), make_double2(P, L));
+                }
             }
         }
         __syncthreads();   // slab and this record buffer are free again
@@ -768,7 +782,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-template <int ET, bool MASS, int PF>
+template <int ET, bool MASS, int PF, bool SCALAR = false>
 static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coords, const int32_t* tdesc,
                         const int2* tnode, const uint16_t* tloc, const uint32_t* twork, const uint32_t* tchunk,
                         double* vals, int weighted, cudaStream_t st) {
@@ -778,8 +792,9 @@ static int launch_tiled(int64_t ntiles, const int32_t* tconn, const double* coor
     FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int64_t grid = (int64_t)sms * T::kCtas;
     if (grid > ntiles) grid = ntiles;
-    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET, MASS, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
-    k_assemble_tiled<ET, MASS, PF><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
+    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_tiled<ET, MASS, PF, SCALAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)T::kSmem));
+    k_assemble_tiled<ET, MASS, PF, SCALAR><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
         ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc), tnode, tloc,
         twork, tchunk, vals, weighted);
     FE_CHECK_LAUNCH("k_assemble_tiled");
@@ -928,7 +943,7 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
     FE_REQUIRE(ntiles >= 0, "negative size");
     const bool irregular = (op & FE_HINT_IRREGULAR_TILES) != 0;   // scheduling hint only: same results
     op &= ~FE_HINT_IRREGULAR_TILES;
-    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS && op != FE_OP_POISSON) {
         set_error("fe_assemble_tiled: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
@@ -940,6 +955,14 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
     const int w = op == FE_OP_WEIGHTED;
     const int2* nd = static_cast<const int2*>(tnode);
 #define FE_TILED_ARGS ntiles, tconn, coords, tdesc, nd, tloc, twork, tchunk, vals
+    if (op == FE_OP_POISSON) {      // one dof per node: vals[nptr[n] + p]
+        switch (elem_type) {
+            case FE_QUAD4: return launch_tiled<FE_QUAD4, false, 0, true>(FE_TILED_ARGS, 0, st);
+            case FE_TRI3: return launch_tiled<FE_TRI3, false, 3, true>(FE_TILED_ARGS, 0, st);
+            case FE_QUAD9: return launch_tiled<FE_QUAD9, false, 0, true>(FE_TILED_ARGS, 0, st);
+            default: break;
+        }
+    }
     switch (elem_type) {
         case FE_QUAD4:
             if (op == FE_OP_MASS) return launch_tiled<FE_QUAD4, true, 0>(FE_TILED_ARGS, 1, st);

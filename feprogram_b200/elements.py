@@ -87,7 +87,9 @@ class FemProblem:
 
         Keyword-only extensions: ``device`` (torch device, default current CUDA device) and
         ``operator`` ("reference" = un-weighted B^T B detJ as elements.py:162, "weighted" = times gpWei,
-        "mass" = sum_g gpWei H^T H detJ from the reference's H / gpWei tables, on the same CSR pattern);
+        "mass" = sum_g gpWei H^T H detJ from the reference's H / gpWei tables, on the same CSR pattern,
+        "poisson" = the scalar operator with ONE dof per node, sum_g grad N_a . grad N_b detJ = ``K[0::2, 0::2]`` of
+        the reference matrix, bit for bit: dof = node, bottom side Dirichlet, left side nodal load);
         ``renumber``: solve on a Morton-renumbered copy of the mesh (None = only when the input numbering has no
         locality, e.g. BASELINE cfg5's shuffled tags).  Everything visible -- dof numbering, ``K``, ``brhs``,
         the solution -- stays in the reference's numbering; ``K`` is then assembled on demand in that numbering.
@@ -103,7 +105,8 @@ class FemProblem:
         self._device = device
         self._trace = [] if trace else None
         self._renumber = renumber
-        self._operator = {"reference": 0, "weighted": 1, "mass": 2}[operator]
+        self._operator = {"reference": 0, "weighted": 1, "mass": 2, "poisson": 3}[operator]
+        self.ndof = 1 if operator == "poisson" else 2         # dofs per node (the reference: 2, elements.py:148)
         self._dev = None        # device-side state, created on first assemble()
         self._K_host = None
         self._brhs_host = None
@@ -175,6 +178,8 @@ class FemProblem:
         the symmetrically eliminated matrix."""
         if mode not in ("reference", "corrected"):
             raise ValueError("mode must be 'reference' or 'corrected'")
+        if mode == "corrected" and self.ndof != 2:
+            raise ValueError("mode='corrected' is defined for the two-dof operators")
         self._bc_mode = mode
         self._traction = (float(traction[0]), float(traction[1]))
         self._load_edges = None
@@ -184,12 +189,15 @@ class FemProblem:
         dofSetDir = [[0, 1], [], [], []]
         dofSetNeu = [[], [], [], [0, 1]]
         dirDof, neuDof = set(), set()
+        nd = self.ndof
         for enu, nodes in enumerate(bcNodesList):
             tags = np.fromiter((int(t) for t in nodes), dtype=np.int64)
             for k in dofSetDir[enu]:
-                dirDof.update(((tags - 1) * 2 + k).tolist())
+                if k < nd:
+                    dirDof.update(((tags - 1) * nd + k).tolist())
             for m in dofSetNeu[enu]:
-                neuDof.update(((tags - 1) * 2 + m).tolist())
+                if m < nd:
+                    neuDof.update(((tags - 1) * nd + m).tolist())
         if verbose:
             print(dirDof)
             print(neuDof)
@@ -200,7 +208,7 @@ class FemProblem:
 
     # --------------------------------------------------------------- small helpers (elements.py:143-163)
     def getRowData(self, elemNodesTag):
-        dofs = [(int(x) - 1) * 2 + y for x in elemNodesTag for y in (0, 1)]
+        dofs = [(int(x) - 1) * self.ndof + y for x in elemNodesTag for y in range(self.ndof)]
         m = len(dofs)
         return [d for d in dofs for _ in range(m)], dofs * m
 
@@ -218,7 +226,7 @@ class FemProblem:
         return Vec[ind].reshape((2, 4))
 
     def initialVector(self):
-        return np.ones(self.nnode * 2)
+        return np.ones(self.nnode * self.ndof)
 
     def assembleMatrix(self, vec):
         return 0
@@ -228,8 +236,8 @@ class FemProblem:
         import torch
         st = self._state()
         u = torch.from_numpy(np.ascontiguousarray(np.asarray(U, dtype=np.float64).reshape(-1))).to(st["coords"].device)
-        if u.numel() != 2 * self.nnode:
-            raise ValueError("U must hold 2 values per node")
+        if self.ndof != 2 or u.numel() != 2 * self.nnode:
+            raise ValueError("U must hold 2 values per node (post-processing is defined for the two-dof operators)")
         return st, u
 
     def gaussGradients(self, U):
@@ -340,7 +348,8 @@ class FemProblem:
             d = torch.as_tensor(np.asarray(dofs, dtype=np.int64), device=st["conn"].device)
         if st["perm"] is None:
             return d
-        return 2 * st["perm"][d // 2] + d % 2
+        nd = self.ndof
+        return nd * st["perm"][d // nd] + d % nd
 
     # ---------------------------------------------------------------------- assemble (elements.py:165-200)
     def _bc_early(self, st):
@@ -352,7 +361,7 @@ class FemProblem:
         dev = st["conn"].device
         main = torch.cuda.current_stream(dev)
         side = side_streams(dev)[1]
-        nrows = 2 * self.nnode
+        nrows = self.ndof * self.nnode
         if "rhs" in st:
             side.wait_stream(main)           # re-assembly: a solve on the main stream may still be reading rhs / dirmask
         if "dof_event" in st:
@@ -378,7 +387,7 @@ class FemProblem:
             self._mark("rhs on host", side)
 
     def rhs_host(self):
-        """The assembled right-hand side as a host array (2 * nnode,), reference dof numbering."""
+        """The assembled right-hand side as a host array (ndof * nnode,), reference dof numbering."""
         st = self._dev
         if st is None or not self._assembled:
             raise RuntimeError("assemble() must be called first")
@@ -388,7 +397,7 @@ class FemProblem:
             return st["rhs_host"].numpy()
         rhs = st["rhs"]
         if st["perm"] is not None:
-            rhs = rhs.view(-1, 2)[st["perm"]].reshape(-1)
+            rhs = rhs.view(-1, self.ndof)[st["perm"]].reshape(-1)
         return rhs.cpu().numpy()
 
     def assemble(self):
@@ -404,7 +413,8 @@ class FemProblem:
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
             # overlaps the coordinate upload; the scipy-compatible row_ptr / col_idx (which neither the tile plan nor the
             # numeric kernel reads) are expanded on a side stream, off the critical path
-            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, 2, csr_stream=side_streams(st["conn"].device)[2])
+            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, self.ndof,
+                                         csr_stream=side_streams(st["conn"].device)[2])
             self._mark("symbolic done")
             # the plan waits for the coordinate upload only if it needs coordinates (a lattice numbering does not)
             st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"], coords_ready=self._coords_ready)
@@ -452,13 +462,13 @@ class FemProblem:
             return st["pattern"], st["vals"], st["rhs"], st["dirmask"]
         if "pattern_ref" not in st:
             et = _ELEM_CODES[self.elem.elemType]
-            st["pattern_ref"] = ops.symbolic(st["conn"], self.nnode, et, 2)
+            st["pattern_ref"] = ops.symbolic(st["conn"], self.nnode, et, self.ndof)
             st["plan_ref"] = ops.tile_plan(st["conn"], st["coords"], st["pattern_ref"])
         pat = st["pattern_ref"]
         if "vals_ref" not in st:
             st["vals_ref"] = torch.empty(pat.nnz, dtype=torch.float64, device=st["conn"].device)
             ops.assemble_values(st["conn"], st["coords"], pat, st["plan_ref"], st["vals_ref"], self._operator)
-        back = lambda v: v.view(-1, 2)[st["perm"]].reshape(-1).contiguous()  # noqa: E731
+        back = lambda v: v.view(-1, self.ndof)[st["perm"]].reshape(-1).contiguous()  # noqa: E731
         return pat, st["vals_ref"], back(st["rhs"]), back(st["dirmask"])
 
     def csr_prebc(self):
@@ -470,7 +480,7 @@ class FemProblem:
     @property
     def K(self):
         if not self._assembled:
-            n = self.nnode * 2
+            n = self.nnode * self.ndof
             return sp.lil_matrix((n, n))
         if self._K_host is None:
             import torch
@@ -498,7 +508,7 @@ class FemProblem:
     @property
     def brhs(self):
         if not self._assembled:
-            return sp.lil_matrix((self.nnode * 2, 1))
+            return sp.lil_matrix((self.nnode * self.ndof, 1))
         if self._brhs_host is None:
             self._brhs_host = sp.csc_matrix(np.array(self.rhs_host())[:, None])
         return self._brhs_host
@@ -516,8 +526,9 @@ class FemProblem:
         pat = st["pattern"]
         x = torch.empty(pat.nrows, dtype=torch.float64, device=st["vals"].device)
         maxit = self.maxit if self.maxit is not None else 20 * pat.nrows + 100
+        nodal = (pat.nptr, pat.nadj) if self.ndof == 2 else (None, None)     # node-block SpMV: 2 x 2 blocks only
         info = torch.ops.feprogram.pcg(pat.row_ptr, pat.col_idx, st["vals"], st["rhs"], st["dirmask"], x,
-                                       self.rtol, 0.0, maxit, 50, pat.nptr, pat.nadj)
+                                       self.rtol, 0.0, maxit, 50, *nodal)
         stop = float(info[3])
         self.solver_info = dict(iterations=int(info[0]), relres=float(info[1]), r0=float(info[2]),
                                 converged=stop == 1.0, breakdown=stop < 0.0)
@@ -534,5 +545,5 @@ class FemProblem:
                           % (self.solver_info["iterations"], self.solver_info["relres"], self.rtol), RuntimeWarning)
         st["x"] = x
         if st["perm"] is not None:
-            x = x.view(-1, 2)[st["perm"]].reshape(-1)          # back to the reference's dof numbering
+            x = x.view(-1, self.ndof)[st["perm"]].reshape(-1)  # back to the reference's dof numbering
         return x.cpu().numpy()

@@ -19,7 +19,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FE_BC_ROWS, FE_BC_SYMMETRIC, FE_OP_REFERENCE, FE_OP_WEIGHTED, FE_QUAD4, FE_QUAD9, FE_TRI3  # noqa: F401
+from ._lib import (FE_BC_ROWS, FE_BC_SYMMETRIC, FE_OP_MASS, FE_OP_POISSON, FE_OP_REFERENCE, FE_OP_WEIGHTED,  # noqa: F401
+                   FE_QUAD4, FE_QUAD9, FE_TRI3)
 
 Tensor = torch.Tensor
 
@@ -103,13 +104,14 @@ def tags_to_conn(tags: Tensor) -> Tensor:
 
 @torch.library.custom_op("feprogram::element_matrices", mutates_args=())
 def element_matrices(conn: Tensor, coords: Tensor, elem_type: int, op: int) -> Tensor:
-    """Dense Ke per element, (nelem, 2*nnpe, 2*nnpe) fp64.  fe_element_matrices."""
+    """Dense Ke per element, (nelem, ndof*nnpe, ndof*nnpe) fp64 (ndof = 1 for FE_OP_POISSON, else 2).  fe_element_matrices."""
     _chk_dev(conn, coords)
     _want(conn, torch.int32, "conn")
     _want(coords, torch.float64, "coords")
     nelem, nnpe = conn.shape
+    m = nnpe if op == FE_OP_POISSON else 2 * nnpe
     with torch.cuda.device(conn.device):
-        ke = torch.empty((nelem, 2 * nnpe, 2 * nnpe), dtype=torch.float64, device=conn.device)
+        ke = torch.empty((nelem, m, m), dtype=torch.float64, device=conn.device)
         _lib.check(_lib.lib().fe_element_matrices(elem_type, op, nelem, _ptr(conn), _ptr(coords), _ptr(ke),
                                                   _stream(conn)))
     return ke
@@ -647,7 +649,9 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         wsp = _lib.tile_ws_params(pat.elem_type)
         # "auto": the warp-specialised kernel where it is the faster one (measured: Quad4 1.39 ms against 1.90 ms on cfg2;
         # Tri3's tiles are too small for its per-tile hand-offs: 1.51 ms against 1.25 ms), else the barrier-phased kernel
-        want_ws = kernel == "ws" or (kernel == "auto" and pat.elem_type == FE_QUAD4)
+        # (one-dof patterns: the bulk stores of the warp-specialised kernel need 16-byte aligned row runs, which 8-byte
+        # values do not give -> barrier-phased kernel)
+        want_ws = (kernel == "ws" or (kernel == "auto" and pat.elem_type == FE_QUAD4)) and pat.ndof == 2
         if want_ws and wsp["blob_cap"] > 0:
             # ---- warp-specialised kernel: per-tile record blobs + runs of contiguous CSR rows ----
             wstats = torch.zeros(8, dtype=torch.int32, device=dev)
@@ -717,7 +721,12 @@ def assemble_ws(tconn: Tensor, coords: Tensor, ntiles: int, tdesc: Tensor, blobs
 
 
 def assemble_values(conn: Tensor, coords: Tensor, pat: Pattern, plan: Optional[TilePlan], vals: Tensor, op: int = 0):
-    """Numeric assembly with whichever kernel the plan allows."""
+    """Numeric assembly with whichever kernel the plan allows.  A one-dof pattern (``symbolic(..., ndof=1)``) takes
+    FE_OP_POISSON and nothing else; two-dof patterns take the other operators."""
+    if (pat.ndof == 1) != (op == FE_OP_POISSON):
+        raise ValueError("operator %d does not match a pattern with %d dof per node" % (op, pat.ndof))
+    if vals.numel() != pat.nnz:
+        raise ValueError("vals must hold %d entries" % pat.nnz)
     if plan is not None and plan.warp_specialised:
         torch.ops.feprogram.assemble_ws(plan.tconn, coords, plan.ntiles, plan.tdesc, plan.blobs, plan.truns, vals,
                                         pat.elem_type, op)

@@ -68,6 +68,13 @@ extern "C" {
 #define FE_OP_MASS 2      /* Me[2a+c,2b+c] = sum_g gpWei[g] H_g[a] H_g[b] detJ_g from the reference's own H and
                              gpWei tables (elements.py:94-113, built but unused there; extension); entries
                              across the two components are stored zeros, so K and M share one pattern */
+#define FE_OP_POISSON 3   /* scalar operator, ONE dof per node: Ks[a,b] = sum_g (Dx_a Dx_b + Dy_a Dy_b) detJ_g, i.e.
+                             exactly the even/even sub-block K[0::2, 0::2] of the reference operator
+                             (elements.py:15-23, 153-163; BASELINE's "2D Poisson" wording; extension).  Its CSR
+                             pattern is the node-level pattern itself (row_ptr = nptr, col_idx = nadj) and
+                             vals[nptr[n] + p] is the value of (row n, column nadj[nptr[n] + p]).  Accepted by
+                             fe_element_matrices (Ke is nnpe x nnpe), fe_assemble and fe_assemble_tiled; the
+                             values are bit-identical to the corresponding entries of FE_OP_REFERENCE. */
 
 /* Copies the thread-local message of the last failing call into buf (NUL-terminated). */
 void fe_last_error(char* buf, size_t len);

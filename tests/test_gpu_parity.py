@@ -840,3 +840,91 @@ def test_lattice_numbering_plans_without_coordinates(torch_cuda):
         assert torch.equal(v, v_rows)
         if not shuffle:                      # exact 8 x 16 tiles: 200 x 150 elements -> 13 x 19 tiles
             assert plan.ntiles == 13 * 19
+
+
+# ---- scalar Poisson extension (FE_OP_POISSON, one dof per node; SURVEY "facts at a glance", §8d) -------------------
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_poisson_operator_is_the_even_block_of_the_reference_matrix(torch_cuda, golden, name):
+    """Pattern = node adjacency, bit-exact; values = K[0::2, 0::2] of the reference's frozen matrix (<= 1e-12) and of
+    this library's own two-dof assembly (bit for bit); row kernel == tiled kernel bit for bit; Ke = Ke2[0::2, 0::2]."""
+    torch = torch_cuda
+    from feprogram_b200 import ops
+    z = golden(name)
+    conn0, xy = dev_mesh(torch, z["conn"], z["coords"])
+    nnode, et = z["coords"].shape[0], conn0.shape[1]
+    n2 = len(z["k0_indptr"]) - 1
+    Kref = sp.csr_matrix((z["k0_data"], z["k0_indices"], z["k0_indptr"]), shape=(n2, n2))
+    Ks_ref = orc.poisson_submatrix(Kref)
+    pat = ops.symbolic(conn0, nnode, et, 1)
+    assert pat.row_ptr.dtype == torch.int32 and pat.nnz == Ks_ref.nnz
+    assert np.array_equal(pat.row_ptr.cpu().numpy(), Ks_ref.indptr)
+    assert np.array_equal(pat.col_idx.cpu().numpy(), Ks_ref.indices)
+    v_rows = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v_rows, ops.FE_OP_POISSON)
+    assert rel_max(v_rows.cpu().numpy(), Ks_ref.data) < VAL_TOL
+    # the same bits as the L entries of the two-dof assembly
+    pat2 = ops.symbolic(conn0, nnode, et, 2)
+    v2 = torch.empty(pat2.nnz, dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat2, None, v2, ops.FE_OP_REFERENCE)
+    K2 = sp.csr_matrix((v2.cpu().numpy(), pat2.col_idx.cpu().numpy(), pat2.row_ptr.cpu().numpy()), shape=(n2, n2))
+    assert np.array_equal(orc.poisson_submatrix(K2).data, v_rows.cpu().numpy())
+    plan = ops.tile_plan(conn0, xy, pat)
+    assert plan is not None and not plan.warp_specialised
+    v_tiled = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, plan, v_tiled, ops.FE_OP_POISSON)
+    assert torch.equal(v_tiled, v_rows)
+    ke1 = torch.ops.feprogram.element_matrices(conn0[:8].contiguous(), xy, et, ops.FE_OP_POISSON).cpu().numpy()
+    ke2 = torch.ops.feprogram.element_matrices(conn0[:8].contiguous(), xy, et, ops.FE_OP_REFERENCE).cpu().numpy()
+    assert np.array_equal(ke1, ke2[:, 0::2, 0::2])
+    with pytest.raises(ValueError):
+        ops.assemble_values(conn0, xy, pat, None, v_rows, ops.FE_OP_REFERENCE)
+
+
+@pytest.mark.parametrize("kind,n,perturb,shuffle", [(4, 96, True, False), (4, 200, True, True), (9, 40, True, False),
+                                                     (3, 120, True, True)])
+def test_poisson_tiled_equals_rows_on_larger_meshes(torch_cuda, kind, n, perturb, shuffle):
+    torch = torch_cuda
+    from feprogram_b200 import mesh, ops
+    gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
+    conn, coords, bc = gen(n)
+    mx = 2 * n if kind == 9 else n
+    if perturb:
+        coords = mesh.perturb_interior(coords, mx, mx, 0.2, seed=3)
+    if shuffle:
+        conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, seed=4)
+    conn0, xy = dev_mesh(torch, conn, coords)
+    pat = ops.symbolic(conn0, coords.shape[0], kind, 1)
+    v_rows = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v_rows, ops.FE_OP_POISSON)
+    plan = ops.tile_plan(conn0, xy, pat)
+    assert plan is not None
+    v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, plan, v, ops.FE_OP_POISSON)
+    assert torch.equal(v, v_rows)
+    # constants are in the null space of the scalar stiffness; the matrix is symmetric bit for bit
+    K = sp.csr_matrix((v.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
+                      shape=(pat.nrows, pat.nrows))
+    assert np.abs(K @ np.ones(pat.nrows)).max() < 1e-11 * np.abs(K.data).max()
+    assert abs(K - K.T).max() == 0.0
+    Ks = orc.poisson_submatrix(orc.assemble_csr(conn - 1, coords, kind))
+    assert np.array_equal(K.indptr, Ks.indptr) and np.array_equal(K.indices, Ks.indices)
+    assert rel_max(K.data, Ks.data) < VAL_TOL
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_poisson_facade_solution(torch_cuda, golden, name):
+    """FemProblem(operator="poisson"): same call order, one dof per node, the reference's BC semantics on nodes."""
+    z = golden(name)
+    fem = run_facade(z, operator="poisson")
+    nn = fem.nnode
+    Ks, Kbc, b, u = orc.solve_poisson_path(z["conn"] - 1, z["coords"], bc_sets_of(z))
+    K0 = fem.csr_prebc()
+    assert K0.shape == (nn, nn) and np.array_equal(K0.indptr, Ks.indptr) and np.array_equal(K0.indices, Ks.indices)
+    assert rel_max(K0.data, Ks.data) < VAL_TOL
+    assert np.array_equal(np.asarray(fem.brhs.todense()).ravel(), b)
+    assert rel_max(fem.K.toarray(), Kbc.toarray()) < VAL_TOL
+    U = fem.solveProblem()
+    assert U.shape == (nn,) and fem.solver_info["converged"]
+    assert np.linalg.norm(U - u) / np.linalg.norm(u) < SOL_TOL
+    with pytest.raises(ValueError):
+        fem.setBoundaryConditions(bc_sets_of(z), verbose=False, mode="corrected")

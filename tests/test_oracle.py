@@ -177,3 +177,29 @@ def test_gradient_live_reference():
     want = ref_runner.gauss_gradients(fem, conn, U)
     got = orc.gauss_gradients(conn - 1, coords, U)
     assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("name", FULL_CASES)
+def test_poisson_submatrix_of_the_reference_matrix(golden, name):
+    """FE_OP_POISSON's oracle is K[0::2, 0::2] of the REFERENCE's own pre-BC matrix (frozen in tests/golden), so the
+    scalar operator is pinned to the reference too; its pattern is the node adjacency and it annihilates constants."""
+    z = golden(name)
+    n2 = len(z["k0_indptr"]) - 1
+    Kref = sp.csr_matrix((z["k0_data"], z["k0_indices"], z["k0_indptr"]), shape=(n2, n2))
+    Ks_ref = orc.poisson_submatrix(Kref)
+    conn0 = z["conn"] - 1
+    Ks = orc.poisson_submatrix(orc.assemble_csr(conn0, z["coords"]))
+    nptr, nadj = orc.node_adjacency(conn0, z["coords"].shape[0])
+    assert np.array_equal(Ks.indptr, nptr) and np.array_equal(Ks.indices, nadj)
+    assert np.array_equal(Ks_ref.indptr, Ks.indptr) and np.array_equal(Ks_ref.indices, Ks.indices)
+    assert rel_max(Ks.data, Ks_ref.data) < 1e-12
+    odd = Kref[1::2, :][:, 1::2].tocsr()                 # odd/odd block: the same sums in another order
+    odd.sort_indices()
+    assert rel_max(odd.data, Ks_ref.data) < 1e-13
+    assert np.abs(Ks_ref @ np.ones(Ks.shape[0])).max() < 1e-12 * np.abs(Ks.data).max() * 10
+    assert abs(Ks_ref - Ks_ref.T).max() < 1e-13 * np.abs(Ks.data).max()
+    # whole scalar path: Dirichlet rows are unit rows, loaded nodes carry 1.0, the solve satisfies the system
+    Ks2, Kbc, b, u = orc.solve_poisson_path(conn0, z["coords"], bc_sets_of(z))
+    d, nn = orc.poisson_boundary_dofs(bc_sets_of(z))
+    assert np.array_equal(b[nn], np.ones(len(nn))) and np.count_nonzero(b) == len(nn)
+    assert np.abs(Kbc @ u - b).max() < 1e-9 * max(1.0, np.abs(u).max())
