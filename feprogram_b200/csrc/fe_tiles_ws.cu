@@ -86,16 +86,24 @@ template <int N> struct WsLayout {
     static constexpr unsigned kZeroSrc = (unsigned)(kRows * kSS) << 1;            // the slab's zero block
     static constexpr unsigned kZeroRec = kZeroSrc | (kZeroSrc << kSrcBits);
     static constexpr int kBarBytes = 128;
-    static constexpr int kBlobCap = 10 * 1024;                    // bytes of one record slot
+#ifndef FE_WS_BLOB_CAP
+#define FE_WS_BLOB_CAP (10 * 1024)
+#endif
+#ifndef FE_WS_ROW_RING
+#define FE_WS_ROW_RING 4
+#endif
+    static constexpr int kBlobCap = FE_WS_BLOB_CAP;               // bytes of one record slot
+    static constexpr int kRowRing = FE_WS_ROW_RING;               // connectivity rows staged per producer lane (3 or 4)
     static constexpr int kStageCap = 42 * 1024;                   // bytes of one staging slot (CSR values of a tile)
     static constexpr int kCoordBytes = N * 32 * 16;               // per producer warp and task in flight: node coordinates
     static constexpr size_t kSlabBytes = (size_t)kSlabDoubles * sizeof(double);
-    static constexpr int kProdBytes = kXYDepth * kCoordBytes + 4 * 32 * 16;      // + ring of four connectivity rows per lane
+    static constexpr int kProdBytes = kXYDepth * kCoordBytes + kRowRing * 32 * 16;   // + ring of connectivity rows per lane
     static constexpr size_t kSmem = kBarBytes + 2 * kSlabBytes + (size_t)kRecSlots * kBlobCap + 2 * (size_t)kStageCap +
                                     (size_t)kPW * kProdBytes;
     static_assert((kRows + 1) * kSS < (1 << (kSrcBits - 1)), "slab offset does not fit a source field");
     static_assert(kDW == 1 || kDW == 2, "one DMA warp, or two that take alternate tiles (= one staging slot each)");
     static_assert(kRecSlots >= 2 && kRecSlots <= 4, "record ring: 2..4 slots");
+    static_assert(kRowRing == 3 || kRowRing == 4, "rows of tasks i+2, i+3, i+4 are live at once");
     // A producer warp's consecutive tasks must lie at most two tiles apart: the parity waits on the 2-slot rings can
     // tell "one phase behind" from "current" but not "two phases behind".
     static_assert(kPW <= 2 * kChunks, "too many producer warps for the 2-slot slab ring");
@@ -206,9 +214,9 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         unsigned char* wbuf = coord0 + warp * T::kProdBytes;
         double2* cbuf = reinterpret_cast<double2*>(wbuf);                          // [2][a][lane]
         int4* rbuf = reinterpret_cast<int4*>(wbuf + 2 * T::kCoordBytes);           // [4][lane]
-        auto request_row = [&](int j, int ring) {
+        auto request_row = [&](int j, int ring) {      // ring: slot index in [0, kRowRing)
             const int32_t* p = row_addr(j);
-            int4* dst = rbuf + (ring & 3) * 32 + lane;
+            int4* dst = rbuf + ring * 32 + lane;
 #if defined(FE_WS_WHATIF) && (FE_WS_WHATIF & 8)     // developer timing build: producers load nothing
             p = nullptr;
 #endif
@@ -248,8 +256,8 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         int j = warp;
         {
             const int4 r0 = direct_row(j), r1 = direct_row(j + T::kPW);
-            request_row(j + 2 * T::kPW, 2);
-            request_row(j + 3 * T::kPW, 3);
+            request_row(j + 2 * T::kPW, 2 % T::kRowRing);
+            request_row(j + 3 * T::kPW, 3 % T::kRowRing);
             request_xy(r0, 0);
             asm volatile("cp.async.commit_group;" ::: "memory");
             request_xy(r1, 1);
@@ -259,10 +267,11 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         }
         int k = 0, c = warp;                // tile / chunk of task j (kPW <= 2 * kChunks)
         while (c >= T::kChunks) c -= T::kChunks, ++k;
+        int ring_rd = 2 % T::kRowRing, ring_wr = 4 % T::kRowRing;   // ring slots of the rows of tasks i+2 (read) and i+4 (written)
         for (int it = 0; j < total; j += T::kPW, ++it) {
             const int row = c * 32 + lane;
             const int slot = k & 1, buf = it & 1;
-            request_row(j + 4 * T::kPW, it);                            // ring slot (it + 4) & 3
+            request_row(j + 4 * T::kPW, ring_wr);
             const bool active = act0;
             asm volatile("cp.async.wait_group 1;" ::: "memory");        // coordinates of this task, row of task i+2
             double x[N], y[N];
@@ -274,7 +283,9 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                     y[a] = p.y;
                 }
             }
-            const int4 ahead = rbuf[((it + 2) & 3) * 32 + lane];
+            const int4 ahead = rbuf[ring_rd * 32 + lane];
+            ring_rd = ring_rd + 1 == T::kRowRing ? 0 : ring_rd + 1;
+            ring_wr = ring_wr + 1 == T::kRowRing ? 0 : ring_wr + 1;
             request_xy(ahead, buf);                                     // task i+2: in flight for two task times
             asm volatile("cp.async.commit_group;" ::: "memory");
             double ke[3 * T::kBlocks];
