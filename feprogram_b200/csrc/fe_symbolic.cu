@@ -71,18 +71,58 @@ __device__ __forceinline__ int build_adjacency(int nnpe, const int32_t* __restri
     return cnt;
 }
 
-__global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, int nnpe, const int32_t* __restrict__ conn,
+// Fast form of build_adjacency: the list lives in shared memory, entry i of thread t at s[i * 128 + t] (conflict
+// free), at most kFastAdj entries.  Returns the count, or -1 when the node has more distinct neighbours than that
+// (the caller then takes the general thread-local path above; structured and typical unstructured 2-D meshes
+// never do: 9 / 25 / 7 neighbours for Quad4 / Quad9 / Tri3 lattices).
+constexpr int kFastAdj = 32;
+template <int NNPE>
+__device__ __forceinline__ int build_adjacency_smem(const int32_t* __restrict__ conn, const int32_t* __restrict__ einc,
+                                                    int k0, int k1, int* s) {
+    int cnt = 0;
+    for (int k = k0; k < k1; ++k) {
+        const int64_t e = einc[k] >> 4;
+        int row[NNPE];
+        if constexpr (NNPE == 4) {
+            const int4 r = __ldg(reinterpret_cast<const int4*>(conn) + e);
+            row[0] = r.x, row[1] = r.y, row[2] = r.z, row[3] = r.w;
+        } else {
+#pragma unroll
+            for (int b = 0; b < NNPE; ++b) row[b] = __ldg(conn + e * NNPE + b);
+        }
+#pragma unroll
+        for (int b = 0; b < NNPE; ++b) {
+            const int v = row[b];
+            int j = cnt;
+            while (j > 0 && s[(j - 1) * 128] > v) --j;
+            if (j > 0 && s[(j - 1) * 128] == v) continue;
+            if (cnt == kFastAdj) return -1;
+            for (int i = cnt; i > j; --i) s[i * 128] = s[(i - 1) * 128];
+            s[j * 128] = v;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
+template <int NNPE>
+__global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, const int32_t* __restrict__ conn,
                                                          const int32_t* __restrict__ eptr,
                                                          const int32_t* __restrict__ einc, int32_t* __restrict__ ndeg,
                                                          int32_t* __restrict__ status) {
+    __shared__ int s_list[kFastAdj * 128];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n > nnode) return;
     if (n == nnode) {  // slot for the grand total after the scan
         ndeg[n] = 0;
         return;
     }
-    int list[kMaxAdj];
-    int cnt = build_adjacency(nnpe, conn, einc, eptr[n], eptr[n + 1], list);
+    const int k0 = eptr[n], k1 = eptr[n + 1];
+    int cnt = build_adjacency_smem<NNPE>(conn, einc, k0, k1, s_list + threadIdx.x);
+    if (cnt < 0) {                                   // rare: more than kFastAdj neighbours
+        int list[kMaxAdj];
+        cnt = build_adjacency(NNPE, conn, einc, k0, k1, list);
+    }
     if (cnt < 0) {
         atomicMax(status, 1);
         cnt = 0;
@@ -90,30 +130,62 @@ __global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, int nnpe
     ndeg[n] = cnt;
 }
 
-__global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, int nnpe, const int32_t* __restrict__ conn,
+template <int NNPE>
+__global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int32_t* __restrict__ conn,
                                                         const int32_t* __restrict__ eptr,
                                                         const int32_t* __restrict__ einc,
                                                         const int32_t* __restrict__ nptr, int32_t* __restrict__ nadj,
                                                         uint8_t* __restrict__ epos) {
+    __shared__ int s_list[kFastAdj * 128];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= nnode) return;
-    int list[kMaxAdj];
     const int k0 = eptr[n], k1 = eptr[n + 1];
-    const int cnt = build_adjacency(nnpe, conn, einc, k0, k1, list);
-    if (cnt < 0) return;
     const int p0 = nptr[n];
-    for (int i = 0; i < cnt; ++i) nadj[p0 + i] = list[i];
+    int* s = s_list + threadIdx.x;
+    int cnt = build_adjacency_smem<NNPE>(conn, einc, k0, k1, s);
+    if (cnt < 0) {                                   // rare: the general thread-local path
+        int list[kMaxAdj];
+        cnt = build_adjacency(NNPE, conn, einc, k0, k1, list);
+        if (cnt < 0) return;
+        for (int i = 0; i < cnt; ++i) nadj[p0 + i] = list[i];
+        for (int k = k0; k < k1; ++k) {
+            const int64_t e = einc[k] >> 4;
+            for (int b = 0; b < NNPE; ++b) {
+                const int v = conn[e * NNPE + b];
+                int lo = 0, hi = cnt - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (list[mid] < v) lo = mid + 1;
+                    else hi = mid;
+                }
+                epos[(int64_t)k * NNPE + b] = (uint8_t)lo;
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < cnt; ++i) nadj[p0 + i] = s[i * 128];
     for (int k = k0; k < k1; ++k) {
         const int64_t e = einc[k] >> 4;
-        for (int b = 0; b < nnpe; ++b) {
-            const int v = conn[e * nnpe + b];
+        unsigned packed[(NNPE + 3) / 4];
+#pragma unroll
+        for (int w = 0; w < (NNPE + 3) / 4; ++w) packed[w] = 0u;
+#pragma unroll
+        for (int b = 0; b < NNPE; ++b) {
+            const int v = __ldg(conn + e * NNPE + b);
             int lo = 0, hi = cnt - 1;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (list[mid] < v) lo = mid + 1;
+                if (s[mid * 128] < v) lo = mid + 1;
                 else hi = mid;
             }
-            epos[(int64_t)k * nnpe + b] = (uint8_t)lo;
+            packed[b >> 2] |= (unsigned)lo << (8 * (b & 3));
+        }
+        uint8_t* dst = epos + (int64_t)k * NNPE;
+        if constexpr (NNPE == 4) {
+            *reinterpret_cast<unsigned*>(dst) = packed[0];             // 4-byte aligned: k * 4
+        } else {
+#pragma unroll
+            for (int b = 0; b < NNPE; ++b) dst[b] = (uint8_t)(packed[b >> 2] >> (8 * (b & 3)));
         }
     }
 }
@@ -228,7 +300,12 @@ int fe_adjacency_count(int elem_type, int64_t nnode, const int32_t* conn, const 
     cudaStream_t st = as_stream(stream);
     k_zero_i32<<<1, 32, 0, st>>>(status, 1);
     FE_CHECK_LAUNCH("k_zero_i32");
-    k_adjacency_count<<<grid_for(nnode + 1, 128), 128, 0, st>>>(nnode, nnpe, conn, eptr, einc, nptr, status);
+    const unsigned grid = grid_for(nnode + 1, 128);
+    switch (nnpe) {
+        case 4: k_adjacency_count<4><<<grid, 128, 0, st>>>(nnode, conn, eptr, einc, nptr, status); break;
+        case 9: k_adjacency_count<9><<<grid, 128, 0, st>>>(nnode, conn, eptr, einc, nptr, status); break;
+        default: k_adjacency_count<3><<<grid, 128, 0, st>>>(nnode, conn, eptr, einc, nptr, status); break;
+    }
     FE_CHECK_LAUNCH("k_adjacency_count");
     return exclusive_scan_i32(nptr, nptr, nnode + 1, scan_ws, st);
 }
@@ -243,8 +320,13 @@ int fe_adjacency_fill(int elem_type, int64_t nnode, const int32_t* conn, const i
     }
     FE_REQUIRE(nnode >= 0 && conn && eptr && einc && nptr && nadj && epos, "null pointer or negative size");
     if (nnode == 0) return FE_OK;
-    k_adjacency_fill<<<grid_for(nnode, 128), 128, 0, as_stream(stream)>>>(nnode, nnpe, conn, eptr, einc, nptr, nadj,
-                                                                         epos);
+    const unsigned grid = grid_for(nnode, 128);
+    cudaStream_t st = as_stream(stream);
+    switch (nnpe) {
+        case 4: k_adjacency_fill<4><<<grid, 128, 0, st>>>(nnode, conn, eptr, einc, nptr, nadj, epos); break;
+        case 9: k_adjacency_fill<9><<<grid, 128, 0, st>>>(nnode, conn, eptr, einc, nptr, nadj, epos); break;
+        default: k_adjacency_fill<3><<<grid, 128, 0, st>>>(nnode, conn, eptr, einc, nptr, nadj, epos); break;
+    }
     FE_CHECK_LAUNCH("k_adjacency_fill");
     return FE_OK;
 }

@@ -557,6 +557,7 @@ __global__ void __launch_bounds__(128) k_tile_ws_runs(int64_t ntiles, const int3
 }
 
 // One thread per tile-node slot: node descriptor, records (one per neighbour position), item locators.
+constexpr int kWsMaxDeg = 32;           // neighbours per node the plan of the warp-specialised kernel represents
 __global__ void __launch_bounds__(128) k_tile_ws_records(
     int64_t nslots, int nnpe, const int32_t* __restrict__ tile_nodes, const int32_t* __restrict__ owner,
     const int32_t* __restrict__ tile_nptr, const int32_t* __restrict__ tile_hptr, const int32_t* __restrict__ noff,
@@ -564,6 +565,7 @@ __global__ void __launch_bounds__(128) k_tile_ws_records(
     const uint8_t* __restrict__ epos, const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr,
     const int32_t* __restrict__ nadj, const int32_t* __restrict__ blob_off, unsigned char* __restrict__ blobs,
     int32_t* __restrict__ stats, int te, int he, int ss) {
+    __shared__ uint32_t s_rec[kWsMaxDeg * 128];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     const int n = tile_nodes[i];
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(128) k_tile_ws_records(
     const int self = cnt > 0 ? (int)epos[(int64_t)k0 * nnpe + (einc[k0] & 15)] : 0;
     (void)nadj;
     const int soff = 2 * woff;                                                    // staging offset / 16 inside the tile's slot
-    if (cnt > 15 || deg > 127 || deg > kMaxAdj || soff > 0xFFFF || ioff >= (1 << 28)) {   // not representable
+    if (cnt > 15 || deg > kWsMaxDeg || soff > 0xFFFF || ioff >= (1 << 28)) {   // not representable
         atomicMax(stats + 4, 1);
         return;
     }
@@ -593,8 +595,11 @@ __global__ void __launch_bounds__(128) k_tile_ws_records(
     node[ln] = make_uint2((unsigned)soff | ((unsigned)deg << 16) | ((unsigned)self << 23),
                           (unsigned)cnt | ((unsigned)ioff << 4));
     const unsigned kZeroSrc = (unsigned)((te + he) * ss) << 1;
-    unsigned short src[kMaxAdj][2];
-    for (int p = 0; p < deg; ++p) src[p][0] = src[p][1] = (unsigned short)kZeroSrc;
+    const unsigned kZeroRec = kZeroSrc | (kZeroSrc << 14);
+    // the node's records are collected in shared memory (entry p of thread t at s_rec[p * 128 + t]: conflict free;
+    // a thread-local array would live in local memory)
+    uint32_t* src = s_rec + threadIdx.x;
+    for (int p = 0; p < deg; ++p) src[p * 128] = kZeroRec;
     for (int j = 0; j < cnt; ++j) {
         const int item = einc[k0 + j];
         const int e = item >> 4, a = item & 15;
@@ -617,16 +622,14 @@ __global__ void __launch_bounds__(128) k_tile_ws_records(
             if (p == self) continue;
             const int blo = a < b ? a : b, bhi = a < b ? b : a;
             const int tri = blo * nnpe - blo * (blo - 1) / 2 + (bhi - blo);
-            const unsigned short s = (unsigned short)(((row * ss + 3 * tri) << 1) | (a > b ? 1 : 0));
-            if (src[p][0] == kZeroSrc) src[p][0] = s;
-            else if (src[p][1] == kZeroSrc) src[p][1] = s;
+            const unsigned sv = (unsigned)(((row * ss + 3 * tri) << 1) | (a > b ? 1 : 0));
+            const uint32_t cur = src[p * 128];
+            if ((cur & 0x3FFFu) == kZeroSrc) src[p * 128] = (cur & ~0x3FFFu) | sv;
+            else if ((cur >> 14) == kZeroSrc) src[p * 128] = (cur & 0x3FFFu) | (sv << 14);
             else atomicMax(stats + 4, 1);  // a node pair shared by more than two elements
         }
     }
-    for (int p = 0; p < maxdeg; ++p) {
-        const unsigned a = p < deg ? src[p][0] : kZeroSrc, b = p < deg ? src[p][1] : kZeroSrc;
-        recs[p * nnp + ln] = a | (b << 14);
-    }
+    for (int p = 0; p < maxdeg; ++p) recs[p * nnp + ln] = p < deg ? src[p * 128] : kZeroRec;
 }
 
 }  // namespace fe
@@ -637,9 +640,9 @@ void fe_tile_ws_params(int elem_type, int32_t out[4]) {
     using namespace fe;
     out[0] = out[1] = out[2] = out[3] = 0;
     if (elem_type == FE_QUAD4) {
-        out[0] = WsLayout<4>::kBlobCap, out[1] = WsLayout<4>::kStageCap, out[2] = 127, out[3] = 256;
+        out[0] = WsLayout<4>::kBlobCap, out[1] = WsLayout<4>::kStageCap, out[2] = kWsMaxDeg, out[3] = 256;
     } else if (elem_type == FE_TRI3) {
-        out[0] = WsLayout<3>::kBlobCap, out[1] = WsLayout<3>::kStageCap, out[2] = 127, out[3] = 256;
+        out[0] = WsLayout<3>::kBlobCap, out[1] = WsLayout<3>::kStageCap, out[2] = kWsMaxDeg, out[3] = 256;
     }
 }
 
