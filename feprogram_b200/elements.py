@@ -413,11 +413,18 @@ class FemProblem:
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
             # overlaps the coordinate upload; the scipy-compatible row_ptr / col_idx (which neither the tile plan nor the
             # numeric kernel reads) are expanded on a side stream, off the critical path
-            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, self.ndof,
-                                         csr_stream=side_streams(st["conn"].device)[2])
+            # A lattice numbering's tiles depend on the connectivity alone: they are formed on the side stream while the
+            # first half of the symbolic kernels runs on this one (the hook is called before the phase's host sync).
+            csr_side = side_streams(st["conn"].device)[2]
+            formed = {}
+
+            def form_tiles(lattice):
+                formed["tiles"] = ops.tile_formation(self.nelem, self.nnode, et, lattice, csr_side)
+            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, self.ndof, csr_stream=csr_side, between=form_tiles)
             self._mark("symbolic done")
             # the plan waits for the coordinate upload only if it needs coordinates (a lattice numbering does not)
-            st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"], coords_ready=self._coords_ready)
+            st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"], coords_ready=self._coords_ready,
+                                       formation=formed.get("tiles"))
             self._mark("plan done")
         self._coords_ready()
         pat = st["pattern"]

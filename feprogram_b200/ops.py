@@ -171,9 +171,7 @@ def incidence(conn: Tensor, nnode: int, elem_type: int) -> Tuple[Tensor, Tensor]
     return eptr, einc
 
 
-@torch.library.custom_op("feprogram::adjacency", mutates_args=())
-def adjacency(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """(nptr[nnode+1] int32, nadj[nnzN] int32, epos[nelem*nnpe*nnpe] uint8).  Syncs once to size nadj."""
+def _adjacency_impl(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int, between=None):
     _chk_dev(conn, eptr, einc)
     nelem, nnpe = conn.shape
     nnode = eptr.numel() - 1
@@ -185,6 +183,8 @@ def adjacency(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int) -> Tuple
         ws = torch.empty(max(1, L.fe_scan_workspace_bytes(nnode + 1)), dtype=torch.uint8, device=dev)
         _lib.check(L.fe_adjacency_count(elem_type, nnode, _ptr(conn), _ptr(eptr), _ptr(einc), _ptr(nptr),
                                         _ptr(status), _ptr(ws), _stream(conn)))
+        if between is not None:
+            between()          # host work that may overlap the kernels queued so far (it must not touch this stream)
         tail = read_i32(nptr[nnode:nnode + 1], status)      # the one host sync of the symbolic phase
         if int(tail[1]) != 0:
             raise _lib.FeError(-4, "a node has more than %d distinct neighbours" % _lib.limits()["max_adj"])
@@ -194,6 +194,12 @@ def adjacency(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int) -> Tuple
         _lib.check(L.fe_adjacency_fill(elem_type, nnode, _ptr(conn), _ptr(eptr), _ptr(einc), _ptr(nptr), _ptr(nadj),
                                        _ptr(epos), _stream(conn)))
     return nptr, nadj, epos
+
+
+@torch.library.custom_op("feprogram::adjacency", mutates_args=())
+def adjacency(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """(nptr[nnode+1] int32, nadj[nnzN] int32, epos[nelem*nnpe*nnpe] uint8).  Syncs once to size nadj."""
+    return _adjacency_impl(conn, eptr, einc, elem_type)
 
 
 @torch.library.custom_op("feprogram::csr_expand", mutates_args=())
@@ -329,7 +335,7 @@ class Pattern:
     row_ptr: Tensor
     col_idx: Tensor
     _max_deg: Optional[int] = None
-    lattice: Optional[Tuple[Tensor, Tensor]] = None    # (Morton keys from a lattice numbering, status) -- fe_lattice_keys
+    lattice: Optional[tuple] = None    # (Morton keys from a lattice numbering, status, event) -- fe_lattice_keys
     csr_event: Optional[object] = None                 # set when row_ptr / col_idx were expanded on a side stream
 
     def csr_ready(self) -> None:
@@ -354,22 +360,25 @@ class Pattern:
         return self.ndof * self.nnode
 
 
-def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2, csr_stream=None) -> Pattern:
+def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2, csr_stream=None, between=None) -> Pattern:
     """CSR pattern + element->slot map for a mesh (conn int32 0-based on the device).  ``csr_stream``: expand the
     scipy-compatible row_ptr / col_idx on that stream (concurrently with whatever follows on the current one); the
-    caller orders later users with ``Pattern.csr_ready()``."""
+    caller orders later users with ``Pattern.csr_ready()``.  ``between(lattice)``: called once the first half of the
+    symbolic kernels is queued and before the phase's host synchronisation -- the facade forms the tiles of a lattice
+    numbering on another stream there (``tile_formation``), concurrently with those kernels."""
     nelem = conn.shape[0]
     lattice = None
     if elem_type == FE_QUAD4 and nelem > 0:
         # is the numbering a row-major lattice?  Then the tile plan needs no coordinates (fe_lattice_keys); the answer
-        # is read back by tile_plan, after the symbolic kernels -- no extra synchronisation here
+        # is read back by tile_plan / tile_formation -- no extra synchronisation here
         with torch.cuda.device(conn.device):
             keys = torch.empty(nelem, dtype=torch.int32, device=conn.device)
             lstat = torch.empty(2, dtype=torch.int32, device=conn.device)
             _lib.check(_lib.lib().fe_lattice_keys(elem_type, nelem, _ptr(conn), _ptr(keys), _ptr(lstat), _stream(conn)))
-        lattice = (keys, lstat)
+            lattice = (keys, lstat, torch.cuda.current_stream(conn.device).record_event())
     eptr, einc = torch.ops.feprogram.incidence(conn, nnode, elem_type)
-    nptr, nadj, epos = torch.ops.feprogram.adjacency(conn, eptr, einc, elem_type)
+    hook = (lambda: between(lattice)) if between is not None else None
+    nptr, nadj, epos = _adjacency_impl(conn, eptr, einc, elem_type, hook)
     nnz = ndof * ndof * nadj.numel()
     ev = None
     if csr_stream is None:
@@ -451,8 +460,69 @@ def _scan_into(src: Tensor, dst: Tensor, ws: Tensor):
     _lib.check(_lib.lib().fe_exclusive_scan_i32(_ptr(src), _ptr(dst), src.numel(), _ptr(ws), _stream(src)))
 
 
+def _form_blocks(elem_type: int, nelem: int, te: int, keys: Tensor, imax: int):
+    """Device-side tile formation on the current stream: counting sort of the elements by Morton block + per-block
+    sort (csrc/fe_tile_form.cu).  One host synchronisation (the tile count).  Returns (ntiles, eperm, eloc,
+    tile_estart) or None when a block overflows."""
+    L = _lib.lib()
+    dev = keys.device
+    st = _stream(keys)
+    shift = te.bit_length() - 1
+    nb = max(1, (1 << (2 * max(1, imax.bit_length()))) >> shift)
+    sb = nb + 1
+    wsf = torch.empty(max(1, L.fe_scan_workspace_bytes(sb)), dtype=torch.uint8, device=dev)
+    tabs = torch.empty((4, sb), dtype=torch.int32, device=dev)          # hist, tpb, ebase, tbase
+    cursor_b = torch.empty(nb, dtype=torch.int32, device=dev)
+    tmp = torch.empty(nelem, dtype=torch.int32, device=dev)
+    fstat = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.check(L.fe_tile_form_count(elem_type, nelem, nb, _ptr(keys), _ptr(tabs[0]), _ptr(tabs[1]),
+                                    _ptr(tabs[2]), _ptr(tabs[3]), _ptr(cursor_b), _ptr(tmp), _ptr(fstat),
+                                    _ptr(wsf), st))
+    ft = read_i32(tabs[3, nb:nb + 1], fstat)                       # host sync: tile count
+    if int(ft[1]) != 0:
+        return None
+    ntiles = int(ft[0])
+    eperm = torch.empty(nelem, dtype=torch.int32, device=dev)
+    eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
+    tile_estart = torch.empty(ntiles + 1, dtype=torch.int32, device=dev)
+    _lib.check(L.fe_tile_form_sort(elem_type, nb, _ptr(tabs[2]), _ptr(tabs[3]), _ptr(tmp), _ptr(keys),
+                                   _ptr(eperm), _ptr(eloc), _ptr(tile_estart), st))
+    return ntiles, eperm, eloc, tile_estart
+
+
+def _lattice_imax(w_lat: int, nnode: int) -> int:
+    return max(w_lat - 1, (nnode + w_lat - 1) // w_lat)
+
+
+def tile_formation(nelem: int, nnode: int, elem_type: int, lattice, stream) -> Optional[dict]:
+    """Early tile formation for a lattice numbering, on ``stream``: element order, tile boundaries and the
+    element -> (tile, row) map depend on the connectivity alone, so they can be built while the symbolic kernels run
+    on the caller's stream (``symbolic(..., between=...)``).  Synchronises ``stream`` only.  Returns None when the
+    numbering is not a lattice (tile_plan then takes its usual route)."""
+    if lattice is None or nelem == 0:
+        return None
+    te = _lib.tile_params(elem_type)["tile_elems"]
+    if te == 0:
+        return None
+    keys, lstat, ev = lattice
+    main = torch.cuda.current_stream(keys.device)
+    with torch.cuda.device(keys.device), torch.cuda.stream(stream):
+        stream.wait_event(ev)
+        keys.record_stream(stream)
+        flag, w = read_i32(lstat)
+        if flag != 0 or w < 2:
+            return None
+        res = _form_blocks(elem_type, nelem, te, keys, min(32767, _lattice_imax(w, nnode)))
+        if res is None:
+            return None
+        done = stream.record_event()
+    for t in res[1:]:
+        t.record_stream(main)
+    return dict(w=w, ntiles=res[0], eperm=res[1], eloc=res[2], tile_estart=res[3], event=done)
+
+
 def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, kernel: str = "auto",
-              coords_ready=None) -> Optional[TilePlan]:
+              coords_ready=None, formation: Optional[dict] = None) -> Optional[TilePlan]:
     """Builds the tile plan; returns None when the mesh does not fit the tiled kernel's capacities
     (the caller then uses the row-tile kernel fe_assemble, which has none).  ``kernel``: "auto" = the
     warp-specialised kernel where it exists (Quad4 / Tri3) and its capacities hold, else the barrier-phased one;
@@ -473,7 +543,13 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, k
     if te == 0 or pat.nelem == 0:
         return None
     ideal = (pat.nelem + te - 1) // te
-    if pat.lattice is not None:
+    if formation is not None and pat.lattice is not None:       # tiles formed ahead of time (tile_formation)
+        torch.cuda.current_stream(conn.device).wait_event(formation["event"])
+        plan = _tile_plan(conn, coords, pat, True, 1.0, "blocks", kernel, lattice=(pat.lattice[0], formation["w"]),
+                          formed=formation)
+        if plan is not None:
+            return plan
+    elif pat.lattice is not None:
         flag, w = read_i32(pat.lattice[1])
         if flag == 0 and w >= 2:
             plan = _tile_plan(conn, coords, pat, True, 1.0, "blocks", kernel, lattice=(pat.lattice[0], w))
@@ -497,7 +573,7 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, k
 
 
 def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_scale: float,
-               mode: str, kernel: str = "auto", lattice=None) -> Optional[TilePlan]:
+               mode: str, kernel: str = "auto", lattice=None, formed: Optional[dict] = None) -> Optional[TilePlan]:
     L = _lib.lib()
     params = _lib.tile_params(pat.elem_type)
     if params["halo_cap"] == 0 or pat.nelem == 0 or pat.nnode == 0:
@@ -510,13 +586,18 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         st = _stream(conn)
         # ---- element order and tile boundaries ----
         idx = None
-        formed = False
         keys = None
-        if lattice is not None:
-            keys, w_lat = lattice                        # keys from the numbering: one cell per element, no coordinates
-            imax_lat = max(w_lat - 1, (nnode + w_lat - 1) // w_lat)
+        if formed is not None:                           # tile_formation() has done this part on another stream
+            ntiles, eperm, eloc, tile_estart = formed["ntiles"], formed["eperm"], formed["eloc"], formed["tile_estart"]
             mode_name = "lattice"
+            formed = True
+        elif lattice is not None:
+            keys, w_lat = lattice                        # keys from the numbering: one cell per element, no coordinates
+            imax_lat = _lattice_imax(w_lat, nnode)
+            mode_name = "lattice"
+            formed = False
         elif morton:
+            formed = False
             # cell: holds ~ one element (Tri3: the two triangles of a quad).  Its AREA comes from the sampled mean
             # element area (distortion-proof: perturbing nodes changes extents, not the mean area), its aspect
             # ratio from the sampled mean extents.  All scalars come back in ONE device -> host transfer.
@@ -542,32 +623,16 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
             _lib.check(L.fe_morton_keys(pat.elem_type, nelem, _ptr(conn), _ptr(coords), lo_h[0], lo_h[1], cell[0],
                                         cell[1], _ptr(keys), st))
             imax_lat = None
-        if keys is not None:
-            if mode == "blocks":
-                # device-side formation: counting sort by Morton block + per-block sort (csrc/fe_tile_form.cu)
-                shift = te.bit_length() - 1
-                imax = (min(32767, imax_lat) if imax_lat is not None else
-                        max(min(32767, int(ext[0] / cell[0]) + 1), min(32767, int(ext[1] / cell[1]) + 1)))
-                nb = max(1, (1 << (2 * max(1, imax.bit_length()))) >> shift)
-                sb = nb + 1
-                wsf = torch.empty(max(1, L.fe_scan_workspace_bytes(sb)), dtype=torch.uint8, device=dev)
-                tabs = torch.empty((4, sb), dtype=torch.int32, device=dev)          # hist, tpb, ebase, tbase
-                cursor_b = torch.empty(nb, dtype=torch.int32, device=dev)
-                tmp = torch.empty(nelem, dtype=torch.int32, device=dev)
-                fstat = torch.empty(1, dtype=torch.int32, device=dev)
-                _lib.check(L.fe_tile_form_count(pat.elem_type, nelem, nb, _ptr(keys), _ptr(tabs[0]), _ptr(tabs[1]),
-                                                _ptr(tabs[2]), _ptr(tabs[3]), _ptr(cursor_b), _ptr(tmp), _ptr(fstat),
-                                                _ptr(wsf), st))
-                ft = read_i32(tabs[3, nb:nb + 1], fstat)                       # host sync: tile count
-                if int(ft[1]) == 0:
-                    ntiles = int(ft[0])
-                    eperm = torch.empty(nelem, dtype=torch.int32, device=dev)
-                    eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
-                    tile_estart = torch.empty(ntiles + 1, dtype=torch.int32, device=dev)
-                    _lib.check(L.fe_tile_form_sort(pat.elem_type, nb, _ptr(tabs[2]), _ptr(tabs[3]), _ptr(tmp), _ptr(keys),
-                                                   _ptr(eperm), _ptr(eloc), _ptr(tile_estart), st))
-                    formed = True
-                del tabs, cursor_b, tmp
+        else:
+            formed = False
+        if keys is not None and mode == "blocks":
+            # device-side formation: counting sort by Morton block + per-block sort (csrc/fe_tile_form.cu)
+            imax = (min(32767, imax_lat) if imax_lat is not None else
+                    max(min(32767, int(ext[0] / cell[0]) + 1), min(32767, int(ext[1] / cell[1]) + 1)))
+            res = _form_blocks(pat.elem_type, nelem, te, keys, imax)
+            if res is not None:
+                ntiles, eperm, eloc, tile_estart = res
+                formed = True
         if formed:
             pass
         elif morton:
