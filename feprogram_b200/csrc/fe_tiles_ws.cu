@@ -78,6 +78,10 @@ template <int N> struct WsLayout {
 #endif
     static constexpr int kBatch = FE_WS_BATCH;                    // neighbour positions a consumer thread keeps in flight
     static constexpr int kParts = FE_WS_PARTS;                    // slices of a node's neighbour list (one consumer thread each)
+#ifndef FE_WS_UNITS
+#define FE_WS_UNITS 1
+#endif
+    static constexpr int kUnits = FE_WS_UNITS;                    // work units a consumer warp processes with interleaved loads
     static constexpr int kRecSlots = FE_WS_REC_SLOTS;             // record ring: blobs are requested this many tiles ahead
     static constexpr int kXYDepth = 2;                            // coordinate gathers in flight per producer warp (tasks)
     // record source field: (slab offset in doubles) << 1 | transposed; two of them per record
@@ -85,7 +89,15 @@ template <int N> struct WsLayout {
     static constexpr unsigned kSrcMask = (1u << kSrcBits) - 1u;
     static constexpr unsigned kZeroSrc = (unsigned)(kRows * kSS) << 1;            // the slab's zero block
     static constexpr unsigned kZeroRec = kZeroSrc | (kZeroSrc << kSrcBits);
-    static constexpr int kBarBytes = 128;
+    static constexpr int kBarBytes = 256;
+#ifndef FE_WS_SLAB_SLOTS
+#define FE_WS_SLAB_SLOTS 2
+#endif
+#ifndef FE_WS_STAGE_SLOTS
+#define FE_WS_STAGE_SLOTS 2
+#endif
+    static constexpr int kSlabSlots = FE_WS_SLAB_SLOTS;           // slab ring (producers -> consumers), 2..4
+    static constexpr int kStageSlots = FE_WS_STAGE_SLOTS;         // staging ring (consumers -> DMA warps), 2..4
 #ifndef FE_WS_BLOB_CAP
 #define FE_WS_BLOB_CAP (10 * 1024)
 #endif
@@ -94,19 +106,24 @@ template <int N> struct WsLayout {
 #endif
     static constexpr int kBlobCap = FE_WS_BLOB_CAP;               // bytes of one record slot
     static constexpr int kRowRing = FE_WS_ROW_RING;               // connectivity rows staged per producer lane (3 or 4)
-    static constexpr int kStageCap = 42 * 1024;                   // bytes of one staging slot (CSR values of a tile)
+#ifndef FE_WS_STAGE_CAP
+#define FE_WS_STAGE_CAP (42 * 1024)
+#endif
+    static constexpr int kStageCap = FE_WS_STAGE_CAP;             // bytes of one staging slot (CSR values of a tile)
     static constexpr int kCoordBytes = N * 32 * 16;               // per producer warp and task in flight: node coordinates
     static constexpr size_t kSlabBytes = (size_t)kSlabDoubles * sizeof(double);
     static constexpr int kProdBytes = kXYDepth * kCoordBytes + kRowRing * 32 * 16;   // + ring of connectivity rows per lane
-    static constexpr size_t kSmem = kBarBytes + 2 * kSlabBytes + (size_t)kRecSlots * kBlobCap + 2 * (size_t)kStageCap +
+    static constexpr size_t kSmem = kBarBytes + kSlabSlots * kSlabBytes + (size_t)kRecSlots * kBlobCap +
+                                    kStageSlots * (size_t)kStageCap +
                                     (size_t)kPW * kProdBytes;
     static_assert((kRows + 1) * kSS < (1 << (kSrcBits - 1)), "slab offset does not fit a source field");
     static_assert(kDW == 1 || kDW == 2, "one DMA warp, or two that take alternate tiles (= one staging slot each)");
     static_assert(kRecSlots >= 2 && kRecSlots <= 4, "record ring: 2..4 slots");
     static_assert(kRowRing == 3 || kRowRing == 4, "rows of tasks i+2, i+3, i+4 are live at once");
-    // A producer warp's consecutive tasks must lie at most two tiles apart: the parity waits on the 2-slot rings can
-    // tell "one phase behind" from "current" but not "two phases behind".
-    static_assert(kPW <= 2 * kChunks, "too many producer warps for the 2-slot slab ring");
+    // A parity wait tells "the preceding phase" from "the current one", nothing older.  A producer warp waits on the
+    // slot of a tile it still owes a chunk to, so that slot cannot run more than one phase ahead of it; the bound below
+    // only keeps a warp's consecutive tasks within one turn of the slab ring.
+    static_assert(kPW <= kSlabSlots * kChunks, "too many producer warps for the slab ring");
     static_assert(kRegSplit ? (kPW % 4 == 0 && kCW % 4 == 0 && 32 * (kPW * kRegP + kCW * kRegC + kDWPad * kRegD) <= 65536)
                             : (kPW + kCW + kDW <= 16),
                   "register file: 512 threads x 128 registers, or warp groups with their own counts");
@@ -147,7 +164,11 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32
 // =================================================================================================
 // numeric kernel
 // =================================================================================================
-template <int ET, bool MASS>
+// SCALAR = FE_OP_POISSON (one dof per node, vals[nptr[n] + p] = the L entry of the node pair's block): same plan, same
+// rings; producers evaluate and store only the L entries, consumers stage one 8-byte value per record at
+// (staging offset / 2), and the DMA warps write the runs with coalesced 8-byte stores instead of bulk copies (the runs
+// of 8-byte values are not 16-byte aligned, and the output is a quarter of the two-dof one).
+template <int ET, bool MASS, bool SCALAR = false>
 __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assemble_ws(
     int ntiles, const int32_t* __restrict__ tconn, const double2* __restrict__ coords, const int4* __restrict__ tdesc,
     const unsigned char* __restrict__ blobs, const int4* __restrict__ truns, double* __restrict__ vals, int weighted) {
@@ -158,12 +179,14 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     double* slab0 = reinterpret_cast<double*>(smem + T::kBarBytes);
-    unsigned char* rec0 = smem + T::kBarBytes + 2 * T::kSlabBytes;
+    unsigned char* rec0 = smem + T::kBarBytes + T::kSlabSlots * T::kSlabBytes;
     unsigned char* stage0 = rec0 + T::kRecSlots * T::kBlobCap;
-    unsigned char* coord0 = stage0 + 2 * T::kStageCap;
+    unsigned char* coord0 = stage0 + T::kStageSlots * T::kStageCap;
     // barrier ids (x2 slots each; the record ring has kRecSlots <= 4)
-    enum { B_SLAB_FULL = 0, B_SLAB_EMPTY = 2, B_STAGED = 4, B_STAGE_FREE = 6, B_REC_FULL = 8, B_REC_EMPTY = 12 };
+    enum { B_SLAB_FULL = 0, B_SLAB_EMPTY = 4, B_STAGED = 8, B_STAGE_FREE = 12, B_REC_FULL = 16, B_REC_EMPTY = 20 };
     static_assert(8 * (B_REC_EMPTY + 4) <= T::kBarBytes, "barrier block");
+    constexpr int DS = T::kSlabSlots, DG = T::kStageSlots;
+    static_assert(DS >= 2 && DS <= 4 && DG >= 2 && DG <= 4, "ring depths");
     constexpr int R = T::kRecSlots;
     const uint32_t bar0 = smem_u32(bars);
     auto bar = [&](int id, int slot) { return bar0 + 8u * (uint32_t)(id + slot); };
@@ -172,9 +195,11 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
     const int G = gridDim.x;
     const int K = (ntiles - (int)blockIdx.x + G - 1) / G;       // tiles of this CTA: blockIdx.x + k * G
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < DS; ++s) {
             mbar_init(bar(B_SLAB_FULL, s), T::kChunks);
             mbar_init(bar(B_SLAB_EMPTY, s), T::kCW);
+        }
+        for (int s = 0; s < DG; ++s) {
             mbar_init(bar(B_STAGED, s), T::kCW);
             mbar_init(bar(B_STAGE_FREE, s), 1);
         }
@@ -184,7 +209,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 6) slab0[(tid / 3) * T::kSlabDoubles + T::kZeroRow * SS + (tid % 3)] = 0.0;   // zero block of both slots
+    if (tid < 3 * DS) slab0[(tid / 3) * T::kSlabDoubles + T::kZeroRow * SS + (tid % 3)] = 0.0;   // zero block of every slot
     __syncthreads();
 
     if constexpr (T::kRegSplit) {           // warp-group-uniform: every warp of a group of four runs the same branch
@@ -270,7 +295,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         int ring_rd = 2 % T::kRowRing, ring_wr = 4 % T::kRowRing;   // ring slots of the rows of tasks i+2 (read) and i+4 (written)
         for (int it = 0; j < total; j += T::kPW, ++it) {
             const int row = c * 32 + lane;
-            const int slot = k & 1, buf = it & 1;
+            const int slot = k % DS, buf = it & 1;
             request_row(j + 4 * T::kPW, ring_wr);
             const bool active = act0;
             asm volatile("cp.async.wait_group 1;" ::: "memory");        // coordinates of this task, row of task i+2
@@ -294,14 +319,15 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
 #pragma unroll
                 for (int i = 0; i < 3 * T::kBlocks; ++i) ke[i] = x[i & (N - 1)];
 #else
-                element_tri<ET, MASS>(x, y, weighted != 0, ke);
+                element_tri<ET, MASS, SCALAR>(x, y, weighted != 0, ke);
 #endif
             }
-            mbar_wait(bar(B_SLAB_EMPTY, slot), ((k >> 1) & 1) ^ 1);     // consumers are done with tile k - 2
+            mbar_wait(bar(B_SLAB_EMPTY, slot), ((k / DS) & 1) ^ 1);     // consumers are done with tile k - DS
             if (active) {
                 double* dst = slab0 + slot * T::kSlabDoubles + row * SS;
 #pragma unroll
-                for (int i = 0; i < 3 * T::kBlocks; ++i) dst[i] = ke[i];
+                for (int i = 0; i < 3 * T::kBlocks; ++i)
+                    if (!SCALAR || i % 3 == 0) dst[i] = ke[i];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_SLAB_FULL, slot));
@@ -317,11 +343,11 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         int rslot = 0;
         uint32_t rpar = 0;
         for (int k = 0; k < K; ++k) {
-            const int slot = k & 1;
-            const uint32_t par = (k >> 1) & 1;
+            const int slot = k % DS, gslot = k % DG;
+            const uint32_t par = (k / DS) & 1, gpar = (k / DG) & 1;
             const unsigned char* rec = rec0 + rslot * T::kBlobCap;
             const double* slab = slab0 + slot * T::kSlabDoubles;
-            double* stage = reinterpret_cast<double*>(stage0 + slot * T::kStageCap);
+            double* stage = reinterpret_cast<double*>(stage0 + gslot * T::kStageCap);
             mbar_wait(bar(B_REC_FULL, rslot), rpar);
             const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
             const int nn = (int)hdr.x, nnp = (int)hdr.y;
@@ -339,69 +365,121 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             // thread first sums everything it owns into registers (slab reads + adds: the long part) and only then waits
             // for the slot: the slot is busy for the few store instructions, not for the whole consumer pass.
             bool slot_free = false;
-            for (int u = cw; u < groups * parts; u += T::kCW) {
-                const int g = u / parts, part = u - g * parts;
-                const int ln = g * 32 + lane;
+            // A warp's units are processed kUnits at a time with their loads interleaved (records of all, then slab
+            // blocks of all, then the stores).  Measured on cfg2: 1 unit 1.31 ms, 2 units 1.52 ms, 3 thirds 1.65 ms -- a
+            // consumer pass is not bound by the latency of its dependent chain, and the wider code costs registers.
+            constexpr int NU = T::kUnits;
+            const int nunits = groups * parts;
+            for (int u0 = cw; u0 < nunits; u0 += NU * T::kCW) {
+                int ln[NU], deg[NU], self[NU], p0[NU], p1[NU];
+                uint2 nd[NU];
+                bool diag[NU];
+                double* row0[NU];
+                double Ld[NU], Pd[NU];
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    const int u = u0 + j * T::kCW;
+                    const int g = u / parts, part = u - g * parts;
+                    ln[j] = g * 32 + lane;
 #if defined(FE_WS_WHATIF) && (FE_WS_WHATIF & 2)     // developer timing build: consumers only hand the buffers on
-                const bool live = false;
+                    const bool live = false;
 #else
-                const bool live = ln < nn;
+                    const bool live = u < nunits && ln[j] < nn;
 #endif
-                const uint2 nd = live ? node[ln] : make_uint2(0u, 0u);
-                const int deg = (nd.x >> 16) & 127, self = (nd.x >> 23) & 127;
-                const int p0 = (deg * part) / parts, p1 = (deg * (part + 1)) / parts;
+                    nd[j] = live ? node[ln[j]] : make_uint2(0u, 0u);
+                    deg[j] = (nd[j].x >> 16) & 127, self[j] = (nd[j].x >> 23) & 127;
+                    p0[j] = (deg[j] * part) / parts, p1[j] = (deg[j] * (part + 1)) / parts;
+                    row0[j] = stage + (SCALAR ? (nd[j].x & 0xFFFFu) >> 1 : 2 * (nd[j].x & 0xFFFFu));
+                    diag[j] = live && self[j] >= p0[j] && self[j] < p1[j];
+                    Ld[j] = Pd[j] = 0.0;
+                }
                 // A node's row 2n+1 lies 16 * deg bytes behind its row 2n: for odd degrees (9 on a Quad4 lattice, 7 on a
                 // Tri3 lattice) the two rows fall into different 16-byte bank groups, so letting every other group of
                 // four lanes write row 2n+1 first makes each quarter-warp store hit eight distinct groups.
-                const bool flip = ((lane >> 2) & 1) != 0;
-                double* row0 = stage + 2 * (nd.x & 0xFFFFu);
-                double* row1 = row0 + 2 * deg;
-                double* rowA = flip ? row1 : row0;
-                double* rowB = flip ? row0 : row1;
-                const bool diag = live && self >= p0 && self < p1;
-                double Ld = 0.0, Pd = 0.0;
-                if (diag) {                                             // diagonal block: all incident elements
-                    const int cnt = nd.y & 15, ioff = nd.y >> 4;
-                    for (int q = 0; q < cnt; ++q) {
-                        const unsigned loc = locs[ioff + q];
-                        const int a = loc & 15;
-                        const double* b = slab + (loc >> 4) * SS + 3 * (a * N - ((a * (a - 1)) >> 1));
-                        Ld += b[0];
-                        Pd += b[1];
-                    }
-                }
-                // kBatch neighbour positions in flight per thread: all records, then all slab loads, then the stores
-                for (int pb = p0; pb < p1 || !slot_free; pb += T::kBatch) {
-                    uint32_t r[T::kBatch];
+                const bool flip = !SCALAR && ((lane >> 2) & 1) != 0;
 #pragma unroll
-                    for (int q = 0; q < T::kBatch; ++q) r[q] = pb + q < p1 ? recs[(pb + q) * nnp + ln] : T::kZeroRec;
-                    double L[T::kBatch], P[T::kBatch], Q[T::kBatch];
-#pragma unroll
-                    for (int q = 0; q < T::kBatch; ++q) {
-                        const uint32_t s0 = r[q] & T::kSrcMask, s1 = r[q] >> T::kSrcBits;
-                        const double* b0 = slab + (s0 >> 1);
-                        const double* b1 = slab + (s1 >> 1);                // the zero block if absent
-                        const int f0 = s0 & 1, f1 = s1 & 1;                 // transposed block: P and Q trade places
-                        L[q] = b0[0] + b1[0];
-                        P[q] = b0[1 + f0] + b1[1 + f1];
-                        Q[q] = b0[2 - f0] + b1[2 - f1];
-                    }
-                    if (!slot_free) {                                   // warp-uniform: first store of this warp into the slot
-                        mbar_wait(bar(B_STAGE_FREE, slot), par ^ 1);    // bulk stores of tile k - 2 have read the buffer
-                        slot_free = true;
-                    }
-#pragma unroll
-                    for (int q = 0; q < T::kBatch; ++q) {
-                        const int p = pb + q;
-                        if (p < p1 && p != self) {
-                            *reinterpret_cast<double2*>(rowA + 2 * p) = flip ? make_double2(Q[q], L[q]) : make_double2(L[q], P[q]);
-                            *reinterpret_cast<double2*>(rowB + 2 * p) = flip ? make_double2(L[q], P[q]) : make_double2(Q[q], L[q]);
+                for (int j = 0; j < NU; ++j) {
+                    if (diag[j]) {                                      // diagonal block: all incident elements
+                        const int cnt = nd[j].y & 15, ioff = nd[j].y >> 4;
+                        for (int q = 0; q < cnt; ++q) {
+                            const unsigned loc = locs[ioff + q];
+                            const int a = loc & 15;
+                            const double* b = slab + (loc >> 4) * SS + 3 * (a * N - ((a * (a - 1)) >> 1));
+                            Ld[j] += b[0];
+                            if constexpr (!SCALAR) Pd[j] += b[1];
                         }
                     }
                 }
-                if (diag) {
-                    *reinterpret_cast<double2*>(rowA + 2 * self) = flip ? make_double2(Pd, Ld) : make_double2(Ld, Pd);
-                    *reinterpret_cast<double2*>(rowB + 2 * self) = flip ? make_double2(Ld, Pd) : make_double2(Pd, Ld);
+                // kBatch neighbour positions in flight per thread and unit: all records, then all slab loads, then the stores
+                for (int it = 0;; ++it) {
+                    bool more = !slot_free;
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) more = more || p0[j] + it * T::kBatch < p1[j];
+                    if (!more) break;
+                    uint32_t r[NU][T::kBatch];
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) {
+                        const int pb = p0[j] + it * T::kBatch;
+#pragma unroll
+                        for (int q = 0; q < T::kBatch; ++q) r[j][q] = pb + q < p1[j] ? recs[(pb + q) * nnp + ln[j]] : T::kZeroRec;
+                    }
+                    double L[NU][T::kBatch], P[NU][T::kBatch], Q[NU][T::kBatch];
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) {
+#pragma unroll
+                        for (int q = 0; q < T::kBatch; ++q) {
+                            const uint32_t s0 = r[j][q] & T::kSrcMask, s1 = r[j][q] >> T::kSrcBits;
+                            const double* b0 = slab + (s0 >> 1);
+                            const double* b1 = slab + (s1 >> 1);            // the zero block if absent
+                            const int f0 = s0 & 1, f1 = s1 & 1;             // transposed block: P and Q trade places
+                            L[j][q] = b0[0] + b1[0];
+                            if constexpr (!SCALAR) {
+                                P[j][q] = b0[1 + f0] + b1[1 + f1];
+                                Q[j][q] = b0[2 - f0] + b1[2 - f1];
+                            } else {
+                                P[j][q] = Q[j][q] = 0.0;
+                            }
+                        }
+                    }
+                    if (!slot_free) {                                   // warp-uniform: first store of this warp into the slot
+                        mbar_wait(bar(B_STAGE_FREE, gslot), gpar ^ 1);  // bulk stores of tile k - DG have read the buffer
+                        slot_free = true;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) {
+                        const int pb = p0[j] + it * T::kBatch;
+                        double* row1 = row0[j] + 2 * deg[j];
+                        double* rowA = flip ? row1 : row0[j];
+                        double* rowB = flip ? row0[j] : row1;
+#pragma unroll
+                        for (int q = 0; q < T::kBatch; ++q) {
+                            const int p = pb + q;
+                            if (p < p1[j] && p != self[j]) {
+                                if constexpr (SCALAR) {
+                                    row0[j][p] = L[j][q];
+                                } else {
+                                    *reinterpret_cast<double2*>(rowA + 2 * p) =
+                                        flip ? make_double2(Q[j][q], L[j][q]) : make_double2(L[j][q], P[j][q]);
+                                    *reinterpret_cast<double2*>(rowB + 2 * p) =
+                                        flip ? make_double2(L[j][q], P[j][q]) : make_double2(Q[j][q], L[j][q]);
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NU; ++j) {
+                    if (diag[j]) {
+                        if constexpr (SCALAR) {
+                            row0[j][self[j]] = Ld[j];
+                        } else {
+                            double* row1 = row0[j] + 2 * deg[j];
+                            double* rowA = flip ? row1 : row0[j];
+                            double* rowB = flip ? row0[j] : row1;
+                            *reinterpret_cast<double2*>(rowA + 2 * self[j]) = flip ? make_double2(Pd[j], Ld[j]) : make_double2(Ld[j], Pd[j]);
+                            *reinterpret_cast<double2*>(rowB + 2 * self[j]) = flip ? make_double2(Ld[j], Pd[j]) : make_double2(Pd[j], Ld[j]);
+                        }
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk store
@@ -409,7 +487,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             if (lane == 0) {
                 mbar_arrive(bar(B_SLAB_EMPTY, slot));
                 mbar_arrive(bar(B_REC_EMPTY, rslot));
-                mbar_arrive(bar(B_STAGED, slot));
+                mbar_arrive(bar(B_STAGED, gslot));
             }
             if (++rslot == R) rslot = 0, rpar ^= 1u;
         }
@@ -435,8 +513,8 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         }
         int4 d_cur = desc_of(dw), d_ahead = desc_of(dw + R);
         for (int k = dw; k < K; k += T::kDW) {
-            const int slot = k & 1;
-            const uint32_t par = (k >> 1) & 1;
+            const int slot = k % DG;
+            const uint32_t par = (k / DG) & 1;
             const int4 dn_cur = desc_of(k + T::kDW), dn_ahead = desc_of(k + T::kDW + R);   // next iteration's descriptors
             const int r0 = d_cur.z, nr = d_cur.w;
             int4 run = make_int4(0, 0, 0, 0);
@@ -445,6 +523,28 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             if (lane == 0 && k + R < K) {
                 mbar_wait(bar(B_REC_EMPTY, k % R), (uint32_t)((k / R) & 1));   // (already complete: consumers arrive on it first)
                 issue_rec(k + R, d_ahead);
+            }
+            if constexpr (SCALAR) {
+                // one-dof values: the warp walks the runs and writes each with coalesced 8-byte streaming stores
+                const double* sst = reinterpret_cast<const double*>(stage0 + slot * T::kStageCap);
+                for (int i = 0; i < nr; ++i) {
+                    int4 r;                              // runs 0..31 were fetched ahead of the wait, one per lane
+                    if (i < 32) {
+                        r.x = __shfl_sync(0xffffffffu, run.x, i), r.y = __shfl_sync(0xffffffffu, run.y, i);
+                        r.z = __shfl_sync(0xffffffffu, run.z, i), r.w = __shfl_sync(0xffffffffu, run.w, i);
+                    } else {
+                        r = __ldg(truns + r0 + i);
+                    }
+                    const long long g0 = (long long)(((unsigned long long)(unsigned)r.y << 32) | (unsigned)r.x) >> 1;   // nptr[first]
+                    const double* src = sst + (r.z >> 1);
+                    const int len = r.w >> 1;
+                    for (int e = lane; e < len; e += 32) __stcs(vals + g0 + e, src[e]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_STAGE_FREE, slot));
+                d_cur = dn_cur;
+                d_ahead = dn_ahead;
+                continue;
             }
             const uint32_t sbase = smem_u32(stage0 + slot * T::kStageCap);
             // one bulk store per run: fewer, larger copies drain faster (~35 ns per copy + 34 ps per byte measured)
@@ -469,7 +569,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
     }
 }
 
-template <int ET, bool MASS>
+template <int ET, bool MASS, bool SCALAR = false>
 static int launch_ws(int64_t ntiles, const int32_t* tconn, const double* coords, const int32_t* tdesc, const void* blobs,
                      const void* truns, double* vals, int weighted, cudaStream_t st) {
     using T = WsLayout<Elem<ET>::NNPE>;
@@ -478,8 +578,8 @@ static int launch_ws(int64_t ntiles, const int32_t* tconn, const double* coords,
     FE_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int64_t grid = sms;
     if (grid > ntiles) grid = ntiles;
-    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_ws<ET, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
-    k_assemble_ws<ET, MASS><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
+    FE_CUDA_TRY(cudaFuncSetAttribute(k_assemble_ws<ET, MASS, SCALAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmem));
+    k_assemble_ws<ET, MASS, SCALAR><<<(unsigned)grid, T::kThreads, T::kSmem, st>>>(
         (int)ntiles, tconn, reinterpret_cast<const double2*>(coords), reinterpret_cast<const int4*>(tdesc),
         static_cast<const unsigned char*>(blobs), static_cast<const int4*>(truns), vals, weighted);
     FE_CHECK_LAUNCH("k_assemble_ws");
@@ -681,7 +781,7 @@ int fe_assemble_ws(int elem_type, int op, int64_t ntiles, const int32_t* tconn, 
                    const void* blobs, const void* truns, double* vals, void* stream) {
     using namespace fe;
     FE_REQUIRE(ntiles >= 0 && ntiles < ((int64_t)1 << 31), "bad tile count");
-    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS) {
+    if (op != FE_OP_REFERENCE && op != FE_OP_WEIGHTED && op != FE_OP_MASS && op != FE_OP_POISSON) {
         set_error("fe_assemble_ws: unsupported operator %d", op);
         return FE_ERR_UNSUPPORTED;
     }
@@ -693,6 +793,10 @@ int fe_assemble_ws(int elem_type, int op, int64_t ntiles, const int32_t* tconn, 
     int rc = ensure_tables_tu(st);
     if (rc != FE_OK) return rc;
     const int w = op == FE_OP_WEIGHTED;
+    if (op == FE_OP_POISSON) {      // one dof per node: vals[nptr[n] + p]
+        if (elem_type == FE_QUAD4) return launch_ws<FE_QUAD4, false, true>(ntiles, tconn, coords, tdesc, blobs, truns, vals, 0, st);
+        if (elem_type == FE_TRI3) return launch_ws<FE_TRI3, false, true>(ntiles, tconn, coords, tdesc, blobs, truns, vals, 0, st);
+    }
     switch (elem_type) {
         case FE_QUAD4:
             return op == FE_OP_MASS ? launch_ws<FE_QUAD4, true>(ntiles, tconn, coords, tdesc, blobs, truns, vals, 1, st)

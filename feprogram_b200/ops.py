@@ -714,9 +714,9 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         wsp = _lib.tile_ws_params(pat.elem_type)
         # "auto": the warp-specialised kernel where it is the faster one (measured: Quad4 1.39 ms against 1.90 ms on cfg2;
         # Tri3's tiles are too small for its per-tile hand-offs: 1.51 ms against 1.25 ms), else the barrier-phased kernel
-        # (one-dof patterns: the bulk stores of the warp-specialised kernel need 16-byte aligned row runs, which 8-byte
-        # values do not give -> barrier-phased kernel)
-        want_ws = (kernel == "ws" or (kernel == "auto" and pat.elem_type == FE_QUAD4)) and pat.ndof == 2
+        # (one-dof patterns use the same plan: the kernel's SCALAR form stages 8-byte values and writes the runs with
+        # plain coalesced stores)
+        want_ws = kernel == "ws" or (kernel == "auto" and pat.elem_type == FE_QUAD4)
         if want_ws and wsp["blob_cap"] > 0:
             # ---- warp-specialised kernel: per-tile record blobs + runs of contiguous CSR rows ----
             wstats = torch.zeros(8, dtype=torch.int32, device=dev)

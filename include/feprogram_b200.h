@@ -73,7 +73,8 @@ extern "C" {
                              (elements.py:15-23, 153-163; BASELINE's "2D Poisson" wording; extension).  Its CSR
                              pattern is the node-level pattern itself (row_ptr = nptr, col_idx = nadj) and
                              vals[nptr[n] + p] is the value of (row n, column nadj[nptr[n] + p]).  Accepted by
-                             fe_element_matrices (Ke is nnpe x nnpe), fe_assemble and fe_assemble_tiled; the
+                             fe_element_matrices (Ke is nnpe x nnpe), fe_assemble, fe_assemble_tiled and
+                             fe_assemble_ws; the
                              values are bit-identical to the corresponding entries of FE_OP_REFERENCE. */
 
 /* Copies the thread-local message of the last failing call into buf (NUL-terminated). */
@@ -241,7 +242,9 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
  *                         stats[4] != 0 afterwards means the mesh is not representable (use fe_assemble).
  * The plan is usable iff fe_tile_layout's stats[6] <= out[0], stats[7] <= out[1], stats[0] <= out[3] of
  * fe_tile_ws_params (all 0 for element types this kernel does not handle) and stats[4] == 0 after the build.
- * Blob / run formats are documented in feprogram_b200/csrc/fe_tiles_ws.cu.  vals and blobs must be 16-byte aligned. */
+ * Blob / run formats are documented in feprogram_b200/csrc/fe_tiles_ws.cu.  vals and blobs must be 16-byte aligned.
+ * A node with more than out[2] distinct neighbours makes the plan unrepresentable (stats[4]).  op = FE_OP_POISSON
+ * uses the SAME plan (the plan holds no dof count) and writes one value per node-level non-zero. */
 void fe_tile_ws_params(int elem_type, int32_t out[4]);
 int fe_tile_ws_build(int elem_type, int64_t nslots, int64_t ntiles, const int32_t* tile_nodes, const int32_t* owner,
                      const int32_t* tile_ptr, const int32_t* noff, const int32_t* thalo, const int32_t* eptr,

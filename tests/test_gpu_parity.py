@@ -868,11 +868,15 @@ def test_poisson_operator_is_the_even_block_of_the_reference_matrix(torch_cuda, 
     ops.assemble_values(conn0, xy, pat2, None, v2, ops.FE_OP_REFERENCE)
     K2 = sp.csr_matrix((v2.cpu().numpy(), pat2.col_idx.cpu().numpy(), pat2.row_ptr.cpu().numpy()), shape=(n2, n2))
     assert np.array_equal(orc.poisson_submatrix(K2).data, v_rows.cpu().numpy())
-    plan = ops.tile_plan(conn0, xy, pat)
-    assert plan is not None and not plan.warp_specialised
-    v_tiled = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
-    ops.assemble_values(conn0, xy, pat, plan, v_tiled, ops.FE_OP_POISSON)
-    assert torch.equal(v_tiled, v_rows)
+    for kernel in ("auto", "phased", "ws"):          # warp-specialised (Quad4 default) and barrier-phased kernels
+        plan = ops.tile_plan(conn0, xy, pat, kernel=kernel)
+        if kernel == "ws" and et == 9:
+            assert plan is None
+            continue
+        assert plan is not None and plan.warp_specialised == (kernel == "ws" or (kernel == "auto" and et == 4))
+        v_tiled = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        ops.assemble_values(conn0, xy, pat, plan, v_tiled, ops.FE_OP_POISSON)
+        assert torch.equal(v_tiled, v_rows), kernel
     ke1 = torch.ops.feprogram.element_matrices(conn0[:8].contiguous(), xy, et, ops.FE_OP_POISSON).cpu().numpy()
     ke2 = torch.ops.feprogram.element_matrices(conn0[:8].contiguous(), xy, et, ops.FE_OP_REFERENCE).cpu().numpy()
     assert np.array_equal(ke1, ke2[:, 0::2, 0::2])
@@ -896,11 +900,15 @@ def test_poisson_tiled_equals_rows_on_larger_meshes(torch_cuda, kind, n, perturb
     pat = ops.symbolic(conn0, coords.shape[0], kind, 1)
     v_rows = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
     ops.assemble_values(conn0, xy, pat, None, v_rows, ops.FE_OP_POISSON)
-    plan = ops.tile_plan(conn0, xy, pat)
-    assert plan is not None
-    v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
-    ops.assemble_values(conn0, xy, pat, plan, v, ops.FE_OP_POISSON)
-    assert torch.equal(v, v_rows)
+    for kernel in ("auto", "phased") + (() if kind == 9 else ("ws",)):
+        plan = ops.tile_plan(conn0, xy, pat, kernel=kernel)
+        assert plan is not None, kernel
+        G = 4096                                             # guard zones either side of the output stay untouched
+        buf = torch.full((pat.nnz + 2 * G,), float("nan"), dtype=torch.float64, device="cuda")
+        v = buf[G:G + pat.nnz]
+        ops.assemble_values(conn0, xy, pat, plan, v, ops.FE_OP_POISSON)
+        assert torch.equal(v, v_rows), kernel
+        assert bool(torch.isnan(buf[:G]).all()) and bool(torch.isnan(buf[G + pat.nnz:]).all()), kernel
     # constants are in the null space of the scalar stiffness; the matrix is symmetric bit for bit
     K = sp.csr_matrix((v.cpu().numpy(), pat.col_idx.cpu().numpy(), pat.row_ptr.cpu().numpy()),
                       shape=(pat.nrows, pat.nrows))
