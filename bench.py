@@ -337,6 +337,31 @@ def dist_parity_check(torch, dist, fdist, rank, world, dev, comm):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local):
+    """N > 1: run this rank's host threads on the NUMA node its GPU hangs off, BEFORE any pinned buffer is allocated
+    (first-touch places the pages there), so that eight simultaneous uploads do not all cross one socket link.
+    Best effort: returns the node, or None when the topology files are not there."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -344,6 +369,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_node = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     # the contract is ONE JSON line on stdout: anything libraries print there (NCCL's version banner) goes to stderr
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -578,7 +604,8 @@ def run_ours(args):
             "config": {"workload": "quad4_%dx%d_2dof_reference_operator%s" % (n, (args.ny_per_rank or n) * world if world > 1 else n,
                                                                               "" if world == 1 else "_row_blocks"),
                        "elements": int(nelem_total), "l2": "inputs exceed L2 (no flush needed)" if nelem_total / world > 2e6 else "inputs fit L2",
-                       "symbolic_phase_s": symbolic_s, "partition": "dp%d element row blocks, owned-row assembly with ghost elements" % world},
+                       "symbolic_phase_s": symbolic_s, "partition": "dp%d element row blocks, owned-row assembly with ghost elements" % world,
+                       "host_numa_node_rank0": numa_node},
             "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": asm_gbs / hbm_peak,
                          "traffic": traffic.get(kernel_name),
