@@ -22,6 +22,8 @@ __all__ = [
     "perturb_interior",
     "shuffle_numbering",
     "edge_sets",
+    "unstructured_tri3",
+    "unstructured_quad4",
 ]
 
 
@@ -145,3 +147,58 @@ def boundary_edges(conn1: np.ndarray, nodes) -> np.ndarray:
     for c in cols:
         on &= np.isin(c[bnd], tags)
     return (np.stack([c[bnd[on]] for c in cols], axis=1) - 1).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------
+# genuinely unstructured meshes (varying node degree), the mesh class gmsh hands the reference
+# ----------------------------------------------------------------------------------------
+def _side_sets(coords: np.ndarray):
+    """[bottom, right, top, left] 1-based tag sets of a mesh of the unit square (corners in two sets)."""
+    x, y = coords[:, 0], coords[:, 1]
+    pick = lambda m: set((np.nonzero(m)[0] + 1).tolist())  # noqa: E731
+    return [pick(y == 0.0), pick(x == 1.0), pick(y == 1.0), pick(x == 0.0)]
+
+
+def unstructured_tri3(n: int, seed: int = 0, dtype=np.int64):
+    """Delaunay triangulation of the unit square: an (n+1) x (n+1) jittered point set (boundary points stay on the
+    boundary, interior points move by up to 0.35 h) in RANDOM node order -- node degrees 4..9, no numbering locality.
+    Counter-clockwise triangles.  Needs SciPy (host-side input preparation only)."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = perturb_interior(_lattice(n, n), n, n, 0.35, seed=seed + 1)
+    pts = pts[rng.permutation(pts.shape[0])]
+    tri = Delaunay(pts).simplices.astype(np.int64)
+    a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+    area2 = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])
+    tri = tri[np.abs(area2) > 1e-14]                       # collinear boundary slivers
+    area2 = area2[np.abs(area2) > 1e-14]
+    flip = area2 < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    return (tri + 1).astype(dtype), np.ascontiguousarray(pts), _side_sets(pts)
+
+
+def unstructured_quad4(n: int, seed: int = 0, dtype=np.int64):
+    """All-quad unstructured mesh: every triangle of ``unstructured_tri3`` is split into three quads through its
+    edge midpoints and centroid (what a recombining mesher produces locally): node degrees 3..~10, convex
+    counter-clockwise quads, random node order."""
+    tri, pts, _ = unstructured_tri3(n, seed, np.int64)
+    tri = tri - 1
+    npt = pts.shape[0]
+    e = np.sort(np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]]), axis=1)
+    key = e[:, 0] * npt + e[:, 1]
+    uniq, inv = np.unique(key, return_inverse=True)
+    mid = 0.5 * (pts[uniq // npt] + pts[uniq % npt])
+    nt = tri.shape[0]
+    m01, m12, m20 = (npt + inv[:nt]), (npt + inv[nt:2 * nt]), (npt + inv[2 * nt:])
+    g = npt + uniq.size + np.arange(nt)
+    cen = pts[tri].mean(axis=1)
+    coords = np.concatenate([pts, mid, cen])
+    quads = np.concatenate([np.stack([tri[:, 0], m01, g, m20], axis=1),
+                            np.stack([tri[:, 1], m12, g, m01], axis=1),
+                            np.stack([tri[:, 2], m20, g, m12], axis=1)])
+    rng = np.random.default_rng(seed + 2)
+    quads = quads[rng.permutation(quads.shape[0])]
+    perm = rng.permutation(coords.shape[0])                 # old node -> new node
+    new_coords = np.empty_like(coords)
+    new_coords[perm] = coords
+    return (perm[quads] + 1).astype(dtype), np.ascontiguousarray(new_coords), _side_sets(new_coords)

@@ -24,6 +24,8 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def case_mesh(kind, n, perturbed, shuffled):
+    if kind == "u4":            # genuinely unstructured all-quad mesh (node degrees 4..15, random numbering)
+        return mesh.unstructured_quad4(n, seed=5)
     if kind == 4:
         conn, coords, bc = mesh.structured_quad4(n)
         mx = n
@@ -101,6 +103,8 @@ def post_golden():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["unstructured"]:
+        return full_case("q4_unstructured", "u4", 6, False, False)
     if sys.argv[1:] == ["mass"]:
         return mass_golden()
     if sys.argv[1:] == ["post"]:
@@ -126,6 +130,7 @@ def main():
     full_case("q4_16x16_pert", 4, 16, True, False)
     full_case("q9_4x4", 9, 4, False, False)
     full_case("q9_6x6_pert_shuf", 9, 6, True, True)
+    full_case("q4_unstructured", "u4", 6, False, False)
     # scalar known answers on BASELINE cfg1 and a Quad9 case
     np.savez_compressed(os.path.join(OUT, "scalars.npz"),
                         fields=np.array(["nnz0", "normF0", "trace0", "nnz_bc", "nDir", "nNeu", "Umin", "Umax",

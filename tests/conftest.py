@@ -38,7 +38,7 @@ def golden():
     return load
 
 
-FULL_CASES = ["q4_4x4", "q4_12x12_pert_shuf", "q4_16x16_pert", "q9_4x4", "q9_6x6_pert_shuf"]
+FULL_CASES = ["q4_4x4", "q4_12x12_pert_shuf", "q4_16x16_pert", "q9_4x4", "q9_6x6_pert_shuf", "q4_unstructured"]
 
 
 def bc_sets_of(z):
