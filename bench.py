@@ -206,17 +206,21 @@ def bc_dofs(bc):
                                       2 * (np.array(sorted(s), dtype=np.int64) - 1) + 1])) for s in (bc[0], bc[3])]
 
 
-def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=False, ops_list=(0,), ndof=2):
+def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=False, ops_list=(0,), ndof=2,
+                    unstructured=False):
     """Resident-input timing of one mesh on one GPU: symbolic phase, numeric assembly per operator, SpMV, PCG.
     Returns a dict; used for cfg3 / cfg4 / cfg5 and the strong-scaling single-GPU reference."""
     from feprogram_b200 import mesh, ops
-    gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
-    conn_h, coords_h, bc = gen(n, dtype=np.int32)
-    mx = 2 * n if kind == 9 else n
-    if perturb:
-        coords_h = mesh.perturb_interior(coords_h, mx, mx, 0.2, seed=7)
-    if shuffle:
-        conn_h, coords_h, bc, _ = mesh.shuffle_numbering(conn_h, coords_h, bc, seed=11)
+    if unstructured:       # Delaunay-based, random numbering: `shuffle` then only asks for the renumbered solver copy
+        conn_h, coords_h, bc = (mesh.unstructured_quad4 if kind == 4 else mesh.unstructured_tri3)(n, seed=3, dtype=np.int32)
+    else:
+        gen = {4: mesh.structured_quad4, 9: mesh.structured_quad9, 3: mesh.structured_tri3}[kind]
+        conn_h, coords_h, bc = gen(n, dtype=np.int32)
+        mx = 2 * n if kind == 9 else n
+        if perturb:
+            coords_h = mesh.perturb_interior(coords_h, mx, mx, 0.2, seed=7)
+        if shuffle:
+            conn_h, coords_h, bc, _ = mesh.shuffle_numbering(conn_h, coords_h, bc, seed=11)
     conn = torch.from_numpy(conn_h - 1).to(dev)
     coords = torch.from_numpy(coords_h).to(dev)
     nnode = coords_h.shape[0]
@@ -235,6 +239,7 @@ def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=
     vals = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
     asm_bytes = conn.shape[0] * kind * 4 + nnode * 16 + pat.nnz * 8
     out = {"elements": int(conn.shape[0]), "nnz": int(pat.nnz), "symbolic_phase_s": sym_s, "renumbered": renumbered,
+           "plan": None if plan is None else {k: plan.stats.get(k) for k in ("mode", "ntiles", "kernel", "max_nodes", "max_halo")},
            "kernel": ("k_assemble_ws" if plan is not None and plan.warp_specialised else
                       "k_assemble_tiled" if plan is not None else "k_assemble_rows"),
            "algorithmic_bytes_per_launch": asm_bytes, "assembly": {}}
@@ -245,7 +250,7 @@ def single_gpu_case(torch, dev, kind, n, reps, cg_iters, perturb=False, shuffle=
         out["assembly"][{0: "stiffness", 1: "weighted", 2: "mass", 3: "stiffness"}[op]] = {
             "ms_per_launch": ms, "elements_per_s": conn.shape[0] / ms * 1e3, "gbs": asm_bytes / ms / 1e6}
     ops.assemble_values(conn, coords, pat, plan, vals, ops_list[0] if ndof == 1 else 0)
-    if plan is not None and ndof == 1:      # the timed kernel against the independent row kernel, bit for bit, at this size
+    if plan is not None and (ndof == 1 or unstructured):      # the timed kernel against the independent row kernel, bit for bit, at this size
         v_r = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device=dev)
         ops.assemble_values(conn, coords, pat, None, v_r, ops_list[0])
         out["parity_checked"] = {"kernel": out["kernel"], "against": "k_assemble_rows (independent kernel), NaN-prefilled output",
@@ -683,6 +688,10 @@ def run_other_config(args, torch, dev, hbm_peak, peak_src, real_stdout):
         n = args.n if args.n != 4096 else 2048
         r = single_gpu_case(torch, dev, 9, n, K, args.cg_iters, ops_list=(0, 2))
         workload = "quad9_%dx%d_2dof_stiffness_and_mass" % (n, n)
+    elif args.config == "unstructured":
+        n = args.n if args.n != 4096 else 800
+        r = single_gpu_case(torch, dev, 4, n, K, args.cg_iters, shuffle=True, unstructured=True)
+        workload = "quad4_unstructured_delaunay_split_%d_points_per_side_random_numbering" % (n + 1)
     elif args.config == "poisson":
         n = args.n
         r = single_gpu_case(torch, dev, 4, n, K, args.cg_iters, ops_list=(3,), ndof=1)
@@ -697,7 +706,7 @@ def run_other_config(args, torch, dev, hbm_peak, peak_src, real_stdout):
             "ms_per_step": a["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "elements": r["elements"], "l2": "inputs exceed L2 (no flush needed)",
-                       "symbolic_phase_s": r["symbolic_phase_s"], "renumbered": r["renumbered"]},
+                       "symbolic_phase_s": r["symbolic_phase_s"], "renumbered": r["renumbered"], "plan": r.get("plan")},
             "roofline": {"kernel": r["kernel"], "bound": "hbm", "achieved": a["gbs"], "peak": hbm_peak, "unit": "GB/s",
                          "frac": a["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"], "ms_per_launch": a["ms_per_launch"]},
@@ -715,7 +724,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "poisson"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "poisson", "unstructured"],
                     help="cfg2 = the main line (Quad4 4096^2); cfg3 = Quad9 2048^2 stiffness + mass; cfg5 = Tri3 shuffled; "
                          "poisson = cfg2's scalar one-dof variant (all three on 1 GPU)")
     ap.add_argument("--operator", default=None, choices=["reference", "poisson"], help="alias: --operator poisson = --config poisson")
