@@ -24,7 +24,9 @@ over peer memory against SciPy's direct solve of the assembled system), `e2e_ful
 assemble -> solve -> U on the host at 512 x 512, beside the CPU port's assemble + spsolve).
 
 `--config cfg3` (Quad9 2048^2, stiffness + mass) and `--config cfg5` (Tri3 5000^2 x 2, perturbed, shuffled
-numbering) emit the same line for BASELINE configs[2] / configs[4] on one GPU; `--config poisson` (= `--operator
+numbering) emit the same line for BASELINE configs[2] / configs[4] on one GPU (cfg5 also under torchrun on N GPUs:
+general element-block partition of the shuffled mesh, "scaling": "strong"); `--config unstructured` a Delaunay-based
+all-quad mesh; `--config poisson` (= `--operator
 poisson`) for the scalar one-dof-per-node variant of cfg2 (FE_OP_POISSON = K[0::2, 0::2] of the reference operator).
 """
 from __future__ import annotations
@@ -678,10 +680,104 @@ def strong_cfg4(args, torch, dist, rank, world, dev, part):
     return out
 
 
+def cfg5_multi_gpu(args, torch, dev, hbm_peak, peak_src, real_stdout):
+    """--config cfg5 with N > 1 (BASELINE configs[4]): perturbed Tri3 mesh, randomly shuffled node numbering, general
+    element-block partition over the ranks (partition_mesh: Z-curve local numbering), owned-row assembly without a
+    collective, peer-memory / NCCL PCG.  Every rank generates the same synthetic mesh on the host and keeps its share."""
+    import torch.distributed as dist
+    from feprogram_b200 import dist as fdist
+    from feprogram_b200 import mesh
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = args.n if args.n != 4096 else 5000
+    K, W = args.steps, max(3, args.warmup)
+    conn, coords, bc = mesh.structured_tri3(n, dtype=np.int32)
+    coords = mesh.perturb_interior(coords, n, n, 0.2, 0)
+    conn, coords, bc, _ = mesh.shuffle_numbering(conn, coords, bc, 1)
+    m = fdist.exchange_send_lists(fdist.partition_mesh(conn - 1, coords, rank, world, locality=True))
+    g2l = np.full(coords.shape[0], -1, dtype=np.int64)
+    g2l[m.node_gid] = np.arange(m.nnode)
+
+    def loc(tags):
+        l = g2l[np.fromiter((int(t) for t in tags), dtype=np.int64) - 1]
+        l = l[l >= 0]
+        return np.sort(np.concatenate([2 * l, 2 * l + 1]))
+    nelem_total, nnode_total = conn.shape[0], coords.shape[0]
+    dir_l, neu_l = loc(bc[0]), loc(bc[3])
+    del conn, coords, g2l
+    comm = fdist.DistFemProblem.make_comm(rank, world, dev)
+    p = fdist.DistFemProblem(m, dev, 3, comm)
+    symbolic_s = p.symbolic_s
+    p.set_bc(dir_l, neu_l)
+    halo = "peer-memory (NVLink loads + flag-gated scalar exchange)" if (args.halo == "p2p" and p.enable_p2p()) else "nccl"
+    clk = ClockSampler(dev.index or 0)
+    clk.__enter__()
+
+    def timed(f, reps, warm):
+        for _ in range(warm):
+            f()
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            f()
+        b.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step():
+        p.assemble()
+        p.apply_bc()
+    ms_step = timed(step, K, W)
+    ms_asm = timed(p.assemble, K, 1)
+    x = torch.randn(p.nrows_local, dtype=torch.float64, device=dev)
+    y = torch.empty_like(x)
+    ms_spmv = timed(lambda: p.spmv_owned(x, y), max(K, 5), 3)
+    iters = args.cg_iters
+    p.solve(rtol=0.0, maxit=10, check_every=10, p2p=halo != "nccl")
+    ms_pcg = timed(lambda: p.solve(rtol=0.0, maxit=iters, check_every=iters, p2p=halo != "nccl"), 1, 0)
+    clk.__exit__()
+    stats = torch.tensor([p.pat.nnz, m.conn.shape[0], m.n_owned, m.nnode - m.n_owned, symbolic_s], dtype=torch.float64, device=dev)
+    allst = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(allst, stats)
+    if rank == 0:
+        nnz = sum(float(s[0]) for s in allst)
+        asm_bytes = (nelem_total * 3 * 4 + nnode_total * 16 + nnz * 8) / world
+        spmv_bytes = (12 * nnz + 20 * 2 * nnode_total) / world
+        asm_gbs, spmv_gbs = asm_bytes / ms_asm / 1e6, spmv_bytes / ms_spmv / 1e6
+        line = {"metric": METRIC, "value": nelem_total / ms_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "tri3_%dx%dx2_perturbed_shuffled_numbering" % (n, n), "elements": nelem_total,
+                           "l2": "inputs exceed L2 (no flush needed)", "symbolic_phase_s": max(float(s[4]) for s in allst),
+                           "partition": "dp%d element blocks of the shuffled mesh (general partition, Z-curve local numbering), "
+                                        "owned-row assembly with ghost elements" % world,
+                           "ghost_nodes_per_rank": [int(s[3]) for s in allst],
+                           "tile_plan": None if p.plan is None else p.plan.stats.get("mode")},
+                "roofline": {"kernel": "k_assemble_tiled" if p.plan is not None else "k_assemble_rows", "bound": "hbm",
+                             "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": asm_bytes, "ms_per_launch": ms_asm,
+                             "per": "GPU (owned elements, nodes and non-zeros of a rank)"},
+                "cg": {"spmv_ms": ms_spmv, "spmv_gbs": spmv_gbs, "spmv_frac": spmv_gbs / hbm_peak, "pcg_iters_timed": iters,
+                       "pcg_iters_per_s": iters / ms_pcg * 1e3, "halo": halo},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": 3 * K, "clocks": clk.summary()}
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_other_config(args, torch, dev, hbm_peak, peak_src, real_stdout):
     """--config cfg3 (Quad9 2048^2, stiffness + mass) / cfg5 (Tri3 5000^2 x 2, perturbed, shuffled tags) / poisson (the
     scalar one-dof-per-node variant of cfg2, SURVEY §8d: 104 algorithmic bytes per element): one GPU."""
     K, W = args.steps, max(3, args.warmup)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if args.config != "cfg5":
+            raise SystemExit("--config %s is a one-GPU line; only cfg2 (default) and cfg5 run on N > 1" % args.config)
+        return cfg5_multi_gpu(args, torch, dev, hbm_peak, peak_src, real_stdout)
     clk = ClockSampler(dev.index or 0)
     clk.__enter__()
     if args.config == "cfg3":
