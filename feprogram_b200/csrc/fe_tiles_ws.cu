@@ -47,6 +47,10 @@ template <int N> struct WsLayout {
     static constexpr int kRows = kTE + halo_cap(N);               // slab rows = rows per tile of tconn
     static constexpr int kChunks = (kRows + 31) / 32;             // producer tasks per tile
     static constexpr int kZeroRow = kRows;
+    // Task (tile k, c) evaluates slab rows of chunk (c + k) % kChunks: with as many producer warps as chunks a warp
+    // would otherwise own the same chunk of every tile, and the last chunks of a tile (its halo rows) are partly or
+    // wholly empty -- on a Quad4 lattice one warp in six would idle and two of the busy ones share a scheduler.
+    __host__ __device__ static constexpr int rotated_chunk(int c, int k) { return (c + k) % kChunks; }
     static constexpr int kSlabDoubles = (((kRows + 1) * kSS) + 1) & ~1;
 #ifndef FE_WS_PW
 #define FE_WS_PW 6
@@ -161,6 +165,17 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32
                  : "memory");
 }
 
+#ifdef FE_WS_TRACE      // developer build: per-warp event time stamps (SM clock) of the first kTraceTiles tiles of CTA 0
+constexpr int kTraceTiles = 512, kTraceEvents = 8;
+__device__ long long g_ws_trace[16][kTraceTiles][kTraceEvents];
+#define FE_TRACE(k, ev)                                                                          \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (k) < kTraceTiles) g_ws_trace[threadIdx.x >> 5][(k)][(ev)] = clock64(); \
+    } while (0)
+#else
+#define FE_TRACE(k, ev) ((void)0)
+#endif
+
 // =================================================================================================
 // numeric kernel
 // =================================================================================================
@@ -225,7 +240,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         auto row_addr = [&](int j) -> const int32_t* {
             if (j >= total) return nullptr;
             const int k = j / T::kChunks, c = j - k * T::kChunks;
-            const int row = c * 32 + lane;
+            const int row = T::rotated_chunk(c, k) * 32 + lane;
             if (row >= T::kRows) return nullptr;
             const long long t = (long long)blockIdx.x + (long long)k * G;
             return tconn + (t * T::kRows + row) * N;
@@ -294,11 +309,13 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
         while (c >= T::kChunks) c -= T::kChunks, ++k;
         int ring_rd = 2 % T::kRowRing, ring_wr = 4 % T::kRowRing;   // ring slots of the rows of tasks i+2 (read) and i+4 (written)
         for (int it = 0; j < total; j += T::kPW, ++it) {
-            const int row = c * 32 + lane;
+            const int row = T::rotated_chunk(c, k) * 32 + lane;
             const int slot = k % DS, buf = it & 1;
+            FE_TRACE(k, 0);
             request_row(j + 4 * T::kPW, ring_wr);
             const bool active = act0;
             asm volatile("cp.async.wait_group 1;" ::: "memory");        // coordinates of this task, row of task i+2
+            FE_TRACE(k, 1);
             double x[N], y[N];
             if (active) {
 #pragma unroll
@@ -322,7 +339,9 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                 element_tri<ET, MASS, SCALAR>(x, y, weighted != 0, ke);
 #endif
             }
+            FE_TRACE(k, 2);
             mbar_wait(bar(B_SLAB_EMPTY, slot), ((k / DS) & 1) ^ 1);     // consumers are done with tile k - DS
+            FE_TRACE(k, 3);
             if (active) {
                 double* dst = slab0 + slot * T::kSlabDoubles + row * SS;
 #pragma unroll
@@ -331,6 +350,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(B_SLAB_FULL, slot));
+            FE_TRACE(k, 4);
             act0 = act1;
             act1 = ahead.x >= 0;
             c += T::kPW;
@@ -348,7 +368,9 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             const unsigned char* rec = rec0 + rslot * T::kBlobCap;
             const double* slab = slab0 + slot * T::kSlabDoubles;
             double* stage = reinterpret_cast<double*>(stage0 + gslot * T::kStageCap);
+            FE_TRACE(k, 0);
             mbar_wait(bar(B_REC_FULL, rslot), rpar);
+            FE_TRACE(k, 1);
             const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
             const int nn = (int)hdr.x, nnp = (int)hdr.y;
             const uint2* node = reinterpret_cast<const uint2*>(rec + 16);
@@ -361,6 +383,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             constexpr int parts = T::kParts;
             const int groups = nnp >> 5;
             mbar_wait(bar(B_SLAB_FULL, slot), par);
+            FE_TRACE(k, 2);
             // The staging slot is still being read by the bulk stores of tile k - 2 for most of this tile's time.  So a
             // thread first sums everything it owns into registers (slab reads + adds: the long part) and only then waits
             // for the slot: the slot is busy for the few store instructions, not for the whole consumer pass.
@@ -442,7 +465,9 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                         }
                     }
                     if (!slot_free) {                                   // warp-uniform: first store of this warp into the slot
+                        FE_TRACE(k, 3);
                         mbar_wait(bar(B_STAGE_FREE, gslot), gpar ^ 1);  // bulk stores of tile k - DG have read the buffer
+                        FE_TRACE(k, 4);
                         slot_free = true;
                     }
 #pragma unroll
@@ -489,6 +514,7 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
                 mbar_arrive(bar(B_REC_EMPTY, rslot));
                 mbar_arrive(bar(B_STAGED, gslot));
             }
+            FE_TRACE(k, 5);
             if (++rslot == R) rslot = 0, rpar ^= 1u;
         }
     } else {
@@ -519,7 +545,9 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
             const int r0 = d_cur.z, nr = d_cur.w;
             int4 run = make_int4(0, 0, 0, 0);
             if (lane < nr) run = __ldg(truns + r0 + lane);               // in flight while the consumers finish the tile
+            FE_TRACE(k, 0);
             mbar_wait(bar(B_STAGED, slot), par);
+            FE_TRACE(k, 1);
             if (lane == 0 && k + R < K) {
                 mbar_wait(bar(B_REC_EMPTY, k % R), (uint32_t)((k / R) & 1));   // (already complete: consumers arrive on it first)
                 issue_rec(k + R, d_ahead);
@@ -559,8 +587,10 @@ __global__ void __launch_bounds__(WsLayout<Elem<ET>::NNPE>::kThreads, 1) k_assem
 #endif
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            FE_TRACE(k, 2);
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
+            FE_TRACE(k, 3);
             if (lane == 0) mbar_arrive(bar(B_STAGE_FREE, slot));
             d_cur = dn_cur;
             d_ahead = dn_ahead;
@@ -735,6 +765,15 @@ __global__ void __launch_bounds__(128) k_tile_ws_records(
 }  // namespace fe
 
 extern "C" {
+
+#ifdef FE_WS_TRACE
+int fe_ws_trace_read(void* host, size_t bytes) {          // developer build only
+    using namespace fe;
+    FE_REQUIRE(bytes <= sizeof(g_ws_trace), "too many bytes");
+    FE_CUDA_TRY(cudaMemcpyFromSymbol(host, g_ws_trace, bytes));
+    return FE_OK;
+}
+#endif
 
 void fe_tile_ws_params(int elem_type, int32_t out[4]) {
     using namespace fe;
