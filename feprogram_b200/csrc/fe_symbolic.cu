@@ -34,11 +34,37 @@ __global__ void k_fill_incidence(int64_t nslots, int nnpe, const int32_t* __rest
     einc[eptr[n] + slot] = e * 16 + a;
 }
 
-// In-place insertion sort of each node's (short) incidence segment: ascending element id.
+// In-place sort of each node's (short) incidence segment: ascending element id.  Segments of up to eight entries (every
+// node of a 2-D mesh of decent quality) are loaded with independent loads, sorted in registers by a fixed network of
+// compare-exchanges and written back -- one memory round trip instead of one per insertion step; longer ones take
+// the insertion sort.
 __global__ void k_sort_incidence(int64_t nnode, const int32_t* __restrict__ eptr, int32_t* __restrict__ einc) {
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= nnode) return;
     const int lo = eptr[n], hi = eptr[n + 1];
+    const int cnt = hi - lo;
+    if (cnt <= 1) return;
+    if (cnt <= 8) {
+        int v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = i < cnt ? einc[lo + i] : 0x7fffffff;
+        auto cx = [&](int& a, int& b) {
+            const int x = a < b ? a : b, y = a < b ? b : a;
+            a = x;
+            b = y;
+        };
+        // 19-comparator network for eight keys (Batcher's odd-even merge sort)
+        cx(v[0], v[1]); cx(v[2], v[3]); cx(v[4], v[5]); cx(v[6], v[7]);
+        cx(v[0], v[2]); cx(v[1], v[3]); cx(v[4], v[6]); cx(v[5], v[7]);
+        cx(v[1], v[2]); cx(v[5], v[6]);
+        cx(v[0], v[4]); cx(v[1], v[5]); cx(v[2], v[6]); cx(v[3], v[7]);
+        cx(v[2], v[4]); cx(v[3], v[5]);
+        cx(v[1], v[2]); cx(v[3], v[4]); cx(v[5], v[6]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < cnt) einc[lo + i] = v[i];
+        return;
+    }
     for (int i = lo + 1; i < hi; ++i) {
         const int v = einc[i];
         int j = i;
@@ -71,11 +97,13 @@ __device__ __forceinline__ int build_adjacency(int nnpe, const int32_t* __restri
     return cnt;
 }
 
-// Fast form of build_adjacency: the list lives in shared memory, entry i of thread t at s[i * 128 + t] (conflict
-// free), at most kFastAdj entries.  Returns the count, or -1 when the node has more distinct neighbours than that
-// (the caller then takes the general thread-local path above; structured and typical unstructured 2-D meshes
-// never do: 9 / 25 / 7 neighbours for Quad4 / Quad9 / Tri3 lattices).
-constexpr int kFastAdj = 32;
+// Fast form of build_adjacency: the list lives in shared memory, entry i of thread t at s[i * kAdjStride + t], at most
+// kFastAdj entries.  The odd stride makes both views conflict free: a thread walking its own list (fixed t per lane,
+// same i) and a warp reading the lists of its 32 nodes transposed (k_adjacency_fill's coalesced write-out).  Returns
+// the count, or -1 when the node has more distinct neighbours than that (the caller then takes the general
+// thread-local path above; structured and typical unstructured 2-D meshes never do: 9 / 25 / 7 neighbours for
+// Quad4 / Quad9 / Tri3 lattices).
+constexpr int kFastAdj = 32, kAdjStride = 129;
 template <int NNPE>
 __device__ __forceinline__ int build_adjacency_smem(const int32_t* __restrict__ conn, const int32_t* __restrict__ einc,
                                                     int k0, int k1, int* s) {
@@ -94,11 +122,11 @@ __device__ __forceinline__ int build_adjacency_smem(const int32_t* __restrict__ 
         for (int b = 0; b < NNPE; ++b) {
             const int v = row[b];
             int j = cnt;
-            while (j > 0 && s[(j - 1) * 128] > v) --j;
-            if (j > 0 && s[(j - 1) * 128] == v) continue;
+            while (j > 0 && s[(j - 1) * kAdjStride] > v) --j;
+            if (j > 0 && s[(j - 1) * kAdjStride] == v) continue;
             if (cnt == kFastAdj) return -1;
-            for (int i = cnt; i > j; --i) s[i * 128] = s[(i - 1) * 128];
-            s[j * 128] = v;
+            for (int i = cnt; i > j; --i) s[i * kAdjStride] = s[(i - 1) * kAdjStride];
+            s[j * kAdjStride] = v;
             ++cnt;
         }
     }
@@ -110,7 +138,7 @@ __global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, const in
                                                          const int32_t* __restrict__ eptr,
                                                          const int32_t* __restrict__ einc, int32_t* __restrict__ ndeg,
                                                          int32_t* __restrict__ status) {
-    __shared__ int s_list[kFastAdj * 128];
+    __shared__ int s_list[kFastAdj * kAdjStride];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n > nnode) return;
     if (n == nnode) {  // slot for the grand total after the scan
@@ -130,62 +158,127 @@ __global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, const in
     ndeg[n] = cnt;
 }
 
+// Lane o = the last lane whose (ascending) start offset is <= q: the owner of flat position q of a warp's range.
+__device__ __forceinline__ int owner_lane(int start, int q) {
+    int o = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int c = o + step;
+        if (__shfl_sync(0xffffffffu, start, c) <= q) o = c;
+    }
+    return o;
+}
+
+// nadj (the sorted neighbour list of every node) and epos (for every incidence (node, element) the position of the
+// element's nodes in that node's list).  One thread per node builds the list in shared memory; the lists of a warp's
+// 32 consecutive nodes form ONE contiguous range of nadj, and their incidences one contiguous range of epos, so both
+// are written out flat by the whole warp (coalesced: a thread writing its own row would touch one 32-byte sector per
+// 4-byte store).  A node that exceeds a staging capacity writes its own rows directly.
+constexpr int kPosWords = 16;            // staged epos words per node: 16 incidences (Quad4 / Tri3), 5 (Quad9)
 template <int NNPE>
 __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int32_t* __restrict__ conn,
                                                         const int32_t* __restrict__ eptr,
                                                         const int32_t* __restrict__ einc,
                                                         const int32_t* __restrict__ nptr, int32_t* __restrict__ nadj,
                                                         uint8_t* __restrict__ epos) {
-    __shared__ int s_list[kFastAdj * 128];
+    constexpr int W = (NNPE + 3) / 4;    // words of packed positions per incidence
+    __shared__ int s_list[kFastAdj * kAdjStride];
+    __shared__ unsigned s_pos[kPosWords * kAdjStride];
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= nnode) return;
-    const int k0 = eptr[n], k1 = eptr[n + 1];
-    const int p0 = nptr[n];
+    const bool valid = n < nnode;
+    const int64_t nc = valid ? n : nnode;
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const int k0 = eptr[nc], k1 = valid ? eptr[nc + 1] : k0;
+    const int p0 = nptr[nc];
     int* s = s_list + threadIdx.x;
-    int cnt = build_adjacency_smem<NNPE>(conn, einc, k0, k1, s);
-    if (cnt < 0) {                                   // rare: the general thread-local path
+    int cnt = valid ? build_adjacency_smem<NNPE>(conn, einc, k0, k1, s) : 0;
+    int staged = cnt;                                // entries of nadj this lane leaves to the flat write-out
+    if (cnt < 0) {                                   // rare: the general thread-local path, rows written directly
+        staged = 0;
         int list[kMaxAdj];
         cnt = build_adjacency(NNPE, conn, einc, k0, k1, list);
-        if (cnt < 0) return;
-        for (int i = 0; i < cnt; ++i) nadj[p0 + i] = list[i];
-        for (int k = k0; k < k1; ++k) {
-            const int64_t e = einc[k] >> 4;
-            for (int b = 0; b < NNPE; ++b) {
-                const int v = conn[e * NNPE + b];
-                int lo = 0, hi = cnt - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (list[mid] < v) lo = mid + 1;
-                    else hi = mid;
+        if (cnt >= 0) {
+            for (int i = 0; i < cnt; ++i) nadj[p0 + i] = list[i];
+            for (int k = k0; k < k1; ++k) {
+                const int64_t e = einc[k] >> 4;
+                for (int b = 0; b < NNPE; ++b) {
+                    const int v = conn[e * NNPE + b];
+                    int lo = 0, hi = cnt - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (list[mid] < v) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    epos[(int64_t)k * NNPE + b] = (uint8_t)lo;
                 }
-                epos[(int64_t)k * NNPE + b] = (uint8_t)lo;
             }
         }
-        return;
+        cnt = 0;                                     // nothing more to do for this node below
     }
-    for (int i = 0; i < cnt; ++i) nadj[p0 + i] = s[i * 128];
-    for (int k = k0; k < k1; ++k) {
+    __syncwarp();
+    {   // nadj: flat positions [p0 of lane 0, end of lane 31)
+        const int qb = __shfl_sync(0xffffffffu, p0, 0), qe = __shfl_sync(0xffffffffu, p0 + (staged > 0 ? staged : 0), 31);
+        const int qe_all = __shfl_sync(0xffffffffu, valid ? nptr[nc + 1] : p0, 31);
+        (void)qe;
+        for (int q0 = qb; q0 < qe_all; q0 += 32) {
+            const int q = q0 + lane;
+            const int o = owner_lane(p0, q);
+            const int i = q - __shfl_sync(0xffffffffu, p0, o);
+            const int c = __shfl_sync(0xffffffffu, staged, o);
+            if (q < qe_all && i < c) nadj[q] = s_list[i * kAdjStride + wbase + o];
+        }
+    }
+    // positions: packed bytes per incidence, staged (word w of incidence j at s_pos[(j * W + w) * kAdjStride + t])
+    const int ninc = k1 - k0;
+    const bool pos_staged = cnt > 0 && ninc * W <= kPosWords;
+    for (int k = k0; k < k1 && cnt > 0; ++k) {
         const int64_t e = einc[k] >> 4;
-        unsigned packed[(NNPE + 3) / 4];
+        unsigned packed[W];
 #pragma unroll
-        for (int w = 0; w < (NNPE + 3) / 4; ++w) packed[w] = 0u;
+        for (int w = 0; w < W; ++w) packed[w] = 0u;
 #pragma unroll
         for (int b = 0; b < NNPE; ++b) {
             const int v = __ldg(conn + e * NNPE + b);
             int lo = 0, hi = cnt - 1;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (s[mid * 128] < v) lo = mid + 1;
+                if (s[mid * kAdjStride] < v) lo = mid + 1;
                 else hi = mid;
             }
             packed[b >> 2] |= (unsigned)lo << (8 * (b & 3));
         }
-        uint8_t* dst = epos + (int64_t)k * NNPE;
-        if constexpr (NNPE == 4) {
-            *reinterpret_cast<unsigned*>(dst) = packed[0];             // 4-byte aligned: k * 4
-        } else {
+        if (pos_staged) {
 #pragma unroll
-            for (int b = 0; b < NNPE; ++b) dst[b] = (uint8_t)(packed[b >> 2] >> (8 * (b & 3)));
+            for (int w = 0; w < W; ++w) s_pos[((k - k0) * W + w) * kAdjStride + threadIdx.x] = packed[w];
+        } else {
+            uint8_t* dst = epos + (int64_t)k * NNPE;
+            if constexpr (NNPE == 4) {
+                *reinterpret_cast<unsigned*>(dst) = packed[0];             // 4-byte aligned: k * 4
+            } else {
+#pragma unroll
+                for (int b = 0; b < NNPE; ++b) dst[b] = (uint8_t)(packed[b >> 2] >> (8 * (b & 3)));
+            }
+        }
+    }
+    __syncwarp();
+    {   // epos: flat units [k0 of lane 0, k1 of lane 31) x (one word per incidence for Quad4, else NNPE bytes)
+        constexpr int U = NNPE == 4 ? 1 : NNPE;
+        const int kb = __shfl_sync(0xffffffffu, k0, 0), ke = __shfl_sync(0xffffffffu, k1, 31);
+        const int flag = pos_staged ? 1 : 0;
+        for (long long u0 = (long long)kb * U; u0 < (long long)ke * U; u0 += 32) {
+            const long long u = u0 + lane;
+            const int k = (int)(u / U), b = (int)(u - (long long)k * U);
+            const int o = owner_lane(k0, k);
+            const int j = k - __shfl_sync(0xffffffffu, k0, o);
+            const int ok = __shfl_sync(0xffffffffu, flag, o);
+            if (u < (long long)ke * U && ok) {
+                if constexpr (NNPE == 4) {
+                    reinterpret_cast<unsigned*>(epos)[u] = s_pos[j * kAdjStride + wbase + o];
+                } else {
+                    const unsigned w = s_pos[(j * W + (b >> 2)) * kAdjStride + wbase + o];
+                    epos[u] = (uint8_t)(w >> (8 * (b & 3)));
+                }
+            }
         }
     }
 }

@@ -107,9 +107,14 @@ __global__ void k_tile_owner(int64_t nnode, const int32_t* __restrict__ eptr, co
     if (n >= nnode) return;
     const int k0 = eptr[n], k1 = eptr[n + 1];
     int own = 0x7fffffff;
-    for (int k = k0; k < k1; ++k) {
-        const int t = tile_of(einv, einc[k] >> 4);
-        own = t < own ? t : own;
+    for (int kb = k0; kb < k1; kb += 4) {         // four incidences at a time: independent loads, two round trips per batch
+        int e[4], t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = kb + i < k1 ? einc[kb + i] >> 4 : -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = e[i] >= 0 ? tile_of(einv, e[i]) : 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) own = t[i] < own ? t[i] : own;
     }
     if (k0 == k1) {
         owner[n] = -1;
@@ -119,13 +124,26 @@ __global__ void k_tile_owner(int64_t nnode, const int32_t* __restrict__ eptr, co
     atomicAdd(tile_ncount + own, 1);
 }
 
+// Four consecutive nodes per thread: the owner -> (atomic slot, tile start) -> store chains of the four are
+// independent, so four of them are in flight per thread (the kernel is bound by that latency, not by bandwidth).
 __global__ void k_tile_bucket(int64_t nnode, const int32_t* __restrict__ owner, const int32_t* __restrict__ tile_nptr,
                               int32_t* __restrict__ cursor, int32_t* __restrict__ tile_nodes) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= nnode) return;
-    const int t = owner[n];
-    if (t < 0) return;
-    tile_nodes[tile_nptr[t] + atomicAdd(cursor + t, 1)] = (int32_t)n;
+    const int64_t n0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (n0 >= nnode) return;
+    int t[4], base[4], slot[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = n0 + j < nnode ? owner[n0 + j] : -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        base[j] = slot[j] = 0;
+        if (t[j] >= 0) {
+            base[j] = tile_nptr[t[j]];
+            slot[j] = atomicAdd(cursor + t[j], 1);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (t[j] >= 0) tile_nodes[base[j] + slot[j]] = (int32_t)(n0 + j);
 }
 
 // One thread per tile: sort the tile's node list ascending (deterministic order after the atomic bucket
@@ -163,14 +181,44 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
     int* nodes = s_nodes[w];
     int* cand = s_cand[w];
     int* sorted = s_sorted[w];
-    for (int i = lane; i < nn; i += 32) sorted[i] = tile_nodes[lo + i];
     if (lane == 0) s_ncand[w] = 0;
-    __syncwarp();
-    for (int i = lane; i < nn; i += 32) {       // node ids are distinct: rank = number of smaller ids
-        const int v = sorted[i];
-        int r = 0;
-        for (int j = 0; j < nn; ++j) r += sorted[j] < v;
-        nodes[r] = v;
+    {   // sort the node ids: bitonic network over 256 keys held 8 per lane (key index = 32 * r + lane), padded with
+        // INT_MAX -- exchanges at distance >= 32 are register to register, the others one shuffle per key
+        constexpr int R = kLayoutNodes / 32;
+        int v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = 32 * r + lane < nn ? tile_nodes[lo + 32 * r + lane] : 0x7fffffff;
+#pragma unroll
+        for (int k = 2; k <= kLayoutNodes; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 32) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int q = r ^ (j >> 5);
+                        if (q > r) {                                  // pair (r, q): ascending iff bit k of the index is clear
+                            const bool up = ((32 * r) & k) == 0;
+                            const int a = v[r], b = v[q];
+                            const int mn = a < b ? a : b, mx = a < b ? b : a;
+                            v[r] = up ? mn : mx;
+                            v[q] = up ? mx : mn;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int idx = 32 * r + lane;
+                        const int o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                        const bool up = (idx & k) == 0, lower = (lane & j) == 0;
+                        const int mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+                        v[r] = (up == lower) ? mn : mx;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (32 * r + lane < nn) nodes[32 * r + lane] = v[r];
     }
     __syncwarp();
     int ni = 0, nw = 0, maxcnt = 0, maxdeg = 0, nruns = 0;
@@ -442,6 +490,10 @@ __device__ __forceinline__ void q9_jacobian(const double2* __restrict__ xy, int 
 // Quad9: one of five threads of an element evaluates the block rows A1 (and A2) of the upper triangle --
 // {0}, {1,8}, {2,7}, {3,6}, {4,5}: nine blocks = 27 accumulators each -- reading the element's node
 // coordinates from shared memory.  Same pair arithmetic (and therefore the same bits) as element_row_pair.
+#ifndef FE_Q9_GP_UNROLL
+#define FE_Q9_GP_UNROLL 3
+#endif
+constexpr int kQ9GpUnroll = FE_Q9_GP_UNROLL;      // Gauss points unrolled per trip of the block-row loop
 template <int A1, int A2, bool MASS>
 __device__ __forceinline__ void q9_block_rows(const double* __restrict__ Jrow, double* __restrict__ dst) {
     constexpr int N = 9;
@@ -452,7 +504,7 @@ __device__ __forceinline__ void q9_block_rows(const double* __restrict__ Jrow, d
     for (int i = 0; i < 3 * N1; ++i) acc1[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 3 * N2; ++i) acc2[i] = 0.0;
-#pragma unroll 3
+#pragma unroll kQ9GpUnroll
     for (int g = 0; g < 9; ++g) {
         // Jacobian and scale of this Gauss point: evaluated once per element by q9_jacobians (shared memory)
         const double j00 = Jrow[5 * g], j01 = Jrow[5 * g + 1], j10 = Jrow[5 * g + 2], j11 = Jrow[5 * g + 3];
@@ -597,6 +649,36 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
     int buf = 0;
     double2* s_xy = reinterpret_cast<double2*>(rec_base + 2 * T::kRecBytes);   // Quad9 only
     double* s_jac = reinterpret_cast<double*>(rec_base + 2 * T::kRecBytes + T::kXyBytes);   // Quad9 only
+    // Quad9: the rows' node coordinates are gathered into shared memory by cp.async ONE TILE AHEAD (issued behind
+    // barrier A, in flight during phase 2; s_xy is read only by the Jacobian step, which is over by then), from node
+    // ids each thread loaded one tile earlier still -- so neither of the two dependent DRAM latencies of the gather
+    // sits on a tile.  A thread carries two of the kRows * 9 ids and the "row is live" flag of its slab row.
+    constexpr int kXyEntries = kSingle ? 0 : T::kRows * N;
+    static_assert(kSingle || 2 * kTileThreads >= T::kRows * N, "two coordinate entries per thread cover a tile");
+    int nid0 = -1, nid1 = -1, live_n = -1;          // ids of the NEXT tile to gather / first node of this thread's row there
+    bool live = false;
+    auto load_ids = [&](int64_t tt, int& a, int& b, int& first) {
+        a = b = first = -1;
+        if (tt >= ntiles) return;
+        const int32_t* rows = tconn + tt * T::kRows * N;
+        if (tid < kXyEntries) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(a) : "l"(rows + tid));
+        if (tid + kTileThreads < kXyEntries) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(b) : "l"(rows + tid + kTileThreads));
+        if (rowid < T::kRows) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(first) : "l"(rows + rowid * N));
+    };
+    auto request_xy = [&](int a, int b) {
+        if (a >= 0) cp_async_16(s_xy + tid, coords + a);
+        if (b >= 0) cp_async_16(s_xy + tid + kTileThreads, coords + b);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if constexpr (!kSingle) {
+        int first;
+        load_ids(t, nid0, nid1, first);
+        live = first >= 0;
+        request_xy(nid0, nid1);
+        load_ids(t + gridDim.x, nid0, nid1, live_n);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
 
     for (; t < ntiles; t += gridDim.x) {
         const int64_t tn = t + gridDim.x, tn2 = tn + gridDim.x;
@@ -635,15 +717,9 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 }
             }
         } else {
-            // Quad9: stage the rows' node coordinates, then five threads per row evaluate block rows
-            const int32_t* rows = tconn + t * T::kRows * N;
-            for (int i = tid; i < T::kRows * N; i += kTileThreads) {
-                const int node = __ldg(rows + i);
-                if (node >= 0) s_xy[i] = __ldg(coords + node);
-            }
-            __syncthreads();
+            // Quad9: the rows' node coordinates are in s_xy (gathered one tile ahead); five threads per row share the
+            // nine Jacobians, then evaluate their block rows
             const int row = rowid;
-            const bool live = row < T::kRows && __ldg(rows + row * N) >= 0;
             if (live) {
                 for (int g = part; g < 9; g += T::kParts)
                     q9_jacobian<MASS>(s_xy + row * N, g, weighted != 0, s_jac + row * T::kJacStride + 5 * g);
@@ -697,6 +773,12 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
         // prefetches, in flight during phase 2: descriptor of the tile after next, connectivity row of the tile
         // after next (straight into the register set the next tile just vacated), coordinates of the next tile
         int4 f0 = e0, f1 = e1;
+        if constexpr (!kSingle) {
+            if (more) request_xy(nid0, nid1);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            live = live_n >= 0;
+            load_ids(tn2, nid0, nid1, live_n);
+        }
         if constexpr (kSingle) {
             if (more) {
 #pragma unroll
@@ -770,6 +852,7 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 }
             }
         }
+        if constexpr (!kSingle) asm volatile("cp.async.wait_group 0;" ::: "memory");   // next tile's coordinates (and records)
         __syncthreads();   // slab and this record buffer are free again
         d0 = e0;
         d1 = e1;
@@ -879,7 +962,7 @@ int fe_tile_layout(int elem_type, int64_t nnode, int64_t ntiles, const int32_t* 
     FE_CUDA_TRY(cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
     if (nnode > 0) {
         FE_REQUIRE(owner && tile_nodes && noff && eptr && einc && nptr, "null pointer");
-        k_tile_bucket<<<grid_for(nnode, 256), 256, 0, st>>>(nnode, owner, tile_nptr, cursor, tile_nodes);
+        k_tile_bucket<<<grid_for((nnode + 3) / 4, 256), 256, 0, st>>>(nnode, owner, tile_nptr, cursor, tile_nodes);
         FE_CHECK_LAUNCH("k_tile_bucket");
     }
     const int64_t s = ntiles + 1;

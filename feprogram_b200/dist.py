@@ -256,10 +256,14 @@ class DistFemProblem:
 
         def form_tiles(lattice):
             formed["tiles"] = ops.tile_formation(self.conn.shape[0], local.nnode, elem_type, lattice, csr_side)
+
+        def early_layout(eptr, einc, nptr):          # first half of the plan, concurrent with fe_adjacency_fill
+            formed["layout"] = ops.plan_layout_early(self.conn, elem_type, local.nnode, eptr, einc, nptr,
+                                                     formed.get("tiles"), csr_side)
         self.pat = ops.symbolic(self.conn, local.nnode, elem_type, 2, csr_stream=None if timing else csr_side,
-                                between=form_tiles)
+                                between=form_tiles, after_fill=early_layout)
         self.plan = ops.tile_plan(self.conn, self.coords, self.pat, coords_ready=lambda: main.wait_event(coords_ready),
-                                  formation=formed.get("tiles"))
+                                  formation=formed.get("tiles"), layout=formed.get("layout"))
         main.wait_event(coords_ready)
         self.pat.csr_ready()
         self.symbolic_s = None

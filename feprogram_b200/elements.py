@@ -412,7 +412,8 @@ class FemProblem:
             self._bc_early(st)
         if "pattern" not in st:   # one-time symbolic phase for this mesh: CSR pattern, slot map, tile plan
             # overlaps the coordinate upload; the scipy-compatible row_ptr / col_idx (which neither the tile plan nor the
-            # numeric kernel reads) are expanded on a side stream, off the critical path
+            # numeric kernel reads: they are a pure function of the node-level pattern) are expanded when K, the
+            # reference-numbered system or the solver first asks for them (Pattern.row_ptr)
             # A lattice numbering's tiles depend on the connectivity alone: they are formed on the side stream while the
             # first half of the symbolic kernels runs on this one (the hook is called before the phase's host sync).
             csr_side = side_streams(st["conn"].device)[2]
@@ -420,11 +421,18 @@ class FemProblem:
 
             def form_tiles(lattice):
                 formed["tiles"] = ops.tile_formation(self.nelem, self.nnode, et, lattice, csr_side)
-            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, self.ndof, csr_stream=csr_side, between=form_tiles)
+
+            # ... and the first half of their plan (ownership, node / halo lists, tile-ordered connectivity) needs the
+            # incidence and the node degrees only: it is built on the side stream while fe_adjacency_fill runs here.
+            def early_layout(eptr, einc, nptr):
+                formed["layout"] = ops.plan_layout_early(st["conn_s"], et, self.nnode, eptr, einc, nptr,
+                                                         formed.get("tiles"), csr_side)
+            st["pattern"] = ops.symbolic(st["conn_s"], self.nnode, et, self.ndof, csr="lazy", between=form_tiles,
+                                         after_fill=early_layout)
             self._mark("symbolic done")
             # the plan waits for the coordinate upload only if it needs coordinates (a lattice numbering does not)
             st["plan"] = ops.tile_plan(st["conn_s"], st["coords_s"], st["pattern"], coords_ready=self._coords_ready,
-                                       formation=formed.get("tiles"))
+                                       formation=formed.get("tiles"), layout=formed.get("layout"))
             self._mark("plan done")
         self._coords_ready()
         pat = st["pattern"]

@@ -171,7 +171,7 @@ def incidence(conn: Tensor, nnode: int, elem_type: int) -> Tuple[Tensor, Tensor]
     return eptr, einc
 
 
-def _adjacency_impl(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int, between=None):
+def _adjacency_impl(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int, between=None, after_fill=None):
     _chk_dev(conn, eptr, einc)
     nelem, nnpe = conn.shape
     nnode = eptr.numel() - 1
@@ -193,6 +193,8 @@ def _adjacency_impl(conn: Tensor, eptr: Tensor, einc: Tensor, elem_type: int, be
         epos = torch.empty(max(1, nelem * nnpe * nnpe), dtype=torch.uint8, device=dev)[: nelem * nnpe * nnpe]
         _lib.check(L.fe_adjacency_fill(elem_type, nnode, _ptr(conn), _ptr(eptr), _ptr(einc), _ptr(nptr), _ptr(nadj),
                                        _ptr(epos), _stream(conn)))
+        if after_fill is not None:
+            after_fill(eptr, einc, nptr)       # eptr / einc / nptr are complete (the sync above), nadj / epos are being written
     return nptr, nadj, epos
 
 
@@ -332,8 +334,8 @@ class Pattern:
     nptr: Tensor
     nadj: Tensor
     epos: Tensor
-    row_ptr: Tensor
-    col_idx: Tensor
+    _row_ptr: Optional[Tensor] = None   # scipy-compatible dof-level CSR pattern: expanded eagerly by symbolic(), or on the
+    _col_idx: Optional[Tensor] = None   # first read of row_ptr / col_idx (symbolic(..., csr="lazy"))
     _max_deg: Optional[int] = None
     lattice: Optional[tuple] = None    # (Morton keys from a lattice numbering, status, event) -- fe_lattice_keys
     csr_event: Optional[object] = None                 # set when row_ptr / col_idx were expanded on a side stream
@@ -342,7 +344,24 @@ class Pattern:
         """Orders the current stream after the expansion of row_ptr / col_idx (no-op unless they came from a side stream)."""
         ev, self.csr_event = self.csr_event, None
         if ev is not None:
-            torch.cuda.current_stream(self.row_ptr.device).wait_event(ev)
+            torch.cuda.current_stream(self.nptr.device).wait_event(ev)
+
+    def _expand(self) -> None:
+        if self._col_idx is None:       # lazy pattern: expand now, on the current stream (nptr / nadj are complete on it)
+            self._row_ptr, self._col_idx = torch.ops.feprogram.csr_expand(self.nptr, self.nadj, self.ndof, self.nnz >= 2 ** 31)
+        self.csr_ready()
+
+    @property
+    def row_ptr(self) -> Tensor:
+        """Row pointers of the dof-level CSR matrix (int32, int64 from 2^31 non-zeros): what scipy's K.tocsr() holds."""
+        self._expand()
+        return self._row_ptr
+
+    @property
+    def col_idx(self) -> Tensor:
+        """Column indices of the dof-level CSR matrix (int32), rows in ascending column order."""
+        self._expand()
+        return self._col_idx
 
     @property
     def max_deg(self) -> int:
@@ -353,19 +372,25 @@ class Pattern:
 
     @property
     def nnz(self) -> int:
-        return self.col_idx.numel()
+        return self.ndof * self.ndof * self.nadj.numel()
 
     @property
     def nrows(self) -> int:
         return self.ndof * self.nnode
 
 
-def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2, csr_stream=None, between=None) -> Pattern:
+def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2, csr_stream=None, between=None,
+             after_fill=None, csr: str = "eager") -> Pattern:
     """CSR pattern + element->slot map for a mesh (conn int32 0-based on the device).  ``csr_stream``: expand the
     scipy-compatible row_ptr / col_idx on that stream (concurrently with whatever follows on the current one); the
-    caller orders later users with ``Pattern.csr_ready()``.  ``between(lattice)``: called once the first half of the
+    caller orders later users with ``Pattern.csr_ready()``.  ``csr="lazy"``: do not expand them at all until something
+    reads ``Pattern.row_ptr`` / ``col_idx`` -- the assembly kernels, the node-block SpMV and the PCG solve work on the
+    node-level pattern (nptr, nadj), of which the dof-level one is a pure function (fe_csr_expand).  ``between(lattice)``: called once the first half of the
     symbolic kernels is queued and before the phase's host synchronisation -- the facade forms the tiles of a lattice
-    numbering on another stream there (``tile_formation``), concurrently with those kernels."""
+    numbering on another stream there (``tile_formation``), concurrently with those kernels.
+    ``after_fill(eptr, einc, nptr)``: called right after the last symbolic kernel (fe_adjacency_fill) is queued; its
+    arguments are complete by then, so the facade builds the first half of the tile plan on another stream while that
+    kernel runs (``plan_layout_early``)."""
     nelem = conn.shape[0]
     lattice = None
     if elem_type == FE_QUAD4 and nelem > 0:
@@ -378,10 +403,14 @@ def symbolic(conn: Tensor, nnode: int, elem_type: int, ndof: int = 2, csr_stream
             lattice = (keys, lstat, torch.cuda.current_stream(conn.device).record_event())
     eptr, einc = torch.ops.feprogram.incidence(conn, nnode, elem_type)
     hook = (lambda: between(lattice)) if between is not None else None
-    nptr, nadj, epos = _adjacency_impl(conn, eptr, einc, elem_type, hook)
+    nptr, nadj, epos = _adjacency_impl(conn, eptr, einc, elem_type, hook, after_fill)
     nnz = ndof * ndof * nadj.numel()
     ev = None
-    if csr_stream is None:
+    if csr not in ("eager", "lazy"):
+        raise ValueError("csr must be 'eager' or 'lazy'")
+    if csr == "lazy":
+        row_ptr = col_idx = None
+    elif csr_stream is None:
         row_ptr, col_idx = torch.ops.feprogram.csr_expand(nptr, nadj, ndof, nnz >= 2 ** 31)
     else:
         main = torch.cuda.current_stream(conn.device)
@@ -522,13 +551,14 @@ def tile_formation(nelem: int, nnode: int, elem_type: int, lattice, stream) -> O
 
 
 def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, kernel: str = "auto",
-              coords_ready=None, formation: Optional[dict] = None) -> Optional[TilePlan]:
+              coords_ready=None, formation: Optional[dict] = None, layout: Optional[dict] = None) -> Optional[TilePlan]:
     """Builds the tile plan; returns None when the mesh does not fit the tiled kernel's capacities
     (the caller then uses the row-tile kernel fe_assemble, which has none).  ``kernel``: "auto" = the
     warp-specialised kernel where it exists (Quad4 / Tri3) and its capacities hold, else the barrier-phased one;
     "ws" / "phased" force one of them (tests compare the two bit for bit).  ``coords_ready``: called before the
     coordinates are first read (the facade passes the wait for their upload); a mesh whose numbering is a row-major
-    lattice (Pattern.lattice) gets its tiles from the numbering and never calls it.
+    lattice (Pattern.lattice) gets its tiles from the numbering and never calls it.  ``formation`` / ``layout``: the
+    results of ``tile_formation`` / ``plan_layout_early`` when the caller ran them ahead of time on a side stream.
 
     Elements are ordered along the Morton curve of a grid of one-element cells.  Strategy 1 ("blocks"): a
     tile = one aligned Z-block of 128 cells (exact 8x16 patches on structured meshes).  If that needs many
@@ -543,6 +573,11 @@ def tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool = True, k
     if te == 0 or pat.nelem == 0:
         return None
     ideal = (pat.nelem + te - 1) // te
+    if layout is not None:                 # first half of the plan built ahead of time, on another stream (plan_layout_early)
+        torch.cuda.current_stream(conn.device).wait_event(layout["event"])
+        plan = _plan_records(conn, pat, layout, kernel)
+        if plan is not None:
+            return plan
     if formation is not None and pat.lattice is not None:       # tiles formed ahead of time (tile_formation)
         torch.cuda.current_stream(conn.device).wait_event(formation["event"])
         plan = _tile_plan(conn, coords, pat, True, 1.0, "blocks", kernel, lattice=(pat.lattice[0], formation["w"]),
@@ -676,14 +711,33 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
             eloc = torch.empty(nelem, dtype=torch.int32, device=dev)
             eloc[eperm.long()] = (tid << 8) | row          # tid / row are per sorted position
             del block, flag, seg_start, tid, starts, row, idx
-        if ntiles >= (1 << 23):
-            return None
+        lay = _plan_layout(conn, pat.elem_type, nnode, pat.eptr, pat.einc, pat.nptr, ntiles, eperm, eloc, tile_estart)
+    if lay is None:
+        return None
+    lay["info"].update(morton=morton, cell_scale=cell_scale, mode=mode_name)
+    return _plan_records(conn, pat, lay, kernel)
+
+
+def _plan_layout(conn: Tensor, elem_type: int, nnode: int, eptr: Tensor, einc: Tensor, nptr: Tensor, ntiles: int,
+                 eperm: Tensor, eloc: Tensor, tile_estart: Tensor) -> Optional[dict]:
+    """First half of the plan, on the current stream: node ownership, per-tile node / halo lists and offsets, the
+    tile-ordered connectivity.  Needs the incidence and the node DEGREES (nptr) but neither nadj nor epos, so the facade
+    runs it on a side stream while fe_adjacency_fill is still busy (``plan_layout_early``).  One host synchronisation
+    (every size and capacity).  Returns None when a capacity of the tiled kernels is exceeded."""
+    L = _lib.lib()
+    params = _lib.tile_params(elem_type)
+    hcap = params["halo_cap"]
+    dev = conn.device
+    if ntiles >= (1 << 23):
+        return None
+    with torch.cuda.device(dev):
+        st = _stream(conn)
         s = ntiles + 1
         einv = eloc
         ws = torch.empty(max(1, L.fe_scan_workspace_bytes(s)), dtype=torch.uint8, device=dev)
         owner = torch.empty(nnode, dtype=torch.int32, device=dev)
         tile_ncount = torch.empty(s, dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_owner(nnode, ntiles, _ptr(pat.eptr), _ptr(pat.einc), _ptr(einv), _ptr(owner),
+        _lib.check(L.fe_tile_owner(nnode, ntiles, _ptr(eptr), _ptr(einc), _ptr(einv), _ptr(owner),
                                    _ptr(tile_ncount), st))
         tile_ptr = torch.empty((6, s), dtype=torch.int32, device=dev)     # nodes, items, halo, work, blob / 16, runs
         _scan_into(tile_ncount, tile_ptr[0], ws)
@@ -693,8 +747,8 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         thalo = torch.empty((ntiles, hcap), dtype=torch.int32, device=dev)
         counts = torch.empty((5, s), dtype=torch.int32, device=dev)
         stats = torch.empty(8, dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_layout(pat.elem_type, nnode, ntiles, _ptr(owner), _ptr(tile_ptr[0]), _ptr(pat.eptr), _ptr(pat.einc),
-                                    _ptr(einv), _ptr(pat.nptr), _ptr(cursor), _ptr(tile_nodes), _ptr(noff),
+        _lib.check(L.fe_tile_layout(elem_type, nnode, ntiles, _ptr(owner), _ptr(tile_ptr[0]), _ptr(eptr), _ptr(einc),
+                                    _ptr(einv), _ptr(nptr), _ptr(cursor), _ptr(tile_nodes), _ptr(noff),
                                     _ptr(thalo), _ptr(counts), _ptr(stats), st))
         for r in range(5):
             _scan_into(counts[r], tile_ptr[r + 1], ws)
@@ -703,14 +757,54 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
         max_nodes, max_items, max_halo, max_cnt = (int(v) for v in tail[6:10])
         max_work, max_blob, max_stage = int(tail[11]), int(tail[12]), int(tail[13])
         info = dict(max_nodes=max_nodes, max_items=max_items, max_halo=max_halo, max_cnt=max_cnt, max_work=max_work,
-                    items=n_items, halo_elems=n_halo, work_items=n_work, morton=morton, cell_scale=cell_scale,
-                    mode=mode_name, ntiles=ntiles)
+                    items=n_items, halo_elems=n_halo, work_items=n_work, ntiles=ntiles)
         if (max_nodes > params["max_nodes"] or max_items >= params["max_items"] - 1 or max_halo > hcap
                 or max_work > params["max_work"]):
             return None
         tconn = torch.empty((ntiles, params["tile_rows"], conn.shape[1]), dtype=torch.int32, device=dev)
-        _lib.check(L.fe_tile_conn(pat.elem_type, ntiles, _ptr(conn), _ptr(eperm), _ptr(tile_estart), _ptr(thalo),
+        _lib.check(L.fe_tile_conn(elem_type, ntiles, _ptr(conn), _ptr(eperm), _ptr(tile_estart), _ptr(thalo),
                                   _ptr(tile_ptr), _ptr(tconn), st))
+    return dict(ntiles=ntiles, eloc=eloc, owner=owner, tile_ptr=tile_ptr, tile_nodes=tile_nodes, noff=noff, thalo=thalo,
+                stats=stats, tconn=tconn, info=info, nslots=nslots, n_items=n_items, n_work=n_work, blob16=blob16,
+                nruns=nruns, max_nodes=max_nodes, max_blob=max_blob, max_stage=max_stage)
+
+
+def plan_layout_early(conn: Tensor, elem_type: int, nnode: int, eptr: Tensor, einc: Tensor, nptr: Tensor,
+                      formation: Optional[dict], stream) -> Optional[dict]:
+    """``_plan_layout`` of a lattice numbering on ``stream`` (the one ``tile_formation`` ran on), concurrently with
+    whatever the caller's stream is doing -- the facade calls it right after queueing fe_adjacency_fill, whose inputs
+    (incidence, node degrees) are complete by then (``symbolic(after_fill=...)`` runs behind the phase's host
+    synchronisation).  Synchronises ``stream`` only.  Returns None when there is nothing formed or a capacity fails."""
+    if formation is None:
+        return None
+    dev = conn.device
+    main = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev), torch.cuda.stream(stream):
+        for t in (conn, eptr, einc, nptr):
+            t.record_stream(stream)
+        lay = _plan_layout(conn, elem_type, nnode, eptr, einc, nptr, formation["ntiles"], formation["eperm"],
+                           formation["eloc"], formation["tile_estart"])
+        if lay is None:
+            return None
+        lay["event"] = stream.record_event()
+    for v in lay.values():
+        if isinstance(v, Tensor):
+            v.record_stream(main)
+    lay["info"].update(morton=True, cell_scale=1.0, mode="lattice")
+    return lay
+
+
+def _plan_records(conn: Tensor, pat: Pattern, lay: dict, kernel: str) -> Optional[TilePlan]:
+    """Second half of the plan: the per-tile records of the numeric kernel (needs nadj / epos)."""
+    L = _lib.lib()
+    params = _lib.tile_params(pat.elem_type)
+    dev = conn.device
+    ntiles, einv, owner, tile_ptr, tile_nodes = lay["ntiles"], lay["eloc"], lay["owner"], lay["tile_ptr"], lay["tile_nodes"]
+    noff, thalo, stats, tconn, info = lay["noff"], lay["thalo"], lay["stats"], lay["tconn"], lay["info"]
+    nslots, n_items, n_work, blob16, nruns = lay["nslots"], lay["n_items"], lay["n_work"], lay["blob16"], lay["nruns"]
+    max_nodes, max_blob, max_stage = lay["max_nodes"], lay["max_blob"], lay["max_stage"]
+    with torch.cuda.device(dev):
+        st = _stream(conn)
         wsp = _lib.tile_ws_params(pat.elem_type)
         # "auto": the warp-specialised kernel where it is the faster one (measured: Quad4 1.39 ms against 1.90 ms on cfg2;
         # Tri3's tiles are too small for its per-tile hand-offs: 1.51 ms against 1.25 ms), else the barrier-phased kernel
