@@ -29,12 +29,11 @@ __host__ __device__ constexpr int halo_threads(int nnpe) { return nnpe == 4 ? FE
 // pass by the halo warp, so regular tiles pay nothing.
 __host__ __device__ constexpr int halo_cap(int nnpe) { return nnpe == 4 ? FE_HALO_ELEMS + 16 : nnpe == 9 ? 16 : 64; }
 __host__ __device__ constexpr int tile_parts(int nnpe) { return nnpe == 9 ? 5 : nnpe == 4 ? FE_Q4_PARTS : 1; }   // threads per element
-__host__ __device__ constexpr int tri_bits(int nnpe) { return nnpe == 9 ? 6 : 4; }        // bits of a block index
 __host__ __device__ constexpr int max_nodes(int nnpe) { return nnpe == 9 ? 192 : 2 * tile_elems(nnpe); }
 __host__ __device__ constexpr int max_items(int nnpe) { return nnpe == 9 ? 640 : 8 * tile_elems(nnpe); }
 __host__ __device__ constexpr int max_work(int nnpe) { return nnpe == 9 ? 3072 : 12 * tile_elems(nnpe); }   // x32
 constexpr int kTileCtasPerSm = FE_TILE_CTAS;     // persistent grid = SMs x this
-constexpr unsigned kWorkFirst = 1u << 26, kWorkSelf = 1u << 27;
+constexpr unsigned kWorkFirst = 1u << 28, kWorkSelf = 1u << 29;    // flag bits of a work record (above its two 14-bit sources)
 
 // block index of the pair lo <= hi in the upper triangle (row-major) of an N-node element
 template <int N> __host__ __device__ constexpr int tri_index(int lo, int hi) { return lo * N - lo * (lo - 1) / 2 + (hi - lo); }

@@ -18,8 +18,9 @@
 //   tnode[]   int2 per owned node   {nptr[n], deg | self_pos << 7 | cnt << 14 | item_offset << 18}
 //   tloc[]    uint16 per item       slab row << 4 | a          (items of a node: ascending element id)
 //   thalo[]   int32, HE per tile    halo element ids (ascending)
-//   twork[]   uint32 per work item  src0 | src1 << 13 | first_of_node << 26 | is_self << 27,
-//             src = slab row << 5 | block(lo,hi) << 1 | transposed;  absent src1 points at a zero block
+//   twork[]   uint32 per work item  src0 | src1 << 14 | first_of_node << 28 | is_self << 29,
+//             src = (offset of the block in the slab, in doubles) << 1 | transposed;  an absent source points at the
+//             slab's zero block (ready-made offsets: the numeric kernel adds them to the slab base, nothing to decode)
 //   tchunk[]  uint32 per 32 work items  (local node of the chunk's first item, +1, -1 if that item starts a
 //             node) << 7 | p of that item: lanes rebuild (node, p) with one ballot
 #include "fe_tile_config.cuh"
@@ -41,9 +42,10 @@ template <int N> struct TileLayout {
     static constexpr int kZeroRow = kTE + kHalo;               // slab row of zeros (target of absent sources)
     static constexpr int kMaxNodes = max_nodes(N), kMaxItems = max_items(N), kMaxWork = max_work(N);
     static constexpr int kCtas = N == 9 ? FE_Q9_CTAS : kParts > 1 ? 2 : kTileCtasPerSm;   // persistent CTAs per SM
-    static constexpr int kTriBits = tri_bits(N);
-    static constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
+    static constexpr int kSrcBits = 14;                        // record source field: slab offset << 1 | transposed
+    static constexpr unsigned kSrcMask = (1u << kSrcBits) - 1u;
     static constexpr int kSlabDoubles = (((kZeroRow + 1) * kSlabStride) + 1) & ~1;   // keeps what follows 16-byte aligned
+    static_assert((kZeroRow + 1) * kSlabStride < (1 << (kSrcBits - 1)), "slab offset does not fit a source field");
     // shared copy of the rows' node coordinates (multi-thread-per-element types only)
     static constexpr size_t kXyBytes = N == 9 ? (size_t)kRows * N * 16 : 0;
     // per row: (j00, j01, j10, j11, scale) of every Gauss point (multi-thread-per-element types only)
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
     const uint8_t* __restrict__ epos, const int32_t* __restrict__ einv, const int32_t* __restrict__ nptr,
     const int32_t* __restrict__ nadj, int2* __restrict__ tnode, uint16_t* __restrict__ tloc,
     uint32_t* __restrict__ twork, uint32_t* __restrict__ tchunk, int32_t* __restrict__ stats, int te, int he,
-    int tribits) {
+    int ss) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nslots) return;
     const int n = tile_nodes[i];
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
     }
     tnode[i] = make_int2(p0, deg | (self << 7) | (cnt << 14) | (ioff << 18));
 
-    const unsigned kZeroSrc = (unsigned)(te + he) << (tribits + 1);
+    const unsigned kZeroSrc = (unsigned)((te + he) * ss) << 1;
     unsigned short src[kMaxAdj][2];
     for (int p = 0; p < deg; ++p) src[p][0] = src[p][1] = (unsigned short)kZeroSrc;
     for (int j = 0; j < cnt; ++j) {
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
             if (p == self) continue;
             const int blo = a < b ? a : b, bhi = a < b ? b : a;
             const int tri = blo * nnpe - blo * (blo - 1) / 2 + (bhi - blo);
-            const unsigned short s = (unsigned short)((row << (tribits + 1)) | (tri << 1) | (a > b ? 1 : 0));
+            const unsigned short s = (unsigned short)(((row * ss + 3 * tri) << 1) | (a > b ? 1 : 0));
             if (src[p][0] == kZeroSrc) src[p][0] = s;
             else if (src[p][1] == kZeroSrc) src[p][1] = s;
             else atomicMax(stats + 4, 1);  // a node pair shared by more than two elements
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(128) k_tile_records(
     }
     const int64_t wbase = (int64_t)tile_wptr[t] + woff;
     for (int p = 0; p < deg; ++p) {
-        twork[wbase + p] = (unsigned)src[p][0] | ((unsigned)src[p][1] << 13) | (p == 0 ? kWorkFirst : 0u) |
+        twork[wbase + p] = (unsigned)src[p][0] | ((unsigned)src[p][1] << 14) | (p == 0 ? kWorkFirst : 0u) |
                            (p == self ? kWorkSelf : 0u);
         if (((woff + p) & 31) == 0) tchunk[(wbase + p) >> 5] = ((unsigned)(ln + (p == 0 ? 0 : 1)) << 7) | (unsigned)p;
     }
@@ -813,9 +815,9 @@ __global__ void __launch_bounds__(TileLayout<Elem<ET>::NNPE>::kThreads, TileLayo
                 if (rec == 0u || (rec & kWorkSelf)) continue;   // padding or diagonal block
                 const int2 nd = node[ln];
                 const int deg = nd.y & 127;
-                const unsigned s0 = rec & 0x1FFFu, s1 = (rec >> 13) & 0x1FFFu;
-                const double* b0 = slab + (s0 >> (T::kTriBits + 1)) * SS + 3 * ((s0 >> 1) & T::kTriMask);
-                const double* b1 = slab + (s1 >> (T::kTriBits + 1)) * SS + 3 * ((s1 >> 1) & T::kTriMask);   // zeros if absent
+                const unsigned s0 = rec & T::kSrcMask, s1 = (rec >> T::kSrcBits) & T::kSrcMask;
+                const double* b0 = slab + (s0 >> 1);
+                const double* b1 = slab + (s1 >> 1);                 // the zero block if absent
                 const double L = b0[0] + b1[0];
                 if constexpr (SCALAR) {
                     (void)deg;
@@ -994,7 +996,7 @@ int fe_tile_records(int elem_type, int64_t nslots, const int32_t* tile_nodes, co
     k_tile_records<<<grid_for(nslots, 128), 128, 0, as_stream(stream)>>>(
         nslots, nnpe, tile_nodes, owner, tile_ptr, tile_ptr + s, tile_ptr + 2 * s, tile_ptr + 3 * s, noff, thalo, eptr,
         einc, epos, einv, nptr, nadj, static_cast<int2*>(tnode), tloc, twork, tchunk, stats, tile_elems(nnpe),
-        halo_cap(nnpe), tri_bits(nnpe));
+        halo_cap(nnpe), nnpe == 9 ? TileLayout<9>::kSlabStride : nnpe == 4 ? TileLayout<4>::kSlabStride : TileLayout<3>::kSlabStride);
     FE_CHECK_LAUNCH("k_tile_records");
     return FE_OK;
 }
@@ -1042,7 +1044,7 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
         switch (elem_type) {
             case FE_QUAD4: return launch_tiled<FE_QUAD4, false, 0, true>(FE_TILED_ARGS, 0, st);
             case FE_TRI3: return launch_tiled<FE_TRI3, false, 3, true>(FE_TILED_ARGS, 0, st);
-            case FE_QUAD9: return launch_tiled<FE_QUAD9, false, 0, true>(FE_TILED_ARGS, 0, st);
+            case FE_QUAD9: return launch_tiled<FE_QUAD9, false, 2, true>(FE_TILED_ARGS, 0, st);
             default: break;
         }
     }
@@ -1055,8 +1057,8 @@ int fe_assemble_tiled(int elem_type, int op, int64_t ntiles, const int32_t* tcon
             return op == FE_OP_MASS ? launch_tiled<FE_TRI3, true, 3>(FE_TILED_ARGS, 1, st)
                                     : launch_tiled<FE_TRI3, false, 3>(FE_TILED_ARGS, w, st);
         case FE_QUAD9:
-            return op == FE_OP_MASS ? launch_tiled<FE_QUAD9, true, 0>(FE_TILED_ARGS, 1, st)
-                                    : launch_tiled<FE_QUAD9, false, 0>(FE_TILED_ARGS, w, st);
+            return op == FE_OP_MASS ? launch_tiled<FE_QUAD9, true, 2>(FE_TILED_ARGS, 1, st)
+                                    : launch_tiled<FE_QUAD9, false, 2>(FE_TILED_ARGS, w, st);
 #undef FE_TILED_ARGS
         default:
             set_error("fe_assemble_tiled: element type %d has no tiled kernel (use fe_assemble)", elem_type);
