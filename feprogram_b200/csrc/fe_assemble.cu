@@ -112,10 +112,12 @@ template <int ET, bool MASS, bool SCALAR = false>
 static int launch_assemble_rows(int64_t nnode, const int32_t* conn, const double* coords, const int32_t* eptr,
                                 const int32_t* einc, const uint8_t* epos, const int32_t* nptr, int32_t max_deg,
                                 double* vals, int weighted, cudaStream_t stream) {
-    // rows per CTA: as many as fit a 48 KB tile at the worst-case row-block size, warp multiple
+    // rows per CTA: as many as fit a 48 KB tile at the worst-case row-block size, warp multiple; meshes with nodes of
+    // very high valence (more than 48 neighbours) get one warp of rows on a tile of up to 200 KB
     const size_t per_node = (size_t)max_deg * (SCALAR ? 1 : 4) * sizeof(double);
     int R = (int)((48 * 1024) / per_node);
     R = R >= 128 ? 128 : (R / 32) * 32;
+    if (R < 32 && 32 * per_node <= 200 * 1024) R = 32;
     if (R < 32) {
         set_error("fe_assemble: max_deg %d exceeds the row-tile capacity", (int)max_deg);
         return FE_ERR_CAPACITY;

@@ -486,6 +486,7 @@ static PcgWork carve(void* work, int64_t nrows) {
     return w;
 }
 
+constexpr int64_t kGraphMaxNnz = (int64_t)1 << 27;      // above this an iteration is long enough to hide its launches
 template <typename IdxT>
 static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, const double* vals, const double* rhs,
                     const uint8_t* mask, double* x, double rtol, double atol, int64_t maxit, int check_every,
@@ -509,6 +510,42 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
     k_pcg_init3<<<1, kVecThreads, 0, st>>>(gv, w.partB, rtol, atol, w.scal, nullptr, PeerRed{}, 0);
     FE_CHECK_LAUNCH("k_pcg_init3");
 
+    auto iterate = [&](cudaStream_t s) -> int {          // one PCG iteration = three launches, same arguments every time
+        int ga = 0;
+        const int r = mat_spmv<IdxT, true>(A, w.p, w.Ap, mask, w.partA, w.scal, &ga, s);
+        if (r != FE_OK) return r;
+        k_pcg_update<<<gv, kVecThreads, 0, s>>>(nrows, ga, w.partA, w.p, w.Ap, w.minv, x, w.r, w.partB, w.scal, nullptr,
+                                                PeerRed{}, 0);
+        k_pcg_direction<<<gv, kVecThreads, 0, s>>>(nrows, gv, w.partB, w.r, w.minv, w.p, w.p, w.scal, nullptr, PeerRed{},
+                                                   0);
+        return FE_OK;
+    };
+    // Small systems are bound by launch latency (three launches of a few microseconds each per iteration): a batch of
+    // check_every iterations is captured once into a CUDA graph (on a private stream: the caller's may be the legacy
+    // default stream, which cannot capture) and replayed on the caller's stream.  Large systems launch directly.
+    struct Replay {
+        cudaStream_t cs = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        ~Replay() {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (cs) cudaStreamDestroy(cs);
+        }
+    } replay;
+    if (nnz <= kGraphMaxNnz && check_every >= 4 && maxit >= check_every) {
+        if (cudaStreamCreateWithFlags(&replay.cs, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamBeginCapture(replay.cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int rcc = FE_OK;
+            for (int k = 0; k < check_every && rcc == FE_OK; ++k) rcc = iterate(replay.cs);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(replay.cs, &graph);
+            if (rcc == FE_OK && e == cudaSuccess && graph &&
+                cudaGraphInstantiate(&replay.exec, graph, 0) != cudaSuccess)
+                replay.exec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        (void)cudaGetLastError();        // a failed capture only means direct launches
+    }
+
     double hs[kScalarDoubles];
     int64_t launched = 0;
     for (;;) {
@@ -517,13 +554,11 @@ static int pcg_impl(int64_t nrows, const IdxT* row_ptr, const int32_t* col_idx, 
         if (hs[S_DONE_C] != 0.0 || hs[S_ERR] != 0.0 || launched >= maxit) break;
         int64_t batch = check_every;
         if (launched + batch > maxit) batch = maxit - launched;
-        for (int64_t k = 0; k < batch; ++k) {
-            int ga = 0;
-            if ((rc = mat_spmv<IdxT, true>(A, w.p, w.Ap, mask, w.partA, w.scal, &ga, st)) != FE_OK) return rc;
-            k_pcg_update<<<gv, kVecThreads, 0, st>>>(nrows, ga, w.partA, w.p, w.Ap, w.minv, x, w.r, w.partB, w.scal,
-                                                     nullptr, PeerRed{}, 0);
-            k_pcg_direction<<<gv, kVecThreads, 0, st>>>(nrows, gv, w.partB, w.r, w.minv, w.p, w.p, w.scal, nullptr,
-                                                        PeerRed{}, 0);
+        if (replay.exec && batch == check_every) {
+            FE_CUDA_TRY(cudaGraphLaunch(replay.exec, st));
+        } else {
+            for (int64_t k = 0; k < batch; ++k)
+                if ((rc = iterate(st)) != FE_OK) return rc;
         }
         FE_CHECK_LAUNCH("pcg iteration");
         launched += batch;

@@ -975,3 +975,69 @@ def test_unstructured_meshes_structure_values_kernels_and_solution(torch_cuda, k
         assert np.array_equal(fem.rhs_host(), b)
         assert fem.solver_info["converged"]
         assert np.linalg.norm(U - Uo) / np.linalg.norm(Uo) < SOL_TOL
+
+
+# ---- nodes of very high valence: every capacity of the symbolic write-out (32 staged neighbours, 16 staged incidences)
+# is exceeded by a hub, the nodes around it stay on the fast path -- both in one warp's flat write-out -------------------
+def _fan_mesh(spokes, hubs=3, seed=3):
+    """Tri3 fans: `hubs` hub nodes, each surrounded by a closed ring of `spokes` triangles; a strip of regular
+    triangles joins consecutive rings so that the mesh is connected.  Node ids are shuffled."""
+    rng = np.random.default_rng(seed)
+    coords, tris = [], []
+    for h in range(hubs):
+        base = len(coords)
+        cx = 3.0 * h
+        coords.append((cx, 0.0))
+        ang = 2 * np.pi * np.arange(spokes) / spokes
+        coords.extend(zip(cx + np.cos(ang), np.sin(ang)))
+        for i in range(spokes):
+            tris.append((base, base + 1 + i, base + 1 + (i + 1) % spokes))
+        if h > 0:                                   # a triangle pair between the previous ring and this one
+            prev = base - (spokes + 1)
+            tris.append((prev + 1, base + 1 + spokes // 2, base + 1 + spokes // 2 + 1))
+            tris.append((prev + 1, base + 1 + spokes // 2 + 1, prev + 2))
+    coords = np.asarray(coords, dtype=np.float64)
+    perm = rng.permutation(len(coords))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(coords))
+    conn = inv[np.asarray(tris, dtype=np.int64)] + 1
+    return conn[rng.permutation(len(conn))].astype(np.int32), coords[perm]
+
+
+@pytest.mark.parametrize("spokes", [12, 20, 40, 70])
+def test_high_valence_hubs_symbolic_and_values(torch_cuda, spokes):
+    torch = torch_cuda
+    from feprogram_b200 import ops
+    conn, coords = _fan_mesh(spokes)
+    conn0, xy = dev_mesh(torch, conn, coords)
+    nnode = coords.shape[0]
+    pat = ops.symbolic(conn0, nnode, 3, 2, csr="lazy")
+    assert pat._col_idx is None                      # nothing expanded yet
+    eptr, einc = orc.node_incidence(conn - 1, nnode)
+    nptr, nadj = orc.node_adjacency(conn - 1, nnode)
+    assert np.array_equal(pat.eptr.cpu().numpy(), eptr) and np.array_equal(pat.einc.cpu().numpy(), einc)
+    assert np.array_equal(pat.nptr.cpu().numpy(), nptr) and np.array_equal(pat.nadj.cpu().numpy(), nadj)
+    assert pat.max_deg == spokes + 1
+    epos = pat.epos.cpu().numpy().reshape(-1, 3)     # every incidence: positions of the element's nodes in the owner's list
+    owner = np.repeat(np.arange(nnode), np.diff(eptr))
+    for k in range(len(einc)):
+        seg = nadj[nptr[owner[k]]:nptr[owner[k] + 1]]
+        assert np.array_equal(seg[epos[k]], (conn - 1)[einc[k] // 16])
+    Ko = orc.assemble_csr(conn - 1, coords, 3)
+    assert np.array_equal(pat.row_ptr.cpu().numpy(), Ko.indptr) and np.array_equal(pat.col_idx.cpu().numpy(), Ko.indices)
+    v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v)     # hubs exceed the tile plans' capacities: row kernel
+    assert rel_max(v.cpu().numpy(), Ko.data) < VAL_TOL
+
+
+def test_lazy_and_eager_csr_patterns_are_the_same(torch_cuda, golden):
+    torch = torch_cuda
+    from feprogram_b200 import ops
+    z = golden(FULL_CASES[0])
+    conn0, _ = dev_mesh(torch, z["conn"], z["coords"])
+    nnode = z["coords"].shape[0]
+    eager = ops.symbolic(conn0, nnode, z["conn"].shape[1], 2)
+    lazy = ops.symbolic(conn0, nnode, z["conn"].shape[1], 2, csr="lazy")
+    assert lazy._row_ptr is None and lazy.nnz == eager.nnz == len(z["k0_indices"])
+    assert torch.equal(lazy.row_ptr, eager.row_ptr) and torch.equal(lazy.col_idx, eager.col_idx)
+    assert np.array_equal(lazy.col_idx.cpu().numpy(), z["k0_indices"])
