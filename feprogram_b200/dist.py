@@ -225,22 +225,48 @@ def peer_ghost_tables(m: LocalMesh, group=None):
 class DistFemProblem:
     """Assembly of the owned rows + distributed Jacobi-PCG for one rank (CUDA + NCCL only)."""
 
-    def __init__(self, local: LocalMesh, device, elem_type: int = 4, comm=None, timing: bool = True):
+    def __init__(self, local: LocalMesh, device, elem_type: int = 4, comm=None, timing: bool = True, bc=None,
+                 rhs_out=None):
         """``timing``: bracket the symbolic phase with host synchronisations so that ``symbolic_s`` is its wall time
         on resident connectivity (the bench's resident-input line); False = no synchronisation beyond the phase's own
-        read-backs (``symbolic_s`` is then None), as FemProblem.assemble does."""
+        read-backs (``symbolic_s`` is then None), as FemProblem.assemble does.
+        ``bc = (dir_dofs_local, neu_dofs_local[, value])``: boundary dof sets known up front -- the right-hand side and
+        the Dirichlet mask do not depend on K, so they are built on a side stream while the mesh is still uploading
+        and, with ``rhs_out`` (a pinned host tensor of 2 * n_owned doubles), the owned right-hand side travels to the
+        host at once (what FemProblem.assemble does on one GPU); without ``bc`` call ``set_bc`` afterwards."""
         import torch
         from . import ops
+        from .elements import side_streams
         self.m = local
         self.dev = torch.device(device)
         self.elem_type = elem_type
         self.comm = comm
         torch.cuda.set_device(self.dev)
+        self.nrows_owned = 2 * local.n_owned
+        self.nrows_local = 2 * local.nnode
+        main = torch.cuda.current_stream(self.dev)
+        bc_event = None
+        if bc is not None:                               # tiny uploads, ahead of the mesh on the copy engine
+            d = torch.from_numpy(np.asarray(bc[0], dtype=np.int64)).to(self.dev)
+            n = torch.from_numpy(np.asarray(bc[1], dtype=np.int64)).to(self.dev)
+            value = float(bc[2]) if len(bc) > 2 else 1.0
+            bcs = side_streams(self.dev)[1]
+            bcs.wait_event(main.record_event())
+            with torch.cuda.stream(bcs):
+                self.rhs = torch.empty(self.nrows_local, dtype=torch.float64, device=self.dev)
+                self.dirmask = torch.empty(self.nrows_local, dtype=torch.uint8, device=self.dev)
+                torch.ops.feprogram.bc_rhs(d, n, value, self.rhs, self.dirmask)
+                if rhs_out is not None:
+                    rhs_out.copy_(self.rhs[: self.nrows_owned], non_blocking=True)
+                bc_event = bcs.record_event()
+            for t in (self.rhs, self.dirmask):
+                t.record_stream(main)
+            for t in (d, n):
+                t.record_stream(bcs)
+            self._bc = (d, n, value)
         # connectivity first; the coordinates follow on a side stream while the CSR pattern (which only needs the
         # connectivity) is built -- as FemProblem does (elements.py, _state)
-        main = torch.cuda.current_stream(self.dev)
         self.conn = torch.from_numpy(np.ascontiguousarray(local.conn)).to(self.dev, non_blocking=True)
-        from .elements import side_streams
         side = side_streams(self.dev)[0]
         side.wait_event(main.record_event())
         with torch.cuda.stream(side):
@@ -260,8 +286,9 @@ class DistFemProblem:
         def early_layout(eptr, einc, nptr):          # first half of the plan, concurrent with fe_adjacency_fill
             formed["layout"] = ops.plan_layout_early(self.conn, elem_type, local.nnode, eptr, einc, nptr,
                                                      formed.get("tiles"), csr_side)
-        self.pat = ops.symbolic(self.conn, local.nnode, elem_type, 2, csr_stream=None if timing else csr_side,
-                                between=form_tiles, after_fill=early_layout)
+        # (the dof-level row_ptr / col_idx are expanded when the SpMV / PCG calls first read them: Pattern.row_ptr)
+        self.pat = ops.symbolic(self.conn, local.nnode, elem_type, 2, csr="lazy", between=form_tiles,
+                                after_fill=early_layout)
         self.plan = ops.tile_plan(self.conn, self.coords, self.pat, coords_ready=lambda: main.wait_event(coords_ready),
                                   formation=formed.get("tiles"), layout=formed.get("layout"))
         main.wait_event(coords_ready)
@@ -271,15 +298,16 @@ class DistFemProblem:
             torch.cuda.synchronize(self.dev)
             self.symbolic_s = time.perf_counter() - t0  # may include the tail of the coordinate upload
         self.vals = torch.empty(self.pat.nnz, dtype=torch.float64, device=self.dev)
-        self.nrows_owned = 2 * local.n_owned
-        self.nrows_local = 2 * local.nnode
         self.nnz_owned = 4 * int(self.pat.nptr[local.n_owned].item())   # host copy: the SpMV / PCG calls take it as an argument
         nbr, send_off, send_idx, recv_off = local.halo_arrays(2)
         self._nbr, self._send_off, self._recv_off = nbr, send_off, recv_off       # host arrays (kept alive)
         self.send_idx = torch.from_numpy(send_idx).to(self.dev)
         self.sendbuf = torch.empty(max(1, int(send_off[-1])), dtype=torch.float64, device=self.dev)
-        self.rhs = torch.zeros(self.nrows_local, dtype=torch.float64, device=self.dev)
-        self.dirmask = torch.zeros(self.nrows_local, dtype=torch.uint8, device=self.dev)
+        if bc_event is None:
+            self.rhs = torch.zeros(self.nrows_local, dtype=torch.float64, device=self.dev)
+            self.dirmask = torch.zeros(self.nrows_local, dtype=torch.uint8, device=self.dev)
+        else:
+            main.wait_event(bc_event)
 
     # -- communicator ------------------------------------------------------------------------------
     @staticmethod
@@ -544,17 +572,9 @@ class _BenchPart:
         host = LocalMesh(**{**self.m.__dict__, "conn": conn_p.numpy(), "coords": xy_p.numpy()})
         out = torch.empty(self.p.nrows_owned, dtype=torch.float64).pin_memory()
 
-        from .elements import side_streams
-        down = side_streams(self.dev)[1]
-
         def step():
-            q = DistFemProblem(host, self.dev, 4, self.comm, timing=False)
-            q.set_bc(self.bc["dir"], self.bc["neu"])
-            # the right-hand side does not depend on K: it travels to the host while the matrix is assembled
-            down.wait_event(torch.cuda.current_stream(self.dev).record_event())
-            with torch.cuda.stream(down):
-                out.copy_(q.rhs[: q.nrows_owned], non_blocking=True)
-            q.rhs.record_stream(down)
+            # the right-hand side does not depend on K: built and sent to the host while the mesh is still uploading
+            q = DistFemProblem(host, self.dev, 4, self.comm, timing=False, bc=(self.bc["dir"], self.bc["neu"]), rhs_out=out)
             q.assemble()
             return q.vals.sum().item()
         step()

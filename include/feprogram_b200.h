@@ -297,6 +297,8 @@ int fe_edge_load(int nodes_per_edge, int64_t nedge, const int32_t* edges, const 
  *   -2 = CG breakdown (NaN residual or p.Ap <= 0: the matrix is not SPD on the free dofs; x is not a
  *   solution), -1 = a peer-memory wait timed out (fe_dist_pcg_p2p only; that call also returns an error).
  *   check_every: iterations between host polls (>=1): the one documented synchronisation of this header.
+ *   Systems of up to 2^27 non-zeros (launch-bound iterations) replay each batch of check_every iterations from a
+ *   CUDA graph captured once per call on a private stream of the library; the batches still run on `stream`.
  *   nptr/nadj (optional, may be NULL): node-level pattern of a 2-dof matrix -> node-block SpMV.
  */
 int fe_spmv(int64_t nrows, int64_t nnz, int idx64, const void* row_ptr, const int32_t* col_idx, const double* vals,

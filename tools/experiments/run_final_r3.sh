@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-2 (session 3) measurement batch on one GPU: tests, smoke, bench lines, launch list, ncu captures.
+mkdir -p gpurun_out
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_final_r3.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_final_r3.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/bench_final_r3.json 2> gpurun_out/bench_final_r3.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_r3_ref.json 2>/dev/null; echo "ref rc=$?"
+for c in cfg3 cfg5 poisson unstructured; do
+  timeout 600 python bench.py --config $c > gpurun_out/bench_${c}_r3.json 2> gpurun_out/bench_${c}_r3.err; echo "$c rc=$?"
+done
+timeout 300 python bench.py --steps 2 --warmup 3 --cg-iters 20 --no-cpu --no-strong > /dev/null 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_final_r3.csv python bench.py --steps 2 --warmup 3 --cg-iters 20 --no-cpu --no-strong > gpurun_out/ncu_final_r3.log 2>&1; echo "launch list rc=$?"
+FE_KERNELS=phased timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_assemble_tiled -s 2 -c 1 \
+  -o gpurun_out/prof_q9_final_r3 -f python tools/experiments/exp_ws.py 9 2048 0 3 > gpurun_out/ncu_q9_final_r3.log 2>&1; echo "ncu q9 rc=$?"
+python - <<'PY'
+import json
+for f in ["bench_final_r3","bench_cfg3_r3","bench_cfg5_r3","bench_poisson_r3","bench_unstructured_r3"]:
+    try:
+        r=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
+        print(f, r["value"], r["ms_per_step"], r["roofline"]["frac"], (r.get("e2e") or {}).get("ms_per_step"), r.get("parity_checked"))
+    except Exception as e:
+        print(f, "ERR", e)
+PY
