@@ -25,13 +25,33 @@ __global__ void k_count_incidence(int64_t nslots, const int32_t* __restrict__ co
 __global__ void k_fill_incidence(int64_t nslots, int nnpe, const int32_t* __restrict__ conn,
                                  const int32_t* __restrict__ eptr, int32_t* __restrict__ cursor,
                                  int32_t* __restrict__ einc) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nslots) return;
-    const int n = conn[i];
-    const int e = (int)(i / nnpe);
-    const int a = (int)(i - (int64_t)e * nnpe);
-    const int slot = atomicAdd(cursor + n, 1);
-    einc[eptr[n] + slot] = e * 16 + a;
+    // four consecutive slots per thread: four independent (atomic slot, row start) -> store chains in flight
+    const int64_t i0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= nslots) return;
+    int n[4], slot[4], base[4];
+    if (i0 + 3 < nslots && (reinterpret_cast<uintptr_t>(conn) & 15) == 0) {      // aligned groups of four: one load
+        const int4 c = *reinterpret_cast<const int4*>(conn + i0);
+        n[0] = c.x, n[1] = c.y, n[2] = c.z, n[3] = c.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) n[q] = i0 + q < nslots ? conn[i0 + q] : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        slot[q] = base[q] = 0;
+        if (n[q] >= 0) {
+            slot[q] = atomicAdd(cursor + n[q], 1);
+            base[q] = eptr[n[q]];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (n[q] < 0) continue;
+        const int64_t i = i0 + q;
+        const int e = (int)(i / nnpe);
+        const int a = (int)(i - (int64_t)e * nnpe);
+        einc[base[q] + slot[q]] = e * 16 + a;
+    }
 }
 
 // In-place sort of each node's (short) incidence segment: ascending element id.  Segments of up to eight entries (every
@@ -108,26 +128,37 @@ template <int NNPE>
 __device__ __forceinline__ int build_adjacency_smem(const int32_t* __restrict__ conn, const int32_t* __restrict__ einc,
                                                     int k0, int k1, int* s) {
     int cnt = 0;
-    for (int k = k0; k < k1; ++k) {
-        const int64_t e = einc[k] >> 4;
-        int row[NNPE];
-        if constexpr (NNPE == 4) {
-            const int4 r = __ldg(reinterpret_cast<const int4*>(conn) + e);
-            row[0] = r.x, row[1] = r.y, row[2] = r.z, row[3] = r.w;
-        } else {
+    constexpr int B = NNPE == 9 ? 2 : 4;          // incident elements fetched together: B independent load chains
+    for (int kb = k0; kb < k1; kb += B) {
+        int64_t e[B];
+        int row[B][NNPE];
 #pragma unroll
-            for (int b = 0; b < NNPE; ++b) row[b] = __ldg(conn + e * NNPE + b);
+        for (int q = 0; q < B; ++q) e[q] = kb + q < k1 ? (int64_t)(einc[kb + q] >> 4) : -1;
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            if (e[q] < 0) continue;
+            if constexpr (NNPE == 4) {
+                const int4 r = __ldg(reinterpret_cast<const int4*>(conn) + e[q]);
+                row[q][0] = r.x, row[q][1] = r.y, row[q][2] = r.z, row[q][3] = r.w;
+            } else {
+#pragma unroll
+                for (int b = 0; b < NNPE; ++b) row[q][b] = __ldg(conn + e[q] * NNPE + b);
+            }
         }
 #pragma unroll
-        for (int b = 0; b < NNPE; ++b) {
-            const int v = row[b];
-            int j = cnt;
-            while (j > 0 && s[(j - 1) * kAdjStride] > v) --j;
-            if (j > 0 && s[(j - 1) * kAdjStride] == v) continue;
-            if (cnt == kFastAdj) return -1;
-            for (int i = cnt; i > j; --i) s[i * kAdjStride] = s[(i - 1) * kAdjStride];
-            s[j * kAdjStride] = v;
-            ++cnt;
+        for (int q = 0; q < B; ++q) {
+            if (e[q] < 0) continue;
+#pragma unroll
+            for (int b = 0; b < NNPE; ++b) {
+                const int v = row[q][b];
+                int j = cnt;
+                while (j > 0 && s[(j - 1) * kAdjStride] > v) --j;
+                if (j > 0 && s[(j - 1) * kAdjStride] == v) continue;
+                if (cnt == kFastAdj) return -1;
+                for (int i = cnt; i > j; --i) s[i * kAdjStride] = s[(i - 1) * kAdjStride];
+                s[j * kAdjStride] = v;
+                ++cnt;
+            }
         }
     }
     return cnt;
@@ -374,7 +405,7 @@ int fe_incidence_fill(int elem_type, int64_t nelem, int64_t nnode, const int32_t
     cudaStream_t st = as_stream(stream);
     k_zero_i32<<<grid_for(nnode, 256), 256, 0, st>>>(cursor, nnode);
     FE_CHECK_LAUNCH("k_zero_i32");
-    k_fill_incidence<<<grid_for(nelem * nnpe, 256), 256, 0, st>>>(nelem * nnpe, nnpe, conn, eptr, cursor, einc);
+    k_fill_incidence<<<grid_for((nelem * nnpe + 3) / 4, 256), 256, 0, st>>>(nelem * nnpe, nnpe, conn, eptr, cursor, einc);
     FE_CHECK_LAUNCH("k_fill_incidence");
     k_sort_incidence<<<grid_for(nnode, 256), 256, 0, st>>>(nnode, eptr, einc);
     FE_CHECK_LAUNCH("k_sort_incidence");

@@ -251,11 +251,18 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
             noff[2 * (int64_t)(lo + i)] = ni + si - ci;
             noff[2 * (int64_t)(lo + i) + 1] = nw + sw - cw;
             maxcnt = ci > maxcnt ? ci : maxcnt;
-            for (int k = k0; k < k0 + ci; ++k) {
-                const int e = einc[k] >> 4;
-                if (tile_of(einv, e) == (int)t) continue;
-                const int slot = atomicAdd(&s_ncand[w], 1);
-                if (slot < kLayoutCand) cand[slot] = e;
+            for (int kb = k0; kb < k0 + ci; kb += 4) {      // four incidences at a time: independent load chains
+                int e[4], te4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) e[q] = kb + q < k0 + ci ? einc[kb + q] >> 4 : -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) te4[q] = e[q] >= 0 ? tile_of(einv, e[q]) : (int)t;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (te4[q] == (int)t) continue;
+                    const int slot = atomicAdd(&s_ncand[w], 1);
+                    if (slot < kLayoutCand) cand[slot] = e[q];
+                }
             }
         }
         ni += __shfl_sync(0xffffffffu, si, 31);

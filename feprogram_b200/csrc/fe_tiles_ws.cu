@@ -730,33 +730,67 @@ __global__ void __launch_bounds__(128) k_tile_ws_records(
     // a thread-local array would live in local memory)
     uint32_t* src = s_rec + threadIdx.x;
     for (int p = 0; p < deg; ++p) src[p * 128] = kZeroRec;
-    for (int j = 0; j < cnt; ++j) {
-        const int item = einc[k0 + j];
-        const int e = item >> 4, a = item & 15;
-        const int pos = einv[e];
-        int row;
-        if ((pos >> 8) == t) {
-            row = pos & 255;
-        } else {  // position inside the tile's sorted halo list
-            int l = 0, h = nh - 1;
-            while (l < h) {
-                const int mid = (l + h) >> 1;
-                if (hl[mid] < e) l = mid + 1;
-                else h = mid;
+    // Four incidences at a time: their element ids, (tile, row) words, position bytes and halo-list searches are
+    // independent, so each step has four loads in flight instead of one (the kernel is bound by that latency).
+    for (int jb = 0; jb < cnt; jb += 4) {
+        int item[4], pos[4], lo4[4], hi4[4];
+        unsigned pb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) item[i] = jb + i < cnt ? einc[k0 + jb + i] : -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            pos[i] = item[i] >= 0 ? einv[item[i] >> 4] : (t << 8);
+            pb[i] = 0u;
+            if (item[i] >= 0) {
+                const uint8_t* ep = epos + (int64_t)(k0 + jb + i) * nnpe;
+                if (nnpe == 4) {
+                    pb[i] = *reinterpret_cast<const unsigned*>(ep);            // 4-byte aligned: 4 * incidence
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (b < nnpe) pb[i] |= (unsigned)ep[b] << (8 * b);
+                }
             }
-            row = te + l;
         }
-        locs[ioff + j] = (uint16_t)((row << 4) | a);
-        for (int b = 0; b < nnpe; ++b) {
-            const int p = epos[(int64_t)(k0 + j) * nnpe + b];
-            if (p == self) continue;
-            const int blo = a < b ? a : b, bhi = a < b ? b : a;
-            const int tri = blo * nnpe - blo * (blo - 1) / 2 + (bhi - blo);
-            const unsigned sv = (unsigned)(((row * ss + 3 * tri) << 1) | (a > b ? 1 : 0));
-            const uint32_t cur = src[p * 128];
-            if ((cur & 0x3FFFu) == kZeroSrc) src[p * 128] = (cur & ~0x3FFFu) | sv;
-            else if ((cur >> 14) == kZeroSrc) src[p * 128] = (cur & 0x3FFFu) | (sv << 14);
-            else atomicMax(stats + 4, 1);  // a node pair shared by more than two elements
+        bool searching = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {          // foreign element: its position inside the tile's sorted halo list
+            lo4[i] = 0;
+            hi4[i] = (pos[i] >> 8) == t ? 0 : nh - 1;
+            searching = searching || hi4[i] > 0;
+        }
+        while (searching) {
+            searching = false;
+            int v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = lo4[i] < hi4[i] ? hl[(lo4[i] + hi4[i]) >> 1] : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (lo4[i] < hi4[i]) {
+                    const int mid = (lo4[i] + hi4[i]) >> 1;
+                    if (v[i] < (item[i] >> 4)) lo4[i] = mid + 1;
+                    else hi4[i] = mid;
+                    searching = searching || lo4[i] < hi4[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (item[i] < 0) continue;
+            const int a = item[i] & 15;
+            const int row = (pos[i] >> 8) == t ? (pos[i] & 255) : te + lo4[i];
+            locs[ioff + jb + i] = (uint16_t)((row << 4) | a);
+            for (int b = 0; b < nnpe; ++b) {
+                const int p = (int)((pb[i] >> (8 * b)) & 255u);
+                if (p == self) continue;
+                const int blo = a < b ? a : b, bhi = a < b ? b : a;
+                const int tri = blo * nnpe - blo * (blo - 1) / 2 + (bhi - blo);
+                const unsigned sv = (unsigned)(((row * ss + 3 * tri) << 1) | (a > b ? 1 : 0));
+                const uint32_t cur = src[p * 128];
+                if ((cur & 0x3FFFu) == kZeroSrc) src[p * 128] = (cur & ~0x3FFFu) | sv;
+                else if ((cur >> 14) == kZeroSrc) src[p * 128] = (cur & 0x3FFFu) | (sv << 14);
+                else atomicMax(stats + 4, 1);  // a node pair shared by more than two elements
+            }
         }
     }
     for (int p = 0; p < maxdeg; ++p) recs[p * nnp + ln] = p < deg ? src[p * 128] : kZeroRec;
