@@ -35,6 +35,40 @@ __host__ __device__ constexpr int max_work(int nnpe) { return nnpe == 9 ? 3072 :
 constexpr int kTileCtasPerSm = FE_TILE_CTAS;     // persistent grid = SMs x this
 constexpr unsigned kWorkFirst = 1u << 28, kWorkSelf = 1u << 29;    // flag bits of a work record (above its two 14-bit sources)
 
+// Ascending sort of 32 * R keys held R per lane (key index = 32 * r + lane; pad with INT_MAX): bitonic network, exchanges
+// at distance >= 32 are register to register, the others one shuffle per key.  All 32 lanes must call it.
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort(int (&v)[R], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int q = r ^ (j >> 5);
+                    if (q > r) {                                  // pair (r, q): ascending iff bit k of the index is clear
+                        const bool up = ((32 * r) & k) == 0;
+                        const int a = v[r], b = v[q];
+                        const int mn = a < b ? a : b, mx = a < b ? b : a;
+                        v[r] = up ? mn : mx;
+                        v[q] = up ? mx : mn;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int idx = 32 * r + lane;
+                    const int o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = (idx & k) == 0, lower = (lane & j) == 0;
+                    const int mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
+                    v[r] = (up == lower) ? mn : mx;
+                }
+            }
+        }
+    }
+}
+
 // block index of the pair lo <= hi in the upper triangle (row-major) of an N-node element
 template <int N> __host__ __device__ constexpr int tri_index(int lo, int hi) { return lo * N - lo * (lo - 1) / 2 + (hi - lo); }
 

@@ -109,9 +109,41 @@ __global__ void k_block_scatter(int64_t nelem, const int32_t* __restrict__ keys,
     tmp[ebase[b] + atomicAdd(cursor + b, 1)] = (int32_t)e;
 }
 
-// One warp per non-empty block.  <= TE elements: rank-sort by element id.  More: rank-sort by (key, id), cut into
-// runs of TE, then order every run by element id.
+// One warp per non-empty block.  <= TE elements: sort by element id.  More: rank-sort by (key, id), cut into
+// runs of TE, then order every run by element id.  Two launches: k_block_sort_small takes the blocks of at most
+// min(TE, 256) elements (all of them on regular meshes) with a register bitonic sort and no shared memory, so that
+// the kernel runs at full occupancy; k_block_sort takes the others with rank sorts in shared memory.
 constexpr int kFormWarps = 4;
+__global__ void __launch_bounds__(256) k_block_sort_small(int64_t nb, const int32_t* __restrict__ ebase,
+                                                          const int32_t* __restrict__ tbase,
+                                                          const int32_t* __restrict__ tmp, int te,
+                                                          int32_t* __restrict__ eperm, int32_t* __restrict__ eloc,
+                                                          int32_t* __restrict__ tile_estart) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b > nb) return;
+    if (b == nb) {
+        if (lane == 0) tile_estart[tbase[nb]] = ebase[nb];
+        return;
+    }
+    const int lo = ebase[b], cnt = ebase[b + 1] - lo;
+    if (cnt == 0 || cnt > te || cnt > 256) return;
+    const int t0 = tbase[b];
+    int v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = 32 * r + lane < cnt ? tmp[lo + 32 * r + lane] : 0x7fffffff;
+    warp_bitonic_sort<8>(v, lane);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = 32 * r + lane;
+        if (i < cnt) {
+            eperm[lo + i] = v[r];
+            eloc[v[r]] = (t0 << 8) | i;
+        }
+    }
+    if (lane == 0) tile_estart[t0] = lo;
+}
+
 __global__ void __launch_bounds__(32 * kFormWarps) k_block_sort(int64_t nb, const int32_t* __restrict__ ebase,
                                                                const int32_t* __restrict__ tbase,
                                                                const int32_t* __restrict__ tmp,
@@ -122,49 +154,49 @@ __global__ void __launch_bounds__(32 * kFormWarps) k_block_sort(int64_t nb, cons
     __shared__ int s_b[kFormWarps][kFormCap];
     __shared__ int s_k[kFormWarps][kFormCap];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t b = (int64_t)blockIdx.x * kFormWarps + w;
-    if (b > nb) return;
-    if (b == nb) {
-        if (lane == 0) tile_estart[tbase[nb]] = ebase[nb];
-        return;
-    }
-    const int lo = ebase[b], cnt = ebase[b + 1] - lo;
-    if (cnt == 0 || cnt > kFormCap) return;
-    const int t0 = tbase[b];
-    int* a = s_a[w];
-    int* o = s_b[w];
-    for (int i = lane; i < cnt; i += 32) a[i] = tmp[lo + i];
-    __syncwarp();
-    if (cnt <= te) {
-        for (int i = lane; i < cnt; i += 32) {        // ids are distinct: rank = number of smaller ids
-            const int v = a[i];
-            int r = 0;
-            for (int j = 0; j < cnt; ++j) r += a[j] < v;
-            eperm[lo + r] = v;
-            eloc[v] = (t0 << 8) | r;
+    // persistent warps stride over the blocks (most of them are k_block_sort_small's and are skipped after two loads)
+    for (int64_t b = (int64_t)blockIdx.x * kFormWarps + w; b < nb; b += (int64_t)gridDim.x * kFormWarps) {
+        const int lo = ebase[b], cnt = ebase[b + 1] - lo;
+        if (cnt == 0 || cnt > kFormCap) continue;
+        if (cnt <= te && cnt <= 256) continue;            // k_block_sort_small's
+        const int t0 = tbase[b];
+        int* a = s_a[w];
+        int* o = s_b[w];
+        for (int i = lane; i < cnt; i += 32) a[i] = tmp[lo + i];
+        __syncwarp();
+        if (cnt <= te) {
+            for (int i = lane; i < cnt; i += 32) {        // ids are distinct: rank = number of smaller ids
+                const int v = a[i];
+                int r = 0;
+                for (int j = 0; j < cnt; ++j) r += a[j] < v;
+                eperm[lo + r] = v;
+                eloc[v] = (t0 << 8) | r;
+            }
+            if (lane == 0) tile_estart[t0] = lo;
+            __syncwarp();
+            continue;
         }
-        if (lane == 0) tile_estart[t0] = lo;
-        return;
+        int* kk = s_k[w];
+        for (int i = lane; i < cnt; i += 32) kk[i] = keys[a[i]];
+        __syncwarp();
+        for (int i = lane; i < cnt; i += 32) {            // order by (key, id)
+            const int v = a[i], kv = kk[i];
+            int r = 0;
+            for (int j = 0; j < cnt; ++j) r += (kk[j] < kv) || (kk[j] == kv && a[j] < v);
+            o[r] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < cnt; i += 32) {            // inside each run of TE: order by id
+            const int v = o[i];
+            const int r0 = (i / te) * te, r1 = r0 + te < cnt ? r0 + te : cnt;
+            int r = 0;
+            for (int j = r0; j < r1; ++j) r += o[j] < v;
+            eperm[lo + r0 + r] = v;
+            eloc[v] = ((t0 + i / te) << 8) | r;
+        }
+        for (int q = lane; q * te < cnt; q += 32) tile_estart[t0 + q] = lo + q * te;
+        __syncwarp();                                     // the shared arrays are reused by this warp's next block
     }
-    int* kk = s_k[w];
-    for (int i = lane; i < cnt; i += 32) kk[i] = keys[a[i]];
-    __syncwarp();
-    for (int i = lane; i < cnt; i += 32) {            // order by (key, id)
-        const int v = a[i], kv = kk[i];
-        int r = 0;
-        for (int j = 0; j < cnt; ++j) r += (kk[j] < kv) || (kk[j] == kv && a[j] < v);
-        o[r] = v;
-    }
-    __syncwarp();
-    for (int i = lane; i < cnt; i += 32) {            // inside each run of TE: order by id
-        const int v = o[i];
-        const int r0 = (i / te) * te, r1 = r0 + te < cnt ? r0 + te : cnt;
-        int r = 0;
-        for (int j = r0; j < r1; ++j) r += o[j] < v;
-        eperm[lo + r0 + r] = v;
-        eloc[v] = ((t0 + i / te) << 8) | r;
-    }
-    for (int q = lane; q * te < cnt; q += 32) tile_estart[t0 + q] = lo + q * te;
 }
 
 }  // namespace fe
@@ -250,7 +282,12 @@ int fe_tile_form_sort(int elem_type, int64_t nb, const int32_t* ebase, const int
         return FE_ERR_UNSUPPORTED;
     }
     FE_REQUIRE(nb >= 1 && ebase && tbase && tmp && keys && eperm && eloc && tile_estart, "null pointer or bad size");
-    k_block_sort<<<grid_for(nb + 1, kFormWarps), 32 * kFormWarps, 0, as_stream(stream)>>>(
+    k_block_sort_small<<<grid_for(nb + 1, 8), 256, 0, as_stream(stream)>>>(nb, ebase, tbase, tmp, tile_elems(nnpe), eperm,
+                                                                       eloc, tile_estart);
+    FE_CHECK_LAUNCH("k_block_sort_small");
+    int64_t grid_large = (nb + kFormWarps - 1) / kFormWarps;
+    if (grid_large > 4 * 148) grid_large = 4 * 148;
+    k_block_sort<<<(unsigned)grid_large, 32 * kFormWarps, 0, as_stream(stream)>>>(
         nb, ebase, tbase, tmp, keys, tile_elems(nnpe), eperm, eloc, tile_estart);
     FE_CHECK_LAUNCH("k_block_sort");
     return FE_OK;

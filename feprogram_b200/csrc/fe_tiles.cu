@@ -190,34 +190,7 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
         int v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = 32 * r + lane < nn ? tile_nodes[lo + 32 * r + lane] : 0x7fffffff;
-#pragma unroll
-        for (int k = 2; k <= kLayoutNodes; k <<= 1) {
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                if (j >= 32) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int q = r ^ (j >> 5);
-                        if (q > r) {                                  // pair (r, q): ascending iff bit k of the index is clear
-                            const bool up = ((32 * r) & k) == 0;
-                            const int a = v[r], b = v[q];
-                            const int mn = a < b ? a : b, mx = a < b ? b : a;
-                            v[r] = up ? mn : mx;
-                            v[q] = up ? mx : mn;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int idx = 32 * r + lane;
-                        const int o = __shfl_xor_sync(0xffffffffu, v[r], j);
-                        const bool up = (idx & k) == 0, lower = (lane & j) == 0;
-                        const int mn = v[r] < o ? v[r] : o, mx = v[r] < o ? o : v[r];
-                        v[r] = (up == lower) ? mn : mx;
-                    }
-                }
-            }
-        }
+        warp_bitonic_sort<R>(v, lane);
 #pragma unroll
         for (int r = 0; r < R; ++r)
             if (32 * r + lane < nn) nodes[32 * r + lane] = v[r];
