@@ -18,8 +18,17 @@ __global__ void k_zero_i32(int32_t* p, int64_t n) {
 }
 
 __global__ void k_count_incidence(int64_t nslots, const int32_t* __restrict__ conn, int32_t* __restrict__ deg) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nslots) atomicAdd(deg + conn[i], 1);
+    const int64_t i0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);     // four slots per thread
+    if (i0 >= nslots) return;
+    if (i0 + 3 < nslots && (reinterpret_cast<uintptr_t>(conn) & 15) == 0) {
+        const int4 c = *reinterpret_cast<const int4*>(conn + i0);
+        atomicAdd(deg + c.x, 1);
+        atomicAdd(deg + c.y, 1);
+        atomicAdd(deg + c.z, 1);
+        atomicAdd(deg + c.w, 1);
+    } else {
+        for (int64_t i = i0; i < nslots && i < i0 + 4; ++i) atomicAdd(deg + conn[i], 1);
+    }
 }
 
 __global__ void k_fill_incidence(int64_t nslots, int nnpe, const int32_t* __restrict__ conn,
@@ -164,6 +173,45 @@ __device__ __forceinline__ int build_adjacency_smem(const int32_t* __restrict__ 
     return cnt;
 }
 
+// Quad4 node with at most four incident elements (every regular node): its 16 candidate neighbours are sorted as packed
+// keys (node id << 4 | candidate index: ids below 2^27) by a fixed 63-comparator network (Batcher's odd-even merge
+// sort) in registers, duplicates are dropped by comparing neighbours -- no insertion into a list in memory, no
+// searches: the rank of a key among the distinct ids is also the position the slot map (epos) needs for its candidate.
+// keys[4 q + b] = node b of the q-th incident element; absent elements give 0xFFFFFFFF.  Returns the distinct count;
+// rank[i] = position of sorted key i in the node's list, first[i] = key i starts a new id.
+constexpr int64_t kPackedIdLimit = (int64_t)1 << 27;
+__device__ __forceinline__ void quad4_sorted_candidates(const int32_t* __restrict__ conn, const int32_t* __restrict__ einc,
+                                                        int k0, int ninc, unsigned (&key)[16]) {
+    int e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) e[q] = q < ninc ? einc[k0 + q] >> 4 : -1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int4 r = make_int4(-1, -1, -1, -1);
+        if (e[q] >= 0) r = __ldg(reinterpret_cast<const int4*>(conn) + e[q]);
+        key[4 * q + 0] = e[q] >= 0 ? ((unsigned)r.x << 4) | (unsigned)(4 * q + 0) : 0xFFFFFFFFu;
+        key[4 * q + 1] = e[q] >= 0 ? ((unsigned)r.y << 4) | (unsigned)(4 * q + 1) : 0xFFFFFFFFu;
+        key[4 * q + 2] = e[q] >= 0 ? ((unsigned)r.z << 4) | (unsigned)(4 * q + 2) : 0xFFFFFFFFu;
+        key[4 * q + 3] = e[q] >= 0 ? ((unsigned)r.w << 4) | (unsigned)(4 * q + 3) : 0xFFFFFFFFu;
+    }
+    // Batcher's odd-even merge sort for 16 keys: 63 compare-exchanges on registers
+#define CX(i, j)                                   \
+    {                                              \
+        const unsigned a_ = key[i], b_ = key[j];   \
+        key[i] = a_ < b_ ? a_ : b_;                \
+        key[j] = a_ < b_ ? b_ : a_;                \
+    }
+    CX(0, 1); CX(2, 3); CX(4, 5); CX(6, 7); CX(8, 9); CX(10, 11); CX(12, 13); CX(14, 15);
+    CX(0, 2); CX(1, 3); CX(4, 6); CX(5, 7); CX(8, 10); CX(9, 11); CX(12, 14); CX(13, 15);
+    CX(1, 2); CX(5, 6); CX(9, 10); CX(13, 14); CX(0, 4); CX(1, 5); CX(2, 6); CX(3, 7);
+    CX(8, 12); CX(9, 13); CX(10, 14); CX(11, 15); CX(2, 4); CX(3, 5); CX(10, 12); CX(11, 13);
+    CX(1, 2); CX(3, 4); CX(5, 6); CX(9, 10); CX(11, 12); CX(13, 14); CX(0, 8); CX(1, 9);
+    CX(2, 10); CX(3, 11); CX(4, 12); CX(5, 13); CX(6, 14); CX(7, 15); CX(4, 8); CX(5, 9);
+    CX(6, 10); CX(7, 11); CX(2, 4); CX(3, 5); CX(6, 8); CX(7, 9); CX(10, 12); CX(11, 13);
+    CX(1, 2); CX(3, 4); CX(5, 6); CX(7, 8); CX(9, 10); CX(11, 12); CX(13, 14);
+#undef CX
+}
+
 template <int NNPE>
 __global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, const int32_t* __restrict__ conn,
                                                          const int32_t* __restrict__ eptr,
@@ -177,6 +225,17 @@ __global__ void __launch_bounds__(128) k_adjacency_count(int64_t nnode, const in
         return;
     }
     const int k0 = eptr[n], k1 = eptr[n + 1];
+    if constexpr (NNPE == 4) {
+        if (k1 - k0 <= 4 && nnode < kPackedIdLimit) {        // regular node: sorting network in registers
+            unsigned key[16];
+            quad4_sorted_candidates(conn, einc, k0, k1 - k0, key);
+            int c = key[0] != 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 1; i < 16; ++i) c += key[i] != 0xFFFFFFFFu && (key[i] >> 4) != (key[i - 1] >> 4);
+            ndeg[n] = c;
+            return;
+        }
+    }
     int cnt = build_adjacency_smem<NNPE>(conn, einc, k0, k1, s_list + threadIdx.x);
     if (cnt < 0) {                                   // rare: more than kFastAdj neighbours
         int list[kMaxAdj];
@@ -222,7 +281,35 @@ __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int
     const int k0 = eptr[nc], k1 = valid ? eptr[nc + 1] : k0;
     const int p0 = nptr[nc];
     int* s = s_list + threadIdx.x;
-    int cnt = valid ? build_adjacency_smem<NNPE>(conn, einc, k0, k1, s) : 0;
+    int cnt = 0;
+    bool pos_done = false;                           // positions already staged (the register fast path)
+    bool fast = false;
+    if constexpr (NNPE == 4) fast = valid && k1 - k0 <= 4 && nnode < kPackedIdLimit;
+    if (fast) {
+        if constexpr (NNPE == 4) {
+            unsigned key[16];
+            quad4_sorted_candidates(conn, einc, k0, k1 - k0, key);
+            unsigned words[4] = {0u, 0u, 0u, 0u};    // packed positions of the four incidences
+            int r = -1;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const bool live = key[i] != 0xFFFFFFFFu;
+                const bool first = live && (i == 0 || (key[i] >> 4) != (key[i - 1] >> 4));
+                r += first ? 1 : 0;
+                if (first) s[r * kAdjStride] = (int)(key[i] >> 4);
+                const unsigned o = key[i] & 15u, w = live ? (unsigned)r << (8u * (o & 3u)) : 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) words[q] |= (o >> 2) == (unsigned)q ? w : 0u;
+            }
+            cnt = r + 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < k1 - k0) s_pos[q * kAdjStride + threadIdx.x] = words[q];
+            pos_done = true;
+        }
+    } else if (valid) {
+        cnt = build_adjacency_smem<NNPE>(conn, einc, k0, k1, s);
+    }
     int staged = cnt;                                // entries of nadj this lane leaves to the flat write-out
     if (cnt < 0) {                                   // rare: the general thread-local path, rows written directly
         staged = 0;
@@ -262,7 +349,7 @@ __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int
     // positions: packed bytes per incidence, staged (word w of incidence j at s_pos[(j * W + w) * kAdjStride + t])
     const int ninc = k1 - k0;
     const bool pos_staged = cnt > 0 && ninc * W <= kPosWords;
-    for (int k = k0; k < k1 && cnt > 0; ++k) {
+    for (int k = k0; k < k1 && cnt > 0 && !pos_done; ++k) {
         const int64_t e = einc[k] >> 4;
         unsigned packed[W];
 #pragma unroll
@@ -386,7 +473,7 @@ int fe_incidence_count(int elem_type, int64_t nelem, int64_t nnode, const int32_
     k_zero_i32<<<grid_for(nnode + 1, 256), 256, 0, st>>>(eptr, nnode + 1);
     FE_CHECK_LAUNCH("k_zero_i32");
     if (nelem > 0) {
-        k_count_incidence<<<grid_for(nelem * nnpe, 256), 256, 0, st>>>(nelem * nnpe, conn, eptr);
+        k_count_incidence<<<grid_for((nelem * nnpe + 3) / 4, 256), 256, 0, st>>>(nelem * nnpe, conn, eptr);
         FE_CHECK_LAUNCH("k_count_incidence");
     }
     return exclusive_scan_i32(eptr, eptr, nnode + 1, scan_ws, st);

@@ -80,9 +80,12 @@ __global__ void k_lattice_keys(int64_t nelem, const int4* __restrict__ conn, int
     keys[e] = (int32_t)(spread15f((unsigned)ix) | (spread15f((unsigned)iy) << 1));
 }
 
+// (four elements per thread in the two bucketing kernels: independent atomics in flight)
 __global__ void k_block_hist(int64_t nelem, const int32_t* __restrict__ keys, int shift, int32_t* __restrict__ hist) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < nelem) atomicAdd(hist + (keys[e] >> shift), 1);
+    const int64_t e0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (e0 + q < nelem) atomicAdd(hist + (keys[e0 + q] >> shift), 1);
 }
 
 // tpb[b] = tiles of block b (and tpb[nb] = 0: slot of the grand total after the scan); status |= 1 on oversize blocks
@@ -103,10 +106,21 @@ __global__ void k_block_tiles(int64_t nb, int32_t* __restrict__ hist, int te, in
 __global__ void k_block_scatter(int64_t nelem, const int32_t* __restrict__ keys, int shift,
                                 const int32_t* __restrict__ ebase, int32_t* __restrict__ cursor,
                                 int32_t* __restrict__ tmp) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nelem) return;
-    const int b = keys[e] >> shift;
-    tmp[ebase[b] + atomicAdd(cursor + b, 1)] = (int32_t)e;
+    const int64_t e0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    int b[4], base[4], slot[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b[q] = e0 + q < nelem ? keys[e0 + q] >> shift : -1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        base[q] = slot[q] = 0;
+        if (b[q] >= 0) {
+            base[q] = ebase[b[q]];
+            slot[q] = atomicAdd(cursor + b[q], 1);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (b[q] >= 0) tmp[base[q] + slot[q]] = (int32_t)(e0 + q);
 }
 
 // One warp per non-empty block.  <= TE elements: sort by element id.  More: rank-sort by (key, id), cut into
@@ -154,11 +168,16 @@ __global__ void __launch_bounds__(32 * kFormWarps) k_block_sort(int64_t nb, cons
     __shared__ int s_b[kFormWarps][kFormCap];
     __shared__ int s_k[kFormWarps][kFormCap];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // persistent warps stride over the blocks (most of them are k_block_sort_small's and are skipped after two loads)
-    for (int64_t b = (int64_t)blockIdx.x * kFormWarps + w; b < nb; b += (int64_t)gridDim.x * kFormWarps) {
+    // Persistent warps stride over the blocks 32 at a time: every lane looks at one block's size, the warp then takes
+    // the oversize ones in turn (on regular meshes there are none and the kernel ends after a couple of coalesced loads).
+    for (int64_t b0 = 32 * ((int64_t)blockIdx.x * kFormWarps + w); b0 < nb; b0 += 32 * (int64_t)gridDim.x * kFormWarps) {
+      int c = 0;
+      if (b0 + lane < nb) c = ebase[b0 + lane + 1] - ebase[b0 + lane];
+      unsigned todo = __ballot_sync(0xffffffffu, c > 0 && c <= kFormCap && !(c <= te && c <= 256));   // else: k_block_sort_small's
+      while (todo) {
+        const int64_t b = b0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
         const int lo = ebase[b], cnt = ebase[b + 1] - lo;
-        if (cnt == 0 || cnt > kFormCap) continue;
-        if (cnt <= te && cnt <= 256) continue;            // k_block_sort_small's
         const int t0 = tbase[b];
         int* a = s_a[w];
         int* o = s_b[w];
@@ -196,6 +215,7 @@ __global__ void __launch_bounds__(32 * kFormWarps) k_block_sort(int64_t nb, cons
         }
         for (int q = lane; q * te < cnt; q += 32) tile_estart[t0 + q] = lo + q * te;
         __syncwarp();                                     // the shared arrays are reused by this warp's next block
+      }
     }
 }
 
@@ -256,7 +276,7 @@ int fe_tile_form_count(int elem_type, int64_t nelem, int64_t nb, const int32_t* 
     FE_CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)nb * sizeof(int32_t), st));
     FE_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
     if (nelem > 0) {
-        k_block_hist<<<grid_for(nelem, 256), 256, 0, st>>>(nelem, keys, shift, hist);
+        k_block_hist<<<grid_for((nelem + 3) / 4, 256), 256, 0, st>>>(nelem, keys, shift, hist);
         FE_CHECK_LAUNCH("k_block_hist");
     }
     k_block_tiles<<<grid_for(nb + 1, 256), 256, 0, st>>>(nb, hist, te, tpb, status);
@@ -266,7 +286,7 @@ int fe_tile_form_count(int elem_type, int64_t nelem, int64_t nb, const int32_t* 
     rc = exclusive_scan_i32(tpb, tbase, nb + 1, scan_ws, st);
     if (rc != FE_OK) return rc;
     if (nelem > 0) {
-        k_block_scatter<<<grid_for(nelem, 256), 256, 0, st>>>(nelem, keys, shift, ebase, cursor, tmp);
+        k_block_scatter<<<grid_for((nelem + 3) / 4, 256), 256, 0, st>>>(nelem, keys, shift, ebase, cursor, tmp);
         FE_CHECK_LAUNCH("k_block_scatter");
     }
     return FE_OK;
@@ -285,7 +305,7 @@ int fe_tile_form_sort(int elem_type, int64_t nb, const int32_t* ebase, const int
     k_block_sort_small<<<grid_for(nb + 1, 8), 256, 0, as_stream(stream)>>>(nb, ebase, tbase, tmp, tile_elems(nnpe), eperm,
                                                                        eloc, tile_estart);
     FE_CHECK_LAUNCH("k_block_sort_small");
-    int64_t grid_large = (nb + kFormWarps - 1) / kFormWarps;
+    int64_t grid_large = (nb + 32 * kFormWarps - 1) / (32 * kFormWarps);
     if (grid_large > 4 * 148) grid_large = 4 * 148;
     k_block_sort<<<(unsigned)grid_large, 32 * kFormWarps, 0, as_stream(stream)>>>(
         nb, ebase, tbase, tmp, keys, tile_elems(nnpe), eperm, eloc, tile_estart);
