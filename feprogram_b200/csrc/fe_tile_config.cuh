@@ -35,6 +35,20 @@ __host__ __device__ constexpr int max_work(int nnpe) { return nnpe == 9 ? 3072 :
 constexpr int kTileCtasPerSm = FE_TILE_CTAS;     // persistent grid = SMs x this
 constexpr unsigned kWorkFirst = 1u << 28, kWorkSelf = 1u << 29;    // flag bits of a work record (above its two 14-bit sources)
 
+// Warp-aggregated counter bump: lanes of the (converged) calling set that hit the same counter do ONE atomic between them.
+// Returns the value this lane would have got from its own atomicAdd(counter + idx, 1) in lane order.  idx < 0: no bump.
+__device__ __forceinline__ int warp_agg_inc(int32_t* __restrict__ counter, int idx) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, idx);
+    if (idx < 0) return 0;
+    const int lane = (int)(threadIdx.x & 31u);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter + idx, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 // Ascending sort of 32 * R keys held R per lane (key index = 32 * r + lane; pad with INT_MAX): bitonic network, exchanges
 // at distance >= 32 are register to register, the others one shuffle per key.  All 32 lanes must call it.
 template <int R>

@@ -84,8 +84,7 @@ __global__ void k_lattice_keys(int64_t nelem, const int4* __restrict__ conn, int
 __global__ void k_block_hist(int64_t nelem, const int32_t* __restrict__ keys, int shift, int32_t* __restrict__ hist) {
     const int64_t e0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (e0 + q < nelem) atomicAdd(hist + (keys[e0 + q] >> shift), 1);
+    for (int q = 0; q < 4; ++q) (void)warp_agg_inc(hist, e0 + q < nelem ? keys[e0 + q] >> shift : -1);
 }
 
 // tpb[b] = tiles of block b (and tpb[nb] = 0: slot of the grand total after the scan); status |= 1 on oversize blocks
@@ -112,11 +111,8 @@ __global__ void k_block_scatter(int64_t nelem, const int32_t* __restrict__ keys,
     for (int q = 0; q < 4; ++q) b[q] = e0 + q < nelem ? keys[e0 + q] >> shift : -1;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        base[q] = slot[q] = 0;
-        if (b[q] >= 0) {
-            base[q] = ebase[b[q]];
-            slot[q] = atomicAdd(cursor + b[q], 1);
-        }
+        base[q] = b[q] >= 0 ? ebase[b[q]] : 0;
+        slot[q] = warp_agg_inc(cursor, b[q]);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)

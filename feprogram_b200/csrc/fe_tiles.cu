@@ -123,7 +123,7 @@ __global__ void k_tile_owner(int64_t nnode, const int32_t* __restrict__ eptr, co
         return;
     }
     owner[n] = own;
-    atomicAdd(tile_ncount + own, 1);
+    (void)warp_agg_inc(tile_ncount, own);       // neighbouring nodes mostly share their owner: one atomic per group
 }
 
 // Four consecutive nodes per thread: the owner -> (atomic slot, tile start) -> store chains of the four are
@@ -138,10 +138,8 @@ __global__ void k_tile_bucket(int64_t nnode, const int32_t* __restrict__ owner, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         base[j] = slot[j] = 0;
-        if (t[j] >= 0) {
-            base[j] = tile_nptr[t[j]];
-            slot[j] = atomicAdd(cursor + t[j], 1);
-        }
+        if (t[j] >= 0) base[j] = tile_nptr[t[j]];
+        slot[j] = warp_agg_inc(cursor, t[j]);        // (every lane calls it: the j loop is uniform)
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -154,7 +152,7 @@ __global__ void k_tile_bucket(int64_t nnode, const int32_t* __restrict__ owner, 
 // One warp per tile: (1) sort the tile's owned nodes by id (rank sort in shared memory), (2) per-node item /
 // work offsets by warp scans, (3) the halo list = sorted set of the foreign elements incident to owned nodes
 // (candidates collected in shared memory, rank-sorted, first occurrences compacted).
-constexpr int kLayoutWarps = 4, kLayoutNodes = 256, kLayoutCand = 1024;
+constexpr int kLayoutWarps = 4, kLayoutNodes = 256, kLayoutCand = 512;     // (candidates: foreign incidences of a tile, <= 4 x halo capacity)
 __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
     int64_t ntiles, const int32_t* __restrict__ tile_nptr, int32_t* __restrict__ tile_nodes,
     const int32_t* __restrict__ eptr, const int32_t* __restrict__ einc, const int32_t* __restrict__ einv,
@@ -286,13 +284,18 @@ __global__ void __launch_bounds__(32 * kLayoutWarps) k_tile_layout(
         const int blob = (16 + 8 * nnp + 4 * maxdeg * nnp + 2 * ((ni + 1) & ~1) + 15) & ~15;
         tile_blob16[t] = blob >> 4;
         tile_runs[t] = nruns;
-        atomicMax(stats + 6, blob);
-        atomicMax(stats + 7, 32 * nw);
-        atomicMax(stats + 0, nn);
-        atomicMax(stats + 1, ni);
-        atomicMax(stats + 2, overflow ? he + 1 : nh);
-        atomicMax(stats + 3, maxcnt);
-        atomicMax(stats + 5, nw);
+        // running maxima: seven same-address atomics per tile would serialise in L2 (a million of them on cfg2), so a
+        // tile only issues the ones that can still raise the value it reads (a stale read just costs a spare atomic)
+        auto raise = [&](int k, int v) {
+            if (v > *reinterpret_cast<volatile int32_t*>(stats + k)) atomicMax(stats + k, v);
+        };
+        raise(6, blob);
+        raise(7, 32 * nw);
+        raise(0, nn);
+        raise(1, ni);
+        raise(2, overflow ? he + 1 : nh);
+        raise(3, maxcnt);
+        raise(5, nw);
     }
 }
 
