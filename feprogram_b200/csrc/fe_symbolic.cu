@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int
         if constexpr (NNPE == 4) {
             unsigned key[16];
             quad4_sorted_candidates(conn, einc, k0, k1 - k0, key);
-            unsigned words[4] = {0u, 0u, 0u, 0u};    // packed positions of the four incidences
+            // candidate o = 4 q + b (node b of incidence q) sits at rank r of the list: byte b of the incidence's staged
+            // position word -- stored straight into that word (s_pos[q * kAdjStride + t]) as a byte
+            uint8_t* pos_bytes = reinterpret_cast<uint8_t*>(s_pos + threadIdx.x);
             int r = -1;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -297,14 +299,10 @@ __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int
                 const bool first = live && (i == 0 || (key[i] >> 4) != (key[i - 1] >> 4));
                 r += first ? 1 : 0;
                 if (first) s[r * kAdjStride] = (int)(key[i] >> 4);
-                const unsigned o = key[i] & 15u, w = live ? (unsigned)r << (8u * (o & 3u)) : 0u;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) words[q] |= (o >> 2) == (unsigned)q ? w : 0u;
+                const unsigned o = key[i] & 15u;
+                if (live) pos_bytes[(o >> 2) * (4u * kAdjStride) + (o & 3u)] = (uint8_t)r;
             }
             cnt = r + 1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q < k1 - k0) s_pos[q * kAdjStride + threadIdx.x] = words[q];
             pos_done = true;
         }
     } else if (valid) {
@@ -338,12 +336,21 @@ __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int
         const int qb = __shfl_sync(0xffffffffu, p0, 0), qe = __shfl_sync(0xffffffffu, p0 + (staged > 0 ? staged : 0), 31);
         const int qe_all = __shfl_sync(0xffffffffu, valid ? nptr[nc + 1] : p0, 31);
         (void)qe;
-        for (int q0 = qb; q0 < qe_all; q0 += 32) {
-            const int q = q0 + lane;
-            const int o = owner_lane(p0, q);
-            const int i = q - __shfl_sync(0xffffffffu, p0, o);
-            const int c = __shfl_sync(0xffffffffu, staged, o);
-            if (q < qe_all && i < c) nadj[q] = s_list[i * kAdjStride + wbase + o];
+        const int c0 = __shfl_sync(0xffffffffu, staged, 0);
+        if (c0 > 0 && __all_sync(0xffffffffu, staged == c0)) {
+            // all 32 nodes have the same number of neighbours (the interior of a lattice): owner and entry by division
+            for (int q0 = 0; q0 < 32 * c0; q0 += 32) {
+                const int q = q0 + lane, o = q / c0;
+                nadj[qb + q] = s_list[(q - o * c0) * kAdjStride + wbase + o];
+            }
+        } else {
+            for (int q0 = qb; q0 < qe_all; q0 += 32) {
+                const int q = q0 + lane;
+                const int o = owner_lane(p0, q);
+                const int i = q - __shfl_sync(0xffffffffu, p0, o);
+                const int c = __shfl_sync(0xffffffffu, staged, o);
+                if (q < qe_all && i < c) nadj[q] = s_list[i * kAdjStride + wbase + o];
+            }
         }
     }
     // positions: packed bytes per incidence, staged (word w of incidence j at s_pos[(j * W + w) * kAdjStride + t])
@@ -383,6 +390,14 @@ __global__ void __launch_bounds__(128) k_adjacency_fill(int64_t nnode, const int
         constexpr int U = NNPE == 4 ? 1 : NNPE;
         const int kb = __shfl_sync(0xffffffffu, k0, 0), ke = __shfl_sync(0xffffffffu, k1, 31);
         const int flag = pos_staged ? 1 : 0;
+        const int n0 = __shfl_sync(0xffffffffu, ninc, 0);
+        if (NNPE == 4 && n0 > 0 && __all_sync(0xffffffffu, ninc == n0 && pos_staged)) {
+            // every node of the warp has n0 staged incidences: word u of the warp belongs to lane u / n0
+            for (int u0 = 0; u0 < 32 * n0; u0 += 32) {
+                const int u = u0 + lane, o = u / n0;
+                reinterpret_cast<unsigned*>(epos)[(long long)kb + u] = s_pos[(u - o * n0) * kAdjStride + wbase + o];
+            }
+        } else
         for (long long u0 = (long long)kb * U; u0 < (long long)ke * U; u0 += 32) {
             const long long u = u0 + lane;
             const int k = (int)(u / U), b = (int)(u - (long long)k * U);

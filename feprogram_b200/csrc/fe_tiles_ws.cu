@@ -628,18 +628,24 @@ __global__ void __launch_bounds__(128) k_tile_ws_runs(int64_t ntiles, const int3
                                                       const int32_t* __restrict__ run_off,
                                                       unsigned char* __restrict__ blobs, int4* __restrict__ truns,
                                                       int4* __restrict__ tdesc, int zero_src) {
+    __shared__ int s_nodes[4][256];      // the tile's (sorted) owned nodes: the run walk below reads them many times
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= ntiles) return;
+    int* sn = s_nodes[threadIdx.x >> 5];
     const int lo = tile_nptr[t], nn = tile_nptr[t + 1] - lo;
     const int ni = tile_iptr[t + 1] - tile_iptr[t];
     const int nnp = (nn + 31) & ~31;
+    const bool cached = nn <= 256;       // (larger tiles exceed every capacity: the host discards the plan)
     int maxdeg = 0;
     for (int i = lane; i < nn; i += 32) {
         const int n = tile_nodes[lo + i];
+        if (cached) sn[i] = n;
         const int deg = nptr[n + 1] - nptr[n];
         maxdeg = deg > maxdeg ? deg : maxdeg;
     }
+    __syncwarp();
+    auto node_at = [&](int i) { return cached ? sn[i] : tile_nodes[lo + i]; };
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         const int m = __shfl_xor_sync(0xffffffffu, maxdeg, d);
@@ -667,15 +673,15 @@ __global__ void __launch_bounds__(128) k_tile_ws_runs(int64_t ntiles, const int3
         const int i = i0 + lane;
         int n = -2, start = 0;
         if (i < nn) {
-            n = tile_nodes[lo + i];
-            start = (i == 0 || tile_nodes[lo + i - 1] != n - 1) ? 1 : 0;
+            n = node_at(i);
+            start = (i == 0 || node_at(i - 1) != n - 1) ? 1 : 0;
         }
         const unsigned m = __ballot_sync(0xffffffffu, start != 0);
         if (start) {
             // length: up to the next run start (or the end of the tile)
             int j = i + 1;
-            while (j < nn && tile_nodes[lo + j] == tile_nodes[lo + j - 1] + 1) ++j;
-            const int last = tile_nodes[lo + j - 1];
+            while (j < nn && node_at(j) == node_at(j - 1) + 1) ++j;
+            const int last = node_at(j - 1);
             const long long v2 = 2ll * nptr[n];                                   // value offset / 2 (4 values per node-level nz)
             const int len16 = 2 * (nptr[last + 1] - nptr[n]);                     // 32 bytes per node-level non-zero
             const int st16 = 2 * noff[2 * (int64_t)(lo + i) + 1];                 // staging offset / 16 = 2 * work offset
