@@ -11,8 +11,9 @@ for c in cfg3 cfg5 poisson unstructured; do
 done
 timeout 300 python bench.py --steps 2 --warmup 3 --cg-iters 20 --no-cpu --no-strong > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_final_r3.csv python bench.py --steps 2 --warmup 3 --cg-iters 20 --no-cpu --no-strong > gpurun_out/ncu_final_r3.log 2>&1; echo "launch list rc=$?"
-FE_KERNELS=phased timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_assemble_tiled -s 2 -c 1 \
-  -o gpurun_out/prof_q9_final_r3 -f python tools/experiments/exp_ws.py 9 2048 0 3 > gpurun_out/ncu_q9_final_r3.log 2>&1; echo "ncu q9 rc=$?"
+timeout 400 ncu --set full --clock-control none --import-source on \
+  -k regex:'k_adjacency_fill|k_adjacency_count|k_tile_layout|k_tile_owner|k_tile_ws_records|k_block_sort_small' \
+  -c 6 -o gpurun_out/prof_plan_final_r3 -f python tools/experiments/e2e_probe.py 4096 > gpurun_out/ncu_plan_final_r3.log 2>&1; echo "ncu plan rc=$?"
 python - <<'PY'
 import json
 for f in ["bench_final_r3","bench_cfg3_r3","bench_cfg5_r3","bench_poisson_r3","bench_unstructured_r3"]:
