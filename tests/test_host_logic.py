@@ -120,3 +120,65 @@ def test_partition_invariants_random_meshes(seed):
         if not locality:
             assert np.all(np.diff(owned) > 0)
     assert np.all(owned_count == 1)
+
+
+# ---- the hand-written sorting networks of the symbolic kernels (csrc/fe_symbolic.cu), checked from their source ------
+def _zero_one_sorts(pairs, n):
+    """0-1 principle: a comparator network sorts every input iff it sorts every 0/1 input."""
+    import itertools
+    for bits in itertools.product((0, 1), repeat=n):
+        v = list(bits)
+        for a, b in pairs:
+            if v[a] > v[b]:
+                v[a], v[b] = v[b], v[a]
+        if v != sorted(v):
+            return False
+    return True
+
+
+def test_sorting_networks_in_the_symbolic_kernels_sort():
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "feprogram_b200", "csrc",
+                            "fe_symbolic.cu")).read()
+    # 16 packed candidate keys of a regular Quad4 node (quad4_sorted_candidates): CX(i, j) list
+    body = src[src.index("#define CX(i, j)"):src.index("#undef CX")]
+    pairs16 = [(int(a), int(b)) for a, b in re.findall(r"CX\((\d+), (\d+)\);", body)]
+    assert len(pairs16) == 63 and all(0 <= a < b < 16 for a, b in pairs16)
+    assert _zero_one_sorts(pairs16, 16)
+    # eight incidence entries of a node (k_sort_incidence): cx(v[i], v[j]) list
+    body = src[src.index("19-comparator network"):src.index("einc[lo + i] = v[i];")]
+    pairs8 = [(int(a), int(b)) for a, b in re.findall(r"cx\(v\[(\d+)\], v\[(\d+)\]\);", body)]
+    assert len(pairs8) == 19 and all(0 <= a < b < 8 for a, b in pairs8)
+    assert _zero_one_sorts(pairs8, 8)
+
+
+def test_warp_bitonic_network_sorts_256_keys():
+    """Emulation of warp_bitonic_sort<8> (csrc/fe_tile_config.cuh): 8 keys per lane, key index = 32 r + lane,
+    register exchanges at distance >= 32, shuffles below -- same index logic, random and padded inputs."""
+    rng = np.random.default_rng(5)
+    R = 8
+    for nn in (1, 31, 32, 33, 100, 153, 255, 256):
+        ids = rng.permutation(10 ** 6)[:nn]
+        v = np.full((R, 32), 0x7FFFFFFF, dtype=np.int64)
+        v.reshape(-1)[:nn] = ids
+        lanes = np.arange(32)
+        k = 2
+        while k <= 32 * R:
+            j = k >> 1
+            while j > 0:
+                if j >= 32:
+                    for r in range(R):
+                        q = r ^ (j >> 5)
+                        if q > r:
+                            up = ((32 * r) & k) == 0
+                            mn, mx = np.minimum(v[r], v[q]), np.maximum(v[r], v[q])
+                            v[r], v[q] = (mn, mx) if up else (mx, mn)
+                else:
+                    for r in range(R):
+                        o = v[r][lanes ^ j]
+                        up, lower = ((32 * r + lanes) & k) == 0, (lanes & j) == 0
+                        v[r] = np.where(up == lower, np.minimum(v[r], o), np.maximum(v[r], o))
+                j >>= 1
+            k <<= 1
+        assert np.array_equal(v.reshape(-1)[:nn], np.sort(ids))
