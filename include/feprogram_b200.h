@@ -183,6 +183,8 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
  *                             item, ZERO-INITIALISED by the caller), tchunk (uint32 per 32 work
  *                             items); stats[4] != 0 afterwards means the mesh is not representable
  *                             (use fe_assemble).
+ * Steps 2-5 (and the tile-ordered connectivity, fe_tile_conn) need the incidence and the node DEGREES (nptr) only,
+ * not nadj / epos: a caller may run them concurrently with fe_adjacency_fill (the facade does, on a side stream).
  * The plan is usable iff stats[0] <= out[2], stats[1] < out[3], stats[2] <= out[1], stats[5] <= out[4]
  * of fe_tile_params and stats[4] == 0.  Record formats are documented in feprogram_b200/csrc/fe_tiles.cu. */
 /* Bounding box of the mesh (anchors the Morton grid): out[0..3] <- {xmin, ymin, xmax, ymax} (DEVICE, 32-byte aligned);
@@ -196,7 +198,8 @@ int fe_lattice_keys(int elem_type, int64_t nelem, const int32_t* conn, int32_t* 
 /* Step 1 without a global sort (the default path of the Python facade): fe_tile_form_count buckets the elements
  * by Morton block (keys >> log2(TE); nb blocks) -- histogram, tiles per block, scans, scatter -- after which
  * tbase[nb] = ntiles and status[0] != 0 flags a block of more than 1024 elements (use another tiling);
- * fe_tile_form_sort orders every block in shared memory and writes eperm, eloc and tile_estart[ntiles + 1].
+ * fe_tile_form_sort orders every block (a register bitonic network for blocks of at most one tile, rank sorts in
+ * shared memory for larger ones) and writes eperm, eloc and tile_estart[ntiles + 1].
  * Same result as sorting by (key, element id), cutting blocks into runs of TE and ordering each tile by id.
  * Scratch: hist, tpb, ebase, tbase [nb + 1], cursor [nb], tmp [nelem], status [1] int32; scan_ws for nb + 1. */
 int fe_tile_form_count(int elem_type, int64_t nelem, int64_t nb, const int32_t* keys, int32_t* hist, int32_t* tpb,
