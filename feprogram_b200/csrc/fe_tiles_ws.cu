@@ -155,14 +155,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+#ifndef FE_WS_L2_HINTS
+#define FE_WS_L2_HINTS 0      // developer builds: 1 = output stores evict-first in L2, 2 = record-blob loads too
+#endif
+__device__ __forceinline__ uint64_t l2_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+#if FE_WS_L2_HINTS >= 2
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar), "l"(l2_evict_first())
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
                  "l"(gsrc), "r"(bytes), "r"(bar)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+#if FE_WS_L2_HINTS >= 1
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_src),
+                 "r"(bytes), "l"(l2_evict_first())
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
                  : "memory");
+#endif
 }
 
 #ifdef FE_WS_TRACE      // developer build: per-warp event time stamps (SM clock) of the first kTraceTiles tiles of CTA 0
