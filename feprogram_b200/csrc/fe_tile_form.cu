@@ -49,6 +49,11 @@ __global__ void __launch_bounds__(256) k_bbox(int64_t n, const double2* __restri
 // Lattice numbering: every Quad4 element is {b, b+1, b+W+1, b+W} for one W (what a row-major structured generator --
 // and gmsh's transfinite meshes -- produce).  Then (b mod W, b div W) are the element's lattice coordinates and the
 // Morton keys need no node coordinates: the whole tile plan can be built while the coordinates are still uploading.
+// Generalised form (the local mesh of a rank of a row-block partition: owned node rows first, ghost rows after them):
+// every element is {b, b+1, c+1, c} with b and c in the same column of two node rows of W consecutive ids each, in
+// any row order; the element's row coordinate is then the index of its UPPER node row (c div W), which is unique per
+// element row.  W is read from the middle element, the form (strict / generalised) from the first one, so every
+// thread takes the same decision.
 // status[0] |= 1 when some element does not fit the pattern (the caller then uses fe_morton_keys); status[1] = W.
 __device__ __forceinline__ unsigned spread15f(unsigned v) {
     v &= 0x7fffu;
@@ -61,17 +66,20 @@ __device__ __forceinline__ unsigned spread15f(unsigned v) {
 __global__ void k_lattice_keys(int64_t nelem, const int4* __restrict__ conn, int32_t* __restrict__ keys,
                                int32_t* __restrict__ status) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int4 c0 = __ldg(conn);
-    const int W = c0.w - c0.x;
+    const int4 c0 = __ldg(conn), cm = __ldg(conn + nelem / 2);
+    const int W = cm.w - cm.x;
+    const bool strict = c0.w - c0.x == W;          // rows in lattice order (a single-GPU structured mesh)
     if (e == 0) status[1] = W;
     if (e >= nelem) return;
     const int4 c = __ldg(conn + e);
-    bool ok = W >= 2 && c.y == c.x + 1 && c.z == c.x + W + 1 && c.w == c.x + W;
+    bool ok = W >= 2 && c.y == c.x + 1 && c.z == c.w + 1 && c.x >= 0 && c.w >= 0;
     int ix = 0, iy = 0;
     if (ok) {
-        iy = c.x / W;
-        ix = c.x - iy * W;
-        ok = ix < W - 1 && ix < 32768 && iy < 32768;
+        const int rx = c.x / W, rw = c.w / W;
+        ix = c.x - rx * W;
+        ok = ix == c.w - rw * W && rx != rw && (!strict || rw == rx + 1);
+        iy = strict ? rx : rw;
+        ok = ok && ix < W - 1 && ix < 32768 && iy < 32768;
     }
     if (!ok) {
         atomicOr(status, 1);

@@ -842,6 +842,28 @@ def test_lattice_numbering_plans_without_coordinates(torch_cuda):
             assert plan.ntiles == 13 * 19
 
 
+@pytest.mark.parametrize("rank,world", [(0, 2), (1, 2), (1, 3), (2, 3)])
+def test_row_block_local_meshes_plan_without_coordinates(torch_cuda, rank, world):
+    """The local mesh of a rank of a row-block partition numbers its owned node rows first and the ghost rows after
+    them: not a row-major lattice, but every element still spans two node rows of W consecutive ids -- the generalised
+    form of fe_lattice_keys.  Its tile plan needs no coordinates either (multi-GPU e2e: the plan overlaps their upload)."""
+    torch = torch_cuda
+    from feprogram_b200 import dist as fdist
+    from feprogram_b200 import ops
+    m, _ = fdist.structured_quad4_block(96, 40, rank, world)
+    conn0 = torch.from_numpy(np.ascontiguousarray(m.conn)).cuda()
+    xy = torch.from_numpy(np.ascontiguousarray(m.coords)).cuda()
+    pat = ops.symbolic(conn0, m.nnode, 4, 2)
+    asked = []
+    plan = ops.tile_plan(conn0, xy, pat, coords_ready=lambda: asked.append(1))
+    assert plan is not None and plan.stats["mode"] == "lattice" and not asked
+    v = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, plan, v)
+    v_rows = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+    ops.assemble_values(conn0, xy, pat, None, v_rows)
+    assert torch.equal(v, v_rows)
+
+
 # ---- scalar Poisson extension (FE_OP_POISSON, one dof per node; SURVEY "facts at a glance", §8d) -------------------
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_poisson_operator_is_the_even_block_of_the_reference_matrix(torch_cuda, golden, name):
