@@ -192,6 +192,9 @@ int fe_assemble(int elem_type, int op, int64_t nelem, int64_t nnode, const int32
 int fe_bbox(int64_t nnode, const double* coords, double* scratch, double* out, void* stream);
 /* Morton keys WITHOUT coordinates, for lattice numberings: when every Quad4 element is {b, b+1, b+W+1, b+W} for one W
  * (row-major structured meshes, whatever their geometry), (b mod W, b div W) are the element's lattice coordinates.
+ * Also accepted: {b, b+1, c+1, c} with b, c in the same column of two node rows of W consecutive ids in any row order
+ * (the local mesh of a rank of a row-block partition: owned node rows first, ghost rows after them); the row
+ * coordinate is then c div W.
  * status[0] != 0 afterwards: the mesh does not fit (use fe_morton_keys); status[1] = W.  The tile plan built from
  * these keys needs no coordinates, so the facade builds it while the coordinates are still uploading. */
 int fe_lattice_keys(int elem_type, int64_t nelem, const int32_t* conn, int32_t* keys, int32_t* status, void* stream);

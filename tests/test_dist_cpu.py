@@ -166,3 +166,35 @@ def test_partition_halo_and_distributed_pcg_over_gloo(world, kind, structured):
     bad = [r for r in res if r[1] != "ok"]
     assert not bad, bad[0][2]
     assert len({r[2] for r in res}) == 1          # every rank ran the same number of iterations
+
+
+def test_row_block_local_numbering_fits_the_generalised_lattice_rule():
+    """fe_lattice_keys (csrc/fe_tile_form.cu) lets a rank's tile plan start before its coordinates arrive when every
+    element is {b, b+1, c+1, c} with b, c in the same column of two node rows of W consecutive ids (W read from the
+    middle element; strict row-major form iff the first element has c = b + W).  This restates the rule on the host
+    and checks that the local meshes structured_quad4_block builds satisfy it with one distinct cell per element."""
+    from feprogram_b200 import dist as fd
+
+    def lattice_cells(conn):
+        c0, cm = conn[0], conn[len(conn) // 2]
+        W = int(cm[3] - cm[0])
+        strict = int(c0[3] - c0[0]) == W
+        x, y, z, w = conn.T.astype(np.int64)
+        ok = (W >= 2) & (y == x + 1) & (z == w + 1) & (x >= 0) & (w >= 0)
+        rx, rw = x // W, w // W
+        ix = x - rx * W
+        ok &= (ix == w - rw * W) & (rx != rw) & ((not strict) | (rw == rx + 1)) & (ix < W - 1)
+        return bool(ok.all()), W, strict, ix, np.where(strict, rx, rw)
+
+    for world in (1, 2, 3, 5):
+        for rank in range(world):
+            m, _ = fd.structured_quad4_block(24, 10, rank, world)
+            ok, W, strict, ix, iy = lattice_cells(m.conn)
+            assert ok and W == 25 and strict == (rank == 0)
+            assert len(set(zip(ix.tolist(), iy.tolist()))) == len(m.conn)          # one cell per element
+            assert iy.min() >= 0 and iy.max() < (m.nnode + W - 1) // W             # inside the key range the host sizes
+    # a shuffled numbering does not fit
+    from feprogram_b200 import mesh
+    conn, coords, bc = mesh.structured_quad4(12, 9)
+    conn2, _, _, _ = mesh.shuffle_numbering(conn, coords, bc, seed=4)
+    assert not lattice_cells(conn2 - 1)[0]
