@@ -614,7 +614,7 @@ def _tile_plan(conn: Tensor, coords: Tensor, pat: Pattern, morton: bool, cell_sc
     if params["halo_cap"] == 0 or pat.nelem == 0 or pat.nnode == 0:
         return None
     dev = conn.device
-    te, hcap = params["tile_elems"], params["halo_cap"]
+    te = params["tile_elems"]
     nelem, nnode = pat.nelem, pat.nnode
     mode_name = mode
     with torch.cuda.device(dev):
@@ -797,7 +797,6 @@ def plan_layout_early(conn: Tensor, elem_type: int, nnode: int, eptr: Tensor, ei
 def _plan_records(conn: Tensor, pat: Pattern, lay: dict, kernel: str) -> Optional[TilePlan]:
     """Second half of the plan: the per-tile records of the numeric kernel (needs nadj / epos)."""
     L = _lib.lib()
-    params = _lib.tile_params(pat.elem_type)
     dev = conn.device
     ntiles, einv, owner, tile_ptr, tile_nodes = lay["ntiles"], lay["eloc"], lay["owner"], lay["tile_ptr"], lay["tile_nodes"]
     noff, thalo, stats, tconn, info = lay["noff"], lay["thalo"], lay["stats"], lay["tconn"], lay["info"]
